@@ -1,0 +1,521 @@
+// chb_api.cu - the extern "C" entry points declared in include/channel_b200.h.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/channel_b200.h"
+#include "chb_internal.h"
+
+static thread_local std::string g_err;
+void chb_set_error(const std::string& s) { g_err = s; }
+extern "C" const char* chb_last_error(void) { return g_err.c_str(); }
+extern "C" int chb_version(void) { return 1000; }
+
+#define CHB_REQUIRE(cond, msg)  \
+    do {                        \
+        if (!(cond)) {          \
+            chb_set_error(msg); \
+            return 2;           \
+        }                       \
+    } while (0)
+
+// ---- timing -----------------------------------------------------------------------------
+ScopedKernelTimer::ScopedKernelTimer(chb_handle_s* h_, const char* name_) : h(h_), name(name_), on(h_->timer.on) {
+    if (on) {
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        cudaEventRecord(e0, h->stream);
+    }
+}
+ScopedKernelTimer::~ScopedKernelTimer() {
+    if (on) {
+        cudaEventRecord(e1, h->stream);
+        h->timer.pending.push_back({name, {e0, e1}});
+    }
+}
+void chb_timer_flush(chb_handle_s* h) {
+    if (h->timer.pending.empty()) return;
+    cudaStreamSynchronize(h->stream);
+    for (auto& p : h->timer.pending) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, p.second.first, p.second.second);
+        auto& r = h->timer.recs[p.first];
+        r.ms += ms;
+        r.n += 1;
+        cudaEventDestroy(p.second.first);
+        cudaEventDestroy(p.second.second);
+    }
+    h->timer.pending.clear();
+}
+
+// ---- FFT plans ----------------------------------------------------------------------------
+// radices for n = 2^a 3^b: the 3 first (largest stride), then 8s, then a trailing 4 or 2
+static bool build_plan(int n, FftPlan* pl, std::vector<int>* rev) {
+    pl->n = n;
+    pl->npass = 0;
+    int r = n;
+    if (r % 3 == 0) {
+        pl->radix[pl->npass++] = 3;
+        r /= 3;
+    }
+    if (r % 3 == 0) return false;
+    int a = 0;
+    while (r % 2 == 0) {
+        r /= 2;
+        ++a;
+    }
+    if (r != 1) return false;
+    while (a >= 3) {
+        pl->radix[pl->npass++] = 8;
+        a -= 3;
+    }
+    if (a == 2) pl->radix[pl->npass++] = 4;
+    if (a == 1) pl->radix[pl->npass++] = 2;
+    if (pl->npass > CHB_MAX_PASSES) return false;
+    if (rev) {
+        rev->resize(n);
+        for (int k = 0; k < n; ++k) {
+            int kk = k, pos = 0, stride = n;
+            for (int t = 0; t < pl->npass; ++t) {
+                const int R = pl->radix[t];
+                stride /= R;
+                pos += (kk % R) * stride;
+                kk /= R;
+            }
+            (*rev)[k] = pos;
+        }
+    }
+    return true;
+}
+
+static std::vector<double> twiddles(int n, int count, int denom) {
+    std::vector<double> w(2 * (size_t)count);
+    for (int e = 0; e < count; ++e) {
+        const long double a = 2.0L * 3.14159265358979323846264338327950288L * (long double)e / (long double)denom;
+        w[2 * e] = (double)cosl(a);
+        w[2 * e + 1] = (double)sinl(a);
+    }
+    (void)n;
+    return w;
+}
+
+template <typename T>
+static int dev_alloc(T** p, size_t count) {
+    CHB_CUDA_OK(cudaMalloc((void**)p, count * sizeof(T)));
+    CHB_CUDA_OK(cudaMemset(*p, 0, count * sizeof(T)));
+    return 0;
+}
+template <typename T>
+static int dev_upload(T** p, const std::vector<T>& v) {
+    CHB_CUDA_OK(cudaMalloc((void**)p, v.size() * sizeof(T)));
+    CHB_CUDA_OK(cudaMemcpy(*p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+// ---- multi-GPU (transpose.cu) ----
+int chb_nccl_init(chb_handle_s* h, const char* id);
+void chb_nccl_destroy(chb_handle_s* h);
+int chb_nccl_unique_id(char* id);
+int chb_allreduce_max_cfl(chb_handle_s* h);
+int chb_bcast_scalars(chb_handle_s* h);
+
+extern "C" int chb_get_nccl_unique_id(char* id) { return chb_nccl_unique_id(id); }
+
+// ---- create / destroy ---------------------------------------------------------------------
+extern "C" int chb_create(chb_handle* out, int nx, int ny, int nz, int nxd, int nzd, double alfa0, double beta0,
+                          double ni, double a, double ymin, double ymax, int rank, int nranks, const char* nccl_id,
+                          int device) {
+    (void)a; (void)ymin; (void)ymax;
+    CHB_REQUIRE(out != nullptr, "chb_create: null handle pointer");
+    CHB_REQUIRE(nx >= 1 && ny >= 8 && nz >= 1, "chb_create: need nx>=1, ny>=8, nz>=1");
+    CHB_REQUIRE(nxd >= nx + 1 && nxd % 2 == 0, "chb_create: nxd must be even and >= nx+1");
+    CHB_REQUIRE(nzd >= 2 * nz + 1, "chb_create: nzd must be >= 2nz+1");
+    CHB_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, "chb_create: bad rank/nranks");
+    CHB_REQUIRE((nx + 1) % nranks == 0 && nzd % nranks == 0,
+                "chb_create: nranks must divide nx+1 and nzd (README.md:154)");
+    CHB_REQUIRE(nranks == 1 || nccl_id != nullptr, "chb_create: nccl_id required when nranks>1");
+    int ndev = 0;
+    CHB_CUDA_OK(cudaGetDeviceCount(&ndev));
+    CHB_REQUIRE(ndev > 0, "chb_create: no CUDA device (this library has no CPU fallback)");
+    CHB_CUDA_OK(cudaSetDevice(device));
+    chb_handle_s* h = new chb_handle_s();
+    memset(&h->g, 0, sizeof(h->g));
+    Geometry& g = h->g;
+    g.nx = nx; g.ny = ny; g.nz = nz; g.nxd = nxd; g.nzd = nzd;
+    g.nyp = ny + 3; g.nzt = 2 * nz + 1;
+    g.rank = rank; g.nranks = nranks;
+    // mpi_transpose.f90:214-215
+    g.nx0 = rank * (nx + 1) / nranks; g.nxN = (rank + 1) * (nx + 1) / nranks - 1; g.nxB = g.nxN - g.nx0 + 1;
+    g.nz0 = rank * nzd / nranks; g.nzN = (rank + 1) * nzd / nranks - 1; g.nzB = g.nzN - g.nz0 + 1;
+    g.M = (long long)g.nxB * g.nzt;
+    g.alfa0 = alfa0; g.beta0 = beta0; g.ni = ni;
+    const double PI = 3.1415926535897932384626433832795028841971;  // dnsdata.f90:26
+    g.dx = PI / (alfa0 * nxd); g.dz = 2.0 * PI / (beta0 * nzd); g.factor = 1.0 / (2.0 * nxd * nzd);  // :124
+    h->device = device;
+    h->launches = 0;
+    h->tables_set = false;
+    h->F = nullptr;
+    h->nccl_comm = nullptr;
+    memset(&h->bf, 0, sizeof(h->bf));
+    CHB_CUDA_OK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+
+    std::vector<int> rev;
+    CHB_REQUIRE(build_plan(nzd, &h->plan_z, &rev), "chb_create: nzd must be 2^a or 3*2^a (fftFIT, ffts.f90:78-86)");
+    CHB_REQUIRE(build_plan(nxd, &h->plan_x, nullptr), "chb_create: nxd must be 2^a or 3*2^a (fftFIT, ffts.f90:78-86)");
+    if (dev_upload(&h->rev_z, rev)) return 1;
+    {
+        std::vector<double> wz = twiddles(nzd, nzd, nzd), wx = twiddles(nxd, nxd, nxd), wh = twiddles(nxd, nxd, 2 * nxd);
+        double *pz, *px, *ph;
+        if (dev_upload(&pz, wz) || dev_upload(&px, wx) || dev_upload(&ph, wh)) return 1;
+        h->Wz = (cplx*)pz; h->Wx = (cplx*)px; h->Wh = (cplx*)ph;
+    }
+    const size_t fld = (size_t)g.nyp * g.M;
+    if (dev_alloc(&h->V, 3 * fld) || dev_alloc(&h->rhs, 2 * fld) || dev_alloc(&h->oldrhs, 2 * fld) ||
+        dev_alloc(&h->P, 6 * fld) || dev_alloc(&h->mult, 4 * fld))
+        return 1;
+    // convolution work buffers: chunk of planes sized to ~3 GB
+    {
+        const size_t per_plane = (size_t)9 * nzd * g.nxB * sizeof(cplx) * (nranks > 1 ? 2 : 1);
+        size_t np = (size_t)3 << 30;
+        np /= per_plane;
+        if (np < 1) np = 1;
+        if (np > (size_t)g.nyp) np = g.nyp;
+        h->chunk_planes = (int)np;
+        const size_t na = (size_t)3 * np * nzd * g.nxB, nb = (size_t)6 * np * nzd * g.nxB;
+        if (dev_alloc(&h->A, na) || dev_alloc(&h->B, nb)) return 1;
+        if (nranks > 1) {
+            if (dev_alloc(&h->Ar, na) || dev_alloc(&h->Br, nb)) return 1;
+        } else {
+            h->Ar = h->A;
+            h->Br = h->B;
+        }
+    }
+    if (dev_alloc(&h->t_y, (size_t)g.nyp) || dev_alloc(&h->t_dy, (size_t)g.nyp) ||
+        dev_alloc(&h->t_d0, (size_t)g.nyp * 5) || dev_alloc(&h->t_d1, (size_t)g.nyp * 5) ||
+        dev_alloc(&h->t_d2, (size_t)g.nyp * 5) || dev_alloc(&h->t_d4, (size_t)g.nyp * 5) ||
+        dev_alloc(&h->t_D0mat, (size_t)(ny + 1) * 5) || dev_alloc(&h->mean_scratch, (size_t)(ny + 1) * 5 + g.nyp + 8))
+        return 1;
+    if (dev_alloc(&h->sc, 1)) return 1;
+    CHB_CUDA_OK(cudaMallocHost((void**)&h->sc_host, sizeof(DevScalars)));
+    memset(h->sc_host, 0, sizeof(DevScalars));
+    if (nranks > 1 && chb_nccl_init(h, nccl_id)) return 1;
+    CHB_CUDA_OK(cudaDeviceSynchronize());
+    *out = h;
+    return 0;
+}
+
+extern "C" int chb_destroy(chb_handle h) {
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    chb_timer_flush(h);
+    chb_nccl_destroy(h);
+    cudaFree(h->V); cudaFree(h->rhs); cudaFree(h->oldrhs); cudaFree(h->P); cudaFree(h->mult);
+    if (h->F) cudaFree(h->F);
+    cudaFree(h->A); cudaFree(h->B);
+    if (h->g.nranks > 1) { cudaFree(h->Ar); cudaFree(h->Br); }
+    cudaFree(h->Wz); cudaFree(h->Wx); cudaFree(h->Wh); cudaFree(h->rev_z);
+    cudaFree(h->t_y); cudaFree(h->t_dy); cudaFree(h->t_d0); cudaFree(h->t_d1); cudaFree(h->t_d2); cudaFree(h->t_d4);
+    cudaFree(h->t_D0mat); cudaFree(h->mean_scratch); cudaFree(h->sc);
+    if (h->bf.mask_y) cudaFree(h->bf.mask_y);
+    if (h->bf.mask_z) cudaFree(h->bf.mask_z);
+    cudaFreeHost(h->sc_host);
+    cudaStreamDestroy(h->stream);
+    delete h;
+    return 0;
+}
+
+extern "C" int chb_get_decomposition(chb_handle h, int* nx0, int* nxN, int* nz0, int* nzN) {
+    CHB_REQUIRE(h, "null handle");
+    *nx0 = h->g.nx0; *nxN = h->g.nxN; *nz0 = h->g.nz0; *nzN = h->g.nzN;
+    return 0;
+}
+
+// ---- tables --------------------------------------------------------------------------------
+extern "C" int chb_set_tables(chb_handle h, const double* y, const double* d0, const double* d1, const double* d2,
+                              const double* d4, const double* d140, const double* d14m1, const double* d240,
+                              const double* d24m1, const double* d14n, const double* d14np1, const double* d24n,
+                              const double* d24np1, const double* v0bc, const double* v0m1bc, const double* vnbc,
+                              const double* vnp1bc, const double* eta0bc, const double* eta0m1bc,
+                              const double* etanbc, const double* etanp1bc, const double* D0mat) {
+    CHB_REQUIRE(h, "null handle");
+    CHB_CUDA_OK(cudaSetDevice(h->device));
+    const Geometry& g = h->g;
+    const int ny = g.ny;
+    std::vector<double> dy(g.nyp, 0.0);
+    for (int iy = 1; iy <= ny - 1; ++iy) dy[iy + 1] = 0.5 * (y[iy + 2] - y[iy]);  // dnsdata.f90:155
+    CHB_CUDA_OK(cudaMemcpy(h->t_y, y, sizeof(double) * g.nyp, cudaMemcpyHostToDevice));
+    CHB_CUDA_OK(cudaMemcpy(h->t_dy, dy.data(), sizeof(double) * g.nyp, cudaMemcpyHostToDevice));
+    const double* src[4] = {d0, d1, d2, d4};
+    double* dst[4] = {h->t_d0, h->t_d1, h->t_d2, h->t_d4};
+    for (int t = 0; t < 4; ++t) {
+        std::vector<double> full((size_t)g.nyp * 5, 0.0);
+        memcpy(&full[(size_t)2 * 5], src[t], sizeof(double) * 5 * (ny - 1));  // rows iy=1..ny-1 -> index iy+1
+        CHB_CUDA_OK(cudaMemcpy(dst[t], full.data(), sizeof(double) * full.size(), cudaMemcpyHostToDevice));
+    }
+    CHB_CUDA_OK(cudaMemcpy(h->t_D0mat, D0mat, sizeof(double) * 5 * (ny + 1), cudaMemcpyHostToDevice));
+    DevTables& t = h->tab;
+    t.y = h->t_y; t.dy = h->t_dy; t.d0 = h->t_d0; t.d1 = h->t_d1; t.d2 = h->t_d2; t.d4 = h->t_d4;
+    t.D0mat = h->t_D0mat;
+#define CP5(name) memcpy(t.name, name, sizeof(double) * 5)
+    CP5(d140); CP5(d14m1); CP5(d240); CP5(d24m1); CP5(d14n); CP5(d14np1); CP5(d24n); CP5(d24np1);
+    CP5(v0bc); CP5(v0m1bc); CP5(vnbc); CP5(vnp1bc); CP5(eta0bc); CP5(eta0m1bc); CP5(etanbc); CP5(etanp1bc);
+#undef CP5
+    h->tables_set = true;
+    return 0;
+}
+
+// ---- field transfer --------------------------------------------------------------------------
+static int transfer_V(chb_handle h, double* host, bool upload, bool fortran_layout, cplx* field) {
+    CHB_REQUIRE(h, "null handle");
+    CHB_CUDA_OK(cudaSetDevice(h->device));
+    const Geometry& g = h->g;
+    const size_t fld = (size_t)g.nyp * g.M;
+    CHB_CUDA_OK(cudaStreamSynchronize(h->stream));
+    for (int c = 0; c < 3; ++c) {
+        cplx* dev = field + c * fld;
+        cplx* hc = reinterpret_cast<cplx*>(host) + c * fld;
+        if (!fortran_layout) {
+            if (upload) CHB_CUDA_OK(cudaMemcpyAsync(dev, hc, fld * sizeof(cplx), cudaMemcpyHostToDevice, h->stream));
+            else CHB_CUDA_OK(cudaMemcpyAsync(hc, dev, fld * sizeof(cplx), cudaMemcpyDeviceToHost, h->stream));
+        } else {
+            cplx* stage = h->P;  // products buffer is dead outside buildrhs
+            if (upload) {
+                CHB_CUDA_OK(cudaMemcpyAsync(stage, hc, fld * sizeof(cplx), cudaMemcpyHostToDevice, h->stream));
+                launch_fortran_to_planes(h, stage, dev, c, 0, g.nxB);
+            } else {
+                launch_planes_to_fortran(h, dev, stage, c, 0, g.nxB);
+                CHB_CUDA_OK(cudaMemcpyAsync(hc, stage, fld * sizeof(cplx), cudaMemcpyDeviceToHost, h->stream));
+            }
+        }
+        CHB_CUDA_OK(cudaStreamSynchronize(h->stream));
+    }
+    CHB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+extern "C" int chb_upload_V(chb_handle h, const double* V) { return transfer_V(h, const_cast<double*>(V), true, true, h ? h->V : nullptr); }
+extern "C" int chb_download_V(chb_handle h, double* V) { return transfer_V(h, V, false, true, h ? h->V : nullptr); }
+extern "C" int chb_upload_V_planes(chb_handle h, const double* V) { return transfer_V(h, const_cast<double*>(V), true, false, h ? h->V : nullptr); }
+extern "C" int chb_download_V_planes(chb_handle h, double* V) { return transfer_V(h, V, false, false, h ? h->V : nullptr); }
+extern "C" int chb_download_F_planes(chb_handle h, double* F) {
+    CHB_REQUIRE(h && h->F, "chb_download_F_planes: body force not enabled");
+    return transfer_V(h, F, false, false, h->F);
+}
+
+static int download_n(chb_handle h, double* host, const cplx* dev, int ncomp) {
+    CHB_REQUIRE(h, "null handle");
+    CHB_CUDA_OK(cudaSetDevice(h->device));
+    const size_t n = (size_t)ncomp * h->g.nyp * h->g.M;
+    CHB_CUDA_OK(cudaStreamSynchronize(h->stream));
+    CHB_CUDA_OK(cudaMemcpy(host, dev, n * sizeof(cplx), cudaMemcpyDeviceToHost));
+    return 0;
+}
+extern "C" int chb_download_rhs(chb_handle h, double* p) { return download_n(h, p, h ? h->rhs : nullptr, 2); }
+extern "C" int chb_download_products(chb_handle h, double* p) { return download_n(h, p, h ? h->P : nullptr, 6); }
+
+// ---- scalars ---------------------------------------------------------------------------------
+static int push_scalars(chb_handle h) {
+    CHB_CUDA_OK(cudaMemcpyAsync(h->sc, h->sc_host, sizeof(DevScalars), cudaMemcpyHostToDevice, h->stream));
+    CHB_CUDA_OK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+static int pull_scalars(chb_handle h) {
+    CHB_CUDA_OK(cudaMemcpyAsync(h->sc_host, h->sc, sizeof(DevScalars), cudaMemcpyDeviceToHost, h->stream));
+    CHB_CUDA_OK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int chb_set_wall_velocity(chb_handle h, double u0, double uN) {
+    CHB_REQUIRE(h, "null handle");
+    CHB_CUDA_OK(cudaSetDevice(h->device));
+    if (pull_scalars(h)) return 1;
+    h->sc_host->u0 = u0;
+    h->sc_host->uN = uN;
+    return push_scalars(h);
+}
+
+extern "C" int chb_set_forcing(chb_handle h, double meanpx, double meanpz, double meanflowx, double meanflowz, int CPI,
+                               int CPI_type, double gamma) {
+    CHB_REQUIRE(h, "null handle");
+    CHB_REQUIRE(!CPI || CPI_type == 0 || CPI_type == 1, "Wrong selection of CPI_Type");  // linsolve_blocking.inc:93-95
+    CHB_CUDA_OK(cudaSetDevice(h->device));
+    if (pull_scalars(h)) return 1;
+    DevScalars* s = h->sc_host;
+    s->meanpx = meanpx; s->meanpz = meanpz; s->meanflowx = meanflowx; s->meanflowz = meanflowz;
+    s->CPI = CPI; s->CPI_type = CPI_type; s->gamma = gamma;
+    return push_scalars(h);
+}
+
+// ---- body force ------------------------------------------------------------------------------
+extern "C" int chb_set_body_force_linear(chb_handle h, int enable, const double* A, const double* mask_y,
+                                         const double* mask_z, int exclude_mean) {
+    CHB_REQUIRE(h, "null handle");
+    CHB_CUDA_OK(cudaSetDevice(h->device));
+    const Geometry& g = h->g;
+    h->bf.enabled = enable;
+    if (!enable) return 0;
+    CHB_REQUIRE(A && mask_y && mask_z, "chb_set_body_force_linear: null argument");
+    memcpy(h->bf.A, A, sizeof(double) * 9);
+    h->bf.exclude_mean = exclude_mean;
+    if (!h->F && dev_alloc(&h->F, (size_t)3 * g.nyp * g.M)) return 1;
+    if (!h->bf.mask_y && (dev_alloc(&h->bf.mask_y, (size_t)g.nyp) || dev_alloc(&h->bf.mask_z, (size_t)g.nzt))) return 1;
+    CHB_CUDA_OK(cudaMemcpy(h->bf.mask_y, mask_y, sizeof(double) * g.nyp, cudaMemcpyHostToDevice));
+    CHB_CUDA_OK(cudaMemcpy(h->bf.mask_z, mask_z, sizeof(double) * g.nzt, cudaMemcpyHostToDevice));
+    return 0;
+}
+extern "C" int chb_set_body_force(chb_handle h) {
+    CHB_REQUIRE(h, "null handle");
+    if (!h->bf.enabled) return 0;
+    CHB_CUDA_OK(cudaSetDevice(h->device));
+    launch_body_force(h);
+    CHB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// ---- the hot path ----------------------------------------------------------------------------
+static int convolutions_all(chb_handle h, int compute_cfl, bool products) {
+    const Geometry& g = h->g;
+    const int np = h->chunk_planes;
+    const size_t na = (size_t)3 * np * g.nzB * g.nxB, nb = (size_t)6 * np * g.nzB * g.nxB;
+    for (int p0 = 0; p0 < g.nyp; p0 += np) {
+        const int n = (p0 + np <= g.nyp) ? np : g.nyp - p0;
+        launch_zfwd(h, p0, n);
+        if (g.nranks > 1 && chb_alltoall(h, h->A, h->Ar, na)) return 1;       // zTOx, mpi_transpose.f90:74
+        launch_xpass(h, p0, n, compute_cfl);
+        if (products) {
+            if (g.nranks > 1 && chb_alltoall(h, h->B, h->Br, nb)) return 1;   // xTOz, mpi_transpose.f90:109
+            launch_zbwd(h, p0, n);
+        }
+    }
+    CHB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int chb_cfl_prepass(chb_handle h) {
+    CHB_REQUIRE(h && h->tables_set, "chb_cfl_prepass: tables not set");
+    CHB_CUDA_OK(cudaSetDevice(h->device));
+    if (convolutions_all(h, 1, false)) return 1;
+    launch_meanflow_prepass(h);
+    CHB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int chb_buildrhs(chb_handle h, const double* ode, double deltat, int compute_cfl) {
+    CHB_REQUIRE(h && h->tables_set, "chb_buildrhs: tables not set");
+    CHB_REQUIRE(deltat > 0.0, "chb_buildrhs: deltat must be > 0");
+    CHB_CUDA_OK(cudaSetDevice(h->device));
+    if (h->bf.enabled) launch_force_ghosts(h);
+    if (convolutions_all(h, compute_cfl, true)) return 1;
+    launch_rhs(h, ode, deltat);
+    CHB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int chb_linsolve(chb_handle h, double lambda) {
+    CHB_REQUIRE(h && h->tables_set, "chb_linsolve: tables not set");
+    CHB_CUDA_OK(cudaSetDevice(h->device));
+    launch_linsolve(h, lambda);
+    CHB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+extern "C" int chb_vetaTOuvw(chb_handle h) { CHB_REQUIRE(h, "null handle"); return 0; }
+extern "C" int chb_computeflowrate(chb_handle h, double) { CHB_REQUIRE(h, "null handle"); return 0; }
+
+extern "C" int chb_rk3_step(chb_handle h, double deltat) {
+    static const double RK[3][3] = {{120.0 / 32.0, 2.0, 0.0},                    // dnsdata.f90:70-72
+                                    {120.0 / 8.0, 50.0 / 8.0, 34.0 / 8.0},
+                                    {120.0 / 20.0, 90.0 / 20.0, 50.0 / 20.0}};
+    for (int k = 0; k < 3; ++k) {
+        if (chb_set_body_force(h)) return 1;
+        if (chb_buildrhs(h, RK[k], deltat, k == 2)) return 1;
+        if (chb_linsolve(h, RK[k][0] / deltat)) return 1;
+    }
+    return 0;
+}
+
+extern "C" int chb_get_step_scalars(chb_handle h, double* cfl, double* fr, double* corrpx, double* corrpz,
+                                    double* meanpx, double* meanpz, double* U_lo, double* U_hi, double* W_lo,
+                                    double* W_hi) {
+    CHB_REQUIRE(h, "null handle");
+    CHB_CUDA_OK(cudaSetDevice(h->device));
+    if (h->g.nranks > 1) {
+        if (chb_allreduce_max_cfl(h)) return 1;   // MPI_Allreduce(cfl, MAX), dnsdata.f90:861
+        if (chb_bcast_scalars(h)) return 1;
+    }
+    if (pull_scalars(h)) return 1;
+    chb_timer_flush(h);
+    DevScalars* s = h->sc_host;
+    double c;
+    memcpy(&c, &s->cfl_bits, sizeof(double));
+    if (cfl) *cfl = c;
+    if (fr) memcpy(fr, s->fr, sizeof(double) * 3);
+    if (corrpx) *corrpx = s->corrpx;
+    if (corrpz) *corrpz = s->corrpz;
+    if (meanpx) *meanpx = s->meanpx;
+    if (meanpz) *meanpz = s->meanpz;
+    if (U_lo) memcpy(U_lo, s->U_lo, sizeof(double) * 5);
+    if (U_hi) memcpy(U_hi, s->U_hi, sizeof(double) * 5);
+    if (W_lo) memcpy(W_lo, s->W_lo, sizeof(double) * 5);
+    if (W_hi) memcpy(W_hi, s->W_hi, sizeof(double) * 5);
+    // cfl = 0 (dnsdata.f90:861)
+    CHB_CUDA_OK(cudaMemsetAsync(&h->sc->cfl_bits, 0, sizeof(unsigned long long), h->stream));
+    CHB_CUDA_OK(cudaStreamSynchronize(h->stream));
+    CHB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// ---- diagnostics -----------------------------------------------------------------------------
+extern "C" int chb_sync(chb_handle h) {
+    CHB_REQUIRE(h, "null handle");
+    CHB_CUDA_OK(cudaSetDevice(h->device));
+    CHB_CUDA_OK(cudaStreamSynchronize(h->stream));
+    CHB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+extern "C" long long chb_launch_count(chb_handle h) { return h ? h->launches : -1; }
+extern "C" int chb_timing_enable(chb_handle h, int on) {
+    CHB_REQUIRE(h, "null handle");
+    chb_timer_flush(h);
+    h->timer.on = on != 0;
+    h->timer.recs.clear();
+    return 0;
+}
+extern "C" int chb_timing_report(chb_handle h, char* names, int name_stride, double* ms, long long* launches, int cap) {
+    CHB_REQUIRE(h, "null handle");
+    chb_timer_flush(h);
+    int i = 0;
+    for (auto& kv : h->timer.recs) {
+        if (i < cap) {
+            snprintf(names + (size_t)i * name_stride, name_stride, "%s", kv.first.c_str());
+            ms[i] = kv.second.ms;
+            launches[i] = kv.second.n;
+        }
+        ++i;
+    }
+    return i;
+}
+
+// standalone FFT for the parity tests (conv_kernels.cu)
+int launch_test_fft(const FftPlan& pl, const cplx* W, const int* rev, cplx* data, int nlines, int sign);
+extern "C" int chb_test_fft_lines(int n, int nlines, int sign, double* data_host) {
+    FftPlan pl;
+    std::vector<int> rev;
+    CHB_REQUIRE(build_plan(n, &pl, &rev), "chb_test_fft_lines: n must be 2^a or 3*2^a");
+    int ndev = 0;
+    CHB_CUDA_OK(cudaGetDeviceCount(&ndev));
+    CHB_REQUIRE(ndev > 0, "no CUDA device");
+    std::vector<double> w = twiddles(n, n, n);
+    double* dW = nullptr;
+    int* dRev = nullptr;
+    cplx* dData = nullptr;
+    if (dev_upload(&dW, w) || dev_upload(&dRev, rev)) return 1;
+    CHB_CUDA_OK(cudaMalloc((void**)&dData, sizeof(cplx) * (size_t)n * nlines));
+    CHB_CUDA_OK(cudaMemcpy(dData, data_host, sizeof(cplx) * (size_t)n * nlines, cudaMemcpyHostToDevice));
+    if (launch_test_fft(pl, (const cplx*)dW, dRev, dData, nlines, sign)) return 1;
+    CHB_CUDA_OK(cudaDeviceSynchronize());
+    CHB_CUDA_OK(cudaMemcpy(data_host, dData, sizeof(cplx) * (size_t)n * nlines, cudaMemcpyDeviceToHost));
+    cudaFree(dW); cudaFree(dRev); cudaFree(dData);
+    return 0;
+}

@@ -1,0 +1,137 @@
+// chb_internal.h - handle layout and kernel launchers of libchannel_b200.
+#pragma once
+#include <cuda_runtime.h>
+#include <map>
+#include <string>
+#include <vector>
+#include "fft_device.cuh"
+
+// Coefficient tables of setup_derivatives / setup_boundary_conditions
+// (dnsdata.f90:241-308), passed by value to the y-direction kernels.
+struct DevTables {
+    const double* y;      // [ny+3]      y(-1:ny+1)
+    const double* dy;     // [ny+3]      dy(iy), iy=1..ny-1 (else 0)
+    const double* d0;     // [ny+3][5]   der(iy)%d0(-2:2), zero rows outside 1..ny-1
+    const double* d1;
+    const double* d2;
+    const double* d4;
+    const double* D0mat;  // [ny+1][5]   after LU5decompStep, row i <-> iy=i+1
+    double d140[5], d14m1[5], d240[5], d24m1[5], d14n[5], d14np1[5], d24n[5], d24np1[5];
+    double v0bc[5], v0m1bc[5], vnbc[5], vnp1bc[5], eta0bc[5], eta0m1bc[5], etanbc[5], etanp1bc[5];
+};
+
+// Device-resident scalars of MODULE dnsdata that the path reads and writes.
+struct DevScalars {
+    unsigned long long cfl_bits;  // running max of cfl (non-negative double, ordered as uint64)
+    double fr[3];
+    double corrpx, corrpz;
+    double meanpx, meanpz;
+    double meanflowx, meanflowz;
+    double gamma;
+    double u0, uN;
+    int CPI, CPI_type;
+    double U_lo[5], U_hi[5], W_lo[5], W_hi[5];
+};
+
+struct Geometry {
+    int nx, ny, nz, nxd, nzd;
+    int nyp;        // ny+3 planes (iy=-1..ny+1)
+    int nzt;        // 2nz+1
+    int rank, nranks;
+    int nx0, nxN, nxB;
+    int nz0, nzN, nzB;
+    long long M;    // local columns = nxB*nzt
+    double alfa0, beta0, ni;
+    double dx, dz, factor;
+};
+
+struct BodyForce {
+    int enabled;
+    double A[9];
+    double* mask_y;  // [ny+3]
+    double* mask_z;  // [2nz+1]
+    int exclude_mean;
+};
+
+struct KernelTimer {
+    bool on = false;
+    struct Rec { double ms = 0; long long n = 0; };
+    std::map<std::string, Rec> recs;
+    std::vector<std::pair<std::string, std::pair<cudaEvent_t, cudaEvent_t>>> pending;
+};
+
+struct chb_handle_s {
+    Geometry g;
+    int device;
+    cudaStream_t stream;
+    // fields (device layout [c][iy+1][ixl][iz+nz], complex128)
+    cplx* V;        // [3][nyp][M]
+    cplx* rhs;      // [2][nyp][M]  0 = eta, 1 = D2v (also holds the Step1 result)
+    cplx* oldrhs;   // [2][nyp][M]
+    cplx* F;        // [3][nyp][M] or null
+    cplx* P;        // [6][nyp][M]  spectral products
+    double* mult;   // [4][nyp][M]  L-multipliers of D2vmat / etamat
+    // convolution work buffers for a chunk of planes
+    int chunk_planes;
+    cplx* A;        // z-padded velocity, [peer][3][np][nzB][nxB]
+    cplx* Ar;       // after zTOx (aliases A when nranks==1)
+    cplx* B;        // products after x-pass, [peer][6][np][nzB][nxB]
+    cplx* Br;       // after xTOz (aliases B when nranks==1)
+    // FFT plans and tables
+    FftPlan plan_z, plan_x;
+    cplx* Wz;       // exp(+2 pi i e/nzd)
+    cplx* Wx;       // exp(+2 pi i e/nxd)
+    cplx* Wh;       // exp(+ i pi k/nxd), k=0..nxd/2
+    int* rev_z;     // digit reversal for plan_z
+    // tables
+    DevTables tab;
+    double *t_y, *t_dy, *t_d0, *t_d1, *t_d2, *t_d4, *t_D0mat;
+    bool tables_set;
+    DevScalars* sc;       // device
+    DevScalars* sc_host;  // pinned
+    double* mean_scratch; // [ny+1][5] + 2*(ny+3)
+    BodyForce bf;
+    // multi-GPU
+    void* nccl_comm;
+    // bookkeeping
+    long long launches;
+    KernelTimer timer;
+};
+
+// ---- launchers (conv_kernels.cu) ----
+void launch_zfwd(chb_handle_s* h, int plane0, int nplanes);
+void launch_xpass(chb_handle_s* h, int plane0, int nplanes, int compute_cfl);
+void launch_zbwd(chb_handle_s* h, int plane0, int nplanes);
+// ---- rhs_kernel.cu ----
+void launch_rhs(chb_handle_s* h, const double* ode, double deltat);
+// ---- solve_kernels.cu ----
+void launch_linsolve(chb_handle_s* h, double lambda);
+void launch_meanflow_prepass(chb_handle_s* h);
+// ---- layout_kernels.cu ----
+void launch_fortran_to_planes(chb_handle_s* h, const cplx* src, cplx* dst, int c, int ix0, int nix);
+void launch_planes_to_fortran(chb_handle_s* h, const cplx* src, cplx* dst, int c, int ix0, int nix);
+void launch_body_force(chb_handle_s* h);
+void launch_force_ghosts(chb_handle_s* h);
+// ---- transposes (transpose.cu) ----
+int chb_alltoall(chb_handle_s* h, const cplx* send, cplx* recv, size_t count_per_peer);
+
+// timing helpers
+struct ScopedKernelTimer {
+    chb_handle_s* h;
+    const char* name;
+    cudaEvent_t e0, e1;
+    bool on;
+    ScopedKernelTimer(chb_handle_s* h_, const char* name_);
+    ~ScopedKernelTimer();
+};
+void chb_timer_flush(chb_handle_s* h);
+
+#define CHB_CUDA_OK(call)                                                         \
+    do {                                                                          \
+        cudaError_t e__ = (call);                                                 \
+        if (e__ != cudaSuccess) {                                                 \
+            chb_set_error(std::string(#call) + ": " + cudaGetErrorString(e__));   \
+            return 1;                                                             \
+        }                                                                         \
+    } while (0)
+void chb_set_error(const std::string& s);

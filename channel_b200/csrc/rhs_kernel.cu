@@ -1,0 +1,162 @@
+// rhs_kernel.cu - RHS assembly of the v- and eta-equations (buildrhs, dnsdata.f90:611-673).
+//
+// One thread per wavenumber column (ix,iz), marching through the y-planes once.  The 5-point
+// y-stencils DD(f,k) of the reference (dnsdata.f90:609) are applied in scatter form: every input
+// plane contributes to the five output planes iy-2..iy+2 that are still "in flight", so each
+// product / velocity plane is read from HBM exactly once and the window lives in registers.
+// Because ialfa, ibeta and k2 are per-column constants the explicit terms reduce to
+//   expl_v   = sum_j d0(j) T0v + d1(j) T1v + d2(j) T2v      (dnsdata.f90:638-646)
+//   expl_eta = sum_j d0(j) T0e + d1(j) T1e                  (dnsdata.f90:656-660)
+// with per-plane combinations
+//   T2v = ia*P4 + ib*P5                  T0v = k2*T2v            [- k2*F2]
+//   T1v = ia*ia*P1 + 2*ia*ib*P6 + ib*ib*P3 + k2*P2               [- ia*F1 - ib*F3]
+//   T0e = alfa*beta*(P1-P3) + (beta^2-alfa^2)*P6                 [+ ib*F1 - ia*F3]
+//   T1e = -ib*P4 + ia*P5
+// and the implicit / time-derivative parts (timescheme, dnsdata.f90:486; OS,SQ :476-477)
+//   lin_v   = sum_j [ODE1/dt*(d2-k2*d0) + ni*(d4-2*k2*d2+k2^2*d0)](j) * v(iy+j)
+//   lin_eta = sum_j [ODE1/dt*d0 + ni*(d2-k2*d0)](j) * (ib*u - ia*w)(iy+j)
+// The mean mode (ix=iz=0) uses the real/imag packing of dnsdata.f90:648-654.
+#include "chb_internal.h"
+
+#define RHS_THREADS 128
+
+struct RhsAcc {
+    cplx ev, ee, lv, le;
+};
+
+template <bool HAS_F>
+__global__ void __launch_bounds__(RHS_THREADS)
+rhs_kernel(const cplx* __restrict__ V, const cplx* __restrict__ P, const cplx* __restrict__ F, cplx* __restrict__ rhs,
+           cplx* __restrict__ oldrhs, Geometry g, DevTables tab, const DevScalars* __restrict__ sc, double ode1_dt,
+           double ode2, double ode3) {
+    const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= g.M) return;
+    const int ixl = (int)(m / g.nzt);
+    const int izp = (int)(m - (long long)ixl * g.nzt);
+    const int ix = g.nx0 + ixl;
+    const int iz = izp - g.nz;
+    const double al = g.alfa0 * ix, be = g.beta0 * iz;  // ialfa = i*al, ibeta = i*be (dnsdata.f90:156-157)
+    const double k2 = al * al + be * be;                  // dnsdata.f90:158
+    const bool mean = (ix == 0 && iz == 0);
+    const double ni = g.ni;
+    const double cv0 = ni * k2 * k2 - ode1_dt * k2, cv2 = ode1_dt - 2.0 * ni * k2;  // coefficient of d0, d2 in lin_v
+    const double ce0 = ode1_dt - ni * k2;                                           // coefficient of d0 in lin_eta
+    const size_t plane = (size_t)g.M;
+    const size_t comp = (size_t)g.nyp * plane;
+    const int ny = g.ny;
+
+    RhsAcc acc[5];
+#pragma unroll
+    for (int s = 0; s < 5; ++s) {
+        acc[s].ev = acc[s].ee = acc[s].lv = acc[s].le = make_double2(0.0, 0.0);
+    }
+    double mpx = 0.0, mpz = 0.0;
+    if (mean) {
+        mpx = sc->meanpx;
+        mpz = sc->meanpz;
+    }
+
+    for (int ip = -1; ip <= ny + 1; ++ip) {
+        const size_t off = (size_t)(ip + 1) * plane + m;
+        const cplx p1 = P[0 * comp + off], p2 = P[1 * comp + off], p3 = P[2 * comp + off];
+        const cplx p4 = P[3 * comp + off], p5 = P[4 * comp + off], p6 = P[5 * comp + off];
+        const cplx u = V[0 * comp + off], v = V[1 * comp + off], w = V[2 * comp + off];
+        cplx f1 = make_double2(0, 0), f2 = f1, f3 = f1;
+        if (HAS_F) {
+            f1 = F[0 * comp + off];
+            f2 = F[1 * comp + off];
+            f3 = F[2 * comp + off];
+        }
+        // per-plane combinations (i*al*z = (-al*z.y, al*z.x))
+        cplx T2v, T1v, T0v, T0e, T1e, gg;
+        T2v.x = -(al * p4.y + be * p5.y);
+        T2v.y = al * p4.x + be * p5.x;
+        T1v.x = -(al * al) * p1.x - 2.0 * al * be * p6.x - (be * be) * p3.x + k2 * p2.x;
+        T1v.y = -(al * al) * p1.y - 2.0 * al * be * p6.y - (be * be) * p3.y + k2 * p2.y;
+        T0v.x = k2 * T2v.x;
+        T0v.y = k2 * T2v.y;
+        if (!mean) {
+            T0e.x = al * be * (p1.x - p3.x) + (be * be - al * al) * p6.x;
+            T0e.y = al * be * (p1.y - p3.y) + (be * be - al * al) * p6.y;
+            T1e.x = be * p4.y - al * p5.y;
+            T1e.y = -be * p4.x + al * p5.x;
+            gg.x = -be * u.y + al * w.y;  // ib*u - ia*w
+            gg.y = be * u.x - al * w.x;
+        } else {
+            // expl = (Re rhsu + meanpx) + i (Re rhsw + meanpz), rhsu = -DD(d1,4), rhsw = -DD(d1,5)
+            T0e = make_double2(0.0, 0.0);
+            T1e = make_double2(-p4.x, -p5.x);
+            gg = make_double2(u.x, w.x);  // rD0(V,1,3): Re u + i Re w
+        }
+        if (HAS_F) {
+            T0v.x -= k2 * f2.x;
+            T0v.y -= k2 * f2.y;
+            T1v.x += al * f1.y + be * f3.y;  // -ia*F1 - ib*F3
+            T1v.y -= al * f1.x + be * f3.x;
+            if (!mean) {
+                T0e.x += -be * f1.y + al * f3.y;  // ib*F1 - ia*F3
+                T0e.y += be * f1.x - al * f3.x;
+            } else {
+                T0e.x += f1.x;  // rD0(F,1,3)
+                T0e.y += f3.x;
+            }
+        }
+        // scatter to output planes io = ip-2+s, stencil offset j = ip-io = 2-s
+#pragma unroll
+        for (int s = 0; s < 5; ++s) {
+            const int io = ip - 2 + s;
+            if (io >= 1 && io <= ny - 1) {
+                const int ti = (io + 1) * 5 + (4 - s);
+                const double c0 = __ldg(&tab.d0[ti]), c1 = __ldg(&tab.d1[ti]);
+                const double c2 = __ldg(&tab.d2[ti]), c4 = __ldg(&tab.d4[ti]);
+                const double c02 = c2;
+                acc[s].ev.x += c0 * T0v.x + c1 * T1v.x + c02 * T2v.x;
+                acc[s].ev.y += c0 * T0v.y + c1 * T1v.y + c02 * T2v.y;
+                acc[s].ee.x += c0 * T0e.x + c1 * T1e.x;
+                acc[s].ee.y += c0 * T0e.y + c1 * T1e.y;
+                const double cv = cv0 * c0 + cv2 * c2 + ni * c4;
+                const double ce = ce0 * c0 + ni * c2;
+                acc[s].lv.x += cv * v.x;
+                acc[s].lv.y += cv * v.y;
+                acc[s].le.x += ce * gg.x;
+                acc[s].le.y += ce * gg.y;
+            }
+        }
+        // output plane io = ip-2 is complete: timescheme (dnsdata.f90:486)
+        const int io = ip - 2;
+        if (io >= 1 && io <= ny - 1) {
+            const size_t oo = (size_t)(io + 1) * plane + m;
+            cplx ee = acc[0].ee;
+            if (mean) {
+                ee.x += mpx;
+                ee.y += mpz;
+            }
+            const cplx oe = oldrhs[0 * comp + oo], ov = oldrhs[1 * comp + oo];
+            cplx re, rv;
+            re.x = acc[0].le.x + ode2 * ee.x - ode3 * oe.x;
+            re.y = acc[0].le.y + ode2 * ee.y - ode3 * oe.y;
+            rv.x = acc[0].lv.x + ode2 * acc[0].ev.x - ode3 * ov.x;
+            rv.y = acc[0].lv.y + ode2 * acc[0].ev.y - ode3 * ov.y;
+            rhs[0 * comp + oo] = re;
+            rhs[1 * comp + oo] = rv;
+            oldrhs[0 * comp + oo] = ee;
+            oldrhs[1 * comp + oo] = acc[0].ev;
+        }
+#pragma unroll
+        for (int s = 0; s < 4; ++s) acc[s] = acc[s + 1];
+        acc[4].ev = acc[4].ee = acc[4].lv = acc[4].le = make_double2(0.0, 0.0);
+    }
+}
+
+void launch_rhs(chb_handle_s* h, const double* ode, double deltat) {
+    const Geometry& g = h->g;
+    const int blocks = (int)((g.M + RHS_THREADS - 1) / RHS_THREADS);
+    ScopedKernelTimer tm(h, "rhs");
+    if (h->bf.enabled)
+        rhs_kernel<true><<<blocks, RHS_THREADS, 0, h->stream>>>(h->V, h->P, h->F, h->rhs, h->oldrhs, g, h->tab, h->sc,
+                                                                ode[0] / deltat, ode[1], ode[2]);
+    else
+        rhs_kernel<false><<<blocks, RHS_THREADS, 0, h->stream>>>(h->V, h->P, nullptr, h->rhs, h->oldrhs, g, h->tab,
+                                                                 h->sc, ode[0] / deltat, ode[1], ode[2]);
+    h->launches++;
+}

@@ -1,0 +1,504 @@
+// solve_kernels.cu - per-(ix,iz) pentadiagonal solves for v and eta and the recovery of u,w
+// (linsolve, linsolve_blocking.inc:3-107; LU5decompStep / LeftLU5divStep1 / LeftLU5divStep2,
+// rbparmat_blocking.f90:20-100 with npy=1; COMPLEXderiv, dnsdata.f90:339-373).
+//
+// One thread per column; the wavenumber index is the contiguous one, so every load/store of a
+// warp is a 512-byte coalesced segment.  Four sweeps:
+//   S1 (iy = ny-1 -> 1): build the D2vmat / etamat rows (linsolve_blocking.inc:12-13), fold the
+//       wall BCs (applybc_0/n, dnsdata.f90:458-472), UL-factorise on the fly and apply
+//       LeftLU5divStep1 to both right-hand sides; the two L-multipliers per row and matrix go to
+//       `mult`, the intermediate x overwrites the rhs array.
+//   S2 (iy = 1 -> ny-1): LeftLU5divStep2, then the ghost-node closures (:50-61).
+//   S3 (iy = ny+1 -> -1): compact first derivative of v: d1 stencil, one-sided wall rows, wall
+//       corrections and LeftLU5divStep1 with the pre-factorised D0mat (COMPLEXderiv).
+//   S4 (iy = -1 -> ny+1): LeftLU5divStep2 with D0mat, then u=(ia*vy-ib*eta)/k2, w=(ib*vy+ia*eta)/k2
+//       (linsolve_blocking.inc:99-103).
+// The mean column (0,0) is finished by a single-thread kernel (linsolve_blocking.inc:62-97).
+#include "chb_internal.h"
+
+#define SOLVE_THREADS 128
+
+struct Row5 {
+    double a[5];
+};
+
+// rows of D2vmat / etamat before BC folding                     linsolve_blocking.inc:12-13
+__device__ __forceinline__ void build_rows(const DevTables& tab, int iy, double k2, double lam, double ni, Row5& rv,
+                                           Row5& re) {
+    const int ti = (iy + 1) * 5;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+        const double d0 = __ldg(&tab.d0[ti + j]), d2 = __ldg(&tab.d2[ti + j]), d4 = __ldg(&tab.d4[ti + j]);
+        const double OS = ni * (d4 - 2.0 * k2 * d2 + k2 * k2 * d0);  // dnsdata.f90:476
+        const double SQ = ni * (d2 - k2 * d0);                       // dnsdata.f90:477
+        rv.a[j] = lam * (d2 - k2 * d0) - OS;
+        re.a[j] = lam * d0 - SQ;
+    }
+}
+
+// applybc_n / applybc_0 on the rows they touch                  dnsdata.f90:458-472
+__device__ __forceinline__ void fold_top1(Row5& r, const double* bcn, const double* bcnp1) {  // row ny-1
+    double e = r.a[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) r.a[j] -= e * bcnp1[j] / bcnp1[4];
+    e = r.a[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) r.a[j] -= e * bcn[j] / bcn[3];
+}
+__device__ __forceinline__ void fold_top2(Row5& r, const double* bcn) {  // row ny-2
+    const double e = r.a[4];
+#pragma unroll
+    for (int j = 1; j < 4; ++j) r.a[j] -= e * bcn[j - 1] / bcn[3];
+}
+__device__ __forceinline__ void fold_bot1(Row5& r, const double* bc0, const double* bc0m1) {  // row 1
+    double e = r.a[0];
+#pragma unroll
+    for (int j = 1; j < 5; ++j) r.a[j] -= e * bc0m1[j] / bc0m1[0];
+    e = r.a[1];
+#pragma unroll
+    for (int j = 2; j < 5; ++j) r.a[j] -= e * bc0[j] / bc0[1];
+}
+__device__ __forceinline__ void fold_bot2(Row5& r, const double* bc0) {  // row 2
+    const double e = r.a[0];
+#pragma unroll
+    for (int j = 1; j < 4; ++j) r.a[j] -= e * bc0[j + 1] / bc0[1];
+}
+
+// state of the UL factorisation carried from rows i+1, i+2: their scaled bands -2,-1
+struct LUState {
+    double l1m2, l1m1;  // row i+1: A(i+1,-2), A(i+1,-1)
+    double l2m2, l2m1;  // row i+2
+};
+
+// one row of LU5decompStep (rbparmat_blocking.f90:35-43); returns A(i,0)=1/diag, A(i,1), A(i,2)
+__device__ __forceinline__ void lu_row(Row5& r, LUState& st, double& inv, double& u1, double& u2) {
+    double piv = r.a[4];
+    r.a[3] -= piv * st.l2m1;
+    r.a[2] -= piv * st.l2m2;
+    u2 = piv;
+    piv = r.a[3];
+    r.a[2] -= piv * st.l1m1;
+    r.a[1] -= piv * st.l1m2;
+    u1 = piv;
+    inv = 1.0 / r.a[2];
+    r.a[0] *= inv;
+    r.a[1] *= inv;
+    st.l2m2 = st.l1m2;
+    st.l2m1 = st.l1m1;
+    st.l1m2 = r.a[0];
+    st.l1m1 = r.a[1];
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SOLVE_THREADS)
+solve_s1_kernel(cplx* __restrict__ rhs, double* __restrict__ mult, Geometry g, DevTables tab,
+                const DevScalars* __restrict__ sc, double lam) {
+    const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= g.M) return;
+    const int ixl = (int)(m / g.nzt);
+    const int izp = (int)(m - (long long)ixl * g.nzt);
+    const int ix = g.nx0 + ixl, iz = izp - g.nz;
+    const double al = g.alfa0 * ix, be = g.beta0 * iz;
+    const double k2 = al * al + be * be;
+    const bool mean = (ix == 0 && iz == 0);
+    const int ny = g.ny;
+    const size_t plane = (size_t)g.M, comp = (size_t)g.nyp * plane;
+    // wall data: only the mean mode carries non-zero BCs (bc%eta = u0 / uN), linsolve_blocking.inc:17,31
+    double bc0_eta = 0.0, bcn_eta = 0.0;
+    if (mean) {
+        bc0_eta = sc->u0;
+        bcn_eta = sc->uN;
+    }
+    LUState sv = {0, 0, 0, 0}, se = {0, 0, 0, 0};
+    cplx xv1 = make_double2(0, 0), xv2 = xv1, xe1 = xv1, xe2 = xv1;  // x(i+1), x(i+2)
+    for (int iy = ny - 1; iy >= 1; --iy) {
+        Row5 rv, re;
+        build_rows(tab, iy, k2, lam, g.ni, rv, re);
+        const size_t off = (size_t)(iy + 1) * plane + m;
+        cplx be_ = rhs[0 * comp + off];  // eta rhs
+        cplx bv = rhs[1 * comp + off];   // D2v rhs
+        if (iy == ny - 1) {
+            fold_top1(rv, tab.vnbc, tab.vnp1bc);
+            fold_top1(re, tab.etanbc, tab.etanp1bc);
+            const double cc = re.a[3] * bcn_eta / tab.etanbc[3];  // linsolve_blocking.inc:40
+            be_.x -= cc;
+            rv.a[3] = rv.a[4] = 0.0;  // rbparmat_blocking.f90:29
+            re.a[3] = re.a[4] = 0.0;
+        } else if (iy == ny - 2) {
+            fold_top2(rv, tab.vnbc);
+            fold_top2(re, tab.etanbc);
+            const double cc = re.a[4] * bcn_eta / tab.etanbc[3];  // :41
+            be_.x -= cc;
+            rv.a[4] = 0.0;
+            re.a[4] = 0.0;
+        }
+        if (iy == 1) {
+            fold_bot1(rv, tab.v0bc, tab.v0m1bc);
+            fold_bot1(re, tab.eta0bc, tab.eta0m1bc);
+            const double cc = re.a[1] * bc0_eta / tab.eta0bc[1];  // :26
+            be_.x -= cc;
+        } else if (iy == 2) {
+            fold_bot2(rv, tab.v0bc);
+            fold_bot2(re, tab.eta0bc);
+            const double cc = re.a[0] * bc0_eta / tab.eta0bc[1];  // :27
+            be_.x -= cc;
+        }
+        double inv, u1, u2;
+        lu_row(rv, sv, inv, u1, u2);
+        // LeftLU5divStep1 (rbparmat_blocking.f90:70-72)
+        cplx xv;
+        xv.x = (bv.x - (u1 * xv1.x + u2 * xv2.x)) * inv;
+        xv.y = (bv.y - (u1 * xv1.y + u2 * xv2.y)) * inv;
+        xv2 = xv1;
+        xv1 = xv;
+        lu_row(re, se, inv, u1, u2);
+        cplx xe;
+        xe.x = (be_.x - (u1 * xe1.x + u2 * xe2.x)) * inv;
+        xe.y = (be_.y - (u1 * xe1.y + u2 * xe2.y)) * inv;
+        xe2 = xe1;
+        xe1 = xe;
+        rhs[0 * comp + off] = xe;
+        rhs[1 * comp + off] = xv;
+        // multipliers used by Step2; rbparmat_blocking.f90:45 zeroes A(1,-2:-1), A(2,-2)
+        double mv2 = sv.l1m2, mv1 = sv.l1m1, me2 = se.l1m2, me1 = se.l1m1;
+        if (iy == 1) mv2 = mv1 = me2 = me1 = 0.0;
+        if (iy == 2) mv2 = me2 = 0.0;
+        mult[0 * comp + off] = mv2;
+        mult[1 * comp + off] = mv1;
+        mult[2 * comp + off] = me2;
+        mult[3 * comp + off] = me1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SOLVE_THREADS)
+solve_s2_kernel(const cplx* __restrict__ rhs, const double* __restrict__ mult, cplx* __restrict__ V, Geometry g,
+                DevTables tab, const DevScalars* __restrict__ sc) {
+    const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= g.M) return;
+    const int ixl = (int)(m / g.nzt);
+    const int izp = (int)(m - (long long)ixl * g.nzt);
+    const bool mean = (g.nx0 + ixl == 0 && izp == g.nz);
+    const int ny = g.ny;
+    const size_t plane = (size_t)g.M, comp = (size_t)g.nyp * plane;
+    double bc0_eta = 0.0, bcn_eta = 0.0;
+    if (mean) {
+        bc0_eta = sc->u0;
+        bcn_eta = sc->uN;
+    }
+    cplx v1 = make_double2(0, 0), v2 = v1, v3 = v1, e1 = v1, e2 = v1, e3 = v1;  // b(i-1), b(i-2), b(i-3)
+    for (int iy = 1; iy <= ny - 1; ++iy) {
+        const size_t off = (size_t)(iy + 1) * plane + m;
+        cplx e = rhs[0 * comp + off], v = rhs[1 * comp + off];
+        const double mv2 = mult[0 * comp + off], mv1 = mult[1 * comp + off];
+        const double me2 = mult[2 * comp + off], me1 = mult[3 * comp + off];
+        // LeftLU5divStep2 (rbparmat_blocking.f90:93-95)
+        v.x -= mv2 * v2.x + mv1 * v1.x;
+        v.y -= mv2 * v2.y + mv1 * v1.y;
+        e.x -= me2 * e2.x + me1 * e1.x;
+        e.y -= me2 * e2.y + me1 * e1.y;
+        V[0 * comp + off] = e;
+        V[1 * comp + off] = v;
+        v3 = v2; v2 = v1; v1 = v;
+        e3 = e2; e2 = e1; e1 = e;
+        if (iy == 3) {  // bottom closure needs nodes 1..3 (linsolve_blocking.inc:51-54)
+            const cplx a1 = v3, a2 = v2, a3 = v1, b1 = e3, b2 = e2, b3 = e1;
+            const double* v0bc = tab.v0bc; const double* v0m1 = tab.v0m1bc;
+            const double* e0bc = tab.eta0bc; const double* e0m1 = tab.eta0m1bc;
+            cplx vw, vg, ew, eg;
+            vw.x = (0.0 - (a1.x * v0bc[2] + a2.x * v0bc[3] + a3.x * v0bc[4])) / v0bc[1];
+            vw.y = (0.0 - (a1.y * v0bc[2] + a2.y * v0bc[3] + a3.y * v0bc[4])) / v0bc[1];
+            vg.x = (0.0 - (vw.x * v0m1[1] + a1.x * v0m1[2] + a2.x * v0m1[3] + a3.x * v0m1[4])) / v0m1[0];
+            vg.y = (0.0 - (vw.y * v0m1[1] + a1.y * v0m1[2] + a2.y * v0m1[3] + a3.y * v0m1[4])) / v0m1[0];
+            ew.x = (bc0_eta - (b1.x * e0bc[2] + b2.x * e0bc[3] + b3.x * e0bc[4])) / e0bc[1];
+            ew.y = (0.0 - (b1.y * e0bc[2] + b2.y * e0bc[3] + b3.y * e0bc[4])) / e0bc[1];
+            eg.x = -(ew.x * e0m1[1] + b1.x * e0m1[2] + b2.x * e0m1[3] + b3.x * e0m1[4]) / e0m1[0];
+            eg.y = -(ew.y * e0m1[1] + b1.y * e0m1[2] + b2.y * e0m1[3] + b3.y * e0m1[4]) / e0m1[0];
+            V[0 * comp + 1 * plane + m] = ew;
+            V[0 * comp + 0 * plane + m] = eg;
+            V[1 * comp + 1 * plane + m] = vw;
+            V[1 * comp + 0 * plane + m] = vg;
+        }
+    }
+    {  // top closure (linsolve_blocking.inc:57-60): nodes ny-3..ny-1 = v3,v2,v1
+        const double* vnbc = tab.vnbc; const double* vnp1 = tab.vnp1bc;
+        const double* enbc = tab.etanbc; const double* enp1 = tab.etanp1bc;
+        cplx vw, vg, ew, eg;
+        vw.x = (0.0 - (v3.x * vnbc[0] + v2.x * vnbc[1] + v1.x * vnbc[2])) / vnbc[3];
+        vw.y = (0.0 - (v3.y * vnbc[0] + v2.y * vnbc[1] + v1.y * vnbc[2])) / vnbc[3];
+        vg.x = (0.0 - (v3.x * vnp1[0] + v2.x * vnp1[1] + v1.x * vnp1[2] + vw.x * vnp1[3])) / vnp1[4];
+        vg.y = (0.0 - (v3.y * vnp1[0] + v2.y * vnp1[1] + v1.y * vnp1[2] + vw.y * vnp1[3])) / vnp1[4];
+        ew.x = (bcn_eta - (e3.x * enbc[0] + e2.x * enbc[1] + e1.x * enbc[2])) / enbc[3];
+        ew.y = (0.0 - (e3.y * enbc[0] + e2.y * enbc[1] + e1.y * enbc[2])) / enbc[3];
+        eg.x = -(e3.x * enp1[0] + e2.x * enp1[1] + e1.x * enp1[2] + ew.x * enp1[3]) / enp1[4];
+        eg.y = -(e3.y * enp1[0] + e2.y * enp1[1] + e1.y * enp1[2] + ew.y * enp1[3]) / enp1[4];
+        V[0 * comp + (size_t)(ny + 1) * plane + m] = ew;
+        V[0 * comp + (size_t)(ny + 2) * plane + m] = eg;
+        V[1 * comp + (size_t)(ny + 1) * plane + m] = vw;
+        V[1 * comp + (size_t)(ny + 2) * plane + m] = vg;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ cplx stencil5(const double* c, cplx a0, cplx a1, cplx a2, cplx a3, cplx a4) {
+    cplx r;
+    r.x = c[0] * a0.x + c[1] * a1.x + c[2] * a2.x + c[3] * a3.x + c[4] * a4.x;
+    r.y = c[0] * a0.y + c[1] * a1.y + c[2] * a2.y + c[3] * a3.y + c[4] * a4.y;
+    return r;
+}
+
+// S3: vy (before Step2) -> V comp 3
+__global__ void __launch_bounds__(SOLVE_THREADS)
+solve_s3_kernel(cplx* __restrict__ V, Geometry g, DevTables tab) {
+    const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= g.M) return;
+    const int ixl = (int)(m / g.nzt);
+    const int izp = (int)(m - (long long)ixl * g.nzt);
+    if (g.nx0 + ixl == 0 && izp == g.nz) return;  // mean column: no vetaTOuvw
+    const int ny = g.ny;
+    const size_t plane = (size_t)g.M, comp = (size_t)g.nyp * plane;
+    const cplx* v = V + 1 * comp + m;
+    cplx* out = V + 2 * comp + m;
+#define VAT(iy) v[(size_t)((iy) + 1) * plane]
+    // top one-sided rows (dnsdata.f90:354-355)
+    cplx w4 = VAT(ny + 1), w3 = VAT(ny), w2 = VAT(ny - 1), w1 = VAT(ny - 2), w0 = VAT(ny - 3);
+    const cplx f_n = stencil5(tab.d14n, w0, w1, w2, w3, w4);
+    const cplx f_np1 = stencil5(tab.d14np1, w0, w1, w2, w3, w4);
+    out[(size_t)(ny + 1) * plane] = f_n;
+    out[(size_t)(ny + 2) * plane] = f_np1;
+    // bottom one-sided rows (dnsdata.f90:350-351)
+    cplx f_0, f_m1;
+    {
+        const cplx b0 = VAT(-1), b1 = VAT(0), b2 = VAT(1), b3 = VAT(2), b4 = VAT(3);
+        f_0 = stencil5(tab.d140, b0, b1, b2, b3, b4);
+        f_m1 = stencil5(tab.d14m1, b0, b1, b2, b3, b4);
+        out[(size_t)1 * plane] = f_0;
+        out[(size_t)0 * plane] = f_m1;
+    }
+    cplx x1 = make_double2(0, 0), x2 = x1;
+    // window w0..w4 = v(iy-2..iy+2); currently holds ny-3..ny+1 = window of iy = ny-1
+    for (int iy = ny - 1; iy >= 1; --iy) {
+        const int ti = (iy + 1) * 5;
+        double c[5];
+#pragma unroll
+        for (int j = 0; j < 5; ++j) c[j] = __ldg(&tab.d1[ti + j]);
+        cplx f = stencil5(c, w0, w1, w2, w3, w4);  // dnsdata.f90:358
+        if (iy == ny - 1) {                        // :365
+            const double a = __ldg(&tab.d0[ti + 3]), b = __ldg(&tab.d0[ti + 4]);
+            f.x -= a * f_n.x + b * f_np1.x;
+            f.y -= a * f_n.y + b * f_np1.y;
+        } else if (iy == ny - 2) {                 // :366
+            const double b = __ldg(&tab.d0[ti + 4]);
+            f.x -= b * f_n.x;
+            f.y -= b * f_n.y;
+        }
+        if (iy == 1) {                             // :361
+            const double a = __ldg(&tab.d0[ti + 1]), b = __ldg(&tab.d0[ti + 0]);
+            f.x -= a * f_0.x + b * f_m1.x;
+            f.y -= a * f_0.y + b * f_m1.y;
+        } else if (iy == 2) {                      // :362
+            const double b = __ldg(&tab.d0[ti + 0]);
+            f.x -= b * f_0.x;
+            f.y -= b * f_0.y;
+        }
+        // LeftLU5divStep1 with D0mat (row i = iy-1)
+        const double* A = tab.D0mat + (size_t)(iy - 1) * 5;
+        const double a0 = __ldg(&A[2]), a1 = __ldg(&A[3]), a2 = __ldg(&A[4]);
+        cplx x;
+        x.x = (f.x - (a1 * x1.x + a2 * x2.x)) * a0;
+        x.y = (f.y - (a1 * x1.y + a2 * x2.y)) * a0;
+        x2 = x1;
+        x1 = x;
+        out[(size_t)(iy + 1) * plane] = x;
+        // slide the window down
+        w4 = w3; w3 = w2; w2 = w1; w1 = w0;
+        if (iy - 3 >= -1) w0 = VAT(iy - 3);
+    }
+#undef VAT
+}
+
+// S4: Step2 with D0mat, then u,w
+__global__ void __launch_bounds__(SOLVE_THREADS)
+solve_s4_kernel(cplx* __restrict__ V, Geometry g, DevTables tab) {
+    const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= g.M) return;
+    const int ixl = (int)(m / g.nzt);
+    const int izp = (int)(m - (long long)ixl * g.nzt);
+    const int ix = g.nx0 + ixl, iz = izp - g.nz;
+    if (ix == 0 && iz == 0) return;
+    const double al = g.alfa0 * ix, be = g.beta0 * iz;
+    const double k2 = al * al + be * be;
+    const int ny = g.ny;
+    const size_t plane = (size_t)g.M, comp = (size_t)g.nyp * plane;
+    cplx b1 = make_double2(0, 0), b2 = b1;
+    for (int iy = -1; iy <= ny + 1; ++iy) {
+        const size_t off = (size_t)(iy + 1) * plane + m;
+        cplx vy = V[2 * comp + off];
+        const cplx eta = V[0 * comp + off];
+        if (iy >= 1) {  // rows i=0..ny <-> iy=1..ny+1 (rows ny, ny+1 of D0mat are zero)
+            const double* A = tab.D0mat + (size_t)(iy - 1) * 5;
+            const double am2 = __ldg(&A[0]), am1 = __ldg(&A[1]);
+            vy.x -= am2 * b2.x + am1 * b1.x;
+            vy.y -= am2 * b2.y + am1 * b1.y;
+        }
+        b2 = b1;
+        b1 = vy;
+        // (ia*vy - ib*eta)/k2 ; (ib*vy + ia*eta)/k2
+        cplx u, w;
+        u.x = (-al * vy.y + be * eta.y) / k2;
+        u.y = (al * vy.x - be * eta.x) / k2;
+        w.x = (-be * vy.y - al * eta.y) / k2;
+        w.y = (be * vy.x + al * eta.x) / k2;
+        V[0 * comp + off] = u;
+        V[2 * comp + off] = w;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// yintegr (dnsdata.f90:312-324) on a real column f(iy), iy=-1..ny+1, element stride `st`
+__device__ double yintegr_dev(const double* __restrict__ y, const double* f, size_t st, int ny, int imag_part) {
+    double II = 0.0;
+    for (int iy = 1; iy <= ny - 1; iy += 2) {
+        const double yp1 = y[iy + 2] - y[iy + 1], ym1 = y[iy] - y[iy + 1];
+        const double a1 = -1.0 / 3.0 * ym1 + 1.0 / 6.0 * yp1 + 1.0 / 6.0 * yp1 * yp1 / ym1;
+        const double a3 = +1.0 / 3.0 * yp1 - 1.0 / 6.0 * ym1 - 1.0 / 6.0 * ym1 * ym1 / yp1;
+        const double a2 = yp1 - ym1 - a1 - a3;
+        II = II + a1 * f[(size_t)iy * st + imag_part] + a2 * f[(size_t)(iy + 1) * st + imag_part] +
+             a3 * f[(size_t)(iy + 2) * st + imag_part];
+    }
+    return II;
+}
+
+__device__ void cpi_update(DevScalars* sc, double ni) {
+    if (sc->CPI) {  // linsolve_blocking.inc:87-97, channel.f90:104-114
+        if (sc->CPI_type == 0)
+            sc->meanpx = (1.0 - sc->gamma) * 6.0 * ni / sc->fr[0];
+        else if (sc->CPI_type == 1)
+            sc->meanpx = (1.5 / sc->gamma) * sc->fr[0] * ni;
+    }
+}
+
+__device__ void store_wall_columns(cplx* V, DevScalars* sc, const Geometry& g, size_t m00) {
+    const size_t plane = (size_t)g.M, comp = (size_t)g.nyp * plane;
+    for (int i = 0; i < 5; ++i) {
+        sc->U_lo[i] = V[0 * comp + (size_t)i * plane + m00].x;
+        sc->W_lo[i] = V[2 * comp + (size_t)i * plane + m00].x;
+        sc->U_hi[i] = V[0 * comp + (size_t)(g.ny - 2 + i) * plane + m00].x;
+        sc->W_hi[i] = V[2 * comp + (size_t)(g.ny - 2 + i) * plane + m00].x;
+    }
+}
+
+// mean column (0,0) after S2: linsolve_blocking.inc:62-97.  Single thread; scratch holds the
+// factorised eta00mat [ny+1][5] and ucor [ny+3].
+__global__ void mean_mode_kernel(cplx* __restrict__ V, Geometry g, DevTables tab, DevScalars* sc, double lam,
+                                 double* __restrict__ scratch) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int ny = g.ny, nz = g.nz;
+    const size_t plane = (size_t)g.M, comp = (size_t)g.nyp * plane;
+    const size_t m00 = (size_t)nz;  // ixl=0, izp=nz
+    double* A = scratch;                       // [ny+1][5]
+    double* ucor = scratch + (size_t)(ny + 1) * 5;  // [ny+3], index iy+1
+    // V(:,0,0,3) = Im eta ; V(:,0,0,1) = Re eta            :63-64
+    for (int i = 0; i < ny + 3; ++i) {
+        const cplx e = V[0 * comp + (size_t)i * plane + m00];
+        V[2 * comp + (size_t)i * plane + m00] = make_double2(e.y, 0.0);
+        V[0 * comp + (size_t)i * plane + m00] = make_double2(e.x, 0.0);
+    }
+    // etamat(0,0), factorised again (k2 = 0)
+    LUState st = {0, 0, 0, 0};
+    for (int i = 0; i < 5; ++i) { A[(size_t)(ny - 1) * 5 + i] = 0.0; A[(size_t)ny * 5 + i] = 0.0; }
+    for (int iy = ny - 1; iy >= 1; --iy) {
+        Row5 rv, re;
+        build_rows(tab, iy, 0.0, lam, g.ni, rv, re);
+        if (iy == ny - 1) { fold_top1(re, tab.etanbc, tab.etanp1bc); re.a[3] = re.a[4] = 0.0; }
+        else if (iy == ny - 2) { fold_top2(re, tab.etanbc); re.a[4] = 0.0; }
+        if (iy == 1) fold_bot1(re, tab.eta0bc, tab.eta0m1bc);
+        else if (iy == 2) fold_bot2(re, tab.eta0bc);
+        double inv, u1, u2;
+        lu_row(re, st, inv, u1, u2);
+        double* r = A + (size_t)(iy - 1) * 5;
+        r[0] = st.l1m2; r[1] = st.l1m1; r[2] = inv; r[3] = u1; r[4] = u2;
+    }
+    A[0] = A[1] = 0.0;  // rbparmat_blocking.f90:45
+    A[5] = 0.0;
+    // ucor: rhs 1 on rows 1..ny-1                                :65-68
+    for (int i = 0; i < ny + 3; ++i) ucor[i] = 0.0;
+    for (int iy = 1; iy <= ny - 1; ++iy) ucor[iy + 1] = 1.0;
+    for (int iy = ny - 1; iy >= 1; --iy) {
+        const double* r = A + (size_t)(iy - 1) * 5;
+        ucor[iy + 1] = (ucor[iy + 1] - (r[3] * ucor[iy + 2] + r[4] * ucor[iy + 3])) * r[2];
+    }
+    for (int iy = 1; iy <= ny + 1; ++iy) {
+        const double* r = A + (size_t)(iy - 1) * 5;
+        ucor[iy + 1] = ucor[iy + 1] - (r[0] * ucor[iy - 1] + r[1] * ucor[iy]);
+    }
+    {
+        const double* e0bc = tab.eta0bc; const double* e0m1 = tab.eta0m1bc;
+        const double* enbc = tab.etanbc; const double* enp1 = tab.etanp1bc;
+        ucor[1] = -(ucor[2] * e0bc[2] + ucor[3] * e0bc[3] + ucor[4] * e0bc[4]) / e0bc[1];                      // :70
+        ucor[0] = -(ucor[1] * e0m1[1] + ucor[2] * e0m1[2] + ucor[3] * e0m1[3] + ucor[4] * e0m1[4]) / e0m1[0];  // :71
+        ucor[ny + 1] = -(ucor[ny - 2] * enbc[0] + ucor[ny - 1] * enbc[1] + ucor[ny] * enbc[2]) / enbc[3];      // :74
+        ucor[ny + 2] = -(ucor[ny - 2] * enp1[0] + ucor[ny - 1] * enp1[1] + ucor[ny] * enp1[2] + ucor[ny + 1] * enp1[3]) / enp1[4];  // :75
+    }
+    const double* Ucol = reinterpret_cast<const double*>(V + 0 * comp + m00);
+    const double* Wcol = reinterpret_cast<const double*>(V + 2 * comp + m00);
+    sc->fr[0] = yintegr_dev(tab.y, Ucol, 2 * plane, ny, 0);  // :77
+    sc->fr[1] = yintegr_dev(tab.y, Wcol, 2 * plane, ny, 0);
+    sc->fr[2] = yintegr_dev(tab.y, ucor, 1, ny, 0);
+    if (fabs(sc->meanflowx) > 1.0e-7 && !sc->CPI) {            // :79-82
+        sc->corrpx = (sc->meanflowx - sc->fr[0]) / sc->fr[2];
+        for (int i = 0; i < ny + 3; ++i) V[0 * comp + (size_t)i * plane + m00].x += sc->corrpx * ucor[i];
+    }
+    if (fabs(sc->meanflowz) > 1.0e-7 && !sc->CPI) {            // :83-86
+        sc->corrpz = (sc->meanflowz - sc->fr[1]) / sc->fr[2];
+        for (int i = 0; i < ny + 3; ++i) V[2 * comp + (size_t)i * plane + m00].x += sc->corrpz * ucor[i];
+    }
+    cpi_update(sc, g.ni);
+    store_wall_columns(V, sc, g, m00);
+}
+
+// channel.f90:101-115: flow rates of the initial mean profile and CPI meanpx
+__global__ void meanflow_prepass_kernel(cplx* __restrict__ V, Geometry g, DevTables tab, DevScalars* sc) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const size_t plane = (size_t)g.M, comp = (size_t)g.nyp * plane;
+    const size_t m00 = (size_t)g.nz;
+    const double* Ucol = reinterpret_cast<const double*>(V + 0 * comp + m00);
+    const double* Wcol = reinterpret_cast<const double*>(V + 2 * comp + m00);
+    sc->fr[0] = yintegr_dev(tab.y, Ucol, 2 * plane, g.ny, 0);
+    sc->fr[1] = yintegr_dev(tab.y, Wcol, 2 * plane, g.ny, 0);
+    cpi_update(sc, g.ni);
+    store_wall_columns(V, sc, g, m00);
+}
+
+void launch_linsolve(chb_handle_s* h, double lam) {
+    const Geometry& g = h->g;
+    const int blocks = (int)((g.M + SOLVE_THREADS - 1) / SOLVE_THREADS);
+    {
+        ScopedKernelTimer tm(h, "solve_s1");
+        solve_s1_kernel<<<blocks, SOLVE_THREADS, 0, h->stream>>>(h->rhs, h->mult, g, h->tab, h->sc, lam);
+    }
+    {
+        ScopedKernelTimer tm(h, "solve_s2");
+        solve_s2_kernel<<<blocks, SOLVE_THREADS, 0, h->stream>>>(h->rhs, h->mult, h->V, g, h->tab, h->sc);
+    }
+    {
+        ScopedKernelTimer tm(h, "solve_s3");
+        solve_s3_kernel<<<blocks, SOLVE_THREADS, 0, h->stream>>>(h->V, g, h->tab);
+    }
+    {
+        ScopedKernelTimer tm(h, "solve_s4");
+        solve_s4_kernel<<<blocks, SOLVE_THREADS, 0, h->stream>>>(h->V, g, h->tab);
+    }
+    h->launches += 4;
+    if (g.nx0 == 0) {
+        ScopedKernelTimer tm(h, "mean_mode");
+        mean_mode_kernel<<<1, 32, 0, h->stream>>>(h->V, g, h->tab, h->sc, lam, h->mean_scratch);
+        h->launches++;
+    }
+}
+
+void launch_meanflow_prepass(chb_handle_s* h) {
+    if (h->g.nx0 != 0) return;
+    meanflow_prepass_kernel<<<1, 32, 0, h->stream>>>(h->V, h->g, h->tab, h->sc);
+    h->launches++;
+}

@@ -1,0 +1,130 @@
+// transpose.cu - pencil transposes zTOx / xTOz (mpi_transpose.f90:50-117) across GPUs.
+//
+// The z-pass and x-pass kernels already write one contiguous block per destination rank
+// ("pack") and read one block per source rank ("unpack"), so a transpose is a pure block
+// exchange: rank r sends block j to rank j and receives block q from rank q.  It is issued as
+// one grouped ncclSend/ncclRecv all-to-all on the handle's stream for a whole chunk of y-planes
+// and all 3 (zTOx) or 6 (xTOz) components at once (the reference issues 9 MPI_Alltoall per plane,
+// mpi_transpose.f90:74,109).  NCCL is loaded with dlopen so that single-GPU use has no NCCL
+// dependency.
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <cstring>
+#include <string>
+
+#include "chb_internal.h"
+
+namespace {
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi g_nccl;
+
+bool load_nccl() {
+    if (g_nccl.lib) return true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+        g_nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (g_nccl.lib) break;
+    }
+    if (!g_nccl.lib) {
+        chb_set_error(std::string("cannot dlopen libnccl.so.2: ") + dlerror());
+        return false;
+    }
+#define LOAD(field, sym)                                                   \
+    *(void**)(&g_nccl.field) = dlsym(g_nccl.lib, sym);                     \
+    if (!g_nccl.field) {                                                   \
+        chb_set_error(std::string("libnccl is missing symbol ") + sym);    \
+        return false;                                                      \
+    }
+    LOAD(GetUniqueId, "ncclGetUniqueId");
+    LOAD(CommInitRank, "ncclCommInitRank");
+    LOAD(CommDestroy, "ncclCommDestroy");
+    LOAD(GroupStart, "ncclGroupStart");
+    LOAD(GroupEnd, "ncclGroupEnd");
+    LOAD(Send, "ncclSend");
+    LOAD(Recv, "ncclRecv");
+    LOAD(AllReduce, "ncclAllReduce");
+    LOAD(Broadcast, "ncclBroadcast");
+    LOAD(GetErrorString, "ncclGetErrorString");
+#undef LOAD
+    return true;
+}
+}  // namespace
+
+#define NCCL_OK(call)                                                                         \
+    do {                                                                                      \
+        ncclResult_t r__ = (call);                                                            \
+        if (r__ != ncclSuccess) {                                                             \
+            chb_set_error(std::string(#call) + ": " + g_nccl.GetErrorString(r__));            \
+            return 1;                                                                         \
+        }                                                                                     \
+    } while (0)
+
+int chb_nccl_unique_id(char* id) {
+    if (!load_nccl()) return 1;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+    ncclUniqueId u;
+    NCCL_OK(g_nccl.GetUniqueId(&u));
+    memcpy(id, &u, sizeof(u));
+    return 0;
+}
+
+int chb_nccl_init(chb_handle_s* h, const char* id) {
+    if (!load_nccl()) return 1;
+    ncclUniqueId u;
+    memcpy(&u, id, sizeof(u));
+    ncclComm_t comm;
+    NCCL_OK(g_nccl.CommInitRank(&comm, h->g.nranks, u, h->g.rank));
+    h->nccl_comm = comm;
+    return 0;
+}
+
+void chb_nccl_destroy(chb_handle_s* h) {
+    if (h->nccl_comm) {
+        g_nccl.CommDestroy((ncclComm_t)h->nccl_comm);
+        h->nccl_comm = nullptr;
+    }
+}
+
+// all-to-all of `count` complex elements in total (count/nranks per peer)
+int chb_alltoall(chb_handle_s* h, const cplx* send, cplx* recv, size_t count) {
+    const int P = h->g.nranks;
+    const size_t per = count / P;
+    ncclComm_t comm = (ncclComm_t)h->nccl_comm;
+    ScopedKernelTimer tm(h, "alltoall");
+    NCCL_OK(g_nccl.GroupStart());
+    for (int p = 0; p < P; ++p) {
+        NCCL_OK(g_nccl.Send(send + (size_t)p * per, per * 2, ncclDouble, p, comm, h->stream));
+        NCCL_OK(g_nccl.Recv(recv + (size_t)p * per, per * 2, ncclDouble, p, comm, h->stream));
+    }
+    NCCL_OK(g_nccl.GroupEnd());
+    return 0;
+}
+
+// cfl is a non-negative double stored as its bit pattern: max over uint64 == max over doubles
+int chb_allreduce_max_cfl(chb_handle_s* h) {
+    ncclComm_t comm = (ncclComm_t)h->nccl_comm;
+    NCCL_OK(g_nccl.AllReduce(&h->sc->cfl_bits, &h->sc->cfl_bits, 1, ncclUint64, ncclMax, comm, h->stream));
+    return 0;
+}
+
+// mean-mode scalars live on the rank with nx0==0 (rank 0, has_average mpi_transpose.f90:217)
+int chb_bcast_scalars(chb_handle_s* h) {
+    ncclComm_t comm = (ncclComm_t)h->nccl_comm;
+    char* base = reinterpret_cast<char*>(h->sc) + sizeof(unsigned long long);
+    const size_t bytes = sizeof(DevScalars) - sizeof(unsigned long long);
+    NCCL_OK(g_nccl.Broadcast(base, base, bytes, ncclChar, 0, comm, h->stream));
+    return 0;
+}

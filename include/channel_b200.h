@@ -1,0 +1,157 @@
+/* channel_b200.h - C ABI of the B200-native hot path of davecats/channel.
+ *
+ * The reference has no FFI: the boundary is the Fortran module-procedure
+ * interface between PROGRAM channel (channel.f90) and MODULE dnsdata
+ * (dnsdata.f90), with state shared through module variables.  This header
+ * declares the extern "C" entry points an iso_c_binding shim binds so that the
+ * bodies of init_fft / convolutions / buildrhs / linsolve / vetaTOuvw /
+ * computeflowrate run on the GPU while channel.f90 stays verbatim
+ * (fortran/channel_b200_mod.f90).
+ *
+ * Conventions: plain pointers and sizes only; all reals are double; complex is
+ * double[2] (re,im); host pointers unless the name ends in _d; every function
+ * returns 0 on success or a non-zero error code (text from chb_last_error());
+ * one handle per rank (= per GPU); calls on a handle are not thread-safe; on
+ * nranks>1 every call is collective over the ranks, in the same order (the
+ * reference's MPI convention).  Work is enqueued on the handle's stream; calls
+ * that return host scalars synchronise.
+ *
+ * All file:line citations are into the reference tree.
+ */
+#ifndef CHANNEL_B200_H
+#define CHANNEL_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct chb_handle_s* chb_handle;
+
+#define CHB_NCCL_ID_BYTES 128
+
+/* Text of the last error on this thread. */
+const char* chb_last_error(void);
+
+/* Library/ABI version (major*1000+minor). */
+int chb_version(void);
+
+/* Fill `id` (CHB_NCCL_ID_BYTES) with an NCCL unique id; rank 0 calls it and the
+ * host side broadcasts it (MPI_Bcast in the Fortran shim) before chb_create. */
+int chb_get_nccl_unique_id(char* id);
+
+/* Replaces init_MPI (x-decomposition only: npy must be 1; mpi_transpose.f90:175-272),
+ * init_fft (ffts.f90:35-76) and the device part of init_memory (dnsdata.f90:129-177).
+ * Computes nx0..nxN / nz0..nzN exactly as mpi_transpose.f90:214-215; requires
+ * nranks | (nx+1) and nranks | nzd (README.md:154).  ni is 1/Re (dnsdata.f90:115).
+ * nccl_id may be NULL when nranks==1.  device = CUDA device ordinal. */
+int chb_create(chb_handle* h, int nx, int ny, int nz, int nxd, int nzd,
+               double alfa0, double beta0, double ni, double a, double ymin, double ymax,
+               int rank, int nranks, const char* nccl_id, int device);
+
+/* Replaces free_fft (ffts.f90:110-115) and free_memory (dnsdata.f90:222-229). */
+int chb_destroy(chb_handle h);
+
+/* Local index ranges of this rank (mpi_transpose.f90:214-215). */
+int chb_get_decomposition(chb_handle h, int* nx0, int* nxN, int* nz0, int* nzN);
+
+/* Consumes the output of setup_derivatives (dnsdata.f90:241-286) and
+ * setup_boundary_conditions (dnsdata.f90:290-308), which stay on the host, so the
+ * coefficients are bit-identical to the caller's.
+ *   y[ny+3]            y(-1:ny+1)
+ *   d0,d1,d2,d4        der(1:ny-1)%d*(-2:2), row-major [(ny-1)][5]
+ *   d140..d24np1       wall stencils (-2:2)
+ *   v0bc..etanp1bc     BC vectors (-2:2)
+ *   D0mat              D0mat(1:ny+1,-2:2) AFTER LU5decompStep, row-major [(ny+1)][5] */
+int chb_set_tables(chb_handle h, const double* y,
+                   const double* d0, const double* d1, const double* d2, const double* d4,
+                   const double* d140, const double* d14m1, const double* d240, const double* d24m1,
+                   const double* d14n, const double* d14np1, const double* d24n, const double* d24np1,
+                   const double* v0bc, const double* v0m1bc, const double* vnbc, const double* vnp1bc,
+                   const double* eta0bc, const double* eta0m1bc, const double* etanbc, const double* etanp1bc,
+                   const double* D0mat);
+
+/* Host <-> device field transfer, host layout = Fortran V(-1:ny+1,-nz:nz,nx0:nxN,1:3)
+ * (complex; iy fastest), i.e. what read_restart_file fills (dnsdata.f90:677-720) and
+ * save_restart_file writes (dnsdata.f90:821-848). */
+int chb_upload_V(chb_handle h, const double* V_host);
+int chb_download_V(chb_handle h, double* V_host);
+
+/* Same transfer in the device layout [c][iy+1][ix-nx0][iz+nz] (no transposition). */
+int chb_upload_V_planes(chb_handle h, const double* V_host);
+int chb_download_V_planes(chb_handle h, double* V_host);
+
+/* bc0(0,0)%u=u0; bcn(0,0)%u=uN  (channel.f90:122-124). */
+int chb_set_wall_velocity(chb_handle h, double u0, double uN);
+
+/* Module variables dnsdata.f90:28-32 that the path reads; meanpx is updated on the
+ * device when CPI is on (linsolve_blocking.inc:87-97). */
+int chb_set_forcing(chb_handle h, double meanpx, double meanpz, double meanflowx, double meanflowz,
+                    int CPI, int CPI_type, double gamma);
+
+/* channel.f90:96-115: CFL over planes 1..ny-1 (convolutions with compute_cfl),
+ * flow rates fr(1:2) of the mean profile and the CPI update of meanpx. */
+int chb_cfl_prepass(chb_handle h);
+
+/* Body force, device path for the masked linear forces the reference ships
+ * (body_forces/coriolis/coriolis.inc:29-41, am_f1.inc, am_butterfly.inc):
+ *   F_r(iy,iz,ix) = sum_c A[r][c] * mask(iy,|iz| or iz) * V_c(iy,iz,ix)
+ * A is 3x3 row-major; mask_y[ny+3] and mask_z[2nz+1] are 0/1 factors whose product
+ * is the mask; exclude_mean!=0 leaves F(:,0,0,:) untouched.  Entries outside the
+ * mask keep their previous value (the hooks only assign inside the mask).
+ * enable=0 switches the body force off (bodyforce undefined, header.h:29). */
+int chb_set_body_force_linear(chb_handle h, int enable, const double* A, const double* mask_y,
+                              const double* mask_z, int exclude_mean);
+/* set_body_force() call sites channel.f90:129-131,142-144,155-157. */
+int chb_set_body_force(chb_handle h);
+
+/* Replaces buildrhs (dnsdata.f90:611-673) including every convolutions call
+ * (dnsdata.f90:487-602).  ode = RK?_rai(1:3).  Leaves the RHS of the eta- and
+ * D2v-equations on the device and accumulates cfl (max) when compute_cfl!=0. */
+int chb_buildrhs(chb_handle h, const double* ode, double deltat, int compute_cfl);
+
+/* Replaces linsolve (linsolve_blocking.inc:3-107, blocking semantics: includes the
+ * mean-mode flow-rate / CPI update and the inline vetaTOuvw). lambda = RK(1)/deltat. */
+int chb_linsolve(chb_handle h, double lambda);
+
+/* nonblockingY split (channel.f90:137-139, linsolve_nonblocking.inc:75-159): no-ops,
+ * chb_linsolve already did both; provided so either header.h variant links. */
+int chb_vetaTOuvw(chb_handle h);
+int chb_computeflowrate(chb_handle h, double lambda);
+
+/* One full RK3 step (channel.f90:125-166) = 3 x (set_body_force, buildrhs, linsolve). */
+int chb_rk3_step(chb_handle h, double deltat);
+
+/* What outstats reads (dnsdata.f90:861-878); one small D2H + stream sync.
+ * cfl is the max over ranks and is reset to 0 on the device (dnsdata.f90:861).
+ * U_lo/W_lo = Re V(-1:3,0,0,{1,3}); U_hi/W_hi = Re V(ny-3:ny+1,0,0,{1,3}) (valid on
+ * the rank with nx0==0, broadcast to all). */
+int chb_get_step_scalars(chb_handle h, double* cfl, double* fr, double* corrpx, double* corrpz,
+                         double* meanpx, double* meanpz,
+                         double* U_lo, double* U_hi, double* W_lo, double* W_hi);
+
+/* ---- test / diagnostics accessors (not part of the Fortran binding) ---------- */
+/* RHS left by chb_buildrhs: [2][ny+3][nxB][2nz+1] complex (0=eta, 1=D2v); rows 1..ny-1. */
+int chb_download_rhs(chb_handle h, double* rhs_host);
+/* Spectral products left by chb_buildrhs: [6][ny+3][nxB][2nz+1] complex
+ * = VVdz(izd(iz)+1, ix+1-nx0, 1:6, slot) for every plane (dnsdata.f90:609). */
+int chb_download_products(chb_handle h, double* prod_host);
+/* Body force field in the device layout [3][ny+3][nxB][2nz+1]. */
+int chb_download_F_planes(chb_handle h, double* F_host);
+/* Device timing of the kernels launched since the last reset: fills up to `cap`
+ * entries of (name, total ms, launches); returns the number of distinct kernels. */
+int chb_timing_enable(chb_handle h, int on);
+int chb_timing_report(chb_handle h, char* names, int name_stride, double* ms, long long* launches, int cap);
+/* Number of kernel launches issued by this handle since creation. */
+long long chb_launch_count(chb_handle h);
+/* Algorithmic / NVLink byte counters of the last buildrhs+linsolve. */
+int chb_sync(chb_handle h);
+/* Standalone batched FFT entry points used by the FFT parity tests:
+ * complex lines of length n (sign=+1 backward / -1 forward, unnormalised), in place. */
+int chb_test_fft_lines(int n, int nlines, int sign, double* data_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

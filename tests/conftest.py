@@ -1,0 +1,24 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+def pytest_collection_modifyitems(config, items):
+    # GPU tests must fail loudly rather than skip when the library is missing on a GPU box;
+    # without a GPU they are deselected by -m "not gpu".
+    pass
+
+
+@pytest.fixture(scope="session")
+def lib():
+    from channel_b200 import _lib
+    return _lib.load()
