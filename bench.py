@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""bench.py - RK3 timesteps/s of the channel hot path on N B200s (one process per GPU).
+
+    python bench.py --gpus 1 --steps K --warmup W                  # this repository (CUDA, C ABI)
+    python bench.py --impl reference --gpus 1 --steps K --warmup W # reference algorithm on the host cores
+    torchrun ... bench.py --gpus N ...                             # N ranks, NCCL all-to-all transposes
+
+A "step" is one full RK3 timestep (3 x [set_body_force,] buildrhs, linsolve; channel.f90:118-167)
+on a synthetic perturbed-laminar field.  The workload is a BASELINE.json config:
+by default the largest one that fits a single B200 (config 3, nx,ny,nz = 511,512,511) at every N
+(strong scaling); --workload selects another (1..5 or nx,ny,nz).
+
+Printed JSON (one line, rank 0): the driver contract plus
+  roofline     : dominant kernel, algorithmic HBM bytes / CUDA-event time vs MEASURED_PEAKS.json
+  step_roofline: whole step, B_step = 3*M*(ny+1)*(464+288r) bytes / t_step
+  kernels      : per-kernel share of the step, from CUDA events on the launching stream
+  cpu_baseline : the reference algorithm (oracle/, C + OpenMP) timed on this box's host cores
+  e2e          : the same metric through the C ABI with host buffers (upload V, K steps each with
+                 its Runtimedata scalars read back, download V), host<->device copies included
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {                     # BASELINE.json configs[0..4]
+    "1": dict(nx=16, ny=64, nz=16),
+    "2": dict(nx=191, ny=384, nz=189),
+    "3": dict(nx=511, ny=512, nz=511),
+    "4": dict(nx=1023, ny=1024, nz=1023),
+    "5": dict(nx=383, ny=512, nz=383, couette=True),
+}
+DEFAULT_WORKLOAD = "3"
+C16 = 16  # bytes per complex128
+
+
+def parse_workload(w: str):
+    if w in CONFIGS:
+        d = dict(CONFIGS[w]); d["name"] = f"config{w}"
+        return d
+    nx, ny, nz = (int(x) for x in w.split(","))
+    return dict(nx=nx, ny=ny, nz=nz, name="custom")
+
+
+def algorithmic_bytes(nx, ny, nz, nxd, nzd):
+    """compulsory HBM bytes per kernel family per RK substep and per step."""
+    M = (nx + 1) * (2 * nz + 1)
+    r = nzd / (2 * nz + 1)
+    npl = ny + 3
+    per = {
+        "zfwd": (3 + 3 * r) * C16 * M * npl,
+        "xpass": (3 * r + 6 * r) * C16 * M * npl,
+        "zbwd": (6 * r + 6) * C16 * M * npl,
+        "rhs": (11 + 4) * C16 * M * (ny - 1),
+        "solve": (2 + 3) * C16 * M * (ny - 1),
+    }
+    step = 3.0 * M * (ny + 1) * (464 + 288 * r)
+    return per, step
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index: int, period=0.1):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.sm, self.reasons, self.max_sm = [], set(), None
+        self._halt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.dev = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.dev, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:  # pragma: no cover
+            self.err = repr(e)
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+        }
+        while not self._halt.is_set():
+            try:
+                self.sm.append(nv.nvmlDeviceGetClockInfo(self.dev, nv.NVML_CLOCK_SM))
+                try:
+                    bits = nv.nvmlDeviceGetCurrentClocksEventReasons(self.dev)
+                except Exception:
+                    bits = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.dev)
+                for b, n in names.items():
+                    if bits & b:
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self._halt.wait(self.period)
+
+    def stop(self):
+        self._halt.set()
+        if self.is_alive():
+            self.join(timeout=2)
+        sm = sorted(self.sm)
+        return {"sm_mhz": (sm[len(sm) // 2] if sm else None), "sm_max_mhz": self.max_sm,
+                "reasons": sorted(self.reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ---------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from channel_b200 import Channel, DnsIn, _lib
+    from channel_b200.fields import perturbed_laminar_slab
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (this implementation has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    lib = _lib.load()
+    nccl_id = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        import ctypes as C
+        buf = C.create_string_buffer(128)
+        if rank == 0:
+            _lib.check(lib.chb_get_nccl_unique_id(buf), "chb_get_nccl_unique_id")
+        t = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).cuda()
+        dist.broadcast(t, 0)
+        nccl_id = bytes(t.cpu().numpy().tobytes())
+
+    w = parse_workload(args.workload)
+    couette = bool(w.get("couette"))
+    p = DnsIn(nx=w["nx"], ny=w["ny"], nz=w["nz"], deltat=0.0, cflmax=1.0,
+              CPI=not couette, u0=-1.0 if couette else 0.0, uN=1.0 if couette else 0.0)
+    ch = Channel(p, rank=rank, nranks=world, nccl_id=nccl_id, device=local_rank)
+    if couette:
+        ch.config_coriolis(0.02, 9999999.0, 1.0)      # body_forces/coriolis/coriolis.in as shipped
+    nx, ny, nz, nxd, nzd = ch.nx, ch.ny, ch.nz, ch.nxd, ch.nzd
+    dof = 3 * (2 * nx + 1) * (2 * nz + 1) * ny          # README.md:26 convention
+
+    # synthetic perturbed-laminar field of this rank's x-slab, in the Fortran (Dati.cart.out)
+    # layout V(iy,iz,ix,c), pinned: this is what the driver's read_restart_file would hold
+    Vf = torch.empty((3, ch.nxB, 2 * nz + 1, ny + 3), dtype=torch.complex128).pin_memory()
+    Vn = Vf.numpy()
+    perturbed_laminar_slab(Vn, nx, ny, nz, p.alfa0, p.beta0, ch.nx0, ch.nxB, p.a, p.ymin, p.ymax,
+                           eps=1e-3, couette=couette)
+    vbytes = Vn.nbytes
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ch.upload_V_fortran(Vn)
+    ch.cfl_prepass()
+    ch.outstats()                                      # deltat = cflmax / cfl  (channel.f90:116)
+    for _ in range(args.warmup):
+        ch.step()
+
+    # ---- timed region: K steps, device time on the launching stream, max over ranks ----------
+    ch.timing_enable(True)
+    l0 = ch.launch_count()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    ch.stopwatch_begin()
+    for _ in range(args.steps):
+        ch.step()
+    ms = ch.stopwatch_end()
+    barrier()
+    clocks = sampler.stop()
+    launches = ch.launch_count() - l0
+    kern = ch.timing_report()
+    ch.timing_enable(False)
+    last_line = ch.outstats()
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
+
+    # ---- end to end through the C ABI with host buffers ---------------------------------------
+    barrier()
+    t0 = time.perf_counter()
+    ch.upload_V_fortran(Vn)
+    for _ in range(args.steps):
+        ch.step()                                      # includes chb_get_step_scalars D2H per step
+    ch.download_V_fortran(out=Vn)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    finite = bool(np.isfinite(last_line).all())
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        per, step_bytes = algorithmic_bytes(nx, ny, nz, nxd, nzd)
+        fam = {"zfwd": ["zfwd"], "xpass": ["xpass"], "zbwd": ["zbwd"], "rhs": ["rhs"],
+               "solve": ["solve_s1", "solve_s2", "solve_s3", "solve_s4", "solve"]}
+        total_kernel_ms = sum(v[0] for v in kern.values()) or 1.0
+        kernels = {}
+        for f, names in fam.items():
+            tms = sum(kern[n][0] for n in names if n in kern)
+            if tms <= 0:
+                continue
+            bytes_total = per[f] / world * 3 * args.steps     # per rank, 3 substeps per step
+            kernels[f] = {"ms_per_step": tms / args.steps, "share": tms / total_kernel_ms,
+                          "gbs": bytes_total / (tms * 1e-3) / 1e9,
+                          "frac": bytes_total / (tms * 1e-3) / 1e9 / peak}
+        for n in kern:
+            if not any(n in names for names in fam.values()):
+                kernels[n] = {"ms_per_step": kern[n][0] / args.steps, "share": kern[n][0] / total_kernel_ms}
+        dom = max((k for k in kernels if "gbs" in kernels[k]), key=lambda k: kernels[k]["ms_per_step"])
+        nl = sum(kern[n][1] for n in fam[dom] if n in kern)
+        tms = sum(kern[n][0] for n in fam[dom] if n in kern)
+        bytes_per_launch = per[dom] / world * 3 * args.steps / nl
+        ach = bytes_per_launch / (tms / nl * 1e-3) / 1e9
+        out = {
+            "metric": "rk3_timesteps_per_s", "value": 1000.0 / ms_per_step, "unit": "steps/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "ns_per_dof_step": ms_per_step * 1e6 / dof,
+            "config": {"workload": f"{w['name']}: turbulent-channel grid nx,ny,nz={nx},{ny},{nz} "
+                                   f"(nxd,nzd={nxd},{nzd}), perturbed laminar "
+                                   f"{'Couette+coriolis' if couette else 'Poiseuille, CPI'} field, FP64, cflmax=1",
+                       "dof": dof, "decomposition": f"x-pencils over {world} GPU(s), npy=1",
+                       "l2": "state (%.1f GB/GPU) far larger than the 126 MB L2; no flush needed" % (ch.device_bytes() / 1e9),
+                       "device_bytes_per_gpu": ch.device_bytes()},
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
+                         "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                         "bytes_per_launch": bytes_per_launch, "launches": nl},
+            "step_roofline": {"bytes_per_step": step_bytes, "achieved": step_bytes / (ms_per_step * 1e-3) / 1e9,
+                              "peak": peak * world, "unit": "GB/s",
+                              "frac": step_bytes / (ms_per_step * 1e-3) / 1e9 / (peak * world)},
+            "kernels": kernels,
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "e2e": {"value": args.steps / e2e_s, "unit": "steps/s",
+                    "h2d_bytes_per_step": vbytes * world / args.steps,
+                    "d2h_bytes_per_step": vbytes * world / args.steps + 8 * 40,
+                    "what": "chb_upload_V (pinned Fortran-layout V) + K x (chb_buildrhs/chb_linsolve x3 + "
+                            "chb_get_step_scalars) + chb_download_V, wall clock"},
+            "finite": finite,
+        }
+        if args.cpu_baseline and world == 1:
+            out["cpu_baseline"] = cpu_baseline(w, sample_s=args.cpu_seconds)
+        print(json.dumps(out), flush=True)
+    ch.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------
+def cpu_baseline(w, sample_s=20.0, threads=None):
+    """The reference algorithm (oracle/channel_oracle_c.c, C + OpenMP, plane-by-plane like
+    dnsdata.f90) on this box's host cores, on a bounded sample of the same grid."""
+    from oracle import c_oracle
+    return c_oracle.timed_sample(w["nx"], w["ny"], w["nz"], seconds=sample_s, threads=threads)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    w = parse_workload(args.workload)
+    vals = []
+    cb = None
+    for i in range(args.warmup + args.steps):
+        cb = cpu_baseline(w, sample_s=args.cpu_seconds)
+        if i >= args.warmup:
+            vals.append(cb["value"])
+    v = float(np.mean(vals))
+    cb["value"] = v
+    out = {"impl": "reference", "metric": "rk3_timesteps_per_s", "value": v, "unit": "steps/s",
+           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / v,
+           "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+           "data": "synthetic",
+           "config": {"workload": f"{w['name']}: nx,ny,nz={w['nx']},{w['ny']},{w['nz']} (bounded sample, see cpu_baseline.sample)"},
+           "cpu_baseline": cb,
+           "e2e": {"value": v, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("CHB_WORKLOAD", DEFAULT_WORKLOAD))
+    ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        # each "step" of the reference arm is one bounded sample; keep the whole run to minutes
+        args.cpu_seconds = min(args.cpu_seconds, max(3.0, 120.0 / max(1, args.steps + args.warmup)))
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

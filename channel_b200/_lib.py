@@ -29,6 +29,8 @@ SYMBOLS = {
     "chb_set_tables": (C.c_int, [C.c_void_p] + [c_double_p] * 22),
     "chb_upload_V": (C.c_int, [C.c_void_p, C.c_void_p]),
     "chb_download_V": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "chb_host_register": (C.c_int, [C.c_void_p, C.c_size_t]),
+    "chb_host_unregister": (C.c_int, [C.c_void_p]),
     "chb_upload_V_planes": (C.c_int, [C.c_void_p, C.c_void_p]),
     "chb_download_V_planes": (C.c_int, [C.c_void_p, C.c_void_p]),
     "chb_set_wall_velocity": (C.c_int, [C.c_void_p, C.c_double, C.c_double]),
@@ -49,10 +51,16 @@ SYMBOLS = {
     "chb_timing_report": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, c_double_p, C.POINTER(C.c_longlong), C.c_int]),
     "chb_launch_count": (C.c_longlong, [C.c_void_p]),
     "chb_sync": (C.c_int, [C.c_void_p]),
+    "chb_stopwatch_begin": (C.c_int, [C.c_void_p]),
+    "chb_stopwatch_end": (C.c_int, [C.c_void_p, c_double_p]),
+    "chb_get_stream": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "chb_device_bytes": (C.c_longlong, [C.c_void_p]),
     "chb_test_fft_lines": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "chb_host_fft_fit": (C.c_int, [C.c_int]),
     "chb_host_padded_sizes": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "chb_host_setup_tables": (C.c_int, [C.c_int, C.c_double, C.c_double, C.c_double, C.POINTER(HostTables)]),
+    "chb_host_decomposition": (C.c_int, [C.c_int] * 4 + [C.POINTER(C.c_int)] * 4),
+    "chb_host_transpose_index": (C.c_longlong, [C.c_int] * 9),
     "chb_host_apply_tables": (C.c_int, [C.c_void_p, C.POINTER(HostTables)]),
 }
 

@@ -101,9 +101,11 @@ static std::vector<double> twiddles(int n, int count, int denom) {
     return w;
 }
 
+static thread_local size_t g_alloc_bytes = 0;
 template <typename T>
 static int dev_alloc(T** p, size_t count) {
     CHB_CUDA_OK(cudaMalloc((void**)p, count * sizeof(T)));
+    g_alloc_bytes += count * sizeof(T);
     CHB_CUDA_OK(cudaMemset(*p, 0, count * sizeof(T)));
     return 0;
 }
@@ -141,14 +143,17 @@ extern "C" int chb_create(chb_handle* out, int nx, int ny, int nz, int nxd, int 
     CHB_REQUIRE(ndev > 0, "chb_create: no CUDA device (this library has no CPU fallback)");
     CHB_CUDA_OK(cudaSetDevice(device));
     chb_handle_s* h = new chb_handle_s();
+    g_alloc_bytes = 0;
+    h->sw0 = h->sw1 = nullptr;
     memset(&h->g, 0, sizeof(h->g));
     Geometry& g = h->g;
     g.nx = nx; g.ny = ny; g.nz = nz; g.nxd = nxd; g.nzd = nzd;
     g.nyp = ny + 3; g.nzt = 2 * nz + 1;
     g.rank = rank; g.nranks = nranks;
     // mpi_transpose.f90:214-215
-    g.nx0 = rank * (nx + 1) / nranks; g.nxN = (rank + 1) * (nx + 1) / nranks - 1; g.nxB = g.nxN - g.nx0 + 1;
-    g.nz0 = rank * nzd / nranks; g.nzN = (rank + 1) * nzd / nranks - 1; g.nzB = g.nzN - g.nz0 + 1;
+    chb_decompose(nx + 1, nzd, nranks, rank, &g.nx0, &g.nxN, &g.nz0, &g.nzN);
+    g.nxB = g.nxN - g.nx0 + 1;
+    g.nzB = g.nzN - g.nz0 + 1;
     g.M = (long long)g.nxB * g.nzt;
     g.alfa0 = alfa0; g.beta0 = beta0; g.ni = ni;
     const double PI = 3.1415926535897932384626433832795028841971;  // dnsdata.f90:26
@@ -202,6 +207,7 @@ extern "C" int chb_create(chb_handle* out, int nx, int ny, int nz, int nxd, int 
     memset(h->sc_host, 0, sizeof(DevScalars));
     if (nranks > 1 && chb_nccl_init(h, nccl_id)) return 1;
     CHB_CUDA_OK(cudaDeviceSynchronize());
+    h->dev_bytes = g_alloc_bytes;
     *out = h;
     return 0;
 }
@@ -293,6 +299,16 @@ static int transfer_V(chb_handle h, double* host, bool upload, bool fortran_layo
         CHB_CUDA_OK(cudaStreamSynchronize(h->stream));
     }
     CHB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+extern "C" int chb_host_register(void* ptr, size_t bytes) {
+    CHB_REQUIRE(ptr && bytes, "chb_host_register: null argument");
+    CHB_CUDA_OK(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
+    return 0;
+}
+extern "C" int chb_host_unregister(void* ptr) {
+    CHB_REQUIRE(ptr, "chb_host_unregister: null argument");
+    CHB_CUDA_OK(cudaHostUnregister(ptr));
     return 0;
 }
 extern "C" int chb_upload_V(chb_handle h, const double* V) { return transfer_V(h, const_cast<double*>(V), true, true, h ? h->V : nullptr); }
@@ -474,6 +490,33 @@ extern "C" int chb_sync(chb_handle h) {
     CHB_CUDA_OK(cudaGetLastError());
     return 0;
 }
+extern "C" int chb_stopwatch_begin(chb_handle h) {
+    CHB_REQUIRE(h, "null handle");
+    CHB_CUDA_OK(cudaSetDevice(h->device));
+    if (!h->sw0) {
+        CHB_CUDA_OK(cudaEventCreate(&h->sw0));
+        CHB_CUDA_OK(cudaEventCreate(&h->sw1));
+    }
+    CHB_CUDA_OK(cudaEventRecord(h->sw0, h->stream));
+    return 0;
+}
+extern "C" int chb_stopwatch_end(chb_handle h, double* ms) {
+    CHB_REQUIRE(h && h->sw0 && ms, "chb_stopwatch_end: stopwatch not started");
+    CHB_CUDA_OK(cudaSetDevice(h->device));
+    CHB_CUDA_OK(cudaEventRecord(h->sw1, h->stream));
+    CHB_CUDA_OK(cudaEventSynchronize(h->sw1));
+    float f = 0;
+    CHB_CUDA_OK(cudaEventElapsedTime(&f, h->sw0, h->sw1));
+    *ms = f;
+    CHB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+extern "C" int chb_get_stream(chb_handle h, void** stream) {
+    CHB_REQUIRE(h && stream, "null argument");
+    *stream = (void*)h->stream;
+    return 0;
+}
+extern "C" long long chb_device_bytes(chb_handle h) { return h ? (long long)h->dev_bytes : -1; }
 extern "C" long long chb_launch_count(chb_handle h) { return h ? h->launches : -1; }
 extern "C" int chb_timing_enable(chb_handle h, int on) {
     CHB_REQUIRE(h, "null handle");

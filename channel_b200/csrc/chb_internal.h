@@ -5,6 +5,7 @@
 #include <string>
 #include <vector>
 #include "fft_device.cuh"
+#include "transpose_index.h"
 
 // Coefficient tables of setup_derivatives / setup_boundary_conditions
 // (dnsdata.f90:241-308), passed by value to the y-direction kernels.
@@ -95,6 +96,8 @@ struct chb_handle_s {
     void* nccl_comm;
     // bookkeeping
     long long launches;
+    size_t dev_bytes;
+    cudaEvent_t sw0, sw1;
     KernelTimer timer;
 };
 

@@ -19,10 +19,7 @@
 
 #define CONV_THREADS 256
 
-__device__ __forceinline__ size_t buf_index(int peer, int ncomp, int comp, int np, int pl, int nzB, int izl, int nxB,
-                                            int ixl) {
-    return ((((size_t)peer * ncomp + comp) * np + pl) * nzB + izl) * (size_t)nxB + ixl;
-}
+#define buf_index chb_buf_index
 
 // --------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(CONV_THREADS)

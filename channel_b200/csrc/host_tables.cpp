@@ -10,6 +10,7 @@
 
 #include "../../include/channel_b200.h"
 #include "../../include/channel_b200_host.h"
+#include "transpose_index.h"
 
 namespace {
 
@@ -166,4 +167,15 @@ extern "C" int chb_host_apply_tables(chb_handle h, const chb_host_tables* t) {
     return chb_set_tables(h, t->y, t->d0, t->d1, t->d2, t->d4, t->d140, t->d14m1, t->d240, t->d24m1, t->d14n, t->d14np1,
                           t->d24n, t->d24np1, t->v0bc, t->v0m1bc, t->vnbc, t->vnp1bc, t->eta0bc, t->eta0m1bc, t->etanbc,
                           t->etanp1bc, t->D0mat);
+}
+
+extern "C" int chb_host_decomposition(int nx, int nzd, int nranks, int rank, int* nx0, int* nxN, int* nz0, int* nzN) {
+    if (nranks < 1 || rank < 0 || rank >= nranks || (nx + 1) % nranks != 0 || nzd % nranks != 0) return 2;
+    chb_decompose(nx + 1, nzd, nranks, rank, nx0, nxN, nz0, nzN);
+    return 0;
+}
+
+extern "C" long long chb_host_transpose_index(int peer, int ncomp, int comp, int nplanes, int plane, int nzB, int izl,
+                                              int nxB, int ixl) {
+    return (long long)chb_buf_index(peer, ncomp, comp, nplanes, plane, nzB, izl, nxB, ixl);
 }

@@ -1,0 +1,27 @@
+// transpose_index.h - layout of the pencil-transpose work buffers, shared by the kernels
+// (conv_kernels.cu), the all-to-all (transpose.cu) and the host-side tests.
+//
+// One contiguous block per peer rank so that zTOx / xTOz (mpi_transpose.f90:50-117) are plain
+// block exchanges:  buf[peer][comp][plane][izl][ixl],  izl in [0,nzB), ixl in [0,nxB).
+// On the z side (written by the z-pass, rank r owns x-modes nx0..nxN) peer = owner of the
+// physical z-line = iz_d / nzB; after the exchange, on the x side (rank q owns z-lines
+// nz0..nzN) peer = owner of the x-mode = ix / nxB.
+#pragma once
+#include <stddef.h>
+#ifdef __CUDACC__
+#define CHB_HD __host__ __device__ __forceinline__
+#else
+#define CHB_HD inline
+#endif
+
+CHB_HD size_t chb_buf_index(int peer, int ncomp, int comp, int np, int pl, int nzB, int izl, int nxB, int ixl) {
+    return ((((size_t)peer * ncomp + comp) * np + pl) * nzB + izl) * (size_t)nxB + ixl;
+}
+
+// mpi_transpose.f90:214-215 with npy=1
+CHB_HD void chb_decompose(int nxp1, int nzd, int nranks, int rank, int* nx0, int* nxN, int* nz0, int* nzN) {
+    *nx0 = rank * nxp1 / nranks;
+    *nxN = (rank + 1) * nxp1 / nranks - 1;
+    *nz0 = rank * nzd / nranks;
+    *nzN = (rank + 1) * nzd / nranks - 1;
+}

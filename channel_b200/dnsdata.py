@@ -189,8 +189,9 @@ class Channel:
         assert Vf.shape == (3, self.nxB, 2 * self.nz + 1, self.ny + 3)
         _lib.check(self.lib.chb_upload_V(self.h, Vf.ctypes.data), "chb_upload_V")
 
-    def download_V_fortran(self):
-        Vf = np.empty((3, self.nxB, 2 * self.nz + 1, self.ny + 3), np.complex128)
+    def download_V_fortran(self, out=None):
+        Vf = out if out is not None else np.empty((3, self.nxB, 2 * self.nz + 1, self.ny + 3), np.complex128)
+        assert Vf.flags.c_contiguous and Vf.dtype == np.complex128
         _lib.check(self.lib.chb_download_V(self.h, Vf.ctypes.data), "chb_download_V")
         return Vf
 
@@ -284,6 +285,21 @@ class Channel:
             self.buildrhs(RK, k == 2)
             self.linsolve(RK[0] / self.deltat)
         return self.outstats() if stats else None
+
+    def stopwatch_begin(self):
+        _lib.check(self.lib.chb_stopwatch_begin(self.h), "chb_stopwatch_begin")
+
+    def stopwatch_end(self) -> float:
+        ms = C.c_double()
+        _lib.check(self.lib.chb_stopwatch_end(self.h, C.byref(ms)), "chb_stopwatch_end")
+        return ms.value
+
+    def rk3_step(self):
+        """chb_rk3_step: the three substeps in one C call (no Python in the loop)."""
+        _lib.check(self.lib.chb_rk3_step(self.h, self.deltat), "chb_rk3_step")
+
+    def device_bytes(self):
+        return int(self.lib.chb_device_bytes(self.h))
 
     def launch_count(self):
         return int(self.lib.chb_launch_count(self.h))

@@ -39,3 +39,33 @@ def perturbed_laminar(nx, ny, nz, alfa0, beta0, a=1.5, ymin=0.0, ymax=2.0,
     V[:, :, 0, nz] = 0.0
     V[0, :, 0, nz] = (y - 1.0) if couette else 1.5 * y * (2.0 - y)
     return V
+
+
+def perturbed_laminar_slab(out, nx, ny, nz, alfa0, beta0, nx0, nxB, a=1.5, ymin=0.0, ymax=2.0,
+                           eps=1e-3, seed=20261017, couette=False):
+    """The same field as perturbed_laminar(), for the x-slab ix = nx0..nx0+nxB-1 only, written
+    into `out` in the Fortran / Dati.cart.out layout V(iy,iz,ix,c) = C-order [c][ixl][iz+nz][iy+1]
+    (dnsdata.f90:132).  One BLAS call per component; no full-size temporaries."""
+    assert out.shape == (3, nxB, 2 * nz + 1, ny + 3) and out.dtype == np.complex128
+    y = grid_y(ny, a, ymin, ymax)
+    rng = np.random.default_rng(seed)
+    ix = np.arange(nx + 1); iz = np.arange(-nz, nz + 1)
+    k2 = (alfa0 * ix)[:, None] ** 2 + (beta0 * iz)[None, :] ** 2
+    amp = eps / (1.0 + k2)
+    g = (y * (2.0 - y)) ** 2
+    nshape = 3
+    nzt = 2 * nz + 1
+    for c in range(3):
+        coef = np.empty((nxB, nzt, nshape), np.complex128)
+        shapes = np.empty((nshape, ny + 3), np.complex128)
+        for s in range(nshape):
+            xi = rng.standard_normal((nx + 1, nzt)) + 1j * rng.standard_normal((nx + 1, nzt))
+            coef[:, :, s] = (amp * xi)[nx0:nx0 + nxB]
+            shapes[s] = g * np.cos(0.5 * np.pi * s * y + 0.3 * c)
+        if nx0 == 0:   # Hermitian symmetry on ix=0 and the mean mode, as in perturbed_laminar()
+            coef[0, :nz, :] = np.conj(coef[0, :nz:-1, :])
+            coef[0, nz, :] = 0.0
+        np.matmul(coef.reshape(nxB * nzt, nshape), shapes, out=out[c].reshape(nxB * nzt, ny + 3))
+    if nx0 == 0:
+        out[0, 0, nz, :] = (y - 1.0) if couette else 1.5 * y * (2.0 - y)
+    return out

@@ -78,6 +78,11 @@ int chb_set_tables(chb_handle h, const double* y,
 int chb_upload_V(chb_handle h, const double* V_host);
 int chb_download_V(chb_handle h, double* V_host);
 
+/* Page-lock / unlock a caller-owned host array (the Fortran V) so the transfers above run at
+ * full PCIe rate and asynchronously (cudaHostRegister / cudaHostUnregister). */
+int chb_host_register(void* ptr, size_t bytes);
+int chb_host_unregister(void* ptr);
+
 /* Same transfer in the device layout [c][iy+1][ix-nx0][iz+nz] (no transposition). */
 int chb_upload_V_planes(chb_handle h, const double* V_host);
 int chb_download_V_planes(chb_handle h, double* V_host);
@@ -145,8 +150,17 @@ int chb_timing_enable(chb_handle h, int on);
 int chb_timing_report(chb_handle h, char* names, int name_stride, double* ms, long long* launches, int cap);
 /* Number of kernel launches issued by this handle since creation. */
 long long chb_launch_count(chb_handle h);
-/* Algorithmic / NVLink byte counters of the last buildrhs+linsolve. */
+/* Wait for everything enqueued on the handle's stream. */
 int chb_sync(chb_handle h);
+/* CUDA-event stopwatch on the handle's stream (the stream every kernel of this handle is
+ * launched on): begin records an event, end records a second one, waits for it and returns
+ * the elapsed device time in milliseconds. */
+int chb_stopwatch_begin(chb_handle h);
+int chb_stopwatch_end(chb_handle h, double* ms);
+/* The handle's cudaStream_t (as void*), for callers that enqueue their own work behind it. */
+int chb_get_stream(chb_handle h, void** stream);
+/* Bytes of device memory this handle allocated. */
+long long chb_device_bytes(chb_handle h);
 /* Standalone batched FFT entry points used by the FFT parity tests:
  * complex lines of length n (sign=+1 backward / -1 forward, unnormalised), in place. */
 int chb_test_fft_lines(int n, int nlines, int sign, double* data_host);

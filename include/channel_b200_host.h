@@ -30,6 +30,15 @@ int chb_host_padded_sizes(int nx, int nz, int* nxd, int* nzd);
  * setup_boundary_conditions (dnsdata.f90:290-308) for the full channel, npy=1. */
 int chb_host_setup_tables(int ny, double a, double ymin, double ymax, chb_host_tables* t);
 
+/* init_MPI's x/z index ranges for npy=1 (mpi_transpose.f90:214-215); no GPU needed. */
+int chb_host_decomposition(int nx, int nzd, int nranks, int rank, int* nx0, int* nxN, int* nz0, int* nzN);
+
+/* Element offset (in complex numbers) inside the pencil-transpose work buffers
+ * buf[peer][comp][plane][izl][ixl] that the z-pass / x-pass kernels write and read and that
+ * the all-to-all exchanges block-wise (zTOx / xTOz, mpi_transpose.f90:50-117). */
+long long chb_host_transpose_index(int peer, int ncomp, int comp, int nplanes, int plane, int nzB, int izl,
+                                   int nxB, int ixl);
+
 /* chb_set_tables with the contents of *t. */
 int chb_host_apply_tables(chb_handle h, const chb_host_tables* t);
 

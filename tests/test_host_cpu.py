@@ -1,0 +1,148 @@
+"""CPU tests of the host side and of the C-ABI library surface (no compute calls: no GPU here)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from channel_b200 import DnsIn, _lib, read_dnsin
+from channel_b200.dnsdata import Tables, format_runtimedata, padded_sizes, read_restart_file, save_restart_file
+from channel_b200.fields import perturbed_laminar, perturbed_laminar_slab
+from oracle.channel_oracle import DnsIn as ODnsIn, Oracle
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    names = set()
+    for hdr in ("channel_b200.h", "channel_b200_host.h"):
+        text = open(os.path.join(ROOT, "include", hdr)).read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        names |= set(re.findall(r"\b(chb_[A-Za-z0-9_]+)\s*\(", text))
+    return names
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    lib = _lib.load()
+    decl = declared_symbols()
+    assert len(decl) >= 40
+    for n in decl:
+        assert hasattr(lib, n), f"{n} declared in include/*.h but not exported"
+    # the ctypes table binds exactly the declared set
+    assert set(_lib.SYMBOLS) == decl, set(_lib.SYMBOLS) ^ decl
+    assert lib.chb_version() >= 1000
+
+
+def test_create_without_gpu_fails_loudly():
+    """No CPU fallback: without a CUDA device chb_create returns an error and a message."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    lib = _lib.load()
+    h = C.c_void_p()
+    rc = lib.chb_create(C.byref(h), 16, 64, 16, 32, 48, 0.5, 1.0, 1e-3, 1.5, 0.0, 2.0, 0, 1, None, 0)
+    assert rc != 0 and len(lib.chb_last_error()) > 0
+    from channel_b200 import Channel, ChannelB200Error
+    with pytest.raises(ChannelB200Error):
+        Channel(DnsIn())
+
+
+def test_argument_validation_precedes_device_use():
+    lib = _lib.load()
+    h = C.c_void_p()
+    assert lib.chb_create(C.byref(h), 16, 64, 16, 33, 48, 0.5, 1.0, 1e-3, 1.5, 0.0, 2.0, 0, 1, None, 0) == 2   # odd nxd
+    assert lib.chb_create(C.byref(h), 16, 64, 16, 32, 48, 0.5, 1.0, 1e-3, 1.5, 0.0, 2.0, 0, 2, None, 0) == 2   # 2 !| 17
+    assert b"README.md:154" in lib.chb_last_error()
+    assert lib.chb_buildrhs(None, None, 1.0, 0) != 0
+    assert lib.chb_linsolve(None, 1.0) != 0
+
+
+def test_padded_sizes_and_decomposition():
+    assert padded_sizes(191, 189) == (384, 768) and padded_sizes(1023, 1023) == (1536, 3072)
+    lib = _lib.load()
+    a, b, c, d = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+    cover_x, cover_z = [], []
+    for r in range(8):   # config 4 on 8 GPUs (mpi_transpose.f90:214-215)
+        assert lib.chb_host_decomposition(1023, 3072, 8, r, C.byref(a), C.byref(b), C.byref(c), C.byref(d)) == 0
+        cover_x += list(range(a.value, b.value + 1)); cover_z += list(range(c.value, d.value + 1))
+    assert cover_x == list(range(1024)) and cover_z == list(range(3072))
+    assert lib.chb_host_decomposition(16, 48, 2, 0, C.byref(a), C.byref(b), C.byref(c), C.byref(d)) == 2
+
+
+@pytest.mark.parametrize("ny", [16, 64, 96])
+def test_host_tables_match_oracle(ny):
+    """host_tables.cpp restates setup_derivatives/setup_boundary_conditions (dnsdata.f90:241-308);
+    the numpy oracle restates them independently."""
+    t = Tables(ny, 1.5, 0.0, 2.0)
+    o = Oracle(ODnsIn(nx=4, ny=ny, nz=4))
+    assert np.allclose(t.y, o.y, rtol=0, atol=1e-15)
+    for n in ("d0", "d1", "d2", "d4"):
+        ref = getattr(o, n)[2:ny + 1]
+        assert np.abs(getattr(t, n) - ref).max() <= 1e-12 * np.abs(ref).max(), n
+    assert np.abs(t.D0mat - o.D0mat).max() <= 1e-12 * np.abs(o.D0mat).max()
+    for n in ("d140", "d14m1", "d240", "d24m1", "d14n", "d14np1", "d24n", "d24np1",
+              "v0bc", "v0m1bc", "vnbc", "vnp1bc", "eta0bc", "eta0m1bc", "etanbc", "etanp1bc"):
+        ref = getattr(o, n)
+        assert np.abs(getattr(t, n) - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max()), n
+
+
+DNS_IN = """\
+191 384 189        ! nx, ny, nz
+0.5d0 1.0d0        ! alfa0, beta0
+12431              ! ni (read as Re; inverted by read_dnsin)
+1.5d0 0.0d0 2.0d0  ! a, ymin, ymax
+.TRUE. 1 0.161436d0 ! CPI, CPI_type, gamma
+0.0 0.0            ! meanpx, meanpz
+0.0 0.0            ! meanflowx, meanflowz
+0.0 0.0            ! u0, uN
+0.0 1.0 0.0        ! deltat, cflmax, time
+30.0 -1 7000.0 .TRUE. ! dt_field, dt_save, t_max, time_from_restart
+999999             ! nstep
+1                  ! npy
+"""
+
+
+def test_read_dnsin(tmp_path):
+    f = tmp_path / "dns.in"
+    f.write_text(DNS_IN.replace("d0", "e0"))
+    p = read_dnsin(str(f))
+    assert (p.nx, p.ny, p.nz) == (191, 384, 189) and p.CPI and p.CPI_type == 1
+    assert p.re == 12431.0 and abs(p.gamma - 0.161436) < 1e-15 and p.cflmax == 1.0 and p.npy == 1
+    f.write_text("1 2 3\n")
+    with pytest.raises(ValueError):
+        read_dnsin(str(f))
+
+
+def test_restart_file_roundtrip_and_header_check(tmp_path):
+    """Dati.cart.out: 3 x int32 + 7 x float64 header, then V(iy,iz,ix,c) (dnsdata.f90:683-695,830-846)."""
+    p = DnsIn(nx=5, ny=8, nz=3, re=100.0)
+    V = np.random.default_rng(1).standard_normal((3, 6, 7, 11)) + 0j
+    path = str(tmp_path / "Dati.cart.out")
+    save_restart_file(path, p, 1.25, V)
+    assert os.path.getsize(path) == 68 + V.nbytes
+    t, V2 = read_restart_file(path, p)
+    assert t == 1.25 and np.array_equal(V, V2)
+    with pytest.raises(ValueError):
+        read_restart_file(path, DnsIn(nx=5, ny=8, nz=3, re=101.0))
+    assert len(format_runtimedata(np.arange(11.0)).split()) == 11
+
+
+def test_slab_generator_matches_full_field():
+    nx, ny, nz = 15, 16, 7
+    V = perturbed_laminar(nx, ny, nz, 0.5, 1.0, couette=True)
+    for nx0, nxB in ((0, 16), (0, 8), (8, 8), (12, 4)):
+        out = np.empty((3, nxB, 2 * nz + 1, ny + 3), complex)
+        perturbed_laminar_slab(out, nx, ny, nz, 0.5, 1.0, nx0, nxB, couette=True)
+        assert np.abs(out - np.transpose(V[:, :, nx0:nx0 + nxB], (0, 2, 3, 1))).max() < 1e-18
+    # Hermitian symmetry on the ix=0 line, v(0,0)=0
+    assert np.array_equal(V[:, :, 0, :nz], np.conj(V[:, :, 0, :nz:-1])) and np.all(V[1, :, 0, nz] == 0)
+
+
+def test_bench_algorithmic_bytes_match_survey():
+    import bench
+    per, step = bench.algorithmic_bytes(1023, 1024, 1023, 1536, 3072)
+    assert abs(step - 5.78e12) / 5.78e12 < 0.01             # 5.78 TB/step at config 4
+    per, step = bench.algorithmic_bytes(191, 384, 189, 384, 768)
+    assert abs(step - 88e9) / 88e9 < 0.01                   # 88 GB/step at config 2
+    assert abs(3 * sum(per.values()) - step) / step < 0.02  # per-kernel rows add up to the step total
