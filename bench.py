@@ -191,15 +191,15 @@ def run_b200(args):
     barrier()
     sampler.start()
     ch.stopwatch_begin()
+    last_line = None
     for _ in range(args.steps):
-        ch.step()
+        last_line = ch.step()
     ms = ch.stopwatch_end()
     barrier()
     clocks = sampler.stop()
     launches = ch.launch_count() - l0
     kern = ch.timing_report()
     ch.timing_enable(False)
-    last_line = ch.outstats()
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -55,6 +55,7 @@ SYMBOLS = {
     "chb_stopwatch_end": (C.c_int, [C.c_void_p, c_double_p]),
     "chb_get_stream": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "chb_device_bytes": (C.c_longlong, [C.c_void_p]),
+    "chb_measure_device_peaks": (C.c_int, [c_double_p]),
     "chb_test_fft_lines": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "chb_host_fft_fit": (C.c_int, [C.c_int]),
     "chb_host_padded_sizes": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),

@@ -161,6 +161,9 @@ int chb_stopwatch_end(chb_handle h, double* ms);
 int chb_get_stream(chb_handle h, void** stream);
 /* Bytes of device memory this handle allocated. */
 long long chb_device_bytes(chb_handle h);
+/* Device ceilings measured with this library's own kernels: out[0] = FP64 FMA TFLOP/s,
+ * out[1] = STREAM-style copy GB/s (read+write).  Diagnostics for the roofline report. */
+int chb_measure_device_peaks(double* out);
 /* Standalone batched FFT entry points used by the FFT parity tests:
  * complex lines of length n (sign=+1 backward / -1 forward, unnormalised), in place. */
 int chb_test_fft_lines(int n, int nlines, int sign, double* data_host);
