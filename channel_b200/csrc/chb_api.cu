@@ -1,6 +1,7 @@
 // chb_api.cu - the extern "C" entry points declared in include/channel_b200.h.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -159,6 +160,12 @@ extern "C" int chb_create(chb_handle* out, int nx, int ny, int nz, int nxd, int 
     const double PI = 3.1415926535897932384626433832795028841971;  // dnsdata.f90:26
     g.dx = PI / (alfa0 * nxd); g.dz = 2.0 * PI / (beta0 * nzd); g.factor = 1.0 / (2.0 * nxd * nzd);  // :124
     h->device = device;
+    {
+        const char* e = getenv("CHB_Z_LPC");
+        h->z_lines_per_cta = (e && atoi(e) == 4) ? 4 : 8;
+        e = getenv("CHB_FFT3");
+        h->use_fft3 = (e && atoi(e) == 0) ? 0 : 1;
+    }
     h->launches = 0;
     h->tables_set = false;
     h->F = nullptr;

@@ -74,6 +74,8 @@ struct chb_handle_s {
     double* mult;   // [4][nyp][M]  L-multipliers of D2vmat / etamat
     // convolution work buffers for a chunk of planes
     int chunk_planes;
+    int z_lines_per_cta;  // 4 or 8 (CHB_Z_LPC)
+    int use_fft3;         // register-resident three-stage FFT kernels for the large sizes (CHB_FFT3=0 disables)
     cplx* A;        // z-padded velocity, [peer][3][np][nzB][nxB]
     cplx* Ar;       // after zTOx (aliases A when nranks==1)
     cplx* B;        // products after x-pass, [peer][6][np][nzB][nxB]
@@ -105,6 +107,8 @@ struct chb_handle_s {
 void launch_zfwd(chb_handle_s* h, int plane0, int nplanes);
 void launch_xpass(chb_handle_s* h, int plane0, int nplanes, int compute_cfl);
 void launch_zbwd(chb_handle_s* h, int plane0, int nplanes);
+// ---- zpass3_kernels.cu / xpass3_kernels.cu: false = no specialised kernel for this size ----
+bool launch_z3_fwd_or_bwd(chb_handle_s* h, int plane0, int nplanes, bool fwd);
 // ---- rhs_kernel.cu ----
 void launch_rhs(chb_handle_s* h, const double* ode, double deltat);
 // ---- solve_kernels.cu ----

@@ -225,6 +225,7 @@ static void z_config(chb_handle_s* h, int* tx, int* line_stride, size_t* smem) {
 }
 
 void launch_zfwd(chb_handle_s* h, int plane0, int nplanes) {
+    if (h->use_fft3 && launch_z3_fwd_or_bwd(h, plane0, nplanes, true)) return;
     int tx, ls;
     size_t smem;
     z_config(h, &tx, &ls, &smem);
@@ -237,6 +238,7 @@ void launch_zfwd(chb_handle_s* h, int plane0, int nplanes) {
 }
 
 void launch_zbwd(chb_handle_s* h, int plane0, int nplanes) {
+    if (h->use_fft3 && launch_z3_fwd_or_bwd(h, plane0, nplanes, false)) return;
     int tx, ls;
     size_t smem;
     z_config(h, &tx, &ls, &smem);

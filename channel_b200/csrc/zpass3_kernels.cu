@@ -1,0 +1,196 @@
+// zpass3_kernels.cu - z-direction passes of the nonlinear term for the large transform sizes,
+// built on the register-resident three-stage FFT of fft_regs.cuh.
+//
+//   zfwd3: zero-pad in z + backward complex FFT of length nzd      (dnsdata.f90:504-510, IFT ffts.f90:71)
+//          + zTOx pack: output x-contiguous, one block per destination rank (mpi_transpose.f90:64-71)
+//   zbwd3: xTOz unpack + forward complex FFT of length nzd (FFT ffts.f90:70) + z-truncation
+//          through izd() (DD macro, dnsdata.f90:609)
+//
+// One CTA = LPC neighbouring x-modes (lines), 32 threads per line.  The two stages that touch
+// the z-contiguous side run "warp per line" (only __syncwarp between them); the stage that
+// touches the x-contiguous work buffer runs "cross-line" (consecutive lanes = consecutive
+// lines) so that every global access is LPC*16 contiguous bytes.  Per point: one global read,
+// one global write, two shared-memory exchanges.
+#include "chb_internal.h"
+#include "fft_regs.cuh"
+
+template <class G, int LPC>
+__global__ void __launch_bounds__(LPC * 32)
+zfwd3_kernel(const cplx* __restrict__ V, cplx* __restrict__ A, Geometry g, const cplx* __restrict__ W, int plane0, int np,
+             int LS) {
+    extern __shared__ cplx smem[];
+    constexpr int BCP = G::BC + 1;
+    const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
+    const int ixl0 = blockIdx.x * LPC;
+    const int pli = blockIdx.y, comp = blockIdx.z;
+    const int iyp = plane0 + pli;
+    const int nz = g.nz;
+    {   // ---- stage A, warp per line: global (z-contiguous V line) -> registers -> smem
+        const cplx* __restrict__ src = V + (((size_t)comp * g.nyp + iyp) * g.nxB + ixl0 + wl) * g.nzt;
+        cplx* sm = smem + wl * LS;
+#pragma unroll 1
+        for (int i = 0; i < G::BC / 32; ++i) {
+            const int t1 = lane + 32 * i;
+            cplx x[G::A];
+            static_for<G::A>([&](auto a_) {
+                constexpr int a = decltype(a_)::value;
+                const int n = a * G::BC + t1;
+                cplx v = make_double2(0.0, 0.0);
+                if (n <= nz) v = src[nz + n];                       // V(iy,0:nz)   -> rows 1..nz+1
+                else if (n >= G::N - nz) v = src[n - (G::N - nz)];  // V(iy,-nz:-1) -> rows nzd-nz+1..nzd
+                x[a] = v;
+            });
+            dif_stage_a<G, +1>(x, t1, W);
+            static_for<G::A>([&](auto ka_) {
+                constexpr int ka = decltype(ka_)::value;
+                sm[ka * BCP + t1] = x[ka];
+            });
+        }
+    }
+    __syncwarp();
+    {   // ---- stage B, warp per line, in place
+        cplx* sm = smem + wl * LS;
+        const int cc = lane % G::C;
+        cplx wc[G::B];
+        twiddle_powers<G::B>(ctw<+1>(W, G::A * cc), wc);
+#pragma unroll 1
+        for (int i = 0; i < (G::A * G::C) / 32; ++i) {
+            const int u = lane + 32 * i;
+            cplx* base = sm + (u / G::C) * BCP + cc;
+            cplx x[G::B];
+            static_for<G::B>([&](auto b_) { constexpr int b = decltype(b_)::value; x[b] = base[b * G::C]; });
+            dif_stage_b<G, +1>(x, wc, cc != 0);
+            static_for<G::B>([&](auto b_) { constexpr int b = decltype(b_)::value; base[b * G::C] = x[b]; });
+        }
+    }
+    __syncthreads();
+    {   // ---- stage C, cross-line: smem -> registers -> global (x-contiguous, per destination rank)
+        const int l = threadIdx.x % LPC, q = threadIdx.x / LPC;
+        const cplx* sm = smem + l * LS;
+        const int nzB = g.nzB, nxB = g.nxB;
+#pragma unroll 1
+        for (int i = 0; i < G::AB / 32; ++i) {
+            const int t = q + 32 * i;
+            const cplx* base = sm + (t % G::A) * BCP + (t / G::A) * G::C;
+            cplx x[G::C];
+            static_for<G::C>([&](auto c_) { constexpr int c = decltype(c_)::value; x[c] = base[c]; });
+            Dft<G::C, +1>::run(x);
+            static_for<G::C>([&](auto kc_) {
+                constexpr int kc = decltype(kc_)::value;
+                const int k = t + G::AB * kc;
+                const int peer = (g.nranks > 1) ? k / nzB : 0;
+                A[chb_buf_index(peer, 3, comp, np, pli, nzB, k - peer * nzB, nxB, ixl0 + l)] = x[kc];
+            });
+        }
+    }
+}
+
+template <class G, int LPC>
+__global__ void __launch_bounds__(LPC * 32)
+zbwd3_kernel(const cplx* __restrict__ Br, cplx* __restrict__ P, Geometry g, const cplx* __restrict__ W, int plane0, int np,
+             int LS) {
+    extern __shared__ cplx smem[];
+    constexpr int BCP = G::BC + 1;
+    const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
+    const int ixl0 = blockIdx.x * LPC;
+    const int pli = blockIdx.y, comp = blockIdx.z;  // product index 0..5
+    const int iyp = plane0 + pli;
+    const int nz = g.nz;
+    {   // ---- stage A, cross-line: global (x-contiguous work buffer) -> registers -> smem
+        const int l = threadIdx.x % LPC, q = threadIdx.x / LPC;
+        cplx* sm = smem + l * LS;
+        const int nzB = g.nzB, nxB = g.nxB;
+#pragma unroll 1
+        for (int i = 0; i < G::BC / 32; ++i) {
+            const int t1 = q + 32 * i;
+            cplx x[G::A];
+            static_for<G::A>([&](auto a_) {
+                constexpr int a = decltype(a_)::value;
+                const int n = a * G::BC + t1;
+                const int peer = (g.nranks > 1) ? n / nzB : 0;
+                x[a] = Br[chb_buf_index(peer, 6, comp, np, pli, nzB, n - peer * nzB, nxB, ixl0 + l)];
+            });
+            dif_stage_a<G, -1>(x, t1, W);
+            static_for<G::A>([&](auto ka_) {
+                constexpr int ka = decltype(ka_)::value;
+                sm[ka * BCP + t1] = x[ka];
+            });
+        }
+    }
+    __syncthreads();
+    cplx* sm = smem + wl * LS;
+    {   // ---- stage B, warp per line, in place
+        const int cc = lane % G::C;
+        cplx wc[G::B];
+        twiddle_powers<G::B>(ctw<-1>(W, G::A * cc), wc);
+#pragma unroll 1
+        for (int i = 0; i < (G::A * G::C) / 32; ++i) {
+            const int u = lane + 32 * i;
+            cplx* base = sm + (u / G::C) * BCP + cc;
+            cplx x[G::B];
+            static_for<G::B>([&](auto b_) { constexpr int b = decltype(b_)::value; x[b] = base[b * G::C]; });
+            dif_stage_b<G, -1>(x, wc, cc != 0);
+            static_for<G::B>([&](auto b_) { constexpr int b = decltype(b_)::value; base[b * G::C] = x[b]; });
+        }
+    }
+    __syncwarp();
+    {   // ---- stage C, warp per line: smem -> registers -> global (z-contiguous, truncated to -nz..nz)
+        cplx* __restrict__ dst = P + (((size_t)comp * g.nyp + iyp) * g.nxB + ixl0 + wl) * g.nzt;
+#pragma unroll 1
+        for (int i = 0; i < G::AB / 32; ++i) {
+            const int t = lane + 32 * i;
+            const cplx* base = sm + (t % G::A) * BCP + (t / G::A) * G::C;
+            cplx x[G::C];
+            static_for<G::C>([&](auto c_) { constexpr int c = decltype(c_)::value; x[c] = base[c]; });
+            Dft<G::C, -1>::run(x);
+            static_for<G::C>([&](auto kc_) {
+                constexpr int kc = decltype(kc_)::value;
+                const int k = t + G::AB * kc;                     // izd(iz) = k  (dnsdata.f90:156)
+                if (k <= nz) dst[nz + k] = x[kc];
+                else if (k >= G::N - nz) dst[k - (G::N - nz)] = x[kc];
+            });
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+template <class G, int LPC>
+static bool launch_z3(chb_handle_s* h, int plane0, int nplanes, bool fwd) {
+    constexpr int BCP = G::BC + 1;
+    int LS = G::A * BCP;
+    const int want = (LPC == 8) ? 1 : 2;   // line stride mod 8 that keeps the cross-line accesses conflict-free
+    while (LS % 8 != want) ++LS;
+    const size_t smem = (size_t)LPC * LS * sizeof(cplx);
+    if (h->g.nxB % LPC != 0) return false;
+    dim3 grid(h->g.nxB / LPC, nplanes, fwd ? 3 : 6);
+    if (fwd) {
+        cudaFuncSetAttribute(zfwd3_kernel<G, LPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        ScopedKernelTimer tm(h, "zfwd");
+        zfwd3_kernel<G, LPC><<<grid, LPC * 32, smem, h->stream>>>(h->V, h->A, h->g, h->Wz, plane0, h->chunk_planes, LS);
+    } else {
+        cudaFuncSetAttribute(zbwd3_kernel<G, LPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        ScopedKernelTimer tm(h, "zbwd");
+        zbwd3_kernel<G, LPC><<<grid, LPC * 32, smem, h->stream>>>(h->Br, h->P, h->g, h->Wz, plane0, h->chunk_planes, LS);
+    }
+    h->launches++;
+    return true;
+}
+
+// returns false when no specialised kernel exists for this size (caller falls back to the
+// generic shared-memory passes of conv_kernels.cu)
+bool launch_z3_fwd_or_bwd(chb_handle_s* h, int plane0, int nplanes, bool fwd) {
+    if (h->g.nz < 2) return false;
+    const int lpc = h->z_lines_per_cta;
+    switch (h->g.nzd) {
+        case 768:
+            return lpc == 4 ? launch_z3<Fft3<768, 12, 8, 8>, 4>(h, plane0, nplanes, fwd)
+                            : launch_z3<Fft3<768, 12, 8, 8>, 8>(h, plane0, nplanes, fwd);
+        case 1536:
+            return lpc == 4 ? launch_z3<Fft3<1536, 12, 16, 8>, 4>(h, plane0, nplanes, fwd)
+                            : launch_z3<Fft3<1536, 12, 16, 8>, 8>(h, plane0, nplanes, fwd);
+        case 3072:
+            return launch_z3<Fft3<3072, 12, 16, 16>, 4>(h, plane0, nplanes, fwd);
+        default:
+            return false;
+    }
+}
