@@ -109,6 +109,7 @@ void launch_xpass(chb_handle_s* h, int plane0, int nplanes, int compute_cfl);
 void launch_zbwd(chb_handle_s* h, int plane0, int nplanes);
 // ---- zpass3_kernels.cu / xpass3_kernels.cu: false = no specialised kernel for this size ----
 bool launch_z3_fwd_or_bwd(chb_handle_s* h, int plane0, int nplanes, bool fwd);
+bool launch_x3_pass(chb_handle_s* h, int plane0, int nplanes, int compute_cfl);
 // ---- rhs_kernel.cu ----
 void launch_rhs(chb_handle_s* h, const double* ode, double deltat);
 // ---- solve_kernels.cu ----

@@ -251,6 +251,7 @@ void launch_zbwd(chb_handle_s* h, int plane0, int nplanes) {
 }
 
 void launch_xpass(chb_handle_s* h, int plane0, int nplanes, int compute_cfl) {
+    if (h->use_fft3 && launch_x3_pass(h, plane0, nplanes, compute_cfl)) return;
     const int ls = chb_padded_len(h->g.nxd);
     // lines per CTA: keep >= ~2 CTAs per SM when possible, and at least ~1.5k butterflies of work
     int lx = 1;

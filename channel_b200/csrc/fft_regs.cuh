@@ -36,7 +36,7 @@ __device__ __forceinline__ void static_for(F&& f) {
     static_for_impl(static_cast<F&&>(f), std::make_integer_sequence<int, N>{});
 }
 
-// ---- twiddle constants: cos/sin(2 pi e / R) for R in {6, 8, 12, 16} (multiples of 7.5 degrees) --
+// ---- twiddle constants: cos/sin(2 pi e / R) for R | 48 (multiples of 7.5 degrees) -------------
 __host__ __device__ constexpr double chb_cos48(int m) {  // cos(2 pi m / 48), m in 0..47
     m = ((m % 48) + 48) % 48;
     if (m > 24) m = 48 - m;            // cos symmetric
@@ -45,13 +45,18 @@ __host__ __device__ constexpr double chb_cos48(int m) {  // cos(2 pi m / 48), m 
     double v = 0.0;
     switch (m) {
         case 0: v = 1.0; break;
+        case 1: v = 0.99144486137381041114455752692856; break;   //  7.5
+        case 2: v = 0.96592582628906828674974319972890; break;   // 15
         case 3: v = 0.92387953251128675612818318939679; break;   // 22.5
         case 4: v = 0.86602540378443864676372317075294; break;   // 30
+        case 5: v = 0.79335334029123516457977696150130; break;   // 37.5
         case 6: v = 0.70710678118654752440084436210485; break;   // 45
+        case 7: v = 0.60876142900872063941609754289816; break;   // 52.5
         case 8: v = 0.5; break;                                  // 60
         case 9: v = 0.38268343236508977172845998403040; break;   // 67.5
-        case 12: v = 0.0; break;                                 // 90
-        default: v = 2.0; break;                                 // unused angle: poison
+        case 10: v = 0.25881904510252076234889883762405; break;  // 75
+        case 11: v = 0.13052619222005159154840622789549; break;  // 82.5
+        default: v = 0.0; break;                                 // 90
     }
     return neg ? -v : v;
 }

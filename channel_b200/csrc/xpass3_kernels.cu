@@ -1,0 +1,231 @@
+// xpass3_kernels.cu - x-direction pass of the nonlinear term for the large transform sizes:
+//   zero-pad in x + c2r (RFT ffts.f90:72, dnsdata.f90:535) -> CFL (dnsdata.f90:552-556) -> the six
+//   products * factor (dnsdata.f90:581-584) -> r2c (HFT ffts.f90:74) -> keep modes 0..nx
+//   (xTOz pack, mpi_transpose.f90:99-106)
+// for one physical z-line per group of T = nxd/C threads, fused in one kernel: physical-space data
+// exists only in registers.
+//
+// A real transform of logical length 2M (M = nxd) is a complex transform of length M plus a
+// split/merge pass:
+//   c2r:  Z[n] = (X[n] + conj X[M-n]) + i e^{+i pi n/M} (X[n] - conj X[M-n]),  z = DFT+_M(Z),
+//         r[2m] = Re z[m], r[2m+1] = Im z[m]          (imaginary parts of X[0], X[M] ignored; X[M]=0)
+//   r2c:  Z = DFT-_M(z),  X[j] = (Z[j] + conj Z[M-j])/2 - (i/2) e^{-i pi j/M} (Z[j] - conj Z[M-j])
+// The backward transform runs decimation-in-frequency (natural in, scrambled registers out), the
+// forward one is its transpose (scrambled in, natural out), so the pointwise products sit between
+// the two innermost radix-C butterflies without any reordering (fft_regs.cuh).
+//
+// Shared memory per line: six buffers of A*(BC+1) complex (u,v,w, later the six products, in
+// place).  Per point and transform: two exchanges (backward) / two exchanges + the merge pass
+// (forward) through shared memory; global memory is touched once per input and output mode.
+#include "chb_internal.h"
+#include "fft_regs.cuh"
+
+// x[p] *= w1^p, p = 1..R-1, sequential recurrence (low register pressure)
+template <int R>
+__device__ __forceinline__ void apply_twiddle_seq(cplx* x, cplx w1) {
+    cplx wp = w1;
+    x[1] = cmul(x[1], wp);
+    static_for<R - 2>([&](auto i_) {
+        constexpr int p = decltype(i_)::value + 2;
+        wp = cmul(wp, w1);
+        x[p] = cmul(x[p], wp);
+    });
+}
+
+template <class G, int LPC>
+__global__ void __launch_bounds__(LPC * (G::N / G::C))
+xpass3_kernel(const cplx* __restrict__ Ar, cplx* __restrict__ Bout, Geometry g, const cplx* __restrict__ W,
+              const cplx* __restrict__ Wh, const double* __restrict__ dy, DevScalars* sc, int plane0, int np,
+              int compute_cfl) {
+    constexpr int M = G::N, A = G::A, B = G::B, C = G::C, BC = G::BC;
+    constexpr int T = M / C;           // threads per line = butterflies of the innermost stage
+    constexpr int BCP = BC + 1;
+    constexpr int LB = A * BCP;        // complex per buffer
+    extern __shared__ cplx smem[];
+    const int tl = threadIdx.x % T, l = threadIdx.x / T;
+    const int izl = blockIdx.x * LPC + l;
+    const int pli = blockIdx.y;
+    const int iy = plane0 + pli - 1;
+    const int nx = g.nx, nxB = g.nxB, nzB = g.nzB;
+    const bool multi = g.nranks > 1;
+    cplx* S = smem + (size_t)l * 6 * LB;
+
+    auto in_index = [&](int comp, int k) -> size_t {
+        const int q = multi ? k / nxB : 0;
+        return chb_buf_index(q, 3, comp, np, pli, nzB, izl, nxB, k - q * nxB);
+    };
+
+    // ---- backward stage A: global -> split pass -> radix-A -> smem ---------------------------
+    for (int t1 = tl; t1 < BC; t1 += T) {
+        const cplx wh1 = Wh[t1];   // exp(+i pi t1 / M)
+        const cplx w1 = W[t1];     // exp(+2 pi i t1 / M)
+#pragma unroll 1
+        for (int comp = 0; comp < 3; ++comp) {
+            cplx x[A];
+            static_for<A>([&](auto a_) {
+                constexpr int a = decltype(a_)::value;
+                const int n = a * BC + t1;
+                const int j = M - n;
+                cplx xa = make_double2(0.0, 0.0), xb = make_double2(0.0, 0.0);
+                if (n <= nx) xa = Ar[in_index(comp, n)];
+                if (j <= nx) xb = Ar[in_index(comp, j)];
+                if (a == 0 && t1 == 0) {
+                    x[a] = make_double2(xa.x, xa.x);   // Z[0] = X0 + XM + i (X0 - XM), XM = 0, Im X0 ignored
+                } else {
+                    const cplx s = make_double2(xa.x + xb.x, xa.y - xb.y);
+                    const cplx d = make_double2(xa.x - xb.x, xa.y + xb.y);
+                    const cplx t = cmul(mulw<2 * A, a, +1>(wh1), d);   // e^{i pi n/M} = e^{i pi t1/M} e^{i pi a/A}
+                    x[a] = make_double2(s.x - t.y, s.y + t.x);
+                }
+            });
+            Dft<A, +1>::run(x);
+            if (t1 != 0) apply_twiddle_seq<A>(x, w1);
+            cplx* dst = S + comp * LB + t1;
+            static_for<A>([&](auto ka_) { constexpr int ka = decltype(ka_)::value; dst[ka * BCP] = x[ka]; });
+        }
+    }
+    __syncthreads();
+    // ---- backward stage B, in place ---------------------------------------------------------
+    {
+        const int cc = tl % C;
+        const cplx wc1 = W[A * cc];   // w_BC^cc
+        for (int u = tl; u < A * C; u += T) {
+            cplx* base = S + (u / C) * BCP + cc;
+#pragma unroll 1
+            for (int comp = 0; comp < 3; ++comp) {
+                cplx x[B];
+                static_for<B>([&](auto b_) { constexpr int b = decltype(b_)::value; x[b] = base[comp * LB + b * C]; });
+                Dft<B, +1>::run(x);
+                if (cc != 0) apply_twiddle_seq<B>(x, wc1);
+                static_for<B>([&](auto b_) { constexpr int b = decltype(b_)::value; base[comp * LB + b * C] = x[b]; });
+            }
+        }
+    }
+    __syncthreads();
+    // ---- backward stage C -> physical space -> CFL, products -> forward stage C --------------
+    {
+        const int ka = tl % A, kb = tl / A;
+        cplx* base = S + ka * BCP + kb * C;
+        cplx U[C], V[C], Wv[C];
+        static_for<C>([&](auto c_) {
+            constexpr int c = decltype(c_)::value;
+            U[c] = base[c];
+            V[c] = base[LB + c];
+            Wv[c] = base[2 * LB + c];
+        });
+        Dft<C, +1>::run(U);
+        Dft<C, +1>::run(V);
+        Dft<C, +1>::run(Wv);
+        if (compute_cfl) {   // dnsdata.f90:552-556 (block-uniform branch)
+            double cmax = 0.0;
+            if (iy >= 1 && iy <= g.ny - 1) {
+                const double rdx = 1.0 / g.dx, rdz = 1.0 / g.dz, rdy = 1.0 / dy[iy + 1];
+                static_for<C>([&](auto c_) {
+                    constexpr int c = decltype(c_)::value;
+                    cmax = fmax(cmax, fabs(U[c].x) * rdx + fabs(V[c].x) * rdy + fabs(Wv[c].x) * rdz);
+                    cmax = fmax(cmax, fabs(U[c].y) * rdx + fabs(V[c].y) * rdy + fabs(Wv[c].y) * rdz);
+                });
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) cmax = fmax(cmax, __shfl_xor_sync(0xffffffffu, cmax, o));
+            if ((threadIdx.x & 31) == 0 && cmax > 0.0)
+                atomicMax(&sc->cfl_bits, (unsigned long long)__double_as_longlong(cmax));
+        }
+        const double f = g.factor;
+        const cplx wk1 = ctw<-1>(W, A * kb);   // conj w_BC^kb: forward twiddle of this thread's outputs
+        auto forward_c = [&](cplx* x, int p) {
+            Dft<C, -1>::run(x);
+            if (kb != 0) apply_twiddle_seq<C>(x, wk1);
+            static_for<C>([&](auto c_) { constexpr int c = decltype(c_)::value; base[p * LB + c] = x[c]; });
+        };
+        cplx x[C];
+        // slots (0..5) = (uu, vv, ww, uv, vw, uw) * factor                          dnsdata.f90:581-584
+        static_for<C>([&](auto c_) { constexpr int c = decltype(c_)::value; x[c] = make_double2(U[c].x * V[c].x * f, U[c].y * V[c].y * f); });
+        forward_c(x, 3);
+        static_for<C>([&](auto c_) { constexpr int c = decltype(c_)::value; x[c] = make_double2(V[c].x * Wv[c].x * f, V[c].y * Wv[c].y * f); });
+        forward_c(x, 4);
+        static_for<C>([&](auto c_) { constexpr int c = decltype(c_)::value; x[c] = make_double2(U[c].x * Wv[c].x * f, U[c].y * Wv[c].y * f); });
+        forward_c(x, 5);
+        static_for<C>([&](auto c_) { constexpr int c = decltype(c_)::value; U[c] = make_double2(U[c].x * U[c].x * f, U[c].y * U[c].y * f); });
+        forward_c(U, 0);
+        static_for<C>([&](auto c_) { constexpr int c = decltype(c_)::value; V[c] = make_double2(V[c].x * V[c].x * f, V[c].y * V[c].y * f); });
+        forward_c(V, 1);
+        static_for<C>([&](auto c_) { constexpr int c = decltype(c_)::value; Wv[c] = make_double2(Wv[c].x * Wv[c].x * f, Wv[c].y * Wv[c].y * f); });
+        forward_c(Wv, 2);
+    }
+    __syncthreads();
+    // ---- forward stage B, in place -----------------------------------------------------------
+    {
+        const int cc = tl % C;
+        for (int u = tl; u < A * C; u += T) {
+            cplx* base = S + (u / C) * BCP + cc;
+#pragma unroll 1
+            for (int p = 0; p < 6; ++p) {
+                cplx x[B];
+                static_for<B>([&](auto b_) { constexpr int b = decltype(b_)::value; x[b] = base[p * LB + b * C]; });
+                Dft<B, -1>::run(x);
+                static_for<B>([&](auto b_) { constexpr int b = decltype(b_)::value; base[p * LB + b * C] = x[b]; });
+            }
+        }
+    }
+    __syncthreads();
+    // ---- forward stage A: twiddle, radix-A, natural order back to smem ------------------------
+    for (int t1 = tl; t1 < BC; t1 += T) {
+        const cplx w1 = ctw<-1>(W, t1);
+#pragma unroll 1
+        for (int p = 0; p < 6; ++p) {
+            cplx* col = S + p * LB + t1;
+            cplx x[A];
+            static_for<A>([&](auto ka_) { constexpr int ka = decltype(ka_)::value; x[ka] = col[ka * BCP]; });
+            if (t1 != 0) apply_twiddle_seq<A>(x, w1);
+            Dft<A, -1>::run(x);
+            static_for<A>([&](auto a_) { constexpr int a = decltype(a_)::value; col[a * BCP] = x[a]; });   // Z[a*BC + t1]
+        }
+    }
+    __syncthreads();
+    // ---- merge pass + x-dealiasing (keep modes 0..nx) + store ----------------------------------
+    for (int j = tl; j <= nx; j += T) {
+        const int pj = (j / BC) * BCP + (j % BC);
+        const int jm = (j == 0) ? 0 : M - j;
+        const int pm = (jm / BC) * BCP + (jm % BC);
+        cplx w = Wh[j];
+        w.y = -w.y;   // e^{-i pi j/M}
+        const int q = multi ? j / nxB : 0;
+        const size_t o0 = chb_buf_index(q, 6, 0, np, pli, nzB, izl, nxB, j - q * nxB);
+        const size_t ostride = (size_t)np * nzB * nxB;
+#pragma unroll
+        for (int p = 0; p < 6; ++p) {
+            const cplx z = S[p * LB + pj];
+            const cplx zm = S[p * LB + pm];
+            const cplx e = make_double2(0.5 * (z.x + zm.x), 0.5 * (z.y - zm.y));
+            const cplx d = make_double2(0.5 * (z.x - zm.x), 0.5 * (z.y + zm.y));   // (Z - conj Zm)/2
+            const cplx o = make_double2(d.y, -d.x);                                // -i * d
+            Bout[o0 + p * ostride] = cadd(e, cmul(w, o));
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+template <class G, int LPC>
+static bool launch_x3(chb_handle_s* h, int plane0, int nplanes, int compute_cfl) {
+    constexpr int T = G::N / G::C;
+    constexpr int LB = G::A * (G::BC + 1);
+    if (h->g.nzB % LPC != 0) return false;
+    const size_t smem = (size_t)LPC * 6 * LB * sizeof(cplx);
+    cudaFuncSetAttribute(xpass3_kernel<G, LPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    dim3 grid(h->g.nzB / LPC, nplanes);
+    ScopedKernelTimer tm(h, "xpass");
+    xpass3_kernel<G, LPC><<<grid, LPC * T, smem, h->stream>>>(h->Ar, h->B, h->g, h->Wx, h->Wh, h->t_dy, h->sc, plane0,
+                                                             h->chunk_planes, compute_cfl);
+    h->launches++;
+    return true;
+}
+
+bool launch_x3_pass(chb_handle_s* h, int plane0, int nplanes, int compute_cfl) {
+    switch (h->g.nxd) {
+        case 384: return launch_x3<Fft3<384, 12, 4, 8>, 2>(h, plane0, nplanes, compute_cfl);
+        case 768: return launch_x3<Fft3<768, 12, 8, 8>, 1>(h, plane0, nplanes, compute_cfl);
+        case 1536: return launch_x3<Fft3<1536, 12, 16, 8>, 1>(h, plane0, nplanes, compute_cfl);
+        default: return false;
+    }
+}
