@@ -20,6 +20,30 @@
 #include "chb_internal.h"
 #include "fft_regs.cuh"
 
+// ---- TMA 1-D bulk copy global -> shared with mbarrier completion (cp.async.bulk, SASS UBLKCP) ----
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok)
+                     : "r"(smem_u32(bar)), "r"(parity)
+                     : "memory");
+    } while (!ok);
+}
+
 // x[p] *= w1^p, p = 1..R-1, sequential recurrence (low register pressure)
 template <int R>
 __device__ __forceinline__ void apply_twiddle_seq(cplx* x, cplx w1) {
@@ -50,39 +74,48 @@ xpass3_kernel(const cplx* __restrict__ Ar, cplx* __restrict__ Bout, Geometry g, 
     const bool multi = g.nranks > 1;
     cplx* S = smem + (size_t)l * 6 * LB;
 
-    auto in_index = [&](int comp, int k) -> size_t {
-        const int q = multi ? k / nxB : 0;
-        return chb_buf_index(q, 3, comp, np, pli, nzB, izl, nxB, k - q * nxB);
-    };
-
-    // ---- backward stage A: global -> split pass -> radix-A -> smem ---------------------------
-    for (int t1 = tl; t1 < BC; t1 += T) {
+    // ---- stage the input row (modes 0..nx of u,v,w; one contiguous piece per source rank) in the
+    //      buffers the products will use later: one TMA bulk copy per piece, one latency exposure
+    cplx* IN = S + 3 * LB;             // [comp][0..nx]
+    __shared__ unsigned long long mbar[LPC];
+    if (tl == 0) mbar_init(&mbar[l], 1);
+    __syncthreads();
+    if (tl == 0) {
+        const int P = g.nranks;
+        mbar_expect_tx(&mbar[l], (unsigned)(3 * (nx + 1) * sizeof(cplx)));
+        for (int comp = 0; comp < 3; ++comp)
+            for (int q = 0; q < P; ++q)
+                bulk_g2s(IN + comp * (nx + 1) + q * nxB, Ar + chb_buf_index(q, 3, comp, np, pli, nzB, izl, nxB, 0),
+                         (unsigned)(nxB * sizeof(cplx)), &mbar[l]);
+    }
+    mbar_wait(&mbar[l], 0);
+    // ---- backward stage A: split pass -> radix-A -> smem; tasks = (mode group t1, component) ------
+    for (int task = tl; task < 3 * BC; task += T) {
+        const int comp = task / BC, t1 = task - comp * BC;
         const cplx wh1 = Wh[t1];   // exp(+i pi t1 / M)
         const cplx w1 = W[t1];     // exp(+2 pi i t1 / M)
-#pragma unroll 1
-        for (int comp = 0; comp < 3; ++comp) {
-            cplx x[A];
-            static_for<A>([&](auto a_) {
-                constexpr int a = decltype(a_)::value;
-                const int n = a * BC + t1;
-                const int j = M - n;
-                cplx xa = make_double2(0.0, 0.0), xb = make_double2(0.0, 0.0);
-                if (n <= nx) xa = Ar[in_index(comp, n)];
-                if (j <= nx) xb = Ar[in_index(comp, j)];
-                if (a == 0 && t1 == 0) {
-                    x[a] = make_double2(xa.x, xa.x);   // Z[0] = X0 + XM + i (X0 - XM), XM = 0, Im X0 ignored
-                } else {
-                    const cplx s = make_double2(xa.x + xb.x, xa.y - xb.y);
-                    const cplx d = make_double2(xa.x - xb.x, xa.y + xb.y);
-                    const cplx t = cmul(mulw<2 * A, a, +1>(wh1), d);   // e^{i pi n/M} = e^{i pi t1/M} e^{i pi a/A}
-                    x[a] = make_double2(s.x - t.y, s.y + t.x);
-                }
-            });
-            Dft<A, +1>::run(x);
-            if (t1 != 0) apply_twiddle_seq<A>(x, w1);
-            cplx* dst = S + comp * LB + t1;
-            static_for<A>([&](auto ka_) { constexpr int ka = decltype(ka_)::value; dst[ka * BCP] = x[ka]; });
-        }
+        const cplx* X = IN + comp * (nx + 1);
+        cplx x[A];
+        static_for<A>([&](auto a_) {
+            constexpr int a = decltype(a_)::value;
+            const int n = a * BC + t1;
+            const int j = M - n;
+            cplx xa = make_double2(0.0, 0.0), xb = make_double2(0.0, 0.0);
+            if (n <= nx) xa = X[n];
+            if (j <= nx) xb = X[j];
+            if (a == 0 && t1 == 0) {
+                x[a] = make_double2(xa.x, xa.x);   // Z[0] = X0 + XM + i (X0 - XM), XM = 0, Im X0 ignored
+            } else {
+                const cplx s = make_double2(xa.x + xb.x, xa.y - xb.y);
+                const cplx d = make_double2(xa.x - xb.x, xa.y + xb.y);
+                const cplx t = cmul(mulw<2 * A, a, +1>(wh1), d);   // e^{i pi n/M} = e^{i pi t1/M} e^{i pi a/A}
+                x[a] = make_double2(s.x - t.y, s.y + t.x);
+            }
+        });
+        Dft<A, +1>::run(x);
+        if (t1 != 0) apply_twiddle_seq<A>(x, w1);
+        cplx* dst = S + comp * LB + t1;
+        static_for<A>([&](auto ka_) { constexpr int ka = decltype(ka_)::value; dst[ka * BCP] = x[ka]; });
     }
     __syncthreads();
     // ---- backward stage B, in place ---------------------------------------------------------
@@ -169,18 +202,16 @@ xpass3_kernel(const cplx* __restrict__ Ar, cplx* __restrict__ Bout, Geometry g, 
         }
     }
     __syncthreads();
-    // ---- forward stage A: twiddle, radix-A, natural order back to smem ------------------------
-    for (int t1 = tl; t1 < BC; t1 += T) {
+    // ---- forward stage A: twiddle, radix-A, natural order back to smem; tasks = (t1, product) ------
+    for (int task = tl; task < 6 * BC; task += T) {
+        const int p = task / BC, t1 = task - p * BC;
         const cplx w1 = ctw<-1>(W, t1);
-#pragma unroll 1
-        for (int p = 0; p < 6; ++p) {
-            cplx* col = S + p * LB + t1;
-            cplx x[A];
-            static_for<A>([&](auto ka_) { constexpr int ka = decltype(ka_)::value; x[ka] = col[ka * BCP]; });
-            if (t1 != 0) apply_twiddle_seq<A>(x, w1);
-            Dft<A, -1>::run(x);
-            static_for<A>([&](auto a_) { constexpr int a = decltype(a_)::value; col[a * BCP] = x[a]; });   // Z[a*BC + t1]
-        }
+        cplx* col = S + p * LB + t1;
+        cplx x[A];
+        static_for<A>([&](auto ka_) { constexpr int ka = decltype(ka_)::value; x[ka] = col[ka * BCP]; });
+        if (t1 != 0) apply_twiddle_seq<A>(x, w1);
+        Dft<A, -1>::run(x);
+        static_for<A>([&](auto a_) { constexpr int a = decltype(a_)::value; col[a * BCP] = x[a]; });   // Z[a*BC + t1]
     }
     __syncthreads();
     // ---- merge pass + x-dealiasing (keep modes 0..nx) + store ----------------------------------
@@ -213,6 +244,7 @@ static bool launch_x3(chb_handle_s* h, int plane0, int nplanes, int compute_cfl)
     if (h->g.nzB % LPC != 0) return false;
     const size_t smem = (size_t)LPC * 6 * LB * sizeof(cplx);
     cudaFuncSetAttribute(xpass3_kernel<G, LPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(xpass3_kernel<G, LPC>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     dim3 grid(h->g.nzB / LPC, nplanes);
     ScopedKernelTimer tm(h, "xpass");
     xpass3_kernel<G, LPC><<<grid, LPC * T, smem, h->stream>>>(h->Ar, h->B, h->g, h->Wx, h->Wh, h->t_dy, h->sc, plane0,
