@@ -29,6 +29,7 @@ import time
 
 import numpy as np
 
+os.environ.setdefault("NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout: one JSON line only
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
@@ -237,6 +238,8 @@ def run_b200(args):
                           "gbs": bytes_total / (tms * 1e-3) / 1e9,
                           "frac": bytes_total / (tms * 1e-3) / 1e9 / peak}
         for n in kern:
+            if n.startswith("solve_"):
+                kernels["solve"].setdefault("parts_ms_per_step", {})[n] = kern[n][0] / args.steps
             if not any(n in names for names in fam.values()):
                 kernels[n] = {"ms_per_step": kern[n][0] / args.steps, "share": kern[n][0] / total_kernel_ms}
         dom = max((k for k in kernels if "gbs" in kernels[k]), key=lambda k: kernels[k]["ms_per_step"])

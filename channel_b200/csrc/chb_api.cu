@@ -156,6 +156,7 @@ extern "C" int chb_create(chb_handle* out, int nx, int ny, int nz, int nxd, int 
     g.nxB = g.nxN - g.nx0 + 1;
     g.nzB = g.nzN - g.nz0 + 1;
     g.M = (long long)g.nxB * g.nzt;
+    g.tw = (g.nxB % 8 == 0) ? 3 : 0;
     g.alfa0 = alfa0; g.beta0 = beta0; g.ni = ni;
     const double PI = 3.1415926535897932384626433832795028841971;  // dnsdata.f90:26
     g.dx = PI / (alfa0 * nxd); g.dz = 2.0 * PI / (beta0 * nzd); g.factor = 1.0 / (2.0 * nxd * nzd);  // :124
@@ -185,23 +186,32 @@ extern "C" int chb_create(chb_handle* out, int nx, int ny, int nz, int nxd, int 
     }
     const size_t fld = (size_t)g.nyp * g.M;
     if (dev_alloc(&h->V, 3 * fld) || dev_alloc(&h->rhs, 2 * fld) || dev_alloc(&h->oldrhs, 2 * fld) ||
-        dev_alloc(&h->P, 6 * fld) || dev_alloc(&h->mult, 4 * fld))
+        dev_alloc(&h->P, 6 * fld) || dev_alloc(&h->ckpt, (size_t)((ny - 1) / CHB_SOLVE_K + 1) * 8 * g.M))
         return 1;
-    // convolution work buffers: chunk of planes sized to ~3 GB
+    // convolution work buffers: a chunk of planes sized to ~3 GB per buffer set
     {
-        const size_t per_plane = (size_t)9 * nzd * g.nxB * sizeof(cplx) * (nranks > 1 ? 2 : 1);
+        const char* e = getenv("CHB_P2P");
+        h->p2p = (nranks > 1 && !(e && atoi(e) == 0)) ? 1 : 0;
+        const bool nccl_mode = nranks > 1 && !h->p2p;
+        const size_t per_plane = (size_t)9 * nzd * g.nxB * sizeof(cplx) * (nccl_mode ? 2 : 1);
         size_t np = (size_t)3 << 30;
         np /= per_plane;
         if (np < 1) np = 1;
         if (np > (size_t)g.nyp) np = g.nyp;
         h->chunk_planes = (int)np;
         const size_t na = (size_t)3 * np * nzd * g.nxB, nb = (size_t)6 * np * nzd * g.nxB;
-        if (dev_alloc(&h->A, na) || dev_alloc(&h->B, nb)) return 1;
-        if (nranks > 1) {
-            if (dev_alloc(&h->Ar, na) || dev_alloc(&h->Br, nb)) return 1;
-        } else {
-            h->Ar = h->A;
-            h->Br = h->B;
+        if (dev_alloc(&h->Ar, na) || dev_alloc(&h->Br, nb)) return 1;
+        h->A = h->B = nullptr;
+        h->flags = nullptr;
+        h->epoch = 0;
+        h->n_ipc_opened = 0;
+        if (nccl_mode && (dev_alloc(&h->A, na) || dev_alloc(&h->B, nb))) return 1;
+        if (dev_alloc(&h->flags, (size_t)CHB_MAX_RANKS)) return 1;
+        // pack-side store targets (PeerPtrs): element for peer q at p[q] + index(block = rank, ...)
+        const ptrdiff_t blkA = (ptrdiff_t)(na / nranks), blkB = (ptrdiff_t)(nb / nranks);
+        for (int q = 0; q < nranks; ++q) {
+            h->Aw.p[q] = (nccl_mode ? h->A : h->Ar) + (ptrdiff_t)(q - rank) * blkA;
+            h->Bw.p[q] = (nccl_mode ? h->B : h->Br) + (ptrdiff_t)(q - rank) * blkB;
         }
     }
     if (dev_alloc(&h->t_y, (size_t)g.nyp) || dev_alloc(&h->t_dy, (size_t)g.nyp) ||
@@ -212,7 +222,9 @@ extern "C" int chb_create(chb_handle* out, int nx, int ny, int nz, int nxd, int 
     if (dev_alloc(&h->sc, 1)) return 1;
     CHB_CUDA_OK(cudaMallocHost((void**)&h->sc_host, sizeof(DevScalars)));
     memset(h->sc_host, 0, sizeof(DevScalars));
+    CHB_REQUIRE(nranks <= CHB_MAX_RANKS, "chb_create: at most 8 ranks (one NVSwitch node)");
     if (nranks > 1 && chb_nccl_init(h, nccl_id)) return 1;
+    if (h->p2p && chb_p2p_setup(h, 0, 0)) return 1;
     CHB_CUDA_OK(cudaDeviceSynchronize());
     h->dev_bytes = g_alloc_bytes;
     *out = h;
@@ -225,10 +237,12 @@ extern "C" int chb_destroy(chb_handle h) {
     cudaStreamSynchronize(h->stream);
     chb_timer_flush(h);
     chb_nccl_destroy(h);
-    cudaFree(h->V); cudaFree(h->rhs); cudaFree(h->oldrhs); cudaFree(h->P); cudaFree(h->mult);
+    cudaFree(h->V); cudaFree(h->rhs); cudaFree(h->oldrhs); cudaFree(h->P); cudaFree(h->ckpt);
     if (h->F) cudaFree(h->F);
-    cudaFree(h->A); cudaFree(h->B);
-    if (h->g.nranks > 1) { cudaFree(h->Ar); cudaFree(h->Br); }
+    if (h->p2p) chb_p2p_teardown(h);
+    if (h->A) cudaFree(h->A);
+    if (h->B) cudaFree(h->B);
+    cudaFree(h->Ar); cudaFree(h->Br); cudaFree(h->flags);
     cudaFree(h->Wz); cudaFree(h->Wx); cudaFree(h->Wh); cudaFree(h->rev_z);
     cudaFree(h->t_y); cudaFree(h->t_dy); cudaFree(h->t_d0); cudaFree(h->t_d1); cudaFree(h->t_d2); cudaFree(h->t_d4);
     cudaFree(h->t_D0mat); cudaFree(h->mean_scratch); cudaFree(h->sc);
@@ -401,16 +415,14 @@ extern "C" int chb_set_body_force(chb_handle h) {
 static int convolutions_all(chb_handle h, int compute_cfl, bool products) {
     const Geometry& g = h->g;
     const int np = h->chunk_planes;
-    const size_t na = (size_t)3 * np * g.nzB * g.nxB, nb = (size_t)6 * np * g.nzB * g.nxB;
     for (int p0 = 0; p0 < g.nyp; p0 += np) {
         const int n = (p0 + np <= g.nyp) ? np : g.nyp - p0;
-        launch_zfwd(h, p0, n);
-        if (g.nranks > 1 && chb_alltoall(h, h->A, h->Ar, na)) return 1;       // zTOx, mpi_transpose.f90:74
+        launch_zfwd(h, p0, n);                       // stores straight into the x-side owner's buffer
+        if (chb_exchange(h, true)) return 1;         // zTOx, mpi_transpose.f90:50-83
         launch_xpass(h, p0, n, compute_cfl);
-        if (products) {
-            if (g.nranks > 1 && chb_alltoall(h, h->B, h->Br, nb)) return 1;   // xTOz, mpi_transpose.f90:109
-            launch_zbwd(h, p0, n);
-        }
+        // xTOz, mpi_transpose.f90:88-117; in direct mode the barrier also frees Ar for the next chunk
+        if ((products || h->p2p) && chb_exchange(h, false)) return 1;
+        if (products) launch_zbwd(h, p0, n);
     }
     CHB_CUDA_OK(cudaGetLastError());
     return 0;

@@ -1,5 +1,6 @@
 // chb_internal.h - handle layout and kernel launchers of libchannel_b200.
 #pragma once
+#define CHB_SOLVE_K 8
 #include <cuda_runtime.h>
 #include <map>
 #include <string>
@@ -44,6 +45,7 @@ struct Geometry {
     long long M;    // local columns = nxB*nzt
     double alfa0, beta0, ni;
     double dx, dz, factor;
+    int tw;         // log2 of the x-tile width of the products work buffer (transpose_index.h)
 };
 
 struct BodyForce {
@@ -52,6 +54,16 @@ struct BodyForce {
     double* mask_y;  // [ny+3]
     double* mask_z;  // [2nz+1]
     int exclude_mean;
+};
+
+// Where the pack side of a pencil transpose stores: one base pointer per destination rank.
+// Direct NVLink mode: the peer's receive buffer, mapped through CUDA IPC (the kernels write the
+// transposed data straight into peer HBM, no pack buffer and no separate all-to-all).  NCCL mode:
+// this rank's send buffer.  Single GPU: the local receive buffer.  In all modes the element for
+// peer q lives at p[q] + index(block = this rank, ...).
+#define CHB_MAX_RANKS 8
+struct PeerPtrs {
+    cplx* p[CHB_MAX_RANKS];
 };
 
 struct KernelTimer {
@@ -71,15 +83,22 @@ struct chb_handle_s {
     cplx* oldrhs;   // [2][nyp][M]
     cplx* F;        // [3][nyp][M] or null
     cplx* P;        // [6][nyp][M]  spectral products
-    double* mult;   // [4][nyp][M]  L-multipliers of D2vmat / etamat
+    double* ckpt;   // [nblk][8][M]  UL-recurrence state every CHB_SOLVE_K rows (solve_kernels.cu)
     // convolution work buffers for a chunk of planes
     int chunk_planes;
     int z_lines_per_cta;  // 4 or 8 (CHB_Z_LPC)
     int use_fft3;         // register-resident three-stage FFT kernels for the large sizes (CHB_FFT3=0 disables)
-    cplx* A;        // z-padded velocity, [peer][3][np][nzB][nxB]
-    cplx* Ar;       // after zTOx (aliases A when nranks==1)
-    cplx* B;        // products after x-pass, [peer][6][np][nzB][nxB]
-    cplx* Br;       // after xTOz (aliases B when nranks==1)
+    cplx* A;        // NCCL mode only: send buffer of zTOx, [peer][3][np][nzB][nxB]
+    cplx* Ar;       // z-padded velocity after zTOx, [src rank][3][np][nzB][nxB]
+    cplx* B;        // NCCL mode only: send buffer of xTOz
+    cplx* Br;       // products after xTOz, [src rank][6][np][nxB/2^tw][nzB][2^tw]
+    PeerPtrs Aw, Bw;   // where zfwd / xpass store (see PeerPtrs)
+    int p2p;           // 1 = direct NVLink stores into peer buffers + flag barrier, 0 = NCCL all-to-all
+    unsigned long long* flags;             // [CHB_MAX_RANKS] barrier flags of this rank (IPC-shared)
+    unsigned long long* peer_flags[CHB_MAX_RANKS];
+    unsigned long long epoch;
+    void* ipc_opened[3 * CHB_MAX_RANKS];
+    int n_ipc_opened;
     // FFT plans and tables
     FftPlan plan_z, plan_x;
     cplx* Wz;       // exp(+2 pi i e/nzd)
@@ -122,6 +141,9 @@ void launch_body_force(chb_handle_s* h);
 void launch_force_ghosts(chb_handle_s* h);
 // ---- transposes (transpose.cu) ----
 int chb_alltoall(chb_handle_s* h, const cplx* send, cplx* recv, size_t count_per_peer);
+int chb_p2p_setup(chb_handle_s* h, size_t na, size_t nb);   // maps peer Ar/Br/flags; 0 on success
+void chb_p2p_teardown(chb_handle_s* h);
+int chb_exchange(chb_handle_s* h, bool a_side);             // completes zTOx (a_side) / xTOz on the stream
 
 // timing helpers
 struct ScopedKernelTimer {

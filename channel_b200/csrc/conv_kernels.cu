@@ -23,7 +23,7 @@
 
 // --------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(CONV_THREADS)
-zfwd_kernel(const cplx* __restrict__ V, cplx* __restrict__ A, Geometry g, FftPlan pl, const cplx* __restrict__ W,
+zfwd_kernel(const cplx* __restrict__ V, PeerPtrs Aw, Geometry g, FftPlan pl, const cplx* __restrict__ W,
             const int* __restrict__ rev, int plane0, int np, int tx, int line_stride) {
     extern __shared__ cplx smem[];
     const int ixl0 = blockIdx.x * tx;
@@ -49,7 +49,7 @@ zfwd_kernel(const cplx* __restrict__ V, cplx* __restrict__ A, Geometry g, FftPla
         const int t = idx - izd * nl;
         const int peer = izd / g.nzB;
         const int izl = izd - peer * g.nzB;
-        A[buf_index(peer, 3, c, np, pli, g.nzB, izl, g.nxB, ixl0 + t)] =
+        Aw.p[peer][buf_index(g.rank, 3, c, np, pli, g.nzB, izl, g.nxB, ixl0 + t)] =
             smem[(size_t)t * line_stride + CHB_PAD(__ldg(&rev[izd]))];
     }
 }
@@ -70,7 +70,7 @@ zbwd_kernel(const cplx* __restrict__ Br, cplx* __restrict__ P, Geometry g, FftPl
         const int t = idx - izd * nl;
         const int peer = izd / g.nzB;
         const int izl = izd - peer * g.nzB;
-        smem[(size_t)t * line_stride + CHB_PAD(izd)] = Br[buf_index(peer, 6, c, np, pli, g.nzB, izl, g.nxB, ixl0 + t)];
+        smem[(size_t)t * line_stride + CHB_PAD(izd)] = Br[chb_bufB_index(peer, 6, c, np, pli, g.nzB, izl, g.nxB, ixl0 + t, g.tw)];
     }
     fft_lines<-1, true>(smem, line_stride, nl, pl, W);
     cplx* dst = P + (((size_t)c * g.nyp + iyp) * g.nxB + ixl0) * nzt;
@@ -86,7 +86,7 @@ zbwd_kernel(const cplx* __restrict__ Br, cplx* __restrict__ P, Geometry g, FftPl
 // One CTA = lx physical z-lines of one plane.  Shared memory: slot(c,l) = (c*lx + l)*line_stride,
 // c=0..5; slots 0..2 hold u,v,w (then uu,vv,ww), slots 3..5 hold uv,vw,uw.
 __global__ void __launch_bounds__(CONV_THREADS)
-xpass_kernel(const cplx* __restrict__ Ar, cplx* __restrict__ B, Geometry g, FftPlan pl, const cplx* __restrict__ W,
+xpass_kernel(const cplx* __restrict__ Ar, PeerPtrs Bw, Geometry g, FftPlan pl, const cplx* __restrict__ W,
              const cplx* __restrict__ Wh, const double* __restrict__ dy, DevScalars* sc, int plane0, int np, int lx,
              int line_stride, int compute_cfl) {
     extern __shared__ cplx smem[];
@@ -191,7 +191,7 @@ xpass_kernel(const cplx* __restrict__ Ar, cplx* __restrict__ B, Geometry g, FftP
         w.y = -w.y;
         const cplx r = cadd(e, cmul(w, o));
         const int q = k / nxB;
-        B[buf_index(q, 6, c, np, pli, nzB, izl0 + l, nxB, k - q * nxB)] = r;
+        Bw.p[q][chb_bufB_index(g.rank, 6, c, np, pli, nzB, izl0 + l, nxB, k - q * nxB, g.tw)] = r;
     }
 }
 
@@ -232,7 +232,7 @@ void launch_zfwd(chb_handle_s* h, int plane0, int nplanes) {
     cudaFuncSetAttribute(zfwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dim3 grid((h->g.nxB + tx - 1) / tx, nplanes, 3);
     ScopedKernelTimer tm(h, "zfwd");
-    zfwd_kernel<<<grid, CONV_THREADS, smem, h->stream>>>(h->V, h->A, h->g, h->plan_z, h->Wz, h->rev_z, plane0,
+    zfwd_kernel<<<grid, CONV_THREADS, smem, h->stream>>>(h->V, h->Aw, h->g, h->plan_z, h->Wz, h->rev_z, plane0,
                                                          h->chunk_planes, tx, ls);
     h->launches++;
 }
@@ -260,7 +260,7 @@ void launch_xpass(chb_handle_s* h, int plane0, int nplanes, int compute_cfl) {
     cudaFuncSetAttribute(xpass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dim3 grid(h->g.nzB / lx, nplanes);
     ScopedKernelTimer tm(h, "xpass");
-    xpass_kernel<<<grid, CONV_THREADS, smem, h->stream>>>(h->Ar, h->B, h->g, h->plan_x, h->Wx, h->Wh, h->t_dy, h->sc,
+    xpass_kernel<<<grid, CONV_THREADS, smem, h->stream>>>(h->Ar, h->Bw, h->g, h->plan_x, h->Wx, h->Wh, h->t_dy, h->sc,
                                                           plane0, h->chunk_planes, lx, ls, compute_cfl);
     h->launches++;
 }

@@ -17,6 +17,7 @@
 #include "chb_internal.h"
 
 #define SOLVE_THREADS 128
+#define SOLVE_K CHB_SOLVE_K   // rows between checkpoints of the UL recurrence
 
 struct Row5 {
     double a[5];
@@ -91,7 +92,7 @@ __device__ __forceinline__ void lu_row(Row5& r, LUState& st, double& inv, double
 
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(SOLVE_THREADS)
-solve_s1_kernel(cplx* __restrict__ rhs, double* __restrict__ mult, Geometry g, DevTables tab,
+solve_s1_kernel(cplx* __restrict__ rhs, double* __restrict__ ckpt, Geometry g, DevTables tab,
                 const DevScalars* __restrict__ sc, double lam) {
     const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= g.M) return;
@@ -159,26 +160,28 @@ solve_s1_kernel(cplx* __restrict__ rhs, double* __restrict__ mult, Geometry g, D
         xe1 = xe;
         rhs[0 * comp + off] = xe;
         rhs[1 * comp + off] = xv;
-        // multipliers used by Step2; rbparmat_blocking.f90:45 zeroes A(1,-2:-1), A(2,-2)
-        double mv2 = sv.l1m2, mv1 = sv.l1m1, me2 = se.l1m2, me1 = se.l1m1;
-        if (iy == 1) mv2 = mv1 = me2 = me1 = 0.0;
-        if (iy == 2) mv2 = me2 = 0.0;
-        mult[0 * comp + off] = mv2;
-        mult[1 * comp + off] = mv1;
-        mult[2 * comp + off] = me2;
-        mult[3 * comp + off] = me1;
+        // The L-multipliers Step2 needs are not stored: the state of the UL recurrence is
+        // checkpointed every SOLVE_K rows and solve_s2_kernel recomputes them block by block.
+        if (iy > 1 && (iy - 1) % SOLVE_K == 0) {
+            double* ck = ckpt + ((size_t)((iy - 1) / SOLVE_K - 1) * 8) * plane + m;
+            ck[0 * plane] = sv.l1m2; ck[1 * plane] = sv.l1m1; ck[2 * plane] = sv.l2m2; ck[3 * plane] = sv.l2m1;
+            ck[4 * plane] = se.l1m2; ck[5 * plane] = se.l1m1; ck[6 * plane] = se.l2m2; ck[7 * plane] = se.l2m1;
+        }
     }
 }
 
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(SOLVE_THREADS)
-solve_s2_kernel(const cplx* __restrict__ rhs, const double* __restrict__ mult, cplx* __restrict__ V, Geometry g,
-                DevTables tab, const DevScalars* __restrict__ sc) {
+solve_s2_kernel(const cplx* __restrict__ rhs, const double* __restrict__ ckpt, cplx* __restrict__ V, Geometry g,
+                DevTables tab, const DevScalars* __restrict__ sc, double lam) {
     const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= g.M) return;
     const int ixl = (int)(m / g.nzt);
     const int izp = (int)(m - (long long)ixl * g.nzt);
-    const bool mean = (g.nx0 + ixl == 0 && izp == g.nz);
+    const int ix = g.nx0 + ixl, iz = izp - g.nz;
+    const double al = g.alfa0 * ix, be = g.beta0 * iz;
+    const double k2 = al * al + be * be;
+    const bool mean = (ix == 0 && iz == 0);
     const int ny = g.ny;
     const size_t plane = (size_t)g.M, comp = (size_t)g.nyp * plane;
     double bc0_eta = 0.0, bcn_eta = 0.0;
@@ -187,37 +190,82 @@ solve_s2_kernel(const cplx* __restrict__ rhs, const double* __restrict__ mult, c
         bcn_eta = sc->uN;
     }
     cplx v1 = make_double2(0, 0), v2 = v1, v3 = v1, e1 = v1, e2 = v1, e3 = v1;  // b(i-1), b(i-2), b(i-3)
-    for (int iy = 1; iy <= ny - 1; ++iy) {
-        const size_t off = (size_t)(iy + 1) * plane + m;
-        cplx e = rhs[0 * comp + off], v = rhs[1 * comp + off];
-        const double mv2 = mult[0 * comp + off], mv1 = mult[1 * comp + off];
-        const double me2 = mult[2 * comp + off], me1 = mult[3 * comp + off];
-        // LeftLU5divStep2 (rbparmat_blocking.f90:93-95)
-        v.x -= mv2 * v2.x + mv1 * v1.x;
-        v.y -= mv2 * v2.y + mv1 * v1.y;
-        e.x -= me2 * e2.x + me1 * e1.x;
-        e.y -= me2 * e2.y + me1 * e1.y;
-        V[0 * comp + off] = e;
-        V[1 * comp + off] = v;
-        v3 = v2; v2 = v1; v1 = v;
-        e3 = e2; e2 = e1; e1 = e;
-        if (iy == 3) {  // bottom closure needs nodes 1..3 (linsolve_blocking.inc:51-54)
-            const cplx a1 = v3, a2 = v2, a3 = v1, b1 = e3, b2 = e2, b3 = e1;
-            const double* v0bc = tab.v0bc; const double* v0m1 = tab.v0m1bc;
-            const double* e0bc = tab.eta0bc; const double* e0m1 = tab.eta0m1bc;
-            cplx vw, vg, ew, eg;
-            vw.x = (0.0 - (a1.x * v0bc[2] + a2.x * v0bc[3] + a3.x * v0bc[4])) / v0bc[1];
-            vw.y = (0.0 - (a1.y * v0bc[2] + a2.y * v0bc[3] + a3.y * v0bc[4])) / v0bc[1];
-            vg.x = (0.0 - (vw.x * v0m1[1] + a1.x * v0m1[2] + a2.x * v0m1[3] + a3.x * v0m1[4])) / v0m1[0];
-            vg.y = (0.0 - (vw.y * v0m1[1] + a1.y * v0m1[2] + a2.y * v0m1[3] + a3.y * v0m1[4])) / v0m1[0];
-            ew.x = (bc0_eta - (b1.x * e0bc[2] + b2.x * e0bc[3] + b3.x * e0bc[4])) / e0bc[1];
-            ew.y = (0.0 - (b1.y * e0bc[2] + b2.y * e0bc[3] + b3.y * e0bc[4])) / e0bc[1];
-            eg.x = -(ew.x * e0m1[1] + b1.x * e0m1[2] + b2.x * e0m1[3] + b3.x * e0m1[4]) / e0m1[0];
-            eg.y = -(ew.y * e0m1[1] + b1.y * e0m1[2] + b2.y * e0m1[3] + b3.y * e0m1[4]) / e0m1[0];
-            V[0 * comp + 1 * plane + m] = ew;
-            V[0 * comp + 0 * plane + m] = eg;
-            V[1 * comp + 1 * plane + m] = vw;
-            V[1 * comp + 0 * plane + m] = vg;
+    for (int i0 = 1; i0 <= ny - 1; i0 += SOLVE_K) {
+        // ---- recompute the multipliers of rows i0..i0+K-1 (descending, as solve_s1 did) ----
+        LUState sv = {0, 0, 0, 0}, se = {0, 0, 0, 0};
+        if (i0 + SOLVE_K <= ny - 1) {   // state after row i0+K was processed
+            const double* ck = ckpt + ((size_t)((i0 - 1) / SOLVE_K) * 8) * plane + m;
+            sv.l1m2 = ck[0 * plane]; sv.l1m1 = ck[1 * plane]; sv.l2m2 = ck[2 * plane]; sv.l2m1 = ck[3 * plane];
+            se.l1m2 = ck[4 * plane]; se.l1m1 = ck[5 * plane]; se.l2m2 = ck[6 * plane]; se.l2m1 = ck[7 * plane];
+        }
+        double mv2[SOLVE_K], mv1[SOLVE_K], me2[SOLVE_K], me1[SOLVE_K];
+#pragma unroll
+        for (int k = SOLVE_K - 1; k >= 0; --k) {
+            const int iy = i0 + k;
+            mv2[k] = mv1[k] = me2[k] = me1[k] = 0.0;
+            if (iy <= ny - 1) {
+                Row5 rv, re;
+                build_rows(tab, iy, k2, lam, g.ni, rv, re);
+                if (iy == ny - 1) {
+                    fold_top1(rv, tab.vnbc, tab.vnp1bc);
+                    fold_top1(re, tab.etanbc, tab.etanp1bc);
+                    rv.a[3] = rv.a[4] = 0.0;
+                    re.a[3] = re.a[4] = 0.0;
+                } else if (iy == ny - 2) {
+                    fold_top2(rv, tab.vnbc);
+                    fold_top2(re, tab.etanbc);
+                    rv.a[4] = 0.0;
+                    re.a[4] = 0.0;
+                }
+                if (iy == 1) {
+                    fold_bot1(rv, tab.v0bc, tab.v0m1bc);
+                    fold_bot1(re, tab.eta0bc, tab.eta0m1bc);
+                } else if (iy == 2) {
+                    fold_bot2(rv, tab.v0bc);
+                    fold_bot2(re, tab.eta0bc);
+                }
+                double inv, u1, u2;
+                lu_row(rv, sv, inv, u1, u2);
+                lu_row(re, se, inv, u1, u2);
+                // rbparmat_blocking.f90:45 zeroes A(1,-2:-1), A(2,-2)
+                if (iy >= 3) { mv2[k] = sv.l1m2; me2[k] = se.l1m2; }
+                if (iy >= 2) { mv1[k] = sv.l1m1; me1[k] = se.l1m1; }
+            }
+        }
+        // ---- LeftLU5divStep2 (rbparmat_blocking.f90:93-95), ascending ----
+#pragma unroll
+        for (int k = 0; k < SOLVE_K; ++k) {
+            const int iy = i0 + k;
+            if (iy <= ny - 1) {
+                const size_t off = (size_t)(iy + 1) * plane + m;
+                cplx e = rhs[0 * comp + off], v = rhs[1 * comp + off];
+                v.x -= mv2[k] * v2.x + mv1[k] * v1.x;
+                v.y -= mv2[k] * v2.y + mv1[k] * v1.y;
+                e.x -= me2[k] * e2.x + me1[k] * e1.x;
+                e.y -= me2[k] * e2.y + me1[k] * e1.y;
+                V[0 * comp + off] = e;
+                V[1 * comp + off] = v;
+                v3 = v2; v2 = v1; v1 = v;
+                e3 = e2; e2 = e1; e1 = e;
+                if (iy == 3) {  // bottom closure needs nodes 1..3 (linsolve_blocking.inc:51-54)
+                    const cplx a1 = v3, a2 = v2, a3 = v1, b1 = e3, b2 = e2, b3 = e1;
+                    const double* v0bc = tab.v0bc; const double* v0m1 = tab.v0m1bc;
+                    const double* e0bc = tab.eta0bc; const double* e0m1 = tab.eta0m1bc;
+                    cplx vw, vg, ew, eg;
+                    vw.x = (0.0 - (a1.x * v0bc[2] + a2.x * v0bc[3] + a3.x * v0bc[4])) / v0bc[1];
+                    vw.y = (0.0 - (a1.y * v0bc[2] + a2.y * v0bc[3] + a3.y * v0bc[4])) / v0bc[1];
+                    vg.x = (0.0 - (vw.x * v0m1[1] + a1.x * v0m1[2] + a2.x * v0m1[3] + a3.x * v0m1[4])) / v0m1[0];
+                    vg.y = (0.0 - (vw.y * v0m1[1] + a1.y * v0m1[2] + a2.y * v0m1[3] + a3.y * v0m1[4])) / v0m1[0];
+                    ew.x = (bc0_eta - (b1.x * e0bc[2] + b2.x * e0bc[3] + b3.x * e0bc[4])) / e0bc[1];
+                    ew.y = (0.0 - (b1.y * e0bc[2] + b2.y * e0bc[3] + b3.y * e0bc[4])) / e0bc[1];
+                    eg.x = -(ew.x * e0m1[1] + b1.x * e0m1[2] + b2.x * e0m1[3] + b3.x * e0m1[4]) / e0m1[0];
+                    eg.y = -(ew.y * e0m1[1] + b1.y * e0m1[2] + b2.y * e0m1[3] + b3.y * e0m1[4]) / e0m1[0];
+                    V[0 * comp + 1 * plane + m] = ew;
+                    V[0 * comp + 0 * plane + m] = eg;
+                    V[1 * comp + 1 * plane + m] = vw;
+                    V[1 * comp + 0 * plane + m] = vg;
+                }
+            }
         }
     }
     {  // top closure (linsolve_blocking.inc:57-60): nodes ny-3..ny-1 = v3,v2,v1
@@ -475,11 +523,11 @@ void launch_linsolve(chb_handle_s* h, double lam) {
     const int blocks = (int)((g.M + SOLVE_THREADS - 1) / SOLVE_THREADS);
     {
         ScopedKernelTimer tm(h, "solve_s1");
-        solve_s1_kernel<<<blocks, SOLVE_THREADS, 0, h->stream>>>(h->rhs, h->mult, g, h->tab, h->sc, lam);
+        solve_s1_kernel<<<blocks, SOLVE_THREADS, 0, h->stream>>>(h->rhs, h->ckpt, g, h->tab, h->sc, lam);
     }
     {
         ScopedKernelTimer tm(h, "solve_s2");
-        solve_s2_kernel<<<blocks, SOLVE_THREADS, 0, h->stream>>>(h->rhs, h->mult, h->V, g, h->tab, h->sc);
+        solve_s2_kernel<<<blocks, SOLVE_THREADS, 0, h->stream>>>(h->rhs, h->ckpt, h->V, g, h->tab, h->sc, lam);
     }
     {
         ScopedKernelTimer tm(h, "solve_s3");

@@ -27,6 +27,7 @@ struct NcclApi {
     ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
 };
 NcclApi g_nccl;
@@ -57,6 +58,7 @@ bool load_nccl() {
     LOAD(Recv, "ncclRecv");
     LOAD(AllReduce, "ncclAllReduce");
     LOAD(Broadcast, "ncclBroadcast");
+    LOAD(AllGather, "ncclAllGather");
     LOAD(GetErrorString, "ncclGetErrorString");
 #undef LOAD
     return true;
@@ -127,4 +129,89 @@ int chb_bcast_scalars(chb_handle_s* h) {
     const size_t bytes = sizeof(DevScalars) - sizeof(unsigned long long);
     NCCL_OK(g_nccl.Broadcast(base, base, bytes, ncclChar, 0, comm, h->stream));
     return 0;
+}
+
+// ---- direct NVLink mode ---------------------------------------------------------------------
+// Every rank maps every peer's receive buffers (Ar, Br) and barrier flags through CUDA IPC.  The
+// pack side of zTOx / xTOz then IS the transpose: zfwd / xpass store each element straight into
+// the owner's HBM over NVLink while they compute (PeerPtrs, chb_internal.h).  What is left of the
+// collective is a flag barrier between the producing and the consuming kernel.
+struct IpcBundle {
+    cudaIpcMemHandle_t ar, br, flags;
+};
+
+int chb_p2p_setup(chb_handle_s* h, size_t na, size_t nb) {
+    (void)na; (void)nb;
+    const int P = h->g.nranks, r = h->g.rank;
+    ncclComm_t comm = (ncclComm_t)h->nccl_comm;
+    IpcBundle mine;
+    CHB_CUDA_OK(cudaIpcGetMemHandle(&mine.ar, h->Ar));
+    CHB_CUDA_OK(cudaIpcGetMemHandle(&mine.br, h->Br));
+    CHB_CUDA_OK(cudaIpcGetMemHandle(&mine.flags, h->flags));
+    IpcBundle* d_all = nullptr;
+    CHB_CUDA_OK(cudaMalloc((void**)&d_all, sizeof(IpcBundle) * P));
+    CHB_CUDA_OK(cudaMemcpy(d_all + r, &mine, sizeof(IpcBundle), cudaMemcpyHostToDevice));
+    NCCL_OK(g_nccl.AllGather(d_all + r, d_all, sizeof(IpcBundle), ncclChar, comm, h->stream));
+    CHB_CUDA_OK(cudaStreamSynchronize(h->stream));
+    IpcBundle all[CHB_MAX_RANKS];
+    CHB_CUDA_OK(cudaMemcpy(all, d_all, sizeof(IpcBundle) * P, cudaMemcpyDeviceToHost));
+    cudaFree(d_all);
+    h->n_ipc_opened = 0;
+    for (int q = 0; q < P; ++q) {
+        if (q == r) {
+            h->Aw.p[q] = h->Ar;
+            h->Bw.p[q] = h->Br;
+            h->peer_flags[q] = h->flags;
+            continue;
+        }
+        void *pa = nullptr, *pb = nullptr, *pf = nullptr;
+        CHB_CUDA_OK(cudaIpcOpenMemHandle(&pa, all[q].ar, cudaIpcMemLazyEnablePeerAccess));
+        h->ipc_opened[h->n_ipc_opened++] = pa;
+        CHB_CUDA_OK(cudaIpcOpenMemHandle(&pb, all[q].br, cudaIpcMemLazyEnablePeerAccess));
+        h->ipc_opened[h->n_ipc_opened++] = pb;
+        CHB_CUDA_OK(cudaIpcOpenMemHandle(&pf, all[q].flags, cudaIpcMemLazyEnablePeerAccess));
+        h->ipc_opened[h->n_ipc_opened++] = pf;
+        h->Aw.p[q] = (cplx*)pa;
+        h->Bw.p[q] = (cplx*)pb;
+        h->peer_flags[q] = (unsigned long long*)pf;
+    }
+    return 0;
+}
+
+void chb_p2p_teardown(chb_handle_s* h) {
+    for (int i = 0; i < h->n_ipc_opened; ++i) cudaIpcCloseMemHandle(h->ipc_opened[i]);
+    h->n_ipc_opened = 0;
+}
+
+struct FlagPtrs {
+    unsigned long long* p[CHB_MAX_RANKS];
+};
+
+// thread q: publish "rank `me` has finished epoch e" in peer q's flags, then wait until peer q has
+// published the same in mine.  The producing kernel precedes this one on the stream, so its
+// (remote) stores are complete; the fences order them with the flag for the other GPUs.
+__global__ void p2p_barrier_kernel(FlagPtrs peers, volatile unsigned long long* mine, int me, int P, unsigned long long e) {
+    const int q = threadIdx.x;
+    if (q >= P) return;
+    __threadfence_system();
+    *((volatile unsigned long long*)(peers.p[q] + me)) = e;
+    __threadfence_system();
+    while (mine[q] < e) { __nanosleep(200); }
+    __threadfence_system();
+}
+
+int chb_exchange(chb_handle_s* h, bool a_side) {
+    const Geometry& g = h->g;
+    if (g.nranks == 1) return 0;
+    if (h->p2p) {
+        FlagPtrs fp;
+        for (int q = 0; q < g.nranks; ++q) fp.p[q] = h->peer_flags[q];
+        ScopedKernelTimer tm(h, "p2p_barrier");
+        p2p_barrier_kernel<<<1, 32, 0, h->stream>>>(fp, h->flags, g.rank, g.nranks, ++h->epoch);
+        h->launches++;
+        return 0;
+    }
+    const size_t np = h->chunk_planes;
+    if (a_side) return chb_alltoall(h, h->A, h->Ar, (size_t)3 * np * g.nzd * g.nxB);   // mpi_transpose.f90:74
+    return chb_alltoall(h, h->B, h->Br, (size_t)6 * np * g.nzd * g.nxB);               // mpi_transpose.f90:109
 }

@@ -18,6 +18,15 @@ CHB_HD size_t chb_buf_index(int peer, int ncomp, int comp, int np, int pl, int n
     return ((((size_t)peer * ncomp + comp) * np + pl) * nzB + izl) * (size_t)nxB + ixl;
 }
 
+// The products buffer (x-pass -> z-pass, xTOz) is tiled: 2^tw consecutive x-modes form the
+// innermost index, then the z row, so that the LPC = 2^tw lines one z-pass CTA transforms are one
+// contiguous nzB * 2^tw * 16-byte block:  buf[peer][comp][plane][ixl >> tw][izl][ixl & (2^tw-1)].
+// tw = 0 is the fully transposed layout [ixl][izl].
+CHB_HD size_t chb_bufB_index(int peer, int ncomp, int comp, int np, int pl, int nzB, int izl, int nxB, int ixl, int tw) {
+    return (((((size_t)peer * ncomp + comp) * np + pl) * (size_t)(nxB >> tw) + (ixl >> tw)) * nzB + izl) * ((size_t)1 << tw) +
+           (ixl & ((1 << tw) - 1));
+}
+
 // mpi_transpose.f90:214-215 with npy=1
 CHB_HD void chb_decompose(int nxp1, int nzd, int nranks, int rank, int* nx0, int* nxN, int* nz0, int* nzN) {
     *nx0 = rank * nxp1 / nranks;

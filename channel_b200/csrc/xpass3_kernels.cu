@@ -20,30 +20,6 @@
 #include "chb_internal.h"
 #include "fft_regs.cuh"
 
-// ---- TMA 1-D bulk copy global -> shared with mbarrier completion (cp.async.bulk, SASS UBLKCP) ----
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-    unsigned ok;
-    do {
-        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                     : "=r"(ok)
-                     : "r"(smem_u32(bar)), "r"(parity)
-                     : "memory");
-    } while (!ok);
-}
-
 // x[p] *= w1^p, p = 1..R-1, sequential recurrence (low register pressure)
 template <int R>
 __device__ __forceinline__ void apply_twiddle_seq(cplx* x, cplx w1) {
@@ -58,7 +34,7 @@ __device__ __forceinline__ void apply_twiddle_seq(cplx* x, cplx w1) {
 
 template <class G, int LPC>
 __global__ void __launch_bounds__(LPC * (G::N / G::C))
-xpass3_kernel(const cplx* __restrict__ Ar, cplx* __restrict__ Bout, Geometry g, const cplx* __restrict__ W,
+xpass3_kernel(const cplx* __restrict__ Ar, PeerPtrs Bw, Geometry g, const cplx* __restrict__ W,
               const cplx* __restrict__ Wh, const double* __restrict__ dy, DevScalars* sc, int plane0, int np,
               int compute_cfl) {
     constexpr int M = G::N, A = G::A, B = G::B, C = G::C, BC = G::BC;
@@ -121,7 +97,8 @@ xpass3_kernel(const cplx* __restrict__ Ar, cplx* __restrict__ Bout, Geometry g, 
     // ---- backward stage B, in place ---------------------------------------------------------
     {
         const int cc = tl % C;
-        const cplx wc1 = W[A * cc];   // w_BC^cc
+        cplx wcp[B];
+        twiddle_powers<B>(W[A * cc], wcp);   // w_BC^(cc*kb), shared by the three components
         for (int u = tl; u < A * C; u += T) {
             cplx* base = S + (u / C) * BCP + cc;
 #pragma unroll 1
@@ -129,7 +106,7 @@ xpass3_kernel(const cplx* __restrict__ Ar, cplx* __restrict__ Bout, Geometry g, 
                 cplx x[B];
                 static_for<B>([&](auto b_) { constexpr int b = decltype(b_)::value; x[b] = base[comp * LB + b * C]; });
                 Dft<B, +1>::run(x);
-                if (cc != 0) apply_twiddle_seq<B>(x, wc1);
+                if (cc != 0) static_for<B - 1>([&](auto i_) { constexpr int i = decltype(i_)::value + 1; x[i] = cmul(x[i], wcp[i]); });
                 static_for<B>([&](auto b_) { constexpr int b = decltype(b_)::value; base[comp * LB + b * C] = x[b]; });
             }
         }
@@ -164,11 +141,12 @@ xpass3_kernel(const cplx* __restrict__ Ar, cplx* __restrict__ Bout, Geometry g, 
             if ((threadIdx.x & 31) == 0 && cmax > 0.0)
                 atomicMax(&sc->cfl_bits, (unsigned long long)__double_as_longlong(cmax));
         }
-        const double f = g.factor;
-        const cplx wk1 = ctw<-1>(W, A * kb);   // conj w_BC^kb: forward twiddle of this thread's outputs
+        const double f = 0.5 * g.factor;       // the 1/2 of the merge pass is folded into the products
+        cplx wkp[C];
+        twiddle_powers<C>(ctw<-1>(W, A * kb), wkp);   // conj w_BC^(kb*c'), shared by the six products
         auto forward_c = [&](cplx* x, int p) {
             Dft<C, -1>::run(x);
-            if (kb != 0) apply_twiddle_seq<C>(x, wk1);
+            if (kb != 0) static_for<C - 1>([&](auto i_) { constexpr int i = decltype(i_)::value + 1; x[i] = cmul(x[i], wkp[i]); });
             static_for<C>([&](auto c_) { constexpr int c = decltype(c_)::value; base[p * LB + c] = x[c]; });
         };
         cplx x[C];
@@ -222,14 +200,15 @@ xpass3_kernel(const cplx* __restrict__ Ar, cplx* __restrict__ Bout, Geometry g, 
         cplx w = Wh[j];
         w.y = -w.y;   // e^{-i pi j/M}
         const int q = multi ? j / nxB : 0;
-        const size_t o0 = chb_buf_index(q, 6, 0, np, pli, nzB, izl, nxB, j - q * nxB);
+        cplx* __restrict__ Bout = Bw.p[q];   // the owner of x-mode j (this GPU's or a peer's HBM over NVLink)
+        const size_t o0 = chb_bufB_index(g.rank, 6, 0, np, pli, nzB, izl, nxB, j - q * nxB, g.tw);
         const size_t ostride = (size_t)np * nzB * nxB;
 #pragma unroll
         for (int p = 0; p < 6; ++p) {
             const cplx z = S[p * LB + pj];
             const cplx zm = S[p * LB + pm];
-            const cplx e = make_double2(0.5 * (z.x + zm.x), 0.5 * (z.y - zm.y));
-            const cplx d = make_double2(0.5 * (z.x - zm.x), 0.5 * (z.y + zm.y));   // (Z - conj Zm)/2
+            const cplx e = make_double2(z.x + zm.x, z.y - zm.y);   // (Z + conj Zm)/2, the 1/2 is in the products
+            const cplx d = make_double2(z.x - zm.x, z.y + zm.y);   // (Z - conj Zm)/2
             const cplx o = make_double2(d.y, -d.x);                                // -i * d
             Bout[o0 + p * ostride] = cadd(e, cmul(w, o));
         }
@@ -247,7 +226,7 @@ static bool launch_x3(chb_handle_s* h, int plane0, int nplanes, int compute_cfl)
     cudaFuncSetAttribute(xpass3_kernel<G, LPC>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     dim3 grid(h->g.nzB / LPC, nplanes);
     ScopedKernelTimer tm(h, "xpass");
-    xpass3_kernel<G, LPC><<<grid, LPC * T, smem, h->stream>>>(h->Ar, h->B, h->g, h->Wx, h->Wh, h->t_dy, h->sc, plane0,
+    xpass3_kernel<G, LPC><<<grid, LPC * T, smem, h->stream>>>(h->Ar, h->Bw, h->g, h->Wx, h->Wh, h->t_dy, h->sc, plane0,
                                                              h->chunk_planes, compute_cfl);
     h->launches++;
     return true;

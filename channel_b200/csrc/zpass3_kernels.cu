@@ -16,7 +16,7 @@
 
 template <class G, int LPC>
 __global__ void __launch_bounds__(LPC * 32)
-zfwd3_kernel(const cplx* __restrict__ V, cplx* __restrict__ A, Geometry g, const cplx* __restrict__ W, int plane0, int np,
+zfwd3_kernel(const cplx* __restrict__ V, PeerPtrs Aw, Geometry g, const cplx* __restrict__ W, int plane0, int np,
              int LS) {
     extern __shared__ cplx smem[];
     constexpr int BCP = G::BC + 1;
@@ -25,9 +25,27 @@ zfwd3_kernel(const cplx* __restrict__ V, cplx* __restrict__ A, Geometry g, const
     const int pli = blockIdx.y, comp = blockIdx.z;
     const int iyp = plane0 + pli;
     const int nz = g.nz;
-    {   // ---- stage A, warp per line: global (z-contiguous V line) -> registers -> smem
+    {   // ---- stage A, warp per line.  The z-contiguous V line is staged by TMA bulk copies straight
+        //      into the in-place layout (piece a -> sm + a*BCP), one latency exposure per line;
+        //      the zero padding between nz and nzd-nz is never materialised.
         const cplx* __restrict__ src = V + (((size_t)comp * g.nyp + iyp) * g.nxB + ixl0 + wl) * g.nzt;
         cplx* sm = smem + wl * LS;
+        __shared__ unsigned long long mbar[LPC];
+        if (lane == 0) {
+            mbar_init(&mbar[wl], 1);
+            mbar_expect_tx(&mbar[wl], (unsigned)(g.nzt * sizeof(cplx)));
+            for (int a = 0; a < G::A; ++a) {
+                const int lo = a * G::BC, hi = lo + G::BC - 1;
+                const int h1 = min(hi, nz);                    // rows 1..nz+1        <- V(iy,0:nz)
+                if (h1 >= lo) bulk_g2s(sm + a * BCP, src + nz + lo, (unsigned)((h1 - lo + 1) * sizeof(cplx)), &mbar[wl]);
+                const int l2 = max(lo, G::N - nz);             // rows nzd-nz+1..nzd  <- V(iy,-nz:-1)
+                if (hi >= l2)
+                    bulk_g2s(sm + a * BCP + (l2 - lo), src + (l2 - (G::N - nz)), (unsigned)((hi - l2 + 1) * sizeof(cplx)),
+                             &mbar[wl]);
+            }
+        }
+        __syncwarp();
+        mbar_wait(&mbar[wl], 0);
 #pragma unroll 1
         for (int i = 0; i < G::BC / 32; ++i) {
             const int t1 = lane + 32 * i;
@@ -35,10 +53,7 @@ zfwd3_kernel(const cplx* __restrict__ V, cplx* __restrict__ A, Geometry g, const
             static_for<G::A>([&](auto a_) {
                 constexpr int a = decltype(a_)::value;
                 const int n = a * G::BC + t1;
-                cplx v = make_double2(0.0, 0.0);
-                if (n <= nz) v = src[nz + n];                       // V(iy,0:nz)   -> rows 1..nz+1
-                else if (n >= G::N - nz) v = src[n - (G::N - nz)];  // V(iy,-nz:-1) -> rows nzd-nz+1..nzd
-                x[a] = v;
+                x[a] = (n <= nz || n >= G::N - nz) ? sm[a * BCP + t1] : make_double2(0.0, 0.0);
             });
             dif_stage_a<G, +1>(x, t1, W);
             static_for<G::A>([&](auto ka_) {
@@ -79,7 +94,7 @@ zfwd3_kernel(const cplx* __restrict__ V, cplx* __restrict__ A, Geometry g, const
                 constexpr int kc = decltype(kc_)::value;
                 const int k = t + G::AB * kc;
                 const int peer = (g.nranks > 1) ? k / nzB : 0;
-                A[chb_buf_index(peer, 3, comp, np, pli, nzB, k - peer * nzB, nxB, ixl0 + l)] = x[kc];
+                Aw.p[peer][chb_buf_index(g.rank, 3, comp, np, pli, nzB, k - peer * nzB, nxB, ixl0 + l)] = x[kc];
             });
         }
     }
@@ -96,28 +111,33 @@ zbwd3_kernel(const cplx* __restrict__ Br, cplx* __restrict__ P, Geometry g, cons
     const int pli = blockIdx.y, comp = blockIdx.z;  // product index 0..5
     const int iyp = plane0 + pli;
     const int nz = g.nz;
-    {   // ---- stage A, cross-line: global (x-contiguous work buffer) -> registers -> smem
+    {   // ---- staging, cross-line: the x-contiguous work buffer (LPC*16 contiguous bytes per z row) is
+        //      copied with per-thread 16-byte cp.async straight into the in-place layout of each line;
+        //      all copies of the CTA are in flight at once, one latency exposure
         const int l = threadIdx.x % LPC, q = threadIdx.x / LPC;
-        cplx* sm = smem + l * LS;
+        cplx* sml = smem + l * LS;
         const int nzB = g.nzB, nxB = g.nxB;
-#pragma unroll 1
-        for (int i = 0; i < G::BC / 32; ++i) {
-            const int t1 = q + 32 * i;
-            cplx x[G::A];
-            static_for<G::A>([&](auto a_) {
-                constexpr int a = decltype(a_)::value;
-                const int n = a * G::BC + t1;
-                const int peer = (g.nranks > 1) ? n / nzB : 0;
-                x[a] = Br[chb_buf_index(peer, 6, comp, np, pli, nzB, n - peer * nzB, nxB, ixl0 + l)];
-            });
-            dif_stage_a<G, -1>(x, t1, W);
-            static_for<G::A>([&](auto ka_) {
-                constexpr int ka = decltype(ka_)::value;
-                sm[ka * BCP + t1] = x[ka];
-            });
+#pragma unroll 4
+        for (int n = q; n < G::N; n += 32) {
+            const int peer = (g.nranks > 1) ? n / nzB : 0;
+            cp_async16(sml + (n / G::BC) * BCP + (n % G::BC),
+                       Br + chb_bufB_index(peer, 6, comp, np, pli, nzB, n - peer * nzB, nxB, ixl0 + l, g.tw));
         }
+        cp_async_wait_all();
     }
     __syncthreads();
+    {   // ---- stage A, warp per line, in place
+        cplx* sm = smem + wl * LS;
+#pragma unroll 1
+        for (int i = 0; i < G::BC / 32; ++i) {
+            const int t1 = lane + 32 * i;
+            cplx x[G::A];
+            static_for<G::A>([&](auto a_) { constexpr int a = decltype(a_)::value; x[a] = sm[a * BCP + t1]; });
+            dif_stage_a<G, -1>(x, t1, W);
+            static_for<G::A>([&](auto ka_) { constexpr int ka = decltype(ka_)::value; sm[ka * BCP + t1] = x[ka]; });
+        }
+    }
+    __syncwarp();
     cplx* sm = smem + wl * LS;
     {   // ---- stage B, warp per line, in place
         const int cc = lane % G::C;
@@ -165,10 +185,12 @@ static bool launch_z3(chb_handle_s* h, int plane0, int nplanes, bool fwd) {
     dim3 grid(h->g.nxB / LPC, nplanes, fwd ? 3 : 6);
     if (fwd) {
         cudaFuncSetAttribute(zfwd3_kernel<G, LPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(zfwd3_kernel<G, LPC>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         ScopedKernelTimer tm(h, "zfwd");
-        zfwd3_kernel<G, LPC><<<grid, LPC * 32, smem, h->stream>>>(h->V, h->A, h->g, h->Wz, plane0, h->chunk_planes, LS);
+        zfwd3_kernel<G, LPC><<<grid, LPC * 32, smem, h->stream>>>(h->V, h->Aw, h->g, h->Wz, plane0, h->chunk_planes, LS);
     } else {
         cudaFuncSetAttribute(zbwd3_kernel<G, LPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(zbwd3_kernel<G, LPC>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         ScopedKernelTimer tm(h, "zbwd");
         zbwd3_kernel<G, LPC><<<grid, LPC * 32, smem, h->stream>>>(h->Br, h->P, h->g, h->Wz, plane0, h->chunk_planes, LS);
     }

@@ -1,0 +1,66 @@
+"""Worker for the multi-GPU parity test: launched by torchrun with N ranks (one per GPU).
+Each rank owns an x-slab (mpi_transpose.f90:214-215), runs the CFL pre-pass and a few RK3 steps
+through the C ABI with NCCL all-to-all transposes, and checks its slab against the CPU oracle."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from channel_b200 import Channel, DnsIn, _lib  # noqa: E402
+from channel_b200.fields import perturbed_laminar  # noqa: E402
+from oracle.channel_oracle import DnsIn as ODnsIn, Oracle, coriolis_force  # noqa: E402
+
+
+def main():
+    rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); local = int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = _lib.load()
+
+    def new_nccl_id():          # one unique id per communicator (= per handle), broadcast from rank 0
+        buf = C.create_string_buffer(128)
+        if rank == 0:
+            _lib.check(lib.chb_get_nccl_unique_id(buf), "id")
+        t = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).cuda()
+        dist.broadcast(t, 0)
+        return bytes(t.cpu().numpy().tobytes())
+    grids = [(31, 16, 16, False), (255, 8, 255, False), (31, 16, 16, True)]
+    worst = 0.0
+    for nx, ny, nz, couette in grids:
+        kw = dict(CPI=False, u0=-1.0, uN=1.0) if couette else {}
+        p = DnsIn(nx=nx, ny=ny, nz=nz, re=2000.0, deltat=0.0, cflmax=1.0, **kw)
+        o = Oracle(ODnsIn(**{k: getattr(p, k) for k in ODnsIn.__dataclass_fields__}))
+        V0 = perturbed_laminar(nx, ny, nz, p.alfa0, p.beta0, eps=2e-2, couette=couette)
+        o.V[:] = V0
+        ch = Channel(p, rank=rank, nranks=world, nccl_id=new_nccl_id(), device=local, tables=o)
+        sl = slice(ch.nx0, ch.nxN + 1)
+        ch.upload_V(V0[:, :, sl, :])
+        if couette:
+            o.set_body_force(coriolis_force(0.02, 9999999.0, 1.0)); ch.config_coriolis(0.02, 9999999.0, 1.0)
+        ch.cfl_prepass(); o.cfl_prepass()
+        lg = ch.outstats(); lo = o.outstats()
+        assert np.allclose(lg, lo, rtol=1e-11, atol=1e-13), (rank, lg, lo)
+        for i in range(2):
+            lo = o.step(); lg = ch.step()
+            assert np.allclose(lg[1:9], lo[1:9], rtol=1e-8, atol=1e-10), (rank, i, lg, lo)
+            assert np.allclose(lg[[0, 9, 10]], lo[[0, 9, 10]], rtol=1e-10), (rank, i, lg, lo)
+        Vg = ch.download_V()
+        for c in range(3):
+            ref = o.V[c][:, sl, :]
+            err = float(np.abs(Vg[c] - ref).max() / np.abs(o.V[c]).max())
+            worst = max(worst, err)
+            assert err < 1e-11, (rank, (nx, ny, nz), c, err)
+        ch.close()
+    dist.barrier()
+    if rank == 0:
+        print(f"MGPU_PARITY_OK world={world} worst_rel_err={worst:.2e}")
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
