@@ -23,22 +23,24 @@ extern "C" int chb_version(void) { return 1000; }
     } while (0)
 
 // ---- timing -----------------------------------------------------------------------------
-ScopedKernelTimer::ScopedKernelTimer(chb_handle_s* h_, const char* name_) : h(h_), name(name_), on(h_->timer.on) {
+ScopedKernelTimer::ScopedKernelTimer(chb_handle_s* h_, const char* name_, cudaStream_t st_)
+    : h(h_), name(name_), on(h_->timer.on), st(st_ ? st_ : h_->stream) {
     if (on) {
         cudaEventCreate(&e0);
         cudaEventCreate(&e1);
-        cudaEventRecord(e0, h->stream);
+        cudaEventRecord(e0, st);
     }
 }
 ScopedKernelTimer::~ScopedKernelTimer() {
     if (on) {
-        cudaEventRecord(e1, h->stream);
+        cudaEventRecord(e1, st);
         h->timer.pending.push_back({name, {e0, e1}});
     }
 }
 void chb_timer_flush(chb_handle_s* h) {
     if (h->timer.pending.empty()) return;
     cudaStreamSynchronize(h->stream);
+    cudaStreamSynchronize(h->side_stream);
     for (auto& p : h->timer.pending) {
         float ms = 0;
         cudaEventElapsedTime(&ms, p.second.first, p.second.second);
@@ -156,7 +158,6 @@ extern "C" int chb_create(chb_handle* out, int nx, int ny, int nz, int nxd, int 
     g.nxB = g.nxN - g.nx0 + 1;
     g.nzB = g.nzN - g.nz0 + 1;
     g.M = (long long)g.nxB * g.nzt;
-    g.tw = (g.nxB % 8 == 0) ? 3 : 0;
     g.alfa0 = alfa0; g.beta0 = beta0; g.ni = ni;
     const double PI = 3.1415926535897932384626433832795028841971;  // dnsdata.f90:26
     g.dx = PI / (alfa0 * nxd); g.dz = 2.0 * PI / (beta0 * nzd); g.factor = 1.0 / (2.0 * nxd * nzd);  // :124
@@ -164,8 +165,19 @@ extern "C" int chb_create(chb_handle* out, int nx, int ny, int nz, int nxd, int 
     {
         const char* e = getenv("CHB_Z_LPC");
         h->z_lines_per_cta = (e && atoi(e) == 4) ? 4 : 8;
+        e = getenv("CHB_Z_VAR");
+        h->z_var = (e && atoi(e) == 3) ? 3 : 4;
+        if (h->z_var == 4) h->z_lines_per_cta = 4;
+        e = getenv("CHB_PF_DIST");
+        h->pf_dist = e ? atoi(e) : 0;
+        e = getenv("CHB_X_VAR");
+        h->x_var = e ? atoi(e) : 4;
         e = getenv("CHB_FFT3");
         h->use_fft3 = (e && atoi(e) == 0) ? 0 : 1;
+        // x-tile of the products buffer = the lines one z-pass CTA transforms (transpose_index.h)
+        g.tw = (h->z_lines_per_cta == 4 && g.nxB % 4 == 0) ? 2 : ((g.nxB % 8 == 0) ? 3 : 0);
+        e = getenv("CHB_TW");
+        if (e && (g.nxB % (1 << atoi(e)) == 0)) g.tw = atoi(e);
     }
     h->launches = 0;
     h->tables_set = false;
@@ -173,6 +185,9 @@ extern "C" int chb_create(chb_handle* out, int nx, int ny, int nz, int nxd, int 
     h->nccl_comm = nullptr;
     memset(&h->bf, 0, sizeof(h->bf));
     CHB_CUDA_OK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CHB_CUDA_OK(cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
+    CHB_CUDA_OK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    CHB_CUDA_OK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
 
     std::vector<int> rev;
     CHB_REQUIRE(build_plan(nzd, &h->plan_z, &rev), "chb_create: nzd must be 2^a or 3*2^a (fftFIT, ffts.f90:78-86)");
@@ -249,6 +264,8 @@ extern "C" int chb_destroy(chb_handle h) {
     if (h->bf.mask_y) cudaFree(h->bf.mask_y);
     if (h->bf.mask_z) cudaFree(h->bf.mask_z);
     cudaFreeHost(h->sc_host);
+    cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join);
+    cudaStreamDestroy(h->side_stream);
     cudaStreamDestroy(h->stream);
     delete h;
     return 0;

@@ -77,6 +77,8 @@ struct chb_handle_s {
     Geometry g;
     int device;
     cudaStream_t stream;
+    cudaStream_t side_stream;      // mean-mode column, concurrent with S3/S4 of the solve
+    cudaEvent_t ev_fork, ev_join;
     // fields (device layout [c][iy+1][ixl][iz+nz], complex128)
     cplx* V;        // [3][nyp][M]
     cplx* rhs;      // [2][nyp][M]  0 = eta, 1 = D2v (also holds the Step1 result)
@@ -87,6 +89,9 @@ struct chb_handle_s {
     // convolution work buffers for a chunk of planes
     int chunk_planes;
     int z_lines_per_cta;  // 4 or 8 (CHB_Z_LPC)
+    int z_var;            // 4 = zfwd4/zbwd4 (64 threads per line, 4 lines per CTA), 3 = zfwd3/zbwd3 (CHB_Z_VAR)
+    int x_var;            // x-pass kernel: 4 = xpass4 (small innermost radix), 5 = xpass4 with xpass3's radices, 3 = xpass3 (CHB_X_VAR)
+    int pf_dist;          // L2 prefetch distance of the FFT passes in CTAs (CHB_PF_DIST, 0 = off)
     int use_fft3;         // register-resident three-stage FFT kernels for the large sizes (CHB_FFT3=0 disables)
     cplx* A;        // NCCL mode only: send buffer of zTOx, [peer][3][np][nzB][nxB]
     cplx* Ar;       // z-padded velocity after zTOx, [src rank][3][np][nzB][nxB]
@@ -151,7 +156,8 @@ struct ScopedKernelTimer {
     const char* name;
     cudaEvent_t e0, e1;
     bool on;
-    ScopedKernelTimer(chb_handle_s* h_, const char* name_);
+    cudaStream_t st;
+    ScopedKernelTimer(chb_handle_s* h_, const char* name_, cudaStream_t st_ = nullptr);
     ~ScopedKernelTimer();
 };
 void chb_timer_flush(chb_handle_s* h);

@@ -180,6 +180,13 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
     } while (!ok);
 }
 
+// L2 prefetch of a contiguous range (cp.async.bulk.prefetch.L2, SASS UBLKPF): one instruction, no
+// destination; used to pull the tile of a CTA that will run a few hundred CTAs later into L2 so that
+// HBM keeps streaming while the resident CTAs are in their compute phases.
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+
 // ---- per-thread 16-byte asynchronous copies global -> shared (cp.async, SASS LDGSTS) ------------
 __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");

@@ -91,6 +91,10 @@ __device__ __forceinline__ void lu_row(Row5& r, LUState& st, double& inv, double
 }
 
 // ---------------------------------------------------------------------------------------------
+// COMP = 0: eta equation (etamat), COMP = 1: v equation (D2vmat); blockIdx.y selects nothing, the
+// two components are separate launches of the same grid so that each thread carries one recurrence
+// (half the registers, twice the resident warps).
+template <int COMP>
 __global__ void __launch_bounds__(SOLVE_THREADS)
 solve_s1_kernel(cplx* __restrict__ rhs, double* __restrict__ ckpt, Geometry g, DevTables tab,
                 const DevScalars* __restrict__ sc, double lam) {
@@ -106,71 +110,59 @@ solve_s1_kernel(cplx* __restrict__ rhs, double* __restrict__ ckpt, Geometry g, D
     const size_t plane = (size_t)g.M, comp = (size_t)g.nyp * plane;
     // wall data: only the mean mode carries non-zero BCs (bc%eta = u0 / uN), linsolve_blocking.inc:17,31
     double bc0_eta = 0.0, bcn_eta = 0.0;
-    if (mean) {
+    if (COMP == 0 && mean) {
         bc0_eta = sc->u0;
         bcn_eta = sc->uN;
     }
-    LUState sv = {0, 0, 0, 0}, se = {0, 0, 0, 0};
-    cplx xv1 = make_double2(0, 0), xv2 = xv1, xe1 = xv1, xe2 = xv1;  // x(i+1), x(i+2)
+    const double* bcn = COMP ? tab.vnbc : tab.etanbc;
+    const double* bcnp1 = COMP ? tab.vnp1bc : tab.etanp1bc;
+    const double* bc0 = COMP ? tab.v0bc : tab.eta0bc;
+    const double* bc0m1 = COMP ? tab.v0m1bc : tab.eta0m1bc;
+    cplx* __restrict__ col = rhs + COMP * comp + m;
+    LUState st = {0, 0, 0, 0};
+    cplx x1 = make_double2(0, 0), x2 = x1;  // x(i+1), x(i+2)
     for (int iy = ny - 1; iy >= 1; --iy) {
         Row5 rv, re;
         build_rows(tab, iy, k2, lam, g.ni, rv, re);
-        const size_t off = (size_t)(iy + 1) * plane + m;
-        cplx be_ = rhs[0 * comp + off];  // eta rhs
-        cplx bv = rhs[1 * comp + off];   // D2v rhs
+        Row5& r = COMP ? rv : re;
+        const size_t off = (size_t)(iy + 1) * plane;
+        cplx b = col[off];
         if (iy == ny - 1) {
-            fold_top1(rv, tab.vnbc, tab.vnp1bc);
-            fold_top1(re, tab.etanbc, tab.etanp1bc);
-            const double cc = re.a[3] * bcn_eta / tab.etanbc[3];  // linsolve_blocking.inc:40
-            be_.x -= cc;
-            rv.a[3] = rv.a[4] = 0.0;  // rbparmat_blocking.f90:29
-            re.a[3] = re.a[4] = 0.0;
+            fold_top1(r, bcn, bcnp1);
+            if (COMP == 0) b.x -= r.a[3] * bcn_eta / tab.etanbc[3];  // linsolve_blocking.inc:40
+            r.a[3] = r.a[4] = 0.0;                                   // rbparmat_blocking.f90:29
         } else if (iy == ny - 2) {
-            fold_top2(rv, tab.vnbc);
-            fold_top2(re, tab.etanbc);
-            const double cc = re.a[4] * bcn_eta / tab.etanbc[3];  // :41
-            be_.x -= cc;
-            rv.a[4] = 0.0;
-            re.a[4] = 0.0;
+            fold_top2(r, bcn);
+            if (COMP == 0) b.x -= r.a[4] * bcn_eta / tab.etanbc[3];  // :41
+            r.a[4] = 0.0;
         }
         if (iy == 1) {
-            fold_bot1(rv, tab.v0bc, tab.v0m1bc);
-            fold_bot1(re, tab.eta0bc, tab.eta0m1bc);
-            const double cc = re.a[1] * bc0_eta / tab.eta0bc[1];  // :26
-            be_.x -= cc;
+            fold_bot1(r, bc0, bc0m1);
+            if (COMP == 0) b.x -= r.a[1] * bc0_eta / tab.eta0bc[1];  // :26
         } else if (iy == 2) {
-            fold_bot2(rv, tab.v0bc);
-            fold_bot2(re, tab.eta0bc);
-            const double cc = re.a[0] * bc0_eta / tab.eta0bc[1];  // :27
-            be_.x -= cc;
+            fold_bot2(r, bc0);
+            if (COMP == 0) b.x -= r.a[0] * bc0_eta / tab.eta0bc[1];  // :27
         }
         double inv, u1, u2;
-        lu_row(rv, sv, inv, u1, u2);
+        lu_row(r, st, inv, u1, u2);
         // LeftLU5divStep1 (rbparmat_blocking.f90:70-72)
-        cplx xv;
-        xv.x = (bv.x - (u1 * xv1.x + u2 * xv2.x)) * inv;
-        xv.y = (bv.y - (u1 * xv1.y + u2 * xv2.y)) * inv;
-        xv2 = xv1;
-        xv1 = xv;
-        lu_row(re, se, inv, u1, u2);
-        cplx xe;
-        xe.x = (be_.x - (u1 * xe1.x + u2 * xe2.x)) * inv;
-        xe.y = (be_.y - (u1 * xe1.y + u2 * xe2.y)) * inv;
-        xe2 = xe1;
-        xe1 = xe;
-        rhs[0 * comp + off] = xe;
-        rhs[1 * comp + off] = xv;
+        cplx x;
+        x.x = (b.x - (u1 * x1.x + u2 * x2.x)) * inv;
+        x.y = (b.y - (u1 * x1.y + u2 * x2.y)) * inv;
+        x2 = x1;
+        x1 = x;
+        col[off] = x;
         // The L-multipliers Step2 needs are not stored: the state of the UL recurrence is
         // checkpointed every SOLVE_K rows and solve_s2_kernel recomputes them block by block.
         if (iy > 1 && (iy - 1) % SOLVE_K == 0) {
-            double* ck = ckpt + ((size_t)((iy - 1) / SOLVE_K - 1) * 8) * plane + m;
-            ck[0 * plane] = sv.l1m2; ck[1 * plane] = sv.l1m1; ck[2 * plane] = sv.l2m2; ck[3 * plane] = sv.l2m1;
-            ck[4 * plane] = se.l1m2; ck[5 * plane] = se.l1m1; ck[6 * plane] = se.l2m2; ck[7 * plane] = se.l2m1;
+            double* ck = ckpt + ((size_t)((iy - 1) / SOLVE_K - 1) * 8 + (COMP ? 0 : 4)) * plane + m;
+            ck[0 * plane] = st.l1m2; ck[1 * plane] = st.l1m1; ck[2 * plane] = st.l2m2; ck[3 * plane] = st.l2m1;
         }
     }
 }
 
 // ---------------------------------------------------------------------------------------------
+template <int COMP>
 __global__ void __launch_bounds__(SOLVE_THREADS)
 solve_s2_kernel(const cplx* __restrict__ rhs, const double* __restrict__ ckpt, cplx* __restrict__ V, Geometry g,
                 DevTables tab, const DevScalars* __restrict__ sc, double lam) {
@@ -184,52 +176,55 @@ solve_s2_kernel(const cplx* __restrict__ rhs, const double* __restrict__ ckpt, c
     const bool mean = (ix == 0 && iz == 0);
     const int ny = g.ny;
     const size_t plane = (size_t)g.M, comp = (size_t)g.nyp * plane;
-    double bc0_eta = 0.0, bcn_eta = 0.0;
-    if (mean) {
-        bc0_eta = sc->u0;
-        bcn_eta = sc->uN;
+    double bc0_w = 0.0, bcn_w = 0.0;   // wall value of the unknown: bc%eta for the mean mode, else 0
+    if (COMP == 0 && mean) {
+        bc0_w = sc->u0;
+        bcn_w = sc->uN;
     }
-    cplx v1 = make_double2(0, 0), v2 = v1, v3 = v1, e1 = v1, e2 = v1, e3 = v1;  // b(i-1), b(i-2), b(i-3)
+    const double* bcn = COMP ? tab.vnbc : tab.etanbc;
+    const double* bcnp1 = COMP ? tab.vnp1bc : tab.etanp1bc;
+    const double* bc0 = COMP ? tab.v0bc : tab.eta0bc;
+    const double* bc0m1 = COMP ? tab.v0m1bc : tab.eta0m1bc;
+    const cplx* __restrict__ xin = rhs + COMP * comp + m;
+    cplx* __restrict__ out = V + COMP * comp + m;
+    cplx v1 = make_double2(0, 0), v2 = v1, v3 = v1;  // b(i-1), b(i-2), b(i-3)
     for (int i0 = 1; i0 <= ny - 1; i0 += SOLVE_K) {
         // ---- recompute the multipliers of rows i0..i0+K-1 (descending, as solve_s1 did) ----
-        LUState sv = {0, 0, 0, 0}, se = {0, 0, 0, 0};
+        LUState st = {0, 0, 0, 0};
         if (i0 + SOLVE_K <= ny - 1) {   // state after row i0+K was processed
-            const double* ck = ckpt + ((size_t)((i0 - 1) / SOLVE_K) * 8) * plane + m;
-            sv.l1m2 = ck[0 * plane]; sv.l1m1 = ck[1 * plane]; sv.l2m2 = ck[2 * plane]; sv.l2m1 = ck[3 * plane];
-            se.l1m2 = ck[4 * plane]; se.l1m1 = ck[5 * plane]; se.l2m2 = ck[6 * plane]; se.l2m1 = ck[7 * plane];
+            const double* ck = ckpt + ((size_t)((i0 - 1) / SOLVE_K) * 8 + (COMP ? 0 : 4)) * plane + m;
+            st.l1m2 = ck[0 * plane]; st.l1m1 = ck[1 * plane]; st.l2m2 = ck[2 * plane]; st.l2m1 = ck[3 * plane];
         }
-        double mv2[SOLVE_K], mv1[SOLVE_K], me2[SOLVE_K], me1[SOLVE_K];
+        // prefetch the Step1 results of this block while the multipliers are being recomputed
+        cplx xb[SOLVE_K];
+#pragma unroll
+        for (int k = 0; k < SOLVE_K; ++k) {
+            const int iy = i0 + k;
+            xb[k] = (iy <= ny - 1) ? xin[(size_t)(iy + 1) * plane] : make_double2(0.0, 0.0);
+        }
+        double m2[SOLVE_K], m1[SOLVE_K];
 #pragma unroll
         for (int k = SOLVE_K - 1; k >= 0; --k) {
             const int iy = i0 + k;
-            mv2[k] = mv1[k] = me2[k] = me1[k] = 0.0;
+            m2[k] = m1[k] = 0.0;
             if (iy <= ny - 1) {
                 Row5 rv, re;
                 build_rows(tab, iy, k2, lam, g.ni, rv, re);
+                Row5& r = COMP ? rv : re;
                 if (iy == ny - 1) {
-                    fold_top1(rv, tab.vnbc, tab.vnp1bc);
-                    fold_top1(re, tab.etanbc, tab.etanp1bc);
-                    rv.a[3] = rv.a[4] = 0.0;
-                    re.a[3] = re.a[4] = 0.0;
+                    fold_top1(r, bcn, bcnp1);
+                    r.a[3] = r.a[4] = 0.0;
                 } else if (iy == ny - 2) {
-                    fold_top2(rv, tab.vnbc);
-                    fold_top2(re, tab.etanbc);
-                    rv.a[4] = 0.0;
-                    re.a[4] = 0.0;
+                    fold_top2(r, bcn);
+                    r.a[4] = 0.0;
                 }
-                if (iy == 1) {
-                    fold_bot1(rv, tab.v0bc, tab.v0m1bc);
-                    fold_bot1(re, tab.eta0bc, tab.eta0m1bc);
-                } else if (iy == 2) {
-                    fold_bot2(rv, tab.v0bc);
-                    fold_bot2(re, tab.eta0bc);
-                }
+                if (iy == 1) fold_bot1(r, bc0, bc0m1);
+                else if (iy == 2) fold_bot2(r, bc0);
                 double inv, u1, u2;
-                lu_row(rv, sv, inv, u1, u2);
-                lu_row(re, se, inv, u1, u2);
+                lu_row(r, st, inv, u1, u2);
                 // rbparmat_blocking.f90:45 zeroes A(1,-2:-1), A(2,-2)
-                if (iy >= 3) { mv2[k] = sv.l1m2; me2[k] = se.l1m2; }
-                if (iy >= 2) { mv1[k] = sv.l1m1; me1[k] = se.l1m1; }
+                if (iy >= 3) m2[k] = st.l1m2;
+                if (iy >= 2) m1[k] = st.l1m1;
             }
         }
         // ---- LeftLU5divStep2 (rbparmat_blocking.f90:93-95), ascending ----
@@ -237,53 +232,42 @@ solve_s2_kernel(const cplx* __restrict__ rhs, const double* __restrict__ ckpt, c
         for (int k = 0; k < SOLVE_K; ++k) {
             const int iy = i0 + k;
             if (iy <= ny - 1) {
-                const size_t off = (size_t)(iy + 1) * plane + m;
-                cplx e = rhs[0 * comp + off], v = rhs[1 * comp + off];
-                v.x -= mv2[k] * v2.x + mv1[k] * v1.x;
-                v.y -= mv2[k] * v2.y + mv1[k] * v1.y;
-                e.x -= me2[k] * e2.x + me1[k] * e1.x;
-                e.y -= me2[k] * e2.y + me1[k] * e1.y;
-                V[0 * comp + off] = e;
-                V[1 * comp + off] = v;
+                cplx v = xb[k];
+                v.x -= m2[k] * v2.x + m1[k] * v1.x;
+                v.y -= m2[k] * v2.y + m1[k] * v1.y;
+                out[(size_t)(iy + 1) * plane] = v;
                 v3 = v2; v2 = v1; v1 = v;
-                e3 = e2; e2 = e1; e1 = e;
                 if (iy == 3) {  // bottom closure needs nodes 1..3 (linsolve_blocking.inc:51-54)
-                    const cplx a1 = v3, a2 = v2, a3 = v1, b1 = e3, b2 = e2, b3 = e1;
-                    const double* v0bc = tab.v0bc; const double* v0m1 = tab.v0m1bc;
-                    const double* e0bc = tab.eta0bc; const double* e0m1 = tab.eta0m1bc;
-                    cplx vw, vg, ew, eg;
-                    vw.x = (0.0 - (a1.x * v0bc[2] + a2.x * v0bc[3] + a3.x * v0bc[4])) / v0bc[1];
-                    vw.y = (0.0 - (a1.y * v0bc[2] + a2.y * v0bc[3] + a3.y * v0bc[4])) / v0bc[1];
-                    vg.x = (0.0 - (vw.x * v0m1[1] + a1.x * v0m1[2] + a2.x * v0m1[3] + a3.x * v0m1[4])) / v0m1[0];
-                    vg.y = (0.0 - (vw.y * v0m1[1] + a1.y * v0m1[2] + a2.y * v0m1[3] + a3.y * v0m1[4])) / v0m1[0];
-                    ew.x = (bc0_eta - (b1.x * e0bc[2] + b2.x * e0bc[3] + b3.x * e0bc[4])) / e0bc[1];
-                    ew.y = (0.0 - (b1.y * e0bc[2] + b2.y * e0bc[3] + b3.y * e0bc[4])) / e0bc[1];
-                    eg.x = -(ew.x * e0m1[1] + b1.x * e0m1[2] + b2.x * e0m1[3] + b3.x * e0m1[4]) / e0m1[0];
-                    eg.y = -(ew.y * e0m1[1] + b1.y * e0m1[2] + b2.y * e0m1[3] + b3.y * e0m1[4]) / e0m1[0];
-                    V[0 * comp + 1 * plane + m] = ew;
-                    V[0 * comp + 0 * plane + m] = eg;
-                    V[1 * comp + 1 * plane + m] = vw;
-                    V[1 * comp + 0 * plane + m] = vg;
+                    const cplx a1 = v3, a2 = v2, a3 = v1;
+                    cplx vw, vg;
+                    vw.x = (bc0_w - (a1.x * bc0[2] + a2.x * bc0[3] + a3.x * bc0[4])) / bc0[1];
+                    vw.y = (0.0 - (a1.y * bc0[2] + a2.y * bc0[3] + a3.y * bc0[4])) / bc0[1];
+                    if (COMP) {
+                        vg.x = (0.0 - (vw.x * bc0m1[1] + a1.x * bc0m1[2] + a2.x * bc0m1[3] + a3.x * bc0m1[4])) / bc0m1[0];
+                        vg.y = (0.0 - (vw.y * bc0m1[1] + a1.y * bc0m1[2] + a2.y * bc0m1[3] + a3.y * bc0m1[4])) / bc0m1[0];
+                    } else {
+                        vg.x = -(vw.x * bc0m1[1] + a1.x * bc0m1[2] + a2.x * bc0m1[3] + a3.x * bc0m1[4]) / bc0m1[0];
+                        vg.y = -(vw.y * bc0m1[1] + a1.y * bc0m1[2] + a2.y * bc0m1[3] + a3.y * bc0m1[4]) / bc0m1[0];
+                    }
+                    out[1 * plane] = vw;
+                    out[0 * plane] = vg;
                 }
             }
         }
     }
     {  // top closure (linsolve_blocking.inc:57-60): nodes ny-3..ny-1 = v3,v2,v1
-        const double* vnbc = tab.vnbc; const double* vnp1 = tab.vnp1bc;
-        const double* enbc = tab.etanbc; const double* enp1 = tab.etanp1bc;
-        cplx vw, vg, ew, eg;
-        vw.x = (0.0 - (v3.x * vnbc[0] + v2.x * vnbc[1] + v1.x * vnbc[2])) / vnbc[3];
-        vw.y = (0.0 - (v3.y * vnbc[0] + v2.y * vnbc[1] + v1.y * vnbc[2])) / vnbc[3];
-        vg.x = (0.0 - (v3.x * vnp1[0] + v2.x * vnp1[1] + v1.x * vnp1[2] + vw.x * vnp1[3])) / vnp1[4];
-        vg.y = (0.0 - (v3.y * vnp1[0] + v2.y * vnp1[1] + v1.y * vnp1[2] + vw.y * vnp1[3])) / vnp1[4];
-        ew.x = (bcn_eta - (e3.x * enbc[0] + e2.x * enbc[1] + e1.x * enbc[2])) / enbc[3];
-        ew.y = (0.0 - (e3.y * enbc[0] + e2.y * enbc[1] + e1.y * enbc[2])) / enbc[3];
-        eg.x = -(e3.x * enp1[0] + e2.x * enp1[1] + e1.x * enp1[2] + ew.x * enp1[3]) / enp1[4];
-        eg.y = -(e3.y * enp1[0] + e2.y * enp1[1] + e1.y * enp1[2] + ew.y * enp1[3]) / enp1[4];
-        V[0 * comp + (size_t)(ny + 1) * plane + m] = ew;
-        V[0 * comp + (size_t)(ny + 2) * plane + m] = eg;
-        V[1 * comp + (size_t)(ny + 1) * plane + m] = vw;
-        V[1 * comp + (size_t)(ny + 2) * plane + m] = vg;
+        cplx vw, vg;
+        vw.x = (bcn_w - (v3.x * bcn[0] + v2.x * bcn[1] + v1.x * bcn[2])) / bcn[3];
+        vw.y = (0.0 - (v3.y * bcn[0] + v2.y * bcn[1] + v1.y * bcn[2])) / bcn[3];
+        if (COMP) {
+            vg.x = (0.0 - (v3.x * bcnp1[0] + v2.x * bcnp1[1] + v1.x * bcnp1[2] + vw.x * bcnp1[3])) / bcnp1[4];
+            vg.y = (0.0 - (v3.y * bcnp1[0] + v2.y * bcnp1[1] + v1.y * bcnp1[2] + vw.y * bcnp1[3])) / bcnp1[4];
+        } else {
+            vg.x = -(v3.x * bcnp1[0] + v2.x * bcnp1[1] + v1.x * bcnp1[2] + vw.x * bcnp1[3]) / bcnp1[4];
+            vg.y = -(v3.y * bcnp1[0] + v2.y * bcnp1[1] + v1.y * bcnp1[2] + vw.y * bcnp1[3]) / bcnp1[4];
+        }
+        out[(size_t)(ny + 1) * plane] = vw;
+        out[(size_t)(ny + 2) * plane] = vg;
     }
 }
 
@@ -523,11 +507,24 @@ void launch_linsolve(chb_handle_s* h, double lam) {
     const int blocks = (int)((g.M + SOLVE_THREADS - 1) / SOLVE_THREADS);
     {
         ScopedKernelTimer tm(h, "solve_s1");
-        solve_s1_kernel<<<blocks, SOLVE_THREADS, 0, h->stream>>>(h->rhs, h->ckpt, g, h->tab, h->sc, lam);
+        solve_s1_kernel<0><<<blocks, SOLVE_THREADS, 0, h->stream>>>(h->rhs, h->ckpt, g, h->tab, h->sc, lam);
+        solve_s1_kernel<1><<<blocks, SOLVE_THREADS, 0, h->stream>>>(h->rhs, h->ckpt, g, h->tab, h->sc, lam);
     }
     {
         ScopedKernelTimer tm(h, "solve_s2");
-        solve_s2_kernel<<<blocks, SOLVE_THREADS, 0, h->stream>>>(h->rhs, h->ckpt, h->V, g, h->tab, h->sc, lam);
+        solve_s2_kernel<0><<<blocks, SOLVE_THREADS, 0, h->stream>>>(h->rhs, h->ckpt, h->V, g, h->tab, h->sc, lam);
+        solve_s2_kernel<1><<<blocks, SOLVE_THREADS, 0, h->stream>>>(h->rhs, h->ckpt, h->V, g, h->tab, h->sc, lam);
+    }
+    h->launches += 6;
+    // The mean column (0,0) only needs the result of S2 and is skipped by S3/S4: finish it on the
+    // side stream while S3/S4 run (it is a single-thread recurrence, linsolve_blocking.inc:62-97).
+    const bool mean_here = (g.nx0 == 0);
+    if (mean_here) {
+        cudaEventRecord(h->ev_fork, h->stream);
+        cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0);
+        ScopedKernelTimer tm(h, "mean_mode", h->side_stream);
+        mean_mode_kernel<<<1, 32, 0, h->side_stream>>>(h->V, g, h->tab, h->sc, lam, h->mean_scratch);
+        h->launches++;
     }
     {
         ScopedKernelTimer tm(h, "solve_s3");
@@ -537,11 +534,9 @@ void launch_linsolve(chb_handle_s* h, double lam) {
         ScopedKernelTimer tm(h, "solve_s4");
         solve_s4_kernel<<<blocks, SOLVE_THREADS, 0, h->stream>>>(h->V, g, h->tab);
     }
-    h->launches += 4;
-    if (g.nx0 == 0) {
-        ScopedKernelTimer tm(h, "mean_mode");
-        mean_mode_kernel<<<1, 32, 0, h->stream>>>(h->V, g, h->tab, h->sc, lam, h->mean_scratch);
-        h->launches++;
+    if (mean_here) {
+        cudaEventRecord(h->ev_join, h->side_stream);
+        cudaStreamWaitEvent(h->stream, h->ev_join, 0);
     }
 }
 

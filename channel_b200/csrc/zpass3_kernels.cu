@@ -173,6 +173,216 @@ zbwd3_kernel(const cplx* __restrict__ Br, cplx* __restrict__ P, Geometry g, cons
     }
 }
 
+
+// x[p] *= w1^p, p = 1..R-1, sequential recurrence (low register pressure)
+template <int R>
+__device__ __forceinline__ void z_twiddle_seq(cplx* x, cplx w1) {
+    cplx wp = w1;
+    x[1] = cmul(x[1], wp);
+    static_for<R - 2>([&](auto i_) {
+        constexpr int p = decltype(i_)::value + 2;
+        wp = cmul(wp, w1);
+        x[p] = cmul(x[p], wp);
+    });
+}
+
+// ---------------------------------------------------------------------------------------------
+// zfwd4 / zbwd4: the same three stages with TPL (a multiple of 32) threads per line and
+// block-wide barriers between stages, sized so that MINB CTAs are resident per SM: while one CTA
+// waits for its lines to arrive from HBM another one computes.
+template <class G, int LPC, int TPL, int MINB>
+__global__ void __launch_bounds__(LPC * TPL, MINB)
+zfwd4_kernel(const cplx* __restrict__ V, PeerPtrs Aw, Geometry g, const cplx* __restrict__ W, int plane0, int np,
+             int LS, int pf_dist) {
+    extern __shared__ cplx smem[];
+    constexpr int BCP = G::BC + 1;
+    static_assert(TPL % G::C == 0, "stage-B twiddle must be a per-thread constant");
+    const int tl = threadIdx.x % TPL, wl = threadIdx.x / TPL;
+    const int ixl0 = blockIdx.x * LPC;
+    const int pli = blockIdx.y, comp = blockIdx.z;
+    const int iyp = plane0 + pli;
+    const int nz = g.nz;
+    __shared__ unsigned long long mbar[LPC];
+    {   // ---- stage A, line-major; the V line is staged by TMA bulk copies into the in-place layout
+        const cplx* __restrict__ src = V + (((size_t)comp * g.nyp + iyp) * g.nxB + ixl0 + wl) * g.nzt;
+        cplx* sm = smem + wl * LS;
+        if (threadIdx.x == 32 && pf_dist > 0) {   // L2 prefetch of the LPC lines of the CTA pf_dist ahead in launch order
+            const long long id = blockIdx.x + (long long)gridDim.x * (blockIdx.y + (long long)gridDim.y * blockIdx.z) + pf_dist;
+            const int bx = (int)(id % gridDim.x), by = (int)((id / gridDim.x) % gridDim.y), bz = (int)(id / ((long long)gridDim.x * gridDim.y));
+            if (bz < (int)gridDim.z)
+                bulk_prefetch_l2(V + (((size_t)bz * g.nyp + plane0 + by) * g.nxB + (size_t)bx * LPC) * g.nzt,
+                                 (unsigned)(LPC * g.nzt * sizeof(cplx)));
+        }
+        if (tl == 0) {
+            mbar_init(&mbar[wl], 1);
+            mbar_expect_tx(&mbar[wl], (unsigned)(g.nzt * sizeof(cplx)));
+            for (int a = 0; a < G::A; ++a) {
+                const int lo = a * G::BC, hi = lo + G::BC - 1;
+                const int h1 = min(hi, nz);                    // rows 1..nz+1        <- V(iy,0:nz)
+                if (h1 >= lo) bulk_g2s(sm + a * BCP, src + nz + lo, (unsigned)((h1 - lo + 1) * sizeof(cplx)), &mbar[wl]);
+                const int l2 = max(lo, G::N - nz);             // rows nzd-nz+1..nzd  <- V(iy,-nz:-1)
+                if (hi >= l2)
+                    bulk_g2s(sm + a * BCP + (l2 - lo), src + (l2 - (G::N - nz)), (unsigned)((hi - l2 + 1) * sizeof(cplx)),
+                             &mbar[wl]);
+            }
+        }
+        __syncthreads();
+        mbar_wait(&mbar[wl], 0);
+#pragma unroll 1
+        for (int t1 = tl; t1 < G::BC; t1 += TPL) {
+            cplx x[G::A];
+            static_for<G::A>([&](auto a_) {
+                constexpr int a = decltype(a_)::value;
+                const int n = a * G::BC + t1;
+                x[a] = (n <= nz || n >= G::N - nz) ? sm[a * BCP + t1] : make_double2(0.0, 0.0);
+            });
+            Dft<G::A, +1>::run(x);
+            if (t1 != 0) z_twiddle_seq<G::A>(x, ctw<+1>(W, t1));
+            static_for<G::A>([&](auto ka_) {
+                constexpr int ka = decltype(ka_)::value;
+                sm[ka * BCP + t1] = x[ka];
+            });
+        }
+    }
+    __syncthreads();
+    {   // ---- stage B, line-major, in place
+        cplx* sm = smem + wl * LS;
+        const int cc = tl % G::C;
+        const cplx w1 = ctw<+1>(W, G::A * cc);
+#pragma unroll 1
+        for (int u = tl; u < G::A * G::C; u += TPL) {
+            cplx* base = sm + (u / G::C) * BCP + cc;
+            cplx x[G::B];
+            static_for<G::B>([&](auto b_) { constexpr int b = decltype(b_)::value; x[b] = base[b * G::C]; });
+            Dft<G::B, +1>::run(x);
+            if (cc != 0) z_twiddle_seq<G::B>(x, w1);
+            static_for<G::B>([&](auto b_) { constexpr int b = decltype(b_)::value; base[b * G::C] = x[b]; });
+        }
+    }
+    __syncthreads();
+    {   // ---- stage C, cross-line: smem -> registers -> global (x-contiguous, per destination rank)
+        const int l = threadIdx.x % LPC, q = threadIdx.x / LPC;
+        const cplx* sm = smem + l * LS;
+        const int nzB = g.nzB, nxB = g.nxB;
+        const bool multi = g.nranks > 1;
+#pragma unroll 1
+        for (int t = q; t < G::AB; t += TPL) {
+            const cplx* base = sm + (t % G::A) * BCP + (t / G::A) * G::C;
+            cplx x[G::C];
+            static_for<G::C>([&](auto c_) { constexpr int c = decltype(c_)::value; x[c] = base[c]; });
+            Dft<G::C, +1>::run(x);
+            static_for<G::C>([&](auto kc_) {
+                constexpr int kc = decltype(kc_)::value;
+                const int k = t + G::AB * kc;
+                const int peer = multi ? k / nzB : 0;
+                cplx* dst = multi ? Aw.p[peer] : Aw.p[0];
+                dst[chb_buf_index(g.rank, 3, comp, np, pli, nzB, k - peer * nzB, nxB, ixl0 + l)] = x[kc];
+            });
+        }
+    }
+}
+
+template <class G, int LPC, int TPL, int MINB>
+__global__ void __launch_bounds__(LPC * TPL, MINB)
+zbwd4_kernel(const cplx* __restrict__ Br, cplx* __restrict__ P, Geometry g, const cplx* __restrict__ W, int plane0, int np,
+             int LS, int pf_dist) {
+    extern __shared__ cplx smem[];
+    constexpr int BCP = G::BC + 1;
+    static_assert(TPL % G::C == 0, "stage-B twiddle must be a per-thread constant");
+    const int tl = threadIdx.x % TPL, wl = threadIdx.x / TPL;
+    const int ixl0 = blockIdx.x * LPC;
+    const int pli = blockIdx.y, comp = blockIdx.z;  // product index 0..5
+    const int iyp = plane0 + pli;
+    const int nz = g.nz;
+    {   // ---- staging, cross-line: per-thread 16-byte cp.async straight into the in-place layout
+        const int l = threadIdx.x % LPC, q = threadIdx.x / LPC;
+        cplx* sml = smem + l * LS;
+        const int nzB = g.nzB, nxB = g.nxB;
+        const bool multi = g.nranks > 1;
+        if (threadIdx.x < g.nranks && pf_dist > 0 && (1 << g.tw) == LPC) {
+            // L2 prefetch of the (contiguous, one piece per source rank) tile of the CTA pf_dist ahead
+            const long long id = blockIdx.x + (long long)gridDim.x * (blockIdx.y + (long long)gridDim.y * blockIdx.z) + pf_dist;
+            const int bx = (int)(id % gridDim.x), by = (int)((id / gridDim.x) % gridDim.y), bz = (int)(id / ((long long)gridDim.x * gridDim.y));
+            if (bz < (int)gridDim.z)
+                bulk_prefetch_l2(Br + chb_bufB_index(threadIdx.x, 6, bz, np, by, nzB, 0, nxB, bx * LPC, g.tw),
+                                 (unsigned)(nzB * LPC * sizeof(cplx)));
+        }
+#pragma unroll 4
+        for (int n = q; n < G::N; n += TPL) {
+            const int peer = multi ? n / nzB : 0;
+            cp_async16(sml + (n / G::BC) * BCP + (n % G::BC),
+                       Br + chb_bufB_index(peer, 6, comp, np, pli, nzB, n - peer * nzB, nxB, ixl0 + l, g.tw));
+        }
+        cp_async_wait_all();
+    }
+    __syncthreads();
+    cplx* sm = smem + wl * LS;
+    // ---- stage A, line-major, in place
+#pragma unroll 1
+    for (int t1 = tl; t1 < G::BC; t1 += TPL) {
+        cplx x[G::A];
+        static_for<G::A>([&](auto a_) { constexpr int a = decltype(a_)::value; x[a] = sm[a * BCP + t1]; });
+        Dft<G::A, -1>::run(x);
+        if (t1 != 0) z_twiddle_seq<G::A>(x, ctw<-1>(W, t1));
+        static_for<G::A>([&](auto ka_) { constexpr int ka = decltype(ka_)::value; sm[ka * BCP + t1] = x[ka]; });
+    }
+    __syncthreads();
+    {   // ---- stage B, line-major, in place
+        const int cc = tl % G::C;
+        const cplx w1 = ctw<-1>(W, G::A * cc);
+#pragma unroll 1
+        for (int u = tl; u < G::A * G::C; u += TPL) {
+            cplx* base = sm + (u / G::C) * BCP + cc;
+            cplx x[G::B];
+            static_for<G::B>([&](auto b_) { constexpr int b = decltype(b_)::value; x[b] = base[b * G::C]; });
+            Dft<G::B, -1>::run(x);
+            if (cc != 0) z_twiddle_seq<G::B>(x, w1);
+            static_for<G::B>([&](auto b_) { constexpr int b = decltype(b_)::value; base[b * G::C] = x[b]; });
+        }
+    }
+    __syncthreads();
+    {   // ---- stage C, line-major: smem -> registers -> global (z-contiguous, truncated to -nz..nz)
+        cplx* __restrict__ dst = P + (((size_t)comp * g.nyp + iyp) * g.nxB + ixl0 + wl) * g.nzt;
+#pragma unroll 1
+        for (int t = tl; t < G::AB; t += TPL) {
+            const cplx* base = sm + (t % G::A) * BCP + (t / G::A) * G::C;
+            cplx x[G::C];
+            static_for<G::C>([&](auto c_) { constexpr int c = decltype(c_)::value; x[c] = base[c]; });
+            Dft<G::C, -1>::run(x);
+            static_for<G::C>([&](auto kc_) {
+                constexpr int kc = decltype(kc_)::value;
+                const int k = t + G::AB * kc;                     // izd(iz) = k  (dnsdata.f90:156)
+                if (k <= nz) dst[nz + k] = x[kc];
+                else if (k >= G::N - nz) dst[k - (G::N - nz)] = x[kc];
+            });
+        }
+    }
+}
+
+template <class G, int LPC, int TPL, int MINB>
+static bool launch_z4(chb_handle_s* h, int plane0, int nplanes, bool fwd) {
+    constexpr int BCP = G::BC + 1;
+    int LS = G::A * BCP;
+    const int want = (LPC == 8) ? 1 : (LPC == 4 ? 2 : 4);   // line stride mod 8 that keeps the cross-line accesses conflict-free
+    while (LS % 8 != want) ++LS;
+    const size_t smem = (size_t)LPC * LS * sizeof(cplx);
+    if (h->g.nxB % LPC != 0) return false;
+    dim3 grid(h->g.nxB / LPC, nplanes, fwd ? 3 : 6);
+    if (fwd) {
+        cudaFuncSetAttribute(zfwd4_kernel<G, LPC, TPL, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(zfwd4_kernel<G, LPC, TPL, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        ScopedKernelTimer tm(h, "zfwd");
+        zfwd4_kernel<G, LPC, TPL, MINB><<<grid, LPC * TPL, smem, h->stream>>>(h->V, h->Aw, h->g, h->Wz, plane0, h->chunk_planes, LS, h->pf_dist);
+    } else {
+        cudaFuncSetAttribute(zbwd4_kernel<G, LPC, TPL, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(zbwd4_kernel<G, LPC, TPL, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        ScopedKernelTimer tm(h, "zbwd");
+        zbwd4_kernel<G, LPC, TPL, MINB><<<grid, LPC * TPL, smem, h->stream>>>(h->Br, h->P, h->g, h->Wz, plane0, h->chunk_planes, LS, h->pf_dist);
+    }
+    h->launches++;
+    return true;
+}
+
 // ---------------------------------------------------------------------------------------------
 template <class G, int LPC>
 static bool launch_z3(chb_handle_s* h, int plane0, int nplanes, bool fwd) {
@@ -203,6 +413,14 @@ static bool launch_z3(chb_handle_s* h, int plane0, int nplanes, bool fwd) {
 bool launch_z3_fwd_or_bwd(chb_handle_s* h, int plane0, int nplanes, bool fwd) {
     if (h->g.nz < 2) return false;
     const int lpc = h->z_lines_per_cta;
+    if (h->z_var == 4) {   // lpc is 4 here (chb_create)
+        switch (h->g.nzd) {
+            case 768: return launch_z4<Fft3<768, 12, 8, 8>, 4, 64, 4>(h, plane0, nplanes, fwd);
+            case 1536: return launch_z4<Fft3<1536, 12, 16, 8>, 4, 64, 2>(h, plane0, nplanes, fwd);
+            case 3072: return launch_z4<Fft3<3072, 12, 16, 16>, 4, 64, 1>(h, plane0, nplanes, fwd);
+            default: return false;
+        }
+    }
     switch (h->g.nzd) {
         case 768:
             return lpc == 4 ? launch_z3<Fft3<768, 12, 8, 8>, 4>(h, plane0, nplanes, fwd)

@@ -24,10 +24,16 @@ GRIDS = [
 ]
 
 
-@pytest.mark.parametrize("lpc", ["8", "4"])
+# kernel variants: (CHB_Z_VAR, CHB_Z_LPC, CHB_X_VAR); the first one is the default path
+VARIANTS = [("4", "4", "4"), ("3", "8", "3"), ("3", "4", "6")]
+
+
+@pytest.mark.parametrize("zvar,lpc,xvar", VARIANTS)
 @pytest.mark.parametrize("nx,ny,nz", GRIDS)
-def test_fft3_products_and_step(nx, ny, nz, lpc, monkeypatch):
+def test_fft3_products_and_step(nx, ny, nz, zvar, lpc, xvar, monkeypatch):
+    monkeypatch.setenv("CHB_Z_VAR", zvar)
     monkeypatch.setenv("CHB_Z_LPC", lpc)
+    monkeypatch.setenv("CHB_X_VAR", xvar)
     p, o, ch, V0 = make_pair(nx, ny, nz, eps=5e-2)
     ch.cfl_prepass(); o.cfl_prepass()
     s = ch.get_step_scalars()
