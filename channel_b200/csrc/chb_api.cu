@@ -41,6 +41,7 @@ void chb_timer_flush(chb_handle_s* h) {
     if (h->timer.pending.empty()) return;
     cudaStreamSynchronize(h->stream);
     cudaStreamSynchronize(h->side_stream);
+    for (int L = 0; L < h->nlanes; ++L) cudaStreamSynchronize(h->lane[L].stream);
     for (auto& p : h->timer.pending) {
         float ms = 0;
         cudaEventElapsedTime(&ms, p.second.first, p.second.second);
@@ -128,6 +129,16 @@ int chb_bcast_scalars(chb_handle_s* h);
 
 extern "C" int chb_get_nccl_unique_id(char* id) { return chb_nccl_unique_id(id); }
 
+void chb_select_lane(chb_handle_s* h, int L) {
+    const Lane& ln = h->lane[L];
+    h->cur_lane = L;
+    h->cstream = ln.stream;
+    h->A = ln.A; h->Ar = ln.Ar; h->B = ln.B; h->Br = ln.Br;
+    h->Aw = ln.Aw; h->Bw = ln.Bw;
+    h->flags = ln.flags;
+    for (int q = 0; q < CHB_MAX_RANKS; ++q) h->peer_flags[q] = ln.peer_flags[q];
+}
+
 // ---- create / destroy ---------------------------------------------------------------------
 extern "C" int chb_create(chb_handle* out, int nx, int ny, int nz, int nxd, int nzd, double alfa0, double beta0,
                           double ni, double a, double ymin, double ymax, int rank, int nranks, const char* nccl_id,
@@ -163,21 +174,27 @@ extern "C" int chb_create(chb_handle* out, int nx, int ny, int nz, int nxd, int 
     g.dx = PI / (alfa0 * nxd); g.dz = 2.0 * PI / (beta0 * nzd); g.factor = 1.0 / (2.0 * nxd * nzd);  // :124
     h->device = device;
     {
-        const char* e = getenv("CHB_Z_LPC");
-        h->z_lines_per_cta = (e && atoi(e) == 4) ? 4 : 8;
-        e = getenv("CHB_Z_VAR");
-        h->z_var = (e && atoi(e) == 3) ? 3 : 4;
-        if (h->z_var == 4) h->z_lines_per_cta = 4;
-        e = getenv("CHB_PF_DIST");
-        h->pf_dist = e ? atoi(e) : 0;
-        e = getenv("CHB_X_VAR");
-        h->x_var = e ? atoi(e) : 4;
+        // lines per z-pass CTA.  zbwd: 2 for the long lines (4 CTAs/SM at nzd = 1536), else 4.  zfwd: 4
+        // (a warp's stores into the tiled velocity buffer are 512 contiguous bytes for any value).
+        const char* e = getenv("CHB_ZB_LPC");
+        h->zb_lines_per_cta = e ? atoi(e) : (nzd >= 1536 ? 2 : 4);
+        e = getenv("CHB_ZF_LPC");
+        h->zf_lines_per_cta = e ? atoi(e) : (nzd >= 3072 ? 2 : 4);
         e = getenv("CHB_FFT3");
         h->use_fft3 = (e && atoi(e) == 0) ? 0 : 1;
-        // x-tile of the products buffer = the lines one z-pass CTA transforms (transpose_index.h)
-        g.tw = (h->z_lines_per_cta == 4 && g.nxB % 4 == 0) ? 2 : ((g.nxB % 8 == 0) ? 3 : 0);
+        // x tiles of the work buffers (transpose_index.h): products 8 wide (128-byte store segments in
+        // the x-pass), velocities as wide as the lines of one zfwd CTA
+        g.tw = (g.nxB % 8 == 0) ? 3 : ((g.nxB % 4 == 0) ? 2 : 0);
         e = getenv("CHB_TW");
         if (e && (g.nxB % (1 << atoi(e)) == 0)) g.tw = atoi(e);
+        // single GPU: row-major (the x-pass reads whole 128-byte lines); multi GPU: tiled, so that the
+        // warps of zfwd store 512 contiguous bytes into peer HBM over NVLink
+        g.twa = -1;
+        if (nranks > 1)
+            for (int t = 1; t <= 3; ++t)
+                if ((1 << t) == h->zf_lines_per_cta && g.nxB % (1 << t) == 0) g.twa = t;
+        e = getenv("CHB_TWA");
+        if (e && (atoi(e) < 0 || g.nxB % (1 << atoi(e)) == 0)) g.twa = atoi(e);
     }
     h->launches = 0;
     h->tables_set = false;
@@ -203,31 +220,37 @@ extern "C" int chb_create(chb_handle* out, int nx, int ny, int nz, int nxd, int 
     if (dev_alloc(&h->V, 3 * fld) || dev_alloc(&h->rhs, 2 * fld) || dev_alloc(&h->oldrhs, 2 * fld) ||
         dev_alloc(&h->P, 6 * fld) || dev_alloc(&h->ckpt, (size_t)((ny - 1) / CHB_SOLVE_K + 1) * 8 * g.M))
         return 1;
-    // convolution work buffers: a chunk of planes sized to ~3 GB per buffer set
+    // convolution work buffers: chunks of planes, ~3 GB of buffers in total over the lanes
     {
         const char* e = getenv("CHB_P2P");
         h->p2p = (nranks > 1 && !(e && atoi(e) == 0)) ? 1 : 0;
+        e = getenv("CHB_LANES");
+        h->nlanes = (e && atoi(e) == 2) ? 2 : 1;   // two lanes measured no faster on 1 or 2 GPUs (kernels of one lane fill the GPU)
         const bool nccl_mode = nranks > 1 && !h->p2p;
         const size_t per_plane = (size_t)9 * nzd * g.nxB * sizeof(cplx) * (nccl_mode ? 2 : 1);
-        size_t np = (size_t)3 << 30;
+        size_t np = ((size_t)3 << 30) / h->nlanes;
         np /= per_plane;
         if (np < 1) np = 1;
-        if (np > (size_t)g.nyp) np = g.nyp;
+        if (np > (size_t)(g.nyp + h->nlanes - 1) / h->nlanes) np = (g.nyp + h->nlanes - 1) / h->nlanes;
         h->chunk_planes = (int)np;
         const size_t na = (size_t)3 * np * nzd * g.nxB, nb = (size_t)6 * np * nzd * g.nxB;
-        if (dev_alloc(&h->Ar, na) || dev_alloc(&h->Br, nb)) return 1;
-        h->A = h->B = nullptr;
-        h->flags = nullptr;
-        h->epoch = 0;
         h->n_ipc_opened = 0;
-        if (nccl_mode && (dev_alloc(&h->A, na) || dev_alloc(&h->B, nb))) return 1;
-        if (dev_alloc(&h->flags, (size_t)CHB_MAX_RANKS)) return 1;
-        // pack-side store targets (PeerPtrs): element for peer q at p[q] + index(block = rank, ...)
-        const ptrdiff_t blkA = (ptrdiff_t)(na / nranks), blkB = (ptrdiff_t)(nb / nranks);
-        for (int q = 0; q < nranks; ++q) {
-            h->Aw.p[q] = (nccl_mode ? h->A : h->Ar) + (ptrdiff_t)(q - rank) * blkA;
-            h->Bw.p[q] = (nccl_mode ? h->B : h->Br) + (ptrdiff_t)(q - rank) * blkB;
+        for (int L = 0; L < h->nlanes; ++L) {
+            Lane& ln = h->lane[L];
+            memset(&ln, 0, sizeof(ln));
+            CHB_CUDA_OK(cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking));
+            CHB_CUDA_OK(cudaEventCreateWithFlags(&ln.done, cudaEventDisableTiming));
+            if (dev_alloc(&ln.Ar, na) || dev_alloc(&ln.Br, nb)) return 1;
+            if (nccl_mode && (dev_alloc(&ln.A, na) || dev_alloc(&ln.B, nb))) return 1;
+            if (dev_alloc(&ln.flags, (size_t)CHB_MAX_RANKS)) return 1;
+            // pack-side store targets (PeerPtrs): element for peer q at p[q] + index(block = rank, ...)
+            const ptrdiff_t blkA = (ptrdiff_t)(na / nranks), blkB = (ptrdiff_t)(nb / nranks);
+            for (int q = 0; q < nranks; ++q) {
+                ln.Aw.p[q] = (nccl_mode ? ln.A : ln.Ar) + (ptrdiff_t)(q - rank) * blkA;
+                ln.Bw.p[q] = (nccl_mode ? ln.B : ln.Br) + (ptrdiff_t)(q - rank) * blkB;
+            }
         }
+        chb_select_lane(h, 0);
     }
     if (dev_alloc(&h->t_y, (size_t)g.nyp) || dev_alloc(&h->t_dy, (size_t)g.nyp) ||
         dev_alloc(&h->t_d0, (size_t)g.nyp * 5) || dev_alloc(&h->t_d1, (size_t)g.nyp * 5) ||
@@ -249,15 +272,20 @@ extern "C" int chb_create(chb_handle* out, int nx, int ny, int nz, int nxd, int 
 extern "C" int chb_destroy(chb_handle h) {
     if (!h) return 0;
     cudaSetDevice(h->device);
-    cudaStreamSynchronize(h->stream);
+    cudaDeviceSynchronize();
     chb_timer_flush(h);
     chb_nccl_destroy(h);
     cudaFree(h->V); cudaFree(h->rhs); cudaFree(h->oldrhs); cudaFree(h->P); cudaFree(h->ckpt);
     if (h->F) cudaFree(h->F);
     if (h->p2p) chb_p2p_teardown(h);
-    if (h->A) cudaFree(h->A);
-    if (h->B) cudaFree(h->B);
-    cudaFree(h->Ar); cudaFree(h->Br); cudaFree(h->flags);
+    for (int L = 0; L < h->nlanes; ++L) {
+        Lane& ln = h->lane[L];
+        if (ln.A) cudaFree(ln.A);
+        if (ln.B) cudaFree(ln.B);
+        cudaFree(ln.Ar); cudaFree(ln.Br); cudaFree(ln.flags);
+        cudaEventDestroy(ln.done);
+        cudaStreamDestroy(ln.stream);
+    }
     cudaFree(h->Wz); cudaFree(h->Wx); cudaFree(h->Wh); cudaFree(h->rev_z);
     cudaFree(h->t_y); cudaFree(h->t_dy); cudaFree(h->t_d0); cudaFree(h->t_d1); cudaFree(h->t_d2); cudaFree(h->t_d4);
     cudaFree(h->t_D0mat); cudaFree(h->mean_scratch); cudaFree(h->sc);
@@ -432,14 +460,24 @@ extern "C" int chb_set_body_force(chb_handle h) {
 static int convolutions_all(chb_handle h, int compute_cfl, bool products) {
     const Geometry& g = h->g;
     const int np = h->chunk_planes;
-    for (int p0 = 0; p0 < g.nyp; p0 += np) {
+    // fork: the lanes start after everything queued on the main stream (V complete)
+    CHB_CUDA_OK(cudaEventRecord(h->ev_fork, h->stream));
+    for (int L = 0; L < h->nlanes; ++L) CHB_CUDA_OK(cudaStreamWaitEvent(h->lane[L].stream, h->ev_fork, 0));
+    int c = 0;
+    for (int p0 = 0; p0 < g.nyp; p0 += np, ++c) {
         const int n = (p0 + np <= g.nyp) ? np : g.nyp - p0;
+        chb_select_lane(h, c % h->nlanes);
         launch_zfwd(h, p0, n);                       // stores straight into the x-side owner's buffer
         if (chb_exchange(h, true)) return 1;         // zTOx, mpi_transpose.f90:50-83
         launch_xpass(h, p0, n, compute_cfl);
         // xTOz, mpi_transpose.f90:88-117; in direct mode the barrier also frees Ar for the next chunk
         if ((products || h->p2p) && chb_exchange(h, false)) return 1;
         if (products) launch_zbwd(h, p0, n);
+    }
+    // join
+    for (int L = 0; L < h->nlanes; ++L) {
+        CHB_CUDA_OK(cudaEventRecord(h->lane[L].done, h->lane[L].stream));
+        CHB_CUDA_OK(cudaStreamWaitEvent(h->stream, h->lane[L].done, 0));
     }
     CHB_CUDA_OK(cudaGetLastError());
     return 0;

@@ -46,6 +46,7 @@ struct Geometry {
     double alfa0, beta0, ni;
     double dx, dz, factor;
     int tw;         // log2 of the x-tile width of the products work buffer (transpose_index.h)
+    int twa;        // same for the velocity work buffer; < 0 = row-major
 };
 
 struct BodyForce {
@@ -66,6 +67,20 @@ struct PeerPtrs {
     cplx* p[CHB_MAX_RANKS];
 };
 
+// One pipeline of the nonlinear term: its own stream and pencil-transpose work buffers.  Chunks of
+// y-planes alternate between the lanes, so that the NVLink-bound pack kernels (zfwd, xpass stores
+// into peer HBM) and the FP64-bound x-pass of one chunk overlap the HBM-bound z-passes of another.
+#define CHB_MAX_LANES 2
+struct Lane {
+    cudaStream_t stream;
+    cplx *A, *Ar, *B, *Br;
+    PeerPtrs Aw, Bw;
+    unsigned long long* flags;
+    unsigned long long* peer_flags[CHB_MAX_RANKS];
+    unsigned long long epoch;
+    cudaEvent_t done;
+};
+
 struct KernelTimer {
     bool on = false;
     struct Rec { double ms = 0; long long n = 0; };
@@ -79,6 +94,9 @@ struct chb_handle_s {
     cudaStream_t stream;
     cudaStream_t side_stream;      // mean-mode column, concurrent with S3/S4 of the solve
     cudaEvent_t ev_fork, ev_join;
+    Lane lane[CHB_MAX_LANES];      // the fields A..epoch below are a copy of the lane in use (chb_select_lane)
+    int nlanes, cur_lane;          // CHB_LANES = 1 | 2
+    cudaStream_t cstream;          // stream of the lane in use
     // fields (device layout [c][iy+1][ixl][iz+nz], complex128)
     cplx* V;        // [3][nyp][M]
     cplx* rhs;      // [2][nyp][M]  0 = eta, 1 = D2v (also holds the Step1 result)
@@ -88,10 +106,7 @@ struct chb_handle_s {
     double* ckpt;   // [nblk][8][M]  UL-recurrence state every CHB_SOLVE_K rows (solve_kernels.cu)
     // convolution work buffers for a chunk of planes
     int chunk_planes;
-    int z_lines_per_cta;  // 4 or 8 (CHB_Z_LPC)
-    int z_var;            // 4 = zfwd4/zbwd4 (64 threads per line, 4 lines per CTA), 3 = zfwd3/zbwd3 (CHB_Z_VAR)
-    int x_var;            // x-pass kernel: 4 = xpass4 (small innermost radix), 5 = xpass4 with xpass3's radices, 3 = xpass3 (CHB_X_VAR)
-    int pf_dist;          // L2 prefetch distance of the FFT passes in CTAs (CHB_PF_DIST, 0 = off)
+    int zf_lines_per_cta, zb_lines_per_cta;  // lines per CTA of zfwd / zbwd (CHB_ZF_LPC, CHB_ZB_LPC: 2, 4 or 8)
     int use_fft3;         // register-resident three-stage FFT kernels for the large sizes (CHB_FFT3=0 disables)
     cplx* A;        // NCCL mode only: send buffer of zTOx, [peer][3][np][nzB][nxB]
     cplx* Ar;       // z-padded velocity after zTOx, [src rank][3][np][nzB][nxB]
@@ -102,7 +117,7 @@ struct chb_handle_s {
     unsigned long long* flags;             // [CHB_MAX_RANKS] barrier flags of this rank (IPC-shared)
     unsigned long long* peer_flags[CHB_MAX_RANKS];
     unsigned long long epoch;
-    void* ipc_opened[3 * CHB_MAX_RANKS];
+    void* ipc_opened[3 * CHB_MAX_RANKS * CHB_MAX_LANES];
     int n_ipc_opened;
     // FFT plans and tables
     FftPlan plan_z, plan_x;
@@ -148,7 +163,8 @@ void launch_force_ghosts(chb_handle_s* h);
 int chb_alltoall(chb_handle_s* h, const cplx* send, cplx* recv, size_t count_per_peer);
 int chb_p2p_setup(chb_handle_s* h, size_t na, size_t nb);   // maps peer Ar/Br/flags; 0 on success
 void chb_p2p_teardown(chb_handle_s* h);
-int chb_exchange(chb_handle_s* h, bool a_side);             // completes zTOx (a_side) / xTOz on the stream
+int chb_exchange(chb_handle_s* h, bool a_side);             // completes zTOx (a_side) / xTOz on the lane's stream
+void chb_select_lane(chb_handle_s* h, int lane);            // makes `lane` the one the conv launchers use
 
 // timing helpers
 struct ScopedKernelTimer {

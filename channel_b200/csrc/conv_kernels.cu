@@ -49,7 +49,7 @@ zfwd_kernel(const cplx* __restrict__ V, PeerPtrs Aw, Geometry g, FftPlan pl, con
         const int t = idx - izd * nl;
         const int peer = izd / g.nzB;
         const int izl = izd - peer * g.nzB;
-        Aw.p[peer][buf_index(g.rank, 3, c, np, pli, g.nzB, izl, g.nxB, ixl0 + t)] =
+        Aw.p[peer][chb_bufA_index(g.rank, c, np, pli, g.nzB, izl, g.nxB, ixl0 + t, g.twa)] =
             smem[(size_t)t * line_stride + CHB_PAD(__ldg(&rev[izd]))];
     }
 }
@@ -106,7 +106,7 @@ xpass_kernel(const cplx* __restrict__ Ar, PeerPtrs Bw, Geometry g, FftPlan pl, c
         cplx v = make_double2(0.0, 0.0);
         if (k <= nx) {
             const int q = k / nxB;
-            v = Ar[buf_index(q, 3, c, np, pli, nzB, izl0 + l, nxB, k - q * nxB)];
+            v = Ar[chb_bufA_index(q, c, np, pli, nzB, izl0 + l, nxB, k - q * nxB, g.twa)];
         }
         smem[(size_t)slot * line_stride + CHB_PAD(k)] = v;
     }
@@ -231,8 +231,8 @@ void launch_zfwd(chb_handle_s* h, int plane0, int nplanes) {
     z_config(h, &tx, &ls, &smem);
     cudaFuncSetAttribute(zfwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dim3 grid((h->g.nxB + tx - 1) / tx, nplanes, 3);
-    ScopedKernelTimer tm(h, "zfwd");
-    zfwd_kernel<<<grid, CONV_THREADS, smem, h->stream>>>(h->V, h->Aw, h->g, h->plan_z, h->Wz, h->rev_z, plane0,
+    ScopedKernelTimer tm(h, "zfwd", h->cstream);
+    zfwd_kernel<<<grid, CONV_THREADS, smem, h->cstream>>>(h->V, h->Aw, h->g, h->plan_z, h->Wz, h->rev_z, plane0,
                                                          h->chunk_planes, tx, ls);
     h->launches++;
 }
@@ -244,8 +244,8 @@ void launch_zbwd(chb_handle_s* h, int plane0, int nplanes) {
     z_config(h, &tx, &ls, &smem);
     cudaFuncSetAttribute(zbwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dim3 grid((h->g.nxB + tx - 1) / tx, nplanes, 6);
-    ScopedKernelTimer tm(h, "zbwd");
-    zbwd_kernel<<<grid, CONV_THREADS, smem, h->stream>>>(h->Br, h->P, h->g, h->plan_z, h->Wz, h->rev_z, plane0,
+    ScopedKernelTimer tm(h, "zbwd", h->cstream);
+    zbwd_kernel<<<grid, CONV_THREADS, smem, h->cstream>>>(h->Br, h->P, h->g, h->plan_z, h->Wz, h->rev_z, plane0,
                                                          h->chunk_planes, tx, ls);
     h->launches++;
 }
@@ -259,8 +259,8 @@ void launch_xpass(chb_handle_s* h, int plane0, int nplanes, int compute_cfl) {
     const size_t smem = (size_t)6 * lx * ls * sizeof(cplx);
     cudaFuncSetAttribute(xpass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dim3 grid(h->g.nzB / lx, nplanes);
-    ScopedKernelTimer tm(h, "xpass");
-    xpass_kernel<<<grid, CONV_THREADS, smem, h->stream>>>(h->Ar, h->Bw, h->g, h->plan_x, h->Wx, h->Wh, h->t_dy, h->sc,
+    ScopedKernelTimer tm(h, "xpass", h->cstream);
+    xpass_kernel<<<grid, CONV_THREADS, smem, h->cstream>>>(h->Ar, h->Bw, h->g, h->plan_x, h->Wx, h->Wh, h->t_dy, h->sc,
                                                           plane0, h->chunk_planes, lx, ls, compute_cfl);
     h->launches++;
 }

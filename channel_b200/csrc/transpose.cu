@@ -105,11 +105,11 @@ int chb_alltoall(chb_handle_s* h, const cplx* send, cplx* recv, size_t count) {
     const int P = h->g.nranks;
     const size_t per = count / P;
     ncclComm_t comm = (ncclComm_t)h->nccl_comm;
-    ScopedKernelTimer tm(h, "alltoall");
+    ScopedKernelTimer tm(h, "alltoall", h->cstream);
     NCCL_OK(g_nccl.GroupStart());
     for (int p = 0; p < P; ++p) {
-        NCCL_OK(g_nccl.Send(send + (size_t)p * per, per * 2, ncclDouble, p, comm, h->stream));
-        NCCL_OK(g_nccl.Recv(recv + (size_t)p * per, per * 2, ncclDouble, p, comm, h->stream));
+        NCCL_OK(g_nccl.Send(send + (size_t)p * per, per * 2, ncclDouble, p, comm, h->cstream));
+        NCCL_OK(g_nccl.Recv(recv + (size_t)p * per, per * 2, ncclDouble, p, comm, h->cstream));
     }
     NCCL_OK(g_nccl.GroupEnd());
     return 0;
@@ -144,37 +144,41 @@ int chb_p2p_setup(chb_handle_s* h, size_t na, size_t nb) {
     (void)na; (void)nb;
     const int P = h->g.nranks, r = h->g.rank;
     ncclComm_t comm = (ncclComm_t)h->nccl_comm;
-    IpcBundle mine;
-    CHB_CUDA_OK(cudaIpcGetMemHandle(&mine.ar, h->Ar));
-    CHB_CUDA_OK(cudaIpcGetMemHandle(&mine.br, h->Br));
-    CHB_CUDA_OK(cudaIpcGetMemHandle(&mine.flags, h->flags));
-    IpcBundle* d_all = nullptr;
-    CHB_CUDA_OK(cudaMalloc((void**)&d_all, sizeof(IpcBundle) * P));
-    CHB_CUDA_OK(cudaMemcpy(d_all + r, &mine, sizeof(IpcBundle), cudaMemcpyHostToDevice));
-    NCCL_OK(g_nccl.AllGather(d_all + r, d_all, sizeof(IpcBundle), ncclChar, comm, h->stream));
-    CHB_CUDA_OK(cudaStreamSynchronize(h->stream));
-    IpcBundle all[CHB_MAX_RANKS];
-    CHB_CUDA_OK(cudaMemcpy(all, d_all, sizeof(IpcBundle) * P, cudaMemcpyDeviceToHost));
-    cudaFree(d_all);
     h->n_ipc_opened = 0;
-    for (int q = 0; q < P; ++q) {
-        if (q == r) {
-            h->Aw.p[q] = h->Ar;
-            h->Bw.p[q] = h->Br;
-            h->peer_flags[q] = h->flags;
-            continue;
+    for (int L = 0; L < h->nlanes; ++L) {
+        Lane& ln = h->lane[L];
+        IpcBundle mine;
+        CHB_CUDA_OK(cudaIpcGetMemHandle(&mine.ar, ln.Ar));
+        CHB_CUDA_OK(cudaIpcGetMemHandle(&mine.br, ln.Br));
+        CHB_CUDA_OK(cudaIpcGetMemHandle(&mine.flags, ln.flags));
+        IpcBundle* d_all = nullptr;
+        CHB_CUDA_OK(cudaMalloc((void**)&d_all, sizeof(IpcBundle) * P));
+        CHB_CUDA_OK(cudaMemcpy(d_all + r, &mine, sizeof(IpcBundle), cudaMemcpyHostToDevice));
+        NCCL_OK(g_nccl.AllGather(d_all + r, d_all, sizeof(IpcBundle), ncclChar, comm, h->stream));
+        CHB_CUDA_OK(cudaStreamSynchronize(h->stream));
+        IpcBundle all[CHB_MAX_RANKS];
+        CHB_CUDA_OK(cudaMemcpy(all, d_all, sizeof(IpcBundle) * P, cudaMemcpyDeviceToHost));
+        cudaFree(d_all);
+        for (int q = 0; q < P; ++q) {
+            if (q == r) {
+                ln.Aw.p[q] = ln.Ar;
+                ln.Bw.p[q] = ln.Br;
+                ln.peer_flags[q] = ln.flags;
+                continue;
+            }
+            void *pa = nullptr, *pb = nullptr, *pf = nullptr;
+            CHB_CUDA_OK(cudaIpcOpenMemHandle(&pa, all[q].ar, cudaIpcMemLazyEnablePeerAccess));
+            h->ipc_opened[h->n_ipc_opened++] = pa;
+            CHB_CUDA_OK(cudaIpcOpenMemHandle(&pb, all[q].br, cudaIpcMemLazyEnablePeerAccess));
+            h->ipc_opened[h->n_ipc_opened++] = pb;
+            CHB_CUDA_OK(cudaIpcOpenMemHandle(&pf, all[q].flags, cudaIpcMemLazyEnablePeerAccess));
+            h->ipc_opened[h->n_ipc_opened++] = pf;
+            ln.Aw.p[q] = (cplx*)pa;
+            ln.Bw.p[q] = (cplx*)pb;
+            ln.peer_flags[q] = (unsigned long long*)pf;
         }
-        void *pa = nullptr, *pb = nullptr, *pf = nullptr;
-        CHB_CUDA_OK(cudaIpcOpenMemHandle(&pa, all[q].ar, cudaIpcMemLazyEnablePeerAccess));
-        h->ipc_opened[h->n_ipc_opened++] = pa;
-        CHB_CUDA_OK(cudaIpcOpenMemHandle(&pb, all[q].br, cudaIpcMemLazyEnablePeerAccess));
-        h->ipc_opened[h->n_ipc_opened++] = pb;
-        CHB_CUDA_OK(cudaIpcOpenMemHandle(&pf, all[q].flags, cudaIpcMemLazyEnablePeerAccess));
-        h->ipc_opened[h->n_ipc_opened++] = pf;
-        h->Aw.p[q] = (cplx*)pa;
-        h->Bw.p[q] = (cplx*)pb;
-        h->peer_flags[q] = (unsigned long long*)pf;
     }
+    chb_select_lane(h, 0);
     return 0;
 }
 
@@ -206,8 +210,8 @@ int chb_exchange(chb_handle_s* h, bool a_side) {
     if (h->p2p) {
         FlagPtrs fp;
         for (int q = 0; q < g.nranks; ++q) fp.p[q] = h->peer_flags[q];
-        ScopedKernelTimer tm(h, "p2p_barrier");
-        p2p_barrier_kernel<<<1, 32, 0, h->stream>>>(fp, h->flags, g.rank, g.nranks, ++h->epoch);
+        ScopedKernelTimer tm(h, "p2p_barrier", h->cstream);
+        p2p_barrier_kernel<<<1, 32, 0, h->cstream>>>(fp, h->flags, g.rank, g.nranks, ++h->lane[h->cur_lane].epoch);
         h->launches++;
         return 0;
     }

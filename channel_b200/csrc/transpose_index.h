@@ -27,6 +27,13 @@ CHB_HD size_t chb_bufB_index(int peer, int ncomp, int comp, int np, int pl, int 
            (ixl & ((1 << tw) - 1));
 }
 
+// The velocity buffer (z-pass -> x-pass, zTOx) uses the same tiling with its own tile width twa (the
+// lines one zfwd CTA transforms); twa < 0 selects the row-major layout [izl][ixl] of chb_buf_index.
+CHB_HD size_t chb_bufA_index(int peer, int comp, int np, int pl, int nzB, int izl, int nxB, int ixl, int twa) {
+    return twa < 0 ? chb_buf_index(peer, 3, comp, np, pl, nzB, izl, nxB, ixl)
+                   : chb_bufB_index(peer, 3, comp, np, pl, nzB, izl, nxB, ixl, twa);
+}
+
 // mpi_transpose.f90:214-215 with npy=1
 CHB_HD void chb_decompose(int nxp1, int nzd, int nranks, int rank, int* nx0, int* nxN, int* nz0, int* nzN) {
     *nx0 = rank * nxp1 / nranks;

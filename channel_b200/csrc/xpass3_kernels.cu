@@ -17,7 +17,6 @@
 // Shared memory per line: six buffers of A*(BC+1) complex (u,v,w, later the six products, in
 // place).  Per point and transform: two exchanges (backward) / two exchanges + the merge pass
 // (forward) through shared memory; global memory is touched once per input and output mode.
-#include <cstdlib>
 #include "chb_internal.h"
 #include "fft_regs.cuh"
 
@@ -33,195 +32,10 @@ __device__ __forceinline__ void apply_twiddle_seq(cplx* x, cplx w1) {
     });
 }
 
-template <class G, int LPC>
-__global__ void __launch_bounds__(LPC * (G::N / G::C))
-xpass3_kernel(const cplx* __restrict__ Ar, PeerPtrs Bw, Geometry g, const cplx* __restrict__ W,
-              const cplx* __restrict__ Wh, const double* __restrict__ dy, DevScalars* sc, int plane0, int np,
-              int compute_cfl) {
-    constexpr int M = G::N, A = G::A, B = G::B, C = G::C, BC = G::BC;
-    constexpr int T = M / C;           // threads per line = butterflies of the innermost stage
-    constexpr int BCP = BC + 1;
-    constexpr int LB = A * BCP;        // complex per buffer
-    extern __shared__ cplx smem[];
-    const int tl = threadIdx.x % T, l = threadIdx.x / T;
-    const int izl = blockIdx.x * LPC + l;
-    const int pli = blockIdx.y;
-    const int iy = plane0 + pli - 1;
-    const int nx = g.nx, nxB = g.nxB, nzB = g.nzB;
-    const bool multi = g.nranks > 1;
-    cplx* S = smem + (size_t)l * 6 * LB;
-
-    // ---- stage the input row (modes 0..nx of u,v,w; one contiguous piece per source rank) in the
-    //      buffers the products will use later: one TMA bulk copy per piece, one latency exposure
-    cplx* IN = S + 3 * LB;             // [comp][0..nx]
-    __shared__ unsigned long long mbar[LPC];
-    if (tl == 0) mbar_init(&mbar[l], 1);
-    __syncthreads();
-    if (tl == 0) {
-        const int P = g.nranks;
-        mbar_expect_tx(&mbar[l], (unsigned)(3 * (nx + 1) * sizeof(cplx)));
-        for (int comp = 0; comp < 3; ++comp)
-            for (int q = 0; q < P; ++q)
-                bulk_g2s(IN + comp * (nx + 1) + q * nxB, Ar + chb_buf_index(q, 3, comp, np, pli, nzB, izl, nxB, 0),
-                         (unsigned)(nxB * sizeof(cplx)), &mbar[l]);
-    }
-    mbar_wait(&mbar[l], 0);
-    // ---- backward stage A: split pass -> radix-A -> smem; tasks = (mode group t1, component) ------
-    for (int task = tl; task < 3 * BC; task += T) {
-        const int comp = task / BC, t1 = task - comp * BC;
-        const cplx wh1 = Wh[t1];   // exp(+i pi t1 / M)
-        const cplx w1 = W[t1];     // exp(+2 pi i t1 / M)
-        const cplx* X = IN + comp * (nx + 1);
-        cplx x[A];
-        static_for<A>([&](auto a_) {
-            constexpr int a = decltype(a_)::value;
-            const int n = a * BC + t1;
-            const int j = M - n;
-            cplx xa = make_double2(0.0, 0.0), xb = make_double2(0.0, 0.0);
-            if (n <= nx) xa = X[n];
-            if (j <= nx) xb = X[j];
-            if (a == 0 && t1 == 0) {
-                x[a] = make_double2(xa.x, xa.x);   // Z[0] = X0 + XM + i (X0 - XM), XM = 0, Im X0 ignored
-            } else {
-                const cplx s = make_double2(xa.x + xb.x, xa.y - xb.y);
-                const cplx d = make_double2(xa.x - xb.x, xa.y + xb.y);
-                const cplx t = cmul(mulw<2 * A, a, +1>(wh1), d);   // e^{i pi n/M} = e^{i pi t1/M} e^{i pi a/A}
-                x[a] = make_double2(s.x - t.y, s.y + t.x);
-            }
-        });
-        Dft<A, +1>::run(x);
-        if (t1 != 0) apply_twiddle_seq<A>(x, w1);
-        cplx* dst = S + comp * LB + t1;
-        static_for<A>([&](auto ka_) { constexpr int ka = decltype(ka_)::value; dst[ka * BCP] = x[ka]; });
-    }
-    __syncthreads();
-    // ---- backward stage B, in place ---------------------------------------------------------
-    {
-        const int cc = tl % C;
-        cplx wcp[B];
-        twiddle_powers<B>(W[A * cc], wcp);   // w_BC^(cc*kb), shared by the three components
-        for (int u = tl; u < A * C; u += T) {
-            cplx* base = S + (u / C) * BCP + cc;
-#pragma unroll 1
-            for (int comp = 0; comp < 3; ++comp) {
-                cplx x[B];
-                static_for<B>([&](auto b_) { constexpr int b = decltype(b_)::value; x[b] = base[comp * LB + b * C]; });
-                Dft<B, +1>::run(x);
-                if (cc != 0) static_for<B - 1>([&](auto i_) { constexpr int i = decltype(i_)::value + 1; x[i] = cmul(x[i], wcp[i]); });
-                static_for<B>([&](auto b_) { constexpr int b = decltype(b_)::value; base[comp * LB + b * C] = x[b]; });
-            }
-        }
-    }
-    __syncthreads();
-    // ---- backward stage C -> physical space -> CFL, products -> forward stage C --------------
-    {
-        const int ka = tl % A, kb = tl / A;
-        cplx* base = S + ka * BCP + kb * C;
-        cplx U[C], V[C], Wv[C];
-        static_for<C>([&](auto c_) {
-            constexpr int c = decltype(c_)::value;
-            U[c] = base[c];
-            V[c] = base[LB + c];
-            Wv[c] = base[2 * LB + c];
-        });
-        Dft<C, +1>::run(U);
-        Dft<C, +1>::run(V);
-        Dft<C, +1>::run(Wv);
-        if (compute_cfl) {   // dnsdata.f90:552-556 (block-uniform branch)
-            double cmax = 0.0;
-            if (iy >= 1 && iy <= g.ny - 1) {
-                const double rdx = 1.0 / g.dx, rdz = 1.0 / g.dz, rdy = 1.0 / dy[iy + 1];
-                static_for<C>([&](auto c_) {
-                    constexpr int c = decltype(c_)::value;
-                    cmax = fmax(cmax, fabs(U[c].x) * rdx + fabs(V[c].x) * rdy + fabs(Wv[c].x) * rdz);
-                    cmax = fmax(cmax, fabs(U[c].y) * rdx + fabs(V[c].y) * rdy + fabs(Wv[c].y) * rdz);
-                });
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) cmax = fmax(cmax, __shfl_xor_sync(0xffffffffu, cmax, o));
-            if ((threadIdx.x & 31) == 0 && cmax > 0.0)
-                atomicMax(&sc->cfl_bits, (unsigned long long)__double_as_longlong(cmax));
-        }
-        const double f = 0.5 * g.factor;       // the 1/2 of the merge pass is folded into the products
-        cplx wkp[C];
-        twiddle_powers<C>(ctw<-1>(W, A * kb), wkp);   // conj w_BC^(kb*c'), shared by the six products
-        auto forward_c = [&](cplx* x, int p) {
-            Dft<C, -1>::run(x);
-            if (kb != 0) static_for<C - 1>([&](auto i_) { constexpr int i = decltype(i_)::value + 1; x[i] = cmul(x[i], wkp[i]); });
-            static_for<C>([&](auto c_) { constexpr int c = decltype(c_)::value; base[p * LB + c] = x[c]; });
-        };
-        cplx x[C];
-        // slots (0..5) = (uu, vv, ww, uv, vw, uw) * factor                          dnsdata.f90:581-584
-        static_for<C>([&](auto c_) { constexpr int c = decltype(c_)::value; x[c] = make_double2(U[c].x * V[c].x * f, U[c].y * V[c].y * f); });
-        forward_c(x, 3);
-        static_for<C>([&](auto c_) { constexpr int c = decltype(c_)::value; x[c] = make_double2(V[c].x * Wv[c].x * f, V[c].y * Wv[c].y * f); });
-        forward_c(x, 4);
-        static_for<C>([&](auto c_) { constexpr int c = decltype(c_)::value; x[c] = make_double2(U[c].x * Wv[c].x * f, U[c].y * Wv[c].y * f); });
-        forward_c(x, 5);
-        static_for<C>([&](auto c_) { constexpr int c = decltype(c_)::value; U[c] = make_double2(U[c].x * U[c].x * f, U[c].y * U[c].y * f); });
-        forward_c(U, 0);
-        static_for<C>([&](auto c_) { constexpr int c = decltype(c_)::value; V[c] = make_double2(V[c].x * V[c].x * f, V[c].y * V[c].y * f); });
-        forward_c(V, 1);
-        static_for<C>([&](auto c_) { constexpr int c = decltype(c_)::value; Wv[c] = make_double2(Wv[c].x * Wv[c].x * f, Wv[c].y * Wv[c].y * f); });
-        forward_c(Wv, 2);
-    }
-    __syncthreads();
-    // ---- forward stage B, in place -----------------------------------------------------------
-    {
-        const int cc = tl % C;
-        for (int u = tl; u < A * C; u += T) {
-            cplx* base = S + (u / C) * BCP + cc;
-#pragma unroll 1
-            for (int p = 0; p < 6; ++p) {
-                cplx x[B];
-                static_for<B>([&](auto b_) { constexpr int b = decltype(b_)::value; x[b] = base[p * LB + b * C]; });
-                Dft<B, -1>::run(x);
-                static_for<B>([&](auto b_) { constexpr int b = decltype(b_)::value; base[p * LB + b * C] = x[b]; });
-            }
-        }
-    }
-    __syncthreads();
-    // ---- forward stage A: twiddle, radix-A, natural order back to smem; tasks = (t1, product) ------
-    for (int task = tl; task < 6 * BC; task += T) {
-        const int p = task / BC, t1 = task - p * BC;
-        const cplx w1 = ctw<-1>(W, t1);
-        cplx* col = S + p * LB + t1;
-        cplx x[A];
-        static_for<A>([&](auto ka_) { constexpr int ka = decltype(ka_)::value; x[ka] = col[ka * BCP]; });
-        if (t1 != 0) apply_twiddle_seq<A>(x, w1);
-        Dft<A, -1>::run(x);
-        static_for<A>([&](auto a_) { constexpr int a = decltype(a_)::value; col[a * BCP] = x[a]; });   // Z[a*BC + t1]
-    }
-    __syncthreads();
-    // ---- merge pass + x-dealiasing (keep modes 0..nx) + store ----------------------------------
-    for (int j = tl; j <= nx; j += T) {
-        const int pj = (j / BC) * BCP + (j % BC);
-        const int jm = (j == 0) ? 0 : M - j;
-        const int pm = (jm / BC) * BCP + (jm % BC);
-        cplx w = Wh[j];
-        w.y = -w.y;   // e^{-i pi j/M}
-        const int q = multi ? j / nxB : 0;
-        cplx* __restrict__ Bout = Bw.p[q];   // the owner of x-mode j (this GPU's or a peer's HBM over NVLink)
-        const size_t o0 = chb_bufB_index(g.rank, 6, 0, np, pli, nzB, izl, nxB, j - q * nxB, g.tw);
-        const size_t ostride = (size_t)np * nzB * nxB;
-#pragma unroll
-        for (int p = 0; p < 6; ++p) {
-            const cplx z = S[p * LB + pj];
-            const cplx zm = S[p * LB + pm];
-            const cplx e = make_double2(z.x + zm.x, z.y - zm.y);   // (Z + conj Zm)/2, the 1/2 is in the products
-            const cplx d = make_double2(z.x - zm.x, z.y + zm.y);   // (Z - conj Zm)/2
-            const cplx o = make_double2(d.y, -d.x);                                // -i * d
-            Bout[o0 + p * ostride] = cadd(e, cmul(w, o));
-        }
-    }
-}
-
-
 // ---------------------------------------------------------------------------------------------
-// xpass4: same arithmetic as xpass3 with every stage's butterflies flattened over (component,
-// butterfly) tasks, so that a small innermost radix C (T = M/C threads per line, e.g. C = 4 ->
-// 192 threads for M = 768) keeps all threads busy in every stage and MINB CTAs (lines) per SM give
-// 4-5 warps per scheduler instead of 1.5-2.
+// Every stage's butterflies are flattened over (component, butterfly) tasks, so that a small innermost
+// radix C (T = M/C threads per line, e.g. C = 4 -> 192 threads for M = 768) keeps all threads busy in
+// every stage and MINB CTAs (lines) per SM give 4-5 warps per scheduler.
 template <class G, int LPC, int MINB, bool MULTI>
 __global__ void __launch_bounds__(LPC * (G::N / G::C), MINB)
 xpass4_kernel(const cplx* __restrict__ Ar, const __grid_constant__ PeerPtrs Bw, const __grid_constant__ Geometry g, const cplx* __restrict__ W,
@@ -253,8 +67,11 @@ xpass4_kernel(const cplx* __restrict__ Ar, const __grid_constant__ PeerPtrs Bw, 
             return t;
         }
     };
-    const unsigned rowA = (unsigned)(((size_t)pli * nzB + izl) * nxB);   // + (src rank*3 + comp)*np*nzB*nxB
-    const unsigned cstrA = (unsigned)((size_t)np * nzB * nxB);
+    // velocity buffer: [src rank][comp][plane][x tile][z row][x in tile] (transpose_index.h), 32-bit offsets
+    const unsigned planeA = (unsigned)((size_t)nzB * nxB), cstrA = (unsigned)np * planeA;
+    const unsigned rowA = (unsigned)pli * planeA + (g.twa < 0 ? (unsigned)izl * (unsigned)nxB : ((unsigned)izl << g.twa));
+    const unsigned tmaskA = g.twa < 0 ? 0xffffffffu : (1u << g.twa) - 1u;
+    const unsigned tstrA = g.twa < 0 ? 0u : ((unsigned)nzB << g.twa);   // elements between x tiles
     // ---- backward stage A: split pass -> radix-A -> smem; tasks = (component, mode group t1) --------
 #pragma unroll 1
     for (int task = tl; task < 3 * BC; task += T) {
@@ -264,8 +81,9 @@ xpass4_kernel(const cplx* __restrict__ Ar, const __grid_constant__ PeerPtrs Bw, 
         const cplx* __restrict__ Xc = Ar + rowA + (unsigned)comp * cstrA;
         auto X = [&](int n) -> cplx {   // mode n of this line, zero beyond nx (x zero-padding, dnsdata.f90:535)
             if (n > nx) return make_double2(0.0, 0.0);
-            unsigned o = (unsigned)n;
-            if (multi) { const unsigned qr = (unsigned)n / (unsigned)nxB; o += qr * (3u * cstrA - (unsigned)nxB); }
+            unsigned nl = (unsigned)n, o = 0;
+            if (multi) { const unsigned qr = nl / (unsigned)nxB; nl -= qr * (unsigned)nxB; o = qr * 3u * cstrA; }
+            o += (g.twa < 0) ? nl : ((nl >> g.twa) * tstrA + (nl & tmaskA));
             return __ldg(Xc + o);
         };
         cplx x[A];
@@ -417,8 +235,8 @@ static bool launch_x4(chb_handle_s* h, int plane0, int nplanes, int compute_cfl)
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     dim3 grid(h->g.nzB / LPC, nplanes);
-    ScopedKernelTimer tm(h, "xpass");
-    kern<<<grid, LPC * T, smem, h->stream>>>(h->Ar, h->Bw, h->g, h->Wx, h->Wh, h->t_dy, h->sc, plane0, h->chunk_planes,
+    ScopedKernelTimer tm(h, "xpass", h->cstream);
+    kern<<<grid, LPC * T, smem, h->cstream>>>(h->Ar, h->Bw, h->g, h->Wx, h->Wh, h->t_dy, h->sc, plane0, h->chunk_planes,
                                              compute_cfl);
     h->launches++;
     return true;
@@ -426,303 +244,11 @@ static bool launch_x4(chb_handle_s* h, int plane0, int nplanes, int compute_cfl)
 
 
 // ---------------------------------------------------------------------------------------------
-// xpass6: the split pass (c2r) and the merge pass (r2c) are fused into the outermost radix-A stage
-// by giving one thread BOTH butterflies t1 and BC-t1: the split/merge couples Z[n] with Z[M-n], and
-// M-n = (A-1-a)*BC + (BC-t1), so the partner of every element of butterfly t1 lives in butterfly
-// BC-t1 (the columns t1 = 0 and t1 = BC/2 are their own partners and share one thread).  The input
-// modes are read from HBM straight into registers and the output modes leave from registers:
-// per transform the line crosses shared memory only for the two stage exchanges (4 instead of
-// 6-6.3 shared-memory passes per transform; the kernel was bound by the 128 B/clk shared-memory
-// crossbar), and s, d, t of the split are computed once per pair instead of once per element.
-template <class G, int LPC, int MINB, bool MULTI>
-__global__ void __launch_bounds__(LPC * (G::N / G::C), MINB)
-xpass6_kernel(const cplx* __restrict__ Ar, const __grid_constant__ PeerPtrs Bw, const __grid_constant__ Geometry g, const cplx* __restrict__ W,
-              const cplx* __restrict__ Wh, const double* __restrict__ dy, DevScalars* sc, int plane0, int np,
-              int compute_cfl, int pf_dist) {
-    constexpr int M = G::N, A = G::A, B = G::B, C = G::C, BC = G::BC;
-    constexpr int T = M / C;           // threads per line = butterflies of the innermost stage
-    constexpr int BCP = BC + 1;
-    constexpr int LB = A * BCP;        // complex per buffer
-    constexpr int NB = A * C;          // stage-B butterflies per transform
-    constexpr int HB = BC / 2;
-    constexpr int NP = HB - 1;         // true pairs (t1, BC-t1) per transform
-    static_assert(T % C == 0 && NB % C == 0, "stage-B twiddle must be a per-thread constant");
-    static_assert(A % 2 == 0 && BC % 2 == 0, "pairing needs even A and BC");
-    extern __shared__ cplx smem[];
-    const int tl = threadIdx.x % T, l = threadIdx.x / T;
-    const int izl = blockIdx.x * LPC + l;
-    const int pli = blockIdx.y;
-    const int iy = plane0 + pli - 1;
-    const int nx = g.nx, nxB = g.nxB, nzB = g.nzB;
-    constexpr bool multi = MULTI;
-    cplx* S = smem + (size_t)l * 6 * LB;
-    if (threadIdx.x < 3 * g.nranks && pf_dist > 0) {   // L2 prefetch of the input rows of the CTA pf_dist ahead
-        const long long id = blockIdx.x + (long long)gridDim.x * blockIdx.y + pf_dist;
-        const int bx = (int)(id % gridDim.x), by = (int)(id / gridDim.x);
-        if (by < (int)gridDim.y)
-            bulk_prefetch_l2(Ar + chb_buf_index(threadIdx.x / 3, 3, threadIdx.x % 3, np, by, nzB, bx * LPC, nxB, 0),
-                             (unsigned)(LPC * nxB * sizeof(cplx)));
-    }
-
-    // ---- backward stage A: split pass fused, inputs straight from HBM.  Tasks: 3*NP pairs (t1, BC-t1),
-    //      t1 = 1..BC/2-1, then the 6 self-paired columns (t1 = 0 pairs a with A-a, t1 = BC/2 pairs a with
-    //      A-1-a): those run the same code with the second butterfly switched off.
-    const unsigned rowA = (unsigned)(((size_t)pli * nzB + izl) * nxB);   // + (src rank*3 + comp)*np*nzB*nxB
-    const unsigned cstrA = (unsigned)((size_t)np * nzB * nxB);
-#pragma unroll 1
-    for (int task = tl; task < 3 * NP + 6; task += T) {
-        int comp, t1a, t1b;
-        const bool pair = task < 3 * NP;
-        if (pair) {
-            comp = task / NP;
-            t1a = task - comp * NP + 1;
-            t1b = BC - t1a;
-        } else {
-            const int r = task - 3 * NP;      // 0..5
-            comp = r >> 1;
-            t1a = (r & 1) ? HB : 0;
-            t1b = (r & 1) ? HB : BC;          // "column BC" = column 0 shifted by one: n = (a+1)*BC
-        }
-        const cplx* __restrict__ Xc = Ar + rowA + (unsigned)comp * cstrA;
-        auto X = [&](int n) -> cplx {   // mode n of this line, zero beyond nx (x zero-padding, dnsdata.f90:535)
-            if (n > nx) return make_double2(0.0, 0.0);
-            unsigned o = (unsigned)n;
-            if (multi) { const unsigned qr = (unsigned)n / (unsigned)nxB; o += qr * (3u * cstrA - (unsigned)nxB); }
-            return __ldg(Xc + o);
-        };
-        const cplx wh1 = __ldg(&Wh[t1a]);   // exp(+i pi t1a / M)
-        cplx z1[A], z2[A];
-        static_for<A>([&](auto a_) {
-            constexpr int a = decltype(a_)::value;
-            cplx xa = X(a * BC + t1a);
-            const cplx xb = X((A - 1 - a) * BC + t1b);
-            if (a == 0 && t1a == 0) xa.y = 0.0;                     // Im X[0] is ignored by the c2r transform
-            const cplx s = make_double2(xa.x + xb.x, xa.y - xb.y);
-            const cplx d = make_double2(xa.x - xb.x, xa.y + xb.y);
-            const cplx t = cmul(mulw<2 * A, a, +1>(wh1), d);       // e^{i pi n/M} = e^{i pi t1/M} e^{i pi a/A}
-            z1[a] = make_double2(s.x - t.y, s.y + t.x);             // Z[n]   = s + i t
-            z2[A - 1 - a] = make_double2(s.x + t.y, t.x - s.y);     // Z[M-n] = conj(s) + i conj(t)
-        });
-        cplx* dst = S + comp * LB;
-        Dft<A, +1>::run(z1);
-        if (t1a != 0) apply_twiddle_seq<A>(z1, __ldg(&W[t1a]));
-        static_for<A>([&](auto ka_) { constexpr int ka = decltype(ka_)::value; dst[ka * BCP + t1a] = z1[ka]; });
-        if (pair) {
-            Dft<A, +1>::run(z2);
-            apply_twiddle_seq<A>(z2, __ldg(&W[t1b]));
-            static_for<A>([&](auto ka_) { constexpr int ka = decltype(ka_)::value; dst[ka * BCP + t1b] = z2[ka]; });
-        }
-    }
-    __syncthreads();
-    // ---- backward stage B, in place; tasks = (component, ka, c) ---------------------------------------
-    {
-        const int cc = tl % C;
-        const cplx w1 = __ldg(&W[A * cc]);   // w_BC^cc
-#pragma unroll 1
-        for (int task = tl; task < 3 * NB; task += T) {
-            const int comp = task / NB, u = task - comp * NB;
-            cplx* base = S + comp * LB + (u / C) * BCP + cc;
-            cplx x[B];
-            static_for<B>([&](auto b_) { constexpr int b = decltype(b_)::value; x[b] = base[b * C]; });
-            Dft<B, +1>::run(x);
-            if (cc != 0) apply_twiddle_seq<B>(x, w1);
-            static_for<B>([&](auto b_) { constexpr int b = decltype(b_)::value; base[b * C] = x[b]; });
-        }
-    }
-    __syncthreads();
-    // ---- backward stage C -> physical space -> CFL, products -> forward stage C --------------
-    {
-        const int ka = tl % A, kb = tl / A;
-        cplx* base = S + ka * BCP + kb * C;
-        cplx U[C], V[C], Wv[C];
-        static_for<C>([&](auto c_) {
-            constexpr int c = decltype(c_)::value;
-            U[c] = base[c];
-            V[c] = base[LB + c];
-            Wv[c] = base[2 * LB + c];
-        });
-        Dft<C, +1>::run(U);
-        Dft<C, +1>::run(V);
-        Dft<C, +1>::run(Wv);
-        if (compute_cfl) {   // dnsdata.f90:552-556 (block-uniform branch)
-            double cmax = 0.0;
-            if (iy >= 1 && iy <= g.ny - 1) {
-                const double rdx = 1.0 / g.dx, rdz = 1.0 / g.dz, rdy = 1.0 / dy[iy + 1];
-                static_for<C>([&](auto c_) {
-                    constexpr int c = decltype(c_)::value;
-                    cmax = fmax(cmax, fabs(U[c].x) * rdx + fabs(V[c].x) * rdy + fabs(Wv[c].x) * rdz);
-                    cmax = fmax(cmax, fabs(U[c].y) * rdx + fabs(V[c].y) * rdy + fabs(Wv[c].y) * rdz);
-                });
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) cmax = fmax(cmax, __shfl_xor_sync(0xffffffffu, cmax, o));
-            if ((threadIdx.x & 31) == 0 && cmax > 0.0)
-                atomicMax(&sc->cfl_bits, (unsigned long long)__double_as_longlong(cmax));
-        }
-        const double f = 0.5 * g.factor;       // the 1/2 of the merge pass is folded into the products
-        const cplx wk1 = ctw<-1>(W, A * kb);   // conj w_BC^kb
-        auto forward_c = [&](cplx* x, int p) {
-            Dft<C, -1>::run(x);
-            if (kb != 0) apply_twiddle_seq<C>(x, wk1);
-            static_for<C>([&](auto c_) { constexpr int c = decltype(c_)::value; base[p * LB + c] = x[c]; });
-        };
-        cplx x[C];
-        // slots (0..5) = (uu, vv, ww, uv, vw, uw) * factor                          dnsdata.f90:581-584
-        static_for<C>([&](auto c_) { constexpr int c = decltype(c_)::value; x[c] = make_double2(U[c].x * V[c].x * f, U[c].y * V[c].y * f); });
-        forward_c(x, 3);
-        static_for<C>([&](auto c_) { constexpr int c = decltype(c_)::value; x[c] = make_double2(V[c].x * Wv[c].x * f, V[c].y * Wv[c].y * f); });
-        forward_c(x, 4);
-        static_for<C>([&](auto c_) { constexpr int c = decltype(c_)::value; x[c] = make_double2(U[c].x * Wv[c].x * f, U[c].y * Wv[c].y * f); });
-        forward_c(x, 5);
-        static_for<C>([&](auto c_) { constexpr int c = decltype(c_)::value; U[c] = make_double2(U[c].x * U[c].x * f, U[c].y * U[c].y * f); });
-        forward_c(U, 0);
-        static_for<C>([&](auto c_) { constexpr int c = decltype(c_)::value; V[c] = make_double2(V[c].x * V[c].x * f, V[c].y * V[c].y * f); });
-        forward_c(V, 1);
-        static_for<C>([&](auto c_) { constexpr int c = decltype(c_)::value; Wv[c] = make_double2(Wv[c].x * Wv[c].x * f, Wv[c].y * Wv[c].y * f); });
-        forward_c(Wv, 2);
-    }
-    __syncthreads();
-    // ---- forward stage B, in place; tasks = (product, ka, c) ------------------------------------------
-#pragma unroll 1
-    for (int task = tl; task < 6 * NB; task += T) {
-        const int p = task / NB, u = task - p * NB;
-        cplx* base = S + p * LB + (u / C) * BCP + (u % C);
-        cplx x[B];
-        static_for<B>([&](auto b_) { constexpr int b = decltype(b_)::value; x[b] = base[b * C]; });
-        Dft<B, -1>::run(x);
-        static_for<B>([&](auto b_) { constexpr int b = decltype(b_)::value; base[b * C] = x[b]; });
-    }
-    __syncthreads();
-    // ---- forward stage A + merge pass + x-dealiasing (keep modes 0..nx) + store; tasks as in the
-    //      backward stage A: 6*NP pairs, then the 12 self-paired columns
-    const unsigned rowB = (unsigned)chb_bufB_index(g.rank, 6, 0, np, pli, nzB, izl, nxB, 0, g.tw);
-    const unsigned cstrB = (unsigned)((size_t)np * nzB * nxB);
-    const unsigned tmask = (1u << g.tw) - 1u;
-    cplx* __restrict__ out0 = Bw.p[0];
-#pragma unroll 1
-    for (int task = tl; task < 6 * NP + 12; task += T) {
-        int p, t1a, t1b;
-        const bool pair = task < 6 * NP;
-        int mode = 0;                         // 1: column 0, 2: column BC/2
-        if (pair) {
-            p = task / NP;
-            t1a = task - p * NP + 1;
-            t1b = BC - t1a;
-        } else {
-            const int r = task - 6 * NP;      // 0..11
-            p = r >> 1;
-            mode = 1 + (r & 1);
-            t1a = (r & 1) ? HB : 0;
-            t1b = (r & 1) ? HB : BC;
-        }
-        const cplx* col = S + p * LB;
-        cplx z1[A], z2[A];
-        static_for<A>([&](auto ka_) { constexpr int ka = decltype(ka_)::value; z1[ka] = col[ka * BCP + t1a]; });
-        if (t1a != 0) apply_twiddle_seq<A>(z1, ctw<-1>(W, t1a));
-        Dft<A, -1>::run(z1);            // z1[a] = Z[a*BC + t1a]
-        if (pair) {
-            static_for<A>([&](auto ka_) { constexpr int ka = decltype(ka_)::value; z2[ka] = col[ka * BCP + t1b]; });
-            apply_twiddle_seq<A>(z2, ctw<-1>(W, t1b));
-            Dft<A, -1>::run(z2);        // z2[a] = Z[a*BC + t1b]
-        } else {
-            // column BC/2 is its own partner; column 0 pairs with itself shifted by one (Z[M] := Z[0])
-            static_for<A>([&](auto a_) {
-                constexpr int a = decltype(a_)::value;
-                z2[a] = (mode == 1) ? z1[(a + 1) % A] : z1[a];
-            });
-        }
-        cplx wh1 = __ldg(&Wh[t1a]);
-        wh1.y = -wh1.y;                 // e^{-i pi t1a/M}
-        cplx* __restrict__ outp = out0 + rowB + (unsigned)p * cstrB;
-        // X[j] = e + w o,  X[M-j] = conj(e - w o),  e = Z[j] + conj Z[M-j], o = -i (Z[j] - conj Z[M-j]),
-        // w = e^{-i pi j/M}; the 1/2 is folded into the products
-        auto store = [&](int j, cplx v) {
-            if (j > nx) return;
-            unsigned jl = (unsigned)j;
-            cplx* o = outp;
-            if (multi) {
-                const unsigned qr = jl / (unsigned)nxB;
-                jl -= qr * (unsigned)nxB;
-                o = Bw.p[qr] + rowB + (unsigned)p * cstrB;   // the owner of x-mode j (a peer's HBM over NVLink)
-            }
-            o[((jl >> g.tw) * (unsigned)nzB << g.tw) + (jl & tmask)] = v;
-        };
-        static_for<A>([&](auto a_) {
-            constexpr int a = decltype(a_)::value;
-            const cplx z = z1[a], zm = z2[A - 1 - a];
-            const cplx e = make_double2(z.x + zm.x, z.y - zm.y);
-            const cplx o = make_double2(z.y + zm.y, zm.x - z.x);
-            const cplx r = cmul(mulw<2 * A, a, -1>(wh1), o);
-            store(a * BC + t1a, make_double2(e.x + r.x, e.y + r.y));
-            if (pair) store((A - 1 - a) * BC + t1b, make_double2(e.x - r.x, r.y - e.y));
-        });
-    }
-}
-
-template <class G, int LPC, int MINB>
-static bool launch_x6(chb_handle_s* h, int plane0, int nplanes, int compute_cfl) {
-    constexpr int T = G::N / G::C;
-    constexpr int LB = G::A * (G::BC + 1);
-    if (h->g.nzB % LPC != 0) return false;
-    const size_t smem = (size_t)LPC * 6 * LB * sizeof(cplx);
-    auto kern = (h->g.nranks > 1) ? xpass6_kernel<G, LPC, MINB, true> : xpass6_kernel<G, LPC, MINB, false>;
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    dim3 grid(h->g.nzB / LPC, nplanes);
-    ScopedKernelTimer tm(h, "xpass");
-    kern<<<grid, LPC * T, smem, h->stream>>>(h->Ar, h->Bw, h->g, h->Wx, h->Wh, h->t_dy, h->sc, plane0, h->chunk_planes,
-                                             compute_cfl, h->pf_dist);
-    h->launches++;
-    return true;
-}
-
-// ---------------------------------------------------------------------------------------------
-template <class G, int LPC>
-static bool launch_x3(chb_handle_s* h, int plane0, int nplanes, int compute_cfl) {
-    constexpr int T = G::N / G::C;
-    constexpr int LB = G::A * (G::BC + 1);
-    if (h->g.nzB % LPC != 0) return false;
-    const size_t smem = (size_t)LPC * 6 * LB * sizeof(cplx);
-    cudaFuncSetAttribute(xpass3_kernel<G, LPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(xpass3_kernel<G, LPC>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    dim3 grid(h->g.nzB / LPC, nplanes);
-    ScopedKernelTimer tm(h, "xpass");
-    xpass3_kernel<G, LPC><<<grid, LPC * T, smem, h->stream>>>(h->Ar, h->Bw, h->g, h->Wx, h->Wh, h->t_dy, h->sc, plane0,
-                                                             h->chunk_planes, compute_cfl);
-    h->launches++;
-    return true;
-}
-
 bool launch_x3_pass(chb_handle_s* h, int plane0, int nplanes, int compute_cfl) {
-    const int var = h->x_var;
-    if (var == 6) {
-        switch (h->g.nxd) {
-            case 384: return launch_x6<Fft3<384, 12, 4, 8>, 2, 3>(h, plane0, nplanes, compute_cfl);
-            case 768: return launch_x6<Fft3<768, 12, 8, 8>, 1, 3>(h, plane0, nplanes, compute_cfl);
-            case 1536: return launch_x6<Fft3<1536, 12, 16, 8>, 1, 1>(h, plane0, nplanes, compute_cfl);
-            default: return false;
-        }
-    }
-    if (var == 4) {
-        switch (h->g.nxd) {
-            case 384: return launch_x4<Fft3<384, 12, 8, 4>, 1, 6>(h, plane0, nplanes, compute_cfl);
-            case 768: return launch_x4<Fft3<768, 12, 16, 4>, 1, 3>(h, plane0, nplanes, compute_cfl);
-            case 1536: return launch_x4<Fft3<1536, 12, 16, 8>, 1, 1>(h, plane0, nplanes, compute_cfl);
-            default: return false;
-        }
-    }
-    if (var == 5) {
-        switch (h->g.nxd) {
-            case 384: return launch_x4<Fft3<384, 12, 4, 8>, 2, 3>(h, plane0, nplanes, compute_cfl);
-            case 768: return launch_x4<Fft3<768, 12, 8, 8>, 1, 3>(h, plane0, nplanes, compute_cfl);
-            case 1536: return launch_x4<Fft3<1536, 12, 16, 8>, 1, 1>(h, plane0, nplanes, compute_cfl);
-            default: return false;
-        }
-    }
     switch (h->g.nxd) {
-        case 384: return launch_x3<Fft3<384, 12, 4, 8>, 2>(h, plane0, nplanes, compute_cfl);
-        case 768: return launch_x3<Fft3<768, 12, 8, 8>, 1>(h, plane0, nplanes, compute_cfl);
-        case 1536: return launch_x3<Fft3<1536, 12, 16, 8>, 1>(h, plane0, nplanes, compute_cfl);
+        case 384: return launch_x4<Fft3<384, 12, 8, 4>, 1, 6>(h, plane0, nplanes, compute_cfl);
+        case 768: return launch_x4<Fft3<768, 12, 16, 4>, 1, 3>(h, plane0, nplanes, compute_cfl);
+        case 1536: return launch_x4<Fft3<1536, 12, 16, 8>, 1, 1>(h, plane0, nplanes, compute_cfl);
         default: return false;
     }
 }

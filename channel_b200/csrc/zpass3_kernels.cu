@@ -6,173 +6,14 @@
 //   zbwd3: xTOz unpack + forward complex FFT of length nzd (FFT ffts.f90:70) + z-truncation
 //          through izd() (DD macro, dnsdata.f90:609)
 //
-// One CTA = LPC neighbouring x-modes (lines), 32 threads per line.  The two stages that touch
-// the z-contiguous side run "warp per line" (only __syncwarp between them); the stage that
-// touches the x-contiguous work buffer runs "cross-line" (consecutive lanes = consecutive
-// lines) so that every global access is LPC*16 contiguous bytes.  Per point: one global read,
-// one global write, two shared-memory exchanges.
+// One CTA = LPC neighbouring x-modes (lines), TPL threads per line.  The two stages that touch
+// the z-contiguous side run "line-major"; the stage that touches the work buffer runs
+// "cross-line" (consecutive lanes = consecutive lines, then consecutive z rows), and the work
+// buffers are tiled [x tile of LPC][z row][x in tile] (transpose_index.h) so that a warp's
+// accesses are contiguous.  Per point: one global read, one global write, two shared-memory
+// exchanges.
 #include "chb_internal.h"
 #include "fft_regs.cuh"
-
-template <class G, int LPC>
-__global__ void __launch_bounds__(LPC * 32)
-zfwd3_kernel(const cplx* __restrict__ V, PeerPtrs Aw, Geometry g, const cplx* __restrict__ W, int plane0, int np,
-             int LS) {
-    extern __shared__ cplx smem[];
-    constexpr int BCP = G::BC + 1;
-    const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
-    const int ixl0 = blockIdx.x * LPC;
-    const int pli = blockIdx.y, comp = blockIdx.z;
-    const int iyp = plane0 + pli;
-    const int nz = g.nz;
-    {   // ---- stage A, warp per line.  The z-contiguous V line is staged by TMA bulk copies straight
-        //      into the in-place layout (piece a -> sm + a*BCP), one latency exposure per line;
-        //      the zero padding between nz and nzd-nz is never materialised.
-        const cplx* __restrict__ src = V + (((size_t)comp * g.nyp + iyp) * g.nxB + ixl0 + wl) * g.nzt;
-        cplx* sm = smem + wl * LS;
-        __shared__ unsigned long long mbar[LPC];
-        if (lane == 0) {
-            mbar_init(&mbar[wl], 1);
-            mbar_expect_tx(&mbar[wl], (unsigned)(g.nzt * sizeof(cplx)));
-            for (int a = 0; a < G::A; ++a) {
-                const int lo = a * G::BC, hi = lo + G::BC - 1;
-                const int h1 = min(hi, nz);                    // rows 1..nz+1        <- V(iy,0:nz)
-                if (h1 >= lo) bulk_g2s(sm + a * BCP, src + nz + lo, (unsigned)((h1 - lo + 1) * sizeof(cplx)), &mbar[wl]);
-                const int l2 = max(lo, G::N - nz);             // rows nzd-nz+1..nzd  <- V(iy,-nz:-1)
-                if (hi >= l2)
-                    bulk_g2s(sm + a * BCP + (l2 - lo), src + (l2 - (G::N - nz)), (unsigned)((hi - l2 + 1) * sizeof(cplx)),
-                             &mbar[wl]);
-            }
-        }
-        __syncwarp();
-        mbar_wait(&mbar[wl], 0);
-#pragma unroll 1
-        for (int i = 0; i < G::BC / 32; ++i) {
-            const int t1 = lane + 32 * i;
-            cplx x[G::A];
-            static_for<G::A>([&](auto a_) {
-                constexpr int a = decltype(a_)::value;
-                const int n = a * G::BC + t1;
-                x[a] = (n <= nz || n >= G::N - nz) ? sm[a * BCP + t1] : make_double2(0.0, 0.0);
-            });
-            dif_stage_a<G, +1>(x, t1, W);
-            static_for<G::A>([&](auto ka_) {
-                constexpr int ka = decltype(ka_)::value;
-                sm[ka * BCP + t1] = x[ka];
-            });
-        }
-    }
-    __syncwarp();
-    {   // ---- stage B, warp per line, in place
-        cplx* sm = smem + wl * LS;
-        const int cc = lane % G::C;
-        cplx wc[G::B];
-        twiddle_powers<G::B>(ctw<+1>(W, G::A * cc), wc);
-#pragma unroll 1
-        for (int i = 0; i < (G::A * G::C) / 32; ++i) {
-            const int u = lane + 32 * i;
-            cplx* base = sm + (u / G::C) * BCP + cc;
-            cplx x[G::B];
-            static_for<G::B>([&](auto b_) { constexpr int b = decltype(b_)::value; x[b] = base[b * G::C]; });
-            dif_stage_b<G, +1>(x, wc, cc != 0);
-            static_for<G::B>([&](auto b_) { constexpr int b = decltype(b_)::value; base[b * G::C] = x[b]; });
-        }
-    }
-    __syncthreads();
-    {   // ---- stage C, cross-line: smem -> registers -> global (x-contiguous, per destination rank)
-        const int l = threadIdx.x % LPC, q = threadIdx.x / LPC;
-        const cplx* sm = smem + l * LS;
-        const int nzB = g.nzB, nxB = g.nxB;
-#pragma unroll 1
-        for (int i = 0; i < G::AB / 32; ++i) {
-            const int t = q + 32 * i;
-            const cplx* base = sm + (t % G::A) * BCP + (t / G::A) * G::C;
-            cplx x[G::C];
-            static_for<G::C>([&](auto c_) { constexpr int c = decltype(c_)::value; x[c] = base[c]; });
-            Dft<G::C, +1>::run(x);
-            static_for<G::C>([&](auto kc_) {
-                constexpr int kc = decltype(kc_)::value;
-                const int k = t + G::AB * kc;
-                const int peer = (g.nranks > 1) ? k / nzB : 0;
-                Aw.p[peer][chb_buf_index(g.rank, 3, comp, np, pli, nzB, k - peer * nzB, nxB, ixl0 + l)] = x[kc];
-            });
-        }
-    }
-}
-
-template <class G, int LPC>
-__global__ void __launch_bounds__(LPC * 32)
-zbwd3_kernel(const cplx* __restrict__ Br, cplx* __restrict__ P, Geometry g, const cplx* __restrict__ W, int plane0, int np,
-             int LS) {
-    extern __shared__ cplx smem[];
-    constexpr int BCP = G::BC + 1;
-    const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
-    const int ixl0 = blockIdx.x * LPC;
-    const int pli = blockIdx.y, comp = blockIdx.z;  // product index 0..5
-    const int iyp = plane0 + pli;
-    const int nz = g.nz;
-    {   // ---- staging, cross-line: the x-contiguous work buffer (LPC*16 contiguous bytes per z row) is
-        //      copied with per-thread 16-byte cp.async straight into the in-place layout of each line;
-        //      all copies of the CTA are in flight at once, one latency exposure
-        const int l = threadIdx.x % LPC, q = threadIdx.x / LPC;
-        cplx* sml = smem + l * LS;
-        const int nzB = g.nzB, nxB = g.nxB;
-#pragma unroll 4
-        for (int n = q; n < G::N; n += 32) {
-            const int peer = (g.nranks > 1) ? n / nzB : 0;
-            cp_async16(sml + (n / G::BC) * BCP + (n % G::BC),
-                       Br + chb_bufB_index(peer, 6, comp, np, pli, nzB, n - peer * nzB, nxB, ixl0 + l, g.tw));
-        }
-        cp_async_wait_all();
-    }
-    __syncthreads();
-    {   // ---- stage A, warp per line, in place
-        cplx* sm = smem + wl * LS;
-#pragma unroll 1
-        for (int i = 0; i < G::BC / 32; ++i) {
-            const int t1 = lane + 32 * i;
-            cplx x[G::A];
-            static_for<G::A>([&](auto a_) { constexpr int a = decltype(a_)::value; x[a] = sm[a * BCP + t1]; });
-            dif_stage_a<G, -1>(x, t1, W);
-            static_for<G::A>([&](auto ka_) { constexpr int ka = decltype(ka_)::value; sm[ka * BCP + t1] = x[ka]; });
-        }
-    }
-    __syncwarp();
-    cplx* sm = smem + wl * LS;
-    {   // ---- stage B, warp per line, in place
-        const int cc = lane % G::C;
-        cplx wc[G::B];
-        twiddle_powers<G::B>(ctw<-1>(W, G::A * cc), wc);
-#pragma unroll 1
-        for (int i = 0; i < (G::A * G::C) / 32; ++i) {
-            const int u = lane + 32 * i;
-            cplx* base = sm + (u / G::C) * BCP + cc;
-            cplx x[G::B];
-            static_for<G::B>([&](auto b_) { constexpr int b = decltype(b_)::value; x[b] = base[b * G::C]; });
-            dif_stage_b<G, -1>(x, wc, cc != 0);
-            static_for<G::B>([&](auto b_) { constexpr int b = decltype(b_)::value; base[b * G::C] = x[b]; });
-        }
-    }
-    __syncwarp();
-    {   // ---- stage C, warp per line: smem -> registers -> global (z-contiguous, truncated to -nz..nz)
-        cplx* __restrict__ dst = P + (((size_t)comp * g.nyp + iyp) * g.nxB + ixl0 + wl) * g.nzt;
-#pragma unroll 1
-        for (int i = 0; i < G::AB / 32; ++i) {
-            const int t = lane + 32 * i;
-            const cplx* base = sm + (t % G::A) * BCP + (t / G::A) * G::C;
-            cplx x[G::C];
-            static_for<G::C>([&](auto c_) { constexpr int c = decltype(c_)::value; x[c] = base[c]; });
-            Dft<G::C, -1>::run(x);
-            static_for<G::C>([&](auto kc_) {
-                constexpr int kc = decltype(kc_)::value;
-                const int k = t + G::AB * kc;                     // izd(iz) = k  (dnsdata.f90:156)
-                if (k <= nz) dst[nz + k] = x[kc];
-                else if (k >= G::N - nz) dst[k - (G::N - nz)] = x[kc];
-            });
-        }
-    }
-}
-
 
 // x[p] *= w1^p, p = 1..R-1, sequential recurrence (low register pressure)
 template <int R>
@@ -193,7 +34,7 @@ __device__ __forceinline__ void z_twiddle_seq(cplx* x, cplx w1) {
 template <class G, int LPC, int TPL, int MINB>
 __global__ void __launch_bounds__(LPC * TPL, MINB)
 zfwd4_kernel(const cplx* __restrict__ V, PeerPtrs Aw, Geometry g, const cplx* __restrict__ W, int plane0, int np,
-             int LS, int pf_dist) {
+             int LS) {
     extern __shared__ cplx smem[];
     constexpr int BCP = G::BC + 1;
     static_assert(TPL % G::C == 0, "stage-B twiddle must be a per-thread constant");
@@ -206,13 +47,6 @@ zfwd4_kernel(const cplx* __restrict__ V, PeerPtrs Aw, Geometry g, const cplx* __
     {   // ---- stage A, line-major; the V line is staged by TMA bulk copies into the in-place layout
         const cplx* __restrict__ src = V + (((size_t)comp * g.nyp + iyp) * g.nxB + ixl0 + wl) * g.nzt;
         cplx* sm = smem + wl * LS;
-        if (threadIdx.x == 32 && pf_dist > 0) {   // L2 prefetch of the LPC lines of the CTA pf_dist ahead in launch order
-            const long long id = blockIdx.x + (long long)gridDim.x * (blockIdx.y + (long long)gridDim.y * blockIdx.z) + pf_dist;
-            const int bx = (int)(id % gridDim.x), by = (int)((id / gridDim.x) % gridDim.y), bz = (int)(id / ((long long)gridDim.x * gridDim.y));
-            if (bz < (int)gridDim.z)
-                bulk_prefetch_l2(V + (((size_t)bz * g.nyp + plane0 + by) * g.nxB + (size_t)bx * LPC) * g.nzt,
-                                 (unsigned)(LPC * g.nzt * sizeof(cplx)));
-        }
         if (tl == 0) {
             mbar_init(&mbar[wl], 1);
             mbar_expect_tx(&mbar[wl], (unsigned)(g.nzt * sizeof(cplx)));
@@ -276,7 +110,7 @@ zfwd4_kernel(const cplx* __restrict__ V, PeerPtrs Aw, Geometry g, const cplx* __
                 const int k = t + G::AB * kc;
                 const int peer = multi ? k / nzB : 0;
                 cplx* dst = multi ? Aw.p[peer] : Aw.p[0];
-                dst[chb_buf_index(g.rank, 3, comp, np, pli, nzB, k - peer * nzB, nxB, ixl0 + l)] = x[kc];
+                dst[chb_bufA_index(g.rank, comp, np, pli, nzB, k - peer * nzB, nxB, ixl0 + l, g.twa)] = x[kc];
             });
         }
     }
@@ -285,7 +119,7 @@ zfwd4_kernel(const cplx* __restrict__ V, PeerPtrs Aw, Geometry g, const cplx* __
 template <class G, int LPC, int TPL, int MINB>
 __global__ void __launch_bounds__(LPC * TPL, MINB)
 zbwd4_kernel(const cplx* __restrict__ Br, cplx* __restrict__ P, Geometry g, const cplx* __restrict__ W, int plane0, int np,
-             int LS, int pf_dist) {
+             int LS) {
     extern __shared__ cplx smem[];
     constexpr int BCP = G::BC + 1;
     static_assert(TPL % G::C == 0, "stage-B twiddle must be a per-thread constant");
@@ -299,14 +133,6 @@ zbwd4_kernel(const cplx* __restrict__ Br, cplx* __restrict__ P, Geometry g, cons
         cplx* sml = smem + l * LS;
         const int nzB = g.nzB, nxB = g.nxB;
         const bool multi = g.nranks > 1;
-        if (threadIdx.x < g.nranks && pf_dist > 0 && (1 << g.tw) == LPC) {
-            // L2 prefetch of the (contiguous, one piece per source rank) tile of the CTA pf_dist ahead
-            const long long id = blockIdx.x + (long long)gridDim.x * (blockIdx.y + (long long)gridDim.y * blockIdx.z) + pf_dist;
-            const int bx = (int)(id % gridDim.x), by = (int)((id / gridDim.x) % gridDim.y), bz = (int)(id / ((long long)gridDim.x * gridDim.y));
-            if (bz < (int)gridDim.z)
-                bulk_prefetch_l2(Br + chb_bufB_index(threadIdx.x, 6, bz, np, by, nzB, 0, nxB, bx * LPC, g.tw),
-                                 (unsigned)(nzB * LPC * sizeof(cplx)));
-        }
 #pragma unroll 4
         for (int n = q; n < G::N; n += TPL) {
             const int peer = multi ? n / nzB : 0;
@@ -371,66 +197,33 @@ static bool launch_z4(chb_handle_s* h, int plane0, int nplanes, bool fwd) {
     if (fwd) {
         cudaFuncSetAttribute(zfwd4_kernel<G, LPC, TPL, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(zfwd4_kernel<G, LPC, TPL, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        ScopedKernelTimer tm(h, "zfwd");
-        zfwd4_kernel<G, LPC, TPL, MINB><<<grid, LPC * TPL, smem, h->stream>>>(h->V, h->Aw, h->g, h->Wz, plane0, h->chunk_planes, LS, h->pf_dist);
+        ScopedKernelTimer tm(h, "zfwd", h->cstream);
+        zfwd4_kernel<G, LPC, TPL, MINB><<<grid, LPC * TPL, smem, h->cstream>>>(h->V, h->Aw, h->g, h->Wz, plane0, h->chunk_planes, LS);
     } else {
         cudaFuncSetAttribute(zbwd4_kernel<G, LPC, TPL, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(zbwd4_kernel<G, LPC, TPL, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        ScopedKernelTimer tm(h, "zbwd");
-        zbwd4_kernel<G, LPC, TPL, MINB><<<grid, LPC * TPL, smem, h->stream>>>(h->Br, h->P, h->g, h->Wz, plane0, h->chunk_planes, LS, h->pf_dist);
+        ScopedKernelTimer tm(h, "zbwd", h->cstream);
+        zbwd4_kernel<G, LPC, TPL, MINB><<<grid, LPC * TPL, smem, h->cstream>>>(h->Br, h->P, h->g, h->Wz, plane0, h->chunk_planes, LS);
     }
     h->launches++;
     return true;
 }
 
 // ---------------------------------------------------------------------------------------------
-template <class G, int LPC>
-static bool launch_z3(chb_handle_s* h, int plane0, int nplanes, bool fwd) {
-    constexpr int BCP = G::BC + 1;
-    int LS = G::A * BCP;
-    const int want = (LPC == 8) ? 1 : 2;   // line stride mod 8 that keeps the cross-line accesses conflict-free
-    while (LS % 8 != want) ++LS;
-    const size_t smem = (size_t)LPC * LS * sizeof(cplx);
-    if (h->g.nxB % LPC != 0) return false;
-    dim3 grid(h->g.nxB / LPC, nplanes, fwd ? 3 : 6);
-    if (fwd) {
-        cudaFuncSetAttribute(zfwd3_kernel<G, LPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(zfwd3_kernel<G, LPC>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        ScopedKernelTimer tm(h, "zfwd");
-        zfwd3_kernel<G, LPC><<<grid, LPC * 32, smem, h->stream>>>(h->V, h->Aw, h->g, h->Wz, plane0, h->chunk_planes, LS);
-    } else {
-        cudaFuncSetAttribute(zbwd3_kernel<G, LPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(zbwd3_kernel<G, LPC>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        ScopedKernelTimer tm(h, "zbwd");
-        zbwd3_kernel<G, LPC><<<grid, LPC * 32, smem, h->stream>>>(h->Br, h->P, h->g, h->Wz, plane0, h->chunk_planes, LS);
-    }
-    h->launches++;
-    return true;
-}
-
 // returns false when no specialised kernel exists for this size (caller falls back to the
 // generic shared-memory passes of conv_kernels.cu)
 bool launch_z3_fwd_or_bwd(chb_handle_s* h, int plane0, int nplanes, bool fwd) {
     if (h->g.nz < 2) return false;
-    const int lpc = h->z_lines_per_cta;
-    if (h->z_var == 4) {   // lpc is 4 here (chb_create)
-        switch (h->g.nzd) {
-            case 768: return launch_z4<Fft3<768, 12, 8, 8>, 4, 64, 4>(h, plane0, nplanes, fwd);
-            case 1536: return launch_z4<Fft3<1536, 12, 16, 8>, 4, 64, 2>(h, plane0, nplanes, fwd);
-            case 3072: return launch_z4<Fft3<3072, 12, 16, 16>, 4, 64, 1>(h, plane0, nplanes, fwd);
-            default: return false;
-        }
-    }
-    switch (h->g.nzd) {
-        case 768:
-            return lpc == 4 ? launch_z3<Fft3<768, 12, 8, 8>, 4>(h, plane0, nplanes, fwd)
-                            : launch_z3<Fft3<768, 12, 8, 8>, 8>(h, plane0, nplanes, fwd);
-        case 1536:
-            return lpc == 4 ? launch_z3<Fft3<1536, 12, 16, 8>, 4>(h, plane0, nplanes, fwd)
-                            : launch_z3<Fft3<1536, 12, 16, 8>, 8>(h, plane0, nplanes, fwd);
-        case 3072:
-            return launch_z3<Fft3<3072, 12, 16, 16>, 4>(h, plane0, nplanes, fwd);
-        default:
-            return false;
+    const int lpc = fwd ? h->zf_lines_per_cta : h->zb_lines_per_cta;
+    switch (h->g.nzd * 16 + lpc) {
+        case 768 * 16 + 2: return launch_z4<Fft3<768, 12, 8, 8>, 2, 64, 8>(h, plane0, nplanes, fwd);
+        case 768 * 16 + 4: return launch_z4<Fft3<768, 12, 8, 8>, 4, 64, 4>(h, plane0, nplanes, fwd);
+        case 768 * 16 + 8: return launch_z4<Fft3<768, 12, 8, 8>, 8, 32, 2>(h, plane0, nplanes, fwd);
+        case 1536 * 16 + 2: return launch_z4<Fft3<1536, 12, 16, 8>, 2, 64, 4>(h, plane0, nplanes, fwd);
+        case 1536 * 16 + 4: return launch_z4<Fft3<1536, 12, 16, 8>, 4, 64, 2>(h, plane0, nplanes, fwd);
+        case 1536 * 16 + 8: return launch_z4<Fft3<1536, 12, 16, 8>, 8, 32, 1>(h, plane0, nplanes, fwd);
+        case 3072 * 16 + 2: return launch_z4<Fft3<3072, 12, 16, 16>, 2, 64, 2>(h, plane0, nplanes, fwd);
+        case 3072 * 16 + 4: return launch_z4<Fft3<3072, 12, 16, 16>, 4, 64, 1>(h, plane0, nplanes, fwd);
+        default: return false;
     }
 }

@@ -24,16 +24,19 @@ GRIDS = [
 ]
 
 
-# kernel variants: (CHB_Z_VAR, CHB_Z_LPC, CHB_X_VAR); the first one is the default path
-VARIANTS = [("4", "4", "4"), ("3", "8", "3"), ("3", "4", "6")]
+# kernel variants: lines per CTA of zfwd / zbwd (CHB_ZF_LPC, CHB_ZB_LPC) and the tile width of the
+# velocity work buffer (CHB_TWA; "" = as wide as the zfwd lines, -1 = row-major); the first is the default
+VARIANTS = [("", "", ""), ("8", "4", ""), ("2", "8", "-1"), ("4", "2", "1")]
 
 
-@pytest.mark.parametrize("zvar,lpc,xvar", VARIANTS)
+@pytest.mark.parametrize("zf,zb,twa", VARIANTS)
 @pytest.mark.parametrize("nx,ny,nz", GRIDS)
-def test_fft3_products_and_step(nx, ny, nz, zvar, lpc, xvar, monkeypatch):
-    monkeypatch.setenv("CHB_Z_VAR", zvar)
-    monkeypatch.setenv("CHB_Z_LPC", lpc)
-    monkeypatch.setenv("CHB_X_VAR", xvar)
+def test_fft3_products_and_step(nx, ny, nz, zf, zb, twa, monkeypatch):
+    for k, v in (("CHB_ZF_LPC", zf), ("CHB_ZB_LPC", zb), ("CHB_TWA", twa)):
+        if v:
+            monkeypatch.setenv(k, v)
+        else:
+            monkeypatch.delenv(k, raising=False)
     p, o, ch, V0 = make_pair(nx, ny, nz, eps=5e-2)
     ch.cfl_prepass(); o.cfl_prepass()
     s = ch.get_step_scalars()
