@@ -194,7 +194,7 @@ extern "C" int chb_create(chb_handle* out, int nx, int ny, int nz, int nxd, int 
             for (int t = 1; t <= 3; ++t)
                 if ((1 << t) == h->zf_lines_per_cta && g.nxB % (1 << t) == 0) g.twa = t;
         e = getenv("CHB_TWA");
-        if (e && (atoi(e) < 0 || g.nxB % (1 << atoi(e)) == 0)) g.twa = atoi(e);
+        if (nranks > 1 && e && (atoi(e) < 0 || g.nxB % (1 << atoi(e)) == 0)) g.twa = atoi(e);
     }
     h->launches = 0;
     h->tables_set = false;
@@ -228,7 +228,14 @@ extern "C" int chb_create(chb_handle* out, int nx, int ny, int nz, int nxd, int 
         h->nlanes = (e && atoi(e) == 2) ? 2 : 1;   // two lanes measured no faster on 1 or 2 GPUs (kernels of one lane fill the GPU)
         const bool nccl_mode = nranks > 1 && !h->p2p;
         const size_t per_plane = (size_t)9 * nzd * g.nxB * sizeof(cplx) * (nccl_mode ? 2 : 1);
-        size_t np = ((size_t)3 << 30) / h->nlanes;
+        // budget: CHB_WORK_GB (default 12 GB, at most a quarter of the free device memory); larger chunks
+        // mean fewer launches and fewer partially filled last waves per substep
+        size_t free_b = 0, total_b = 0;
+        CHB_CUDA_OK(cudaMemGetInfo(&free_b, &total_b));
+        e = getenv("CHB_WORK_GB");
+        size_t budget = (size_t)((e ? atof(e) : 12.0) * 1073741824.0);
+        if (budget > free_b / 4) budget = free_b / 4;
+        size_t np = budget / h->nlanes;
         np /= per_plane;
         if (np < 1) np = 1;
         if (np > (size_t)(g.nyp + h->nlanes - 1) / h->nlanes) np = (g.nyp + h->nlanes - 1) / h->nlanes;

@@ -105,9 +105,31 @@ template <int S>
 struct Dft<6, S> {
     __device__ __forceinline__ static void run(cplx* a) { dft_composite<2, 3, S>(a); }
 };
+// 12 = 3 x 4 with coprime factors: Good-Thomas prime-factor mapping, no twiddles between the 3- and
+// 4-point transforms.  n = (4 n1 + 3 n2) mod 12, k = (4 k1 + 9 k2) mod 12:
+//   n k = 4 n1 k1 + 3 n2 k2 (mod 12)  ->  X[k] = sum_{n2} w4^(n2 k2) sum_{n1} w3^(n1 k1) x[n]
 template <int S>
 struct Dft<12, S> {
-    __device__ __forceinline__ static void run(cplx* a) { dft_composite<4, 3, S>(a); }
+    __device__ __forceinline__ static void run(cplx* a) {
+        cplx y[12];   // y[k1*4 + n2]
+        static_for<4>([&](auto n2_) {
+            constexpr int n2 = decltype(n2_)::value;
+            cplx t[3] = {a[(3 * n2) % 12], a[(4 + 3 * n2) % 12], a[(8 + 3 * n2) % 12]};
+            Dft<3, S>::run(t);
+            y[0 * 4 + n2] = t[0];
+            y[1 * 4 + n2] = t[1];
+            y[2 * 4 + n2] = t[2];
+        });
+        static_for<3>([&](auto k1_) {
+            constexpr int k1 = decltype(k1_)::value;
+            cplx u[4] = {y[k1 * 4 + 0], y[k1 * 4 + 1], y[k1 * 4 + 2], y[k1 * 4 + 3]};
+            Dft<4, S>::run(u);
+            static_for<4>([&](auto k2_) {
+                constexpr int k2 = decltype(k2_)::value;
+                a[(4 * k1 + 9 * k2) % 12] = u[k2];
+            });
+        });
+    }
 };
 template <int S>
 struct Dft<16, S> {

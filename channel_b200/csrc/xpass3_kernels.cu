@@ -67,11 +67,13 @@ xpass4_kernel(const cplx* __restrict__ Ar, const __grid_constant__ PeerPtrs Bw, 
             return t;
         }
     };
-    // velocity buffer: [src rank][comp][plane][x tile][z row][x in tile] (transpose_index.h), 32-bit offsets
+    // velocity buffer (transpose_index.h), 32-bit offsets: one GPU: row-major [comp][plane][z row][x];
+    // several: [src rank][comp][plane][x tile][z row][x in tile] (row-major if g.twa < 0)
     const unsigned planeA = (unsigned)((size_t)nzB * nxB), cstrA = (unsigned)np * planeA;
-    const unsigned rowA = (unsigned)pli * planeA + (g.twa < 0 ? (unsigned)izl * (unsigned)nxB : ((unsigned)izl << g.twa));
-    const unsigned tmaskA = g.twa < 0 ? 0xffffffffu : (1u << g.twa) - 1u;
-    const unsigned tstrA = g.twa < 0 ? 0u : ((unsigned)nzB << g.twa);   // elements between x tiles
+    const bool tiledA = multi && g.twa >= 0;
+    const unsigned rowA = (unsigned)pli * planeA + (tiledA ? ((unsigned)izl << g.twa) : (unsigned)izl * (unsigned)nxB);
+    const unsigned tmaskA = tiledA ? (1u << g.twa) - 1u : 0u;
+    const unsigned tstrA = tiledA ? ((unsigned)nzB << g.twa) : 0u;   // elements between x tiles
     // ---- backward stage A: split pass -> radix-A -> smem; tasks = (component, mode group t1) --------
 #pragma unroll 1
     for (int task = tl; task < 3 * BC; task += T) {
@@ -81,9 +83,11 @@ xpass4_kernel(const cplx* __restrict__ Ar, const __grid_constant__ PeerPtrs Bw, 
         const cplx* __restrict__ Xc = Ar + rowA + (unsigned)comp * cstrA;
         auto X = [&](int n) -> cplx {   // mode n of this line, zero beyond nx (x zero-padding, dnsdata.f90:535)
             if (n > nx) return make_double2(0.0, 0.0);
-            unsigned nl = (unsigned)n, o = 0;
-            if (multi) { const unsigned qr = nl / (unsigned)nxB; nl -= qr * (unsigned)nxB; o = qr * 3u * cstrA; }
-            o += (g.twa < 0) ? nl : ((nl >> g.twa) * tstrA + (nl & tmaskA));
+            unsigned o = (unsigned)n;
+            if (multi) {
+                const unsigned qr = (unsigned)n / (unsigned)nxB, nl = (unsigned)n - qr * (unsigned)nxB;
+                o = qr * 3u * cstrA + (tiledA ? ((nl >> g.twa) * tstrA + (nl & tmaskA)) : nl);
+            }
             return __ldg(Xc + o);
         };
         cplx x[A];

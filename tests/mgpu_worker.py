@@ -29,9 +29,15 @@ def main():
         t = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).cuda()
         dist.broadcast(t, 0)
         return bytes(t.cpu().numpy().tobytes())
-    grids = [(31, 16, 16, False), (255, 8, 255, False), (31, 16, 16, True)]
+    # (grid, couette, library options): direct NVLink stores (default), NCCL all-to-all, row-major velocity
+    # buffer + two-lane chunk pipeline
+    grids = [(31, 16, 16, False, {}), (255, 8, 255, False, {}), (255, 8, 255, False, {"CHB_P2P": "0"}),
+             (255, 8, 255, False, {"CHB_TWA": "-1", "CHB_LANES": "2"}), (31, 16, 16, True, {})]
     worst = 0.0
-    for nx, ny, nz, couette in grids:
+    for nx, ny, nz, couette, opts in grids:
+        for k in ("CHB_P2P", "CHB_TWA", "CHB_LANES"):
+            os.environ.pop(k, None)
+        os.environ.update(opts)
         kw = dict(CPI=False, u0=-1.0, uN=1.0) if couette else {}
         p = DnsIn(nx=nx, ny=ny, nz=nz, re=2000.0, deltat=0.0, cflmax=1.0, **kw)
         o = Oracle(ODnsIn(**{k: getattr(p, k) for k in ODnsIn.__dataclass_fields__}))

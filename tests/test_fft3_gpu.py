@@ -25,14 +25,14 @@ GRIDS = [
 
 
 # kernel variants: lines per CTA of zfwd / zbwd (CHB_ZF_LPC, CHB_ZB_LPC) and the tile width of the
-# velocity work buffer (CHB_TWA; "" = as wide as the zfwd lines, -1 = row-major); the first is the default
-VARIANTS = [("", "", ""), ("8", "4", ""), ("2", "8", "-1"), ("4", "2", "1")]
+# products work buffer (CHB_TW); the first is the default
+VARIANTS = [("", "", ""), ("8", "4", "2"), ("2", "8", "0")]
 
 
-@pytest.mark.parametrize("zf,zb,twa", VARIANTS)
+@pytest.mark.parametrize("zf,zb,tw", VARIANTS)
 @pytest.mark.parametrize("nx,ny,nz", GRIDS)
-def test_fft3_products_and_step(nx, ny, nz, zf, zb, twa, monkeypatch):
-    for k, v in (("CHB_ZF_LPC", zf), ("CHB_ZB_LPC", zb), ("CHB_TWA", twa)):
+def test_fft3_products_and_step(nx, ny, nz, zf, zb, tw, monkeypatch):
+    for k, v in (("CHB_ZF_LPC", zf), ("CHB_ZB_LPC", zb), ("CHB_TW", tw)):
         if v:
             monkeypatch.setenv(k, v)
         else:
