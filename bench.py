@@ -120,6 +120,22 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(sm)}
 
 
+def measured_traffic(kernel, nx, ny, nz, world):
+    """DRAM bytes per y-plane of one launch family from the committed `ncu --set full` capture
+    (profiles/*_dram_traffic_*.json: dram__bytes_read.sum + dram__bytes_write.sum / planes), for the
+    workload and GPU count it was captured on; None otherwise."""
+    import glob
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_dram_traffic_*.json")), reverse=True):
+        try:
+            with open(path) as f:
+                d = json.load(f)
+            if d.get("workload") == f"{nx},{ny},{nz}" and int(d.get("n_gpus", 1)) == world and kernel in d["kernels"]:
+                return float(d["kernels"][kernel]["dram_bytes_per_plane"]), os.path.basename(path)
+        except Exception:
+            continue
+    return None, None
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -246,6 +262,8 @@ def run_b200(args):
         tms = sum(kern[n][0] for n in fam[dom] if n in kern)
         bytes_per_launch = per[dom] / world * 3 * args.steps / nl
         ach = bytes_per_launch / (tms / nl * 1e-3) / 1e9
+        tpp, tsrc = measured_traffic(dom, nx, ny, nz, world)
+        traffic = tpp * (ny + 3) * 3 * args.steps / nl if (tpp and dom in ("zfwd", "xpass", "zbwd")) else None
         out = {
             "metric": "rk3_timesteps_per_s", "value": 1000.0 / ms_per_step, "unit": "steps/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
@@ -259,7 +277,7 @@ def run_b200(args):
                        "l2": "state (%.1f GB/GPU) far larger than the 126 MB L2; no flush needed" % (ch.device_bytes() / 1e9),
                        "device_bytes_per_gpu": ch.device_bytes()},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
-                         "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": ach / peak, "traffic": traffic, "traffic_source": tsrc, "peak_source": peak_src,
                          "bytes_per_launch": bytes_per_launch, "launches": nl},
             "step_roofline": {"bytes_per_step": step_bytes, "achieved": step_bytes / (ms_per_step * 1e-3) / 1e9,
                               "peak": peak * world, "unit": "GB/s",
