@@ -1,0 +1,122 @@
+// ydir_emul.cpp - test infrastructure: the y-direction CUDA kernels (rhs_kernel.cu, solve_kernels.cu)
+// compiled with g++ and run thread by thread on the CPU.
+//
+// Those kernels are one thread per wavenumber column with no shared memory, shuffles or atomics, so
+// their source is valid host C++ once the CUDA keywords are neutralised; running it here lets the
+// CPU test suite (-m "not gpu") check the kernel logic -- including the fused flow (rhs_s1_kernel,
+// solve_s24_kernel) against the plain one (rhs_kernel, solve_s1..s4) -- against the numpy oracle
+// without a GPU.  It is a checker only: the product path never loads this library.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+static uint3 e_blockIdx, e_threadIdx;
+static dim3 e_blockDim, e_gridDim;
+#define blockIdx e_blockIdx
+#define threadIdx e_threadIdx
+#define blockDim e_blockDim
+#define gridDim e_gridDim
+template <class T>
+static inline T __ldg(const T* p) { return *p; }
+static inline void __syncthreads() {}
+#undef __launch_bounds__
+#define __launch_bounds__(...)
+
+#define CHB_HOST_EMUL 1
+#include "../../channel_b200/csrc/rhs_kernel.cu"
+#include "../../channel_b200/csrc/solve_kernels.cu"
+
+// run `kern(args...)` for every thread of a 1-D grid
+template <class K, class... Args>
+static void emulate(K kern, int blocks, int threads, Args... args) {
+    e_blockDim = dim3(threads, 1, 1);
+    e_gridDim = dim3(blocks, 1, 1);
+    for (int b = 0; b < blocks; ++b)
+        for (int t = 0; t < threads; ++t) {
+            e_blockIdx = make_uint3(b, 0, 0);
+            e_threadIdx = make_uint3(t, 0, 0);
+            kern(args...);
+        }
+}
+
+extern "C" {
+
+// One substep of the y-direction work on host arrays in the device layout [c][iy+1][ixl][iz+nz]:
+//   V [3][nyp][M] (in: u,v,w; out: u,v,w after linsolve), P [6][nyp][M] products, F [3][nyp][M] or null,
+//   oldrhs [2][nyp][M] (in/out), rhs_out [2][nyp][M] (plain flow: the RHS; fused flow: Step1 results).
+// Tables as chb_set_tables receives them.  scal_io: {meanpx, meanpz, meanflowx, meanflowz, gamma, u0, uN,
+// CPI, CPI_type} in; {fr0, fr1, fr2, corrpx, corrpz, meanpx} out.  fused: 0 plain, 1 fused.
+int chb_emul_ydir_substep(int nx, int ny, int nz, double alfa0, double beta0, double ni, const double* y,
+                          const double* d0, const double* d1, const double* d2, const double* d4,
+                          const double* bc5x16, const double* D0mat, double* V, const double* P, const double* F,
+                          double* oldrhs, double* rhs_out, double* scal_io, double ode1, double ode2, double ode3,
+                          double deltat, int fused) {
+    Geometry g;
+    memset(&g, 0, sizeof(g));
+    g.nx = nx; g.ny = ny; g.nz = nz;
+    g.nyp = ny + 3; g.nzt = 2 * nz + 1;
+    g.rank = 0; g.nranks = 1;
+    g.nx0 = 0; g.nxN = nx; g.nxB = nx + 1;
+    g.M = (long long)g.nxB * g.nzt;
+    g.alfa0 = alfa0; g.beta0 = beta0; g.ni = ni;
+    const int nyp = g.nyp;
+    // tables, as chb_set_tables lays them out (chb_api.cu)
+    std::vector<double> dy(nyp, 0.0), full[4];
+    for (int iy = 1; iy <= ny - 1; ++iy) dy[iy + 1] = 0.5 * (y[iy + 2] - y[iy]);
+    const double* src[4] = {d0, d1, d2, d4};
+    for (int t = 0; t < 4; ++t) {
+        full[t].assign((size_t)nyp * 5, 0.0);
+        memcpy(&full[t][10], src[t], sizeof(double) * 5 * (ny - 1));
+    }
+    DevTables tab;
+    tab.y = y; tab.dy = dy.data();
+    tab.d0 = full[0].data(); tab.d1 = full[1].data(); tab.d2 = full[2].data(); tab.d4 = full[3].data();
+    tab.D0mat = D0mat;
+    double* dst[16] = {tab.d140, tab.d14m1, tab.d240, tab.d24m1, tab.d14n, tab.d14np1, tab.d24n, tab.d24np1,
+                       tab.v0bc, tab.v0m1bc, tab.vnbc, tab.vnp1bc, tab.eta0bc, tab.eta0m1bc, tab.etanbc, tab.etanp1bc};
+    for (int k = 0; k < 16; ++k) memcpy(dst[k], bc5x16 + 5 * k, sizeof(double) * 5);
+    DevScalars sc;
+    memset(&sc, 0, sizeof(sc));
+    sc.meanpx = scal_io[0]; sc.meanpz = scal_io[1]; sc.meanflowx = scal_io[2]; sc.meanflowz = scal_io[3];
+    sc.gamma = scal_io[4]; sc.u0 = scal_io[5]; sc.uN = scal_io[6];
+    sc.CPI = (int)scal_io[7]; sc.CPI_type = (int)scal_io[8];
+
+    const size_t fld = (size_t)nyp * g.M;
+    std::vector<double> ckpt((size_t)((ny - 1) / CHB_SOLVE_K + 1) * 8 * g.M, 0.0);
+    std::vector<double> scratch((size_t)(ny + 1) * 5 + nyp + 8, 0.0);
+    cplx* Vc = reinterpret_cast<cplx*>(V);
+    const cplx* Pc = reinterpret_cast<const cplx*>(P);
+    const cplx* Fc = reinterpret_cast<const cplx*>(F);
+    cplx* oc = reinterpret_cast<cplx*>(oldrhs);
+    cplx* rc = reinterpret_cast<cplx*>(rhs_out);
+    (void)fld;
+    const int T = 128, blocks = (int)((g.M + T - 1) / T);
+    const double lam = ode1 / deltat;
+    if (fused <= 0) {
+        if (F) emulate(rhs_kernel<true>, blocks, T, Vc, Pc, Fc, rc, oc, g, tab, &sc, lam, ode2, ode3);
+        else emulate(rhs_kernel<false>, blocks, T, Vc, Pc, Fc, rc, oc, g, tab, &sc, lam, ode2, ode3);
+        if (fused < 0) return 0;   // RHS only
+        emulate(solve_s1_kernel<0>, blocks, T, rc, ckpt.data(), g, tab, &sc, lam);
+        emulate(solve_s1_kernel<1>, blocks, T, rc, ckpt.data(), g, tab, &sc, lam);
+        emulate(solve_s2_kernel<0>, blocks, T, rc, ckpt.data(), Vc, g, tab, &sc, lam, 0);
+        emulate(solve_s2_kernel<1>, blocks, T, rc, ckpt.data(), Vc, g, tab, &sc, lam, 0);
+        emulate(mean_mode_kernel, 1, 32, Vc, g, tab, &sc, lam, scratch.data());
+        emulate(solve_s3_kernel, blocks, T, Vc, g, tab);
+        emulate(solve_s4_kernel, blocks, T, Vc, g, tab);
+    } else {
+        if (F) emulate(rhs_s1_kernel<true, 2>, blocks, T, Vc, Pc, Fc, rc, oc, ckpt.data(), g, tab, &sc, lam, ode2, ode3);
+        else emulate(rhs_s1_kernel<false, 2>, blocks, T, Vc, Pc, Fc, rc, oc, ckpt.data(), g, tab, &sc, lam, ode2, ode3);
+        emulate(solve_s2_kernel<0>, 1, 32, rc, ckpt.data(), Vc, g, tab, &sc, lam, 1);
+        emulate(mean_mode_kernel, 1, 32, Vc, g, tab, &sc, lam, scratch.data());
+        emulate(solve_s2_kernel<1>, blocks, T, rc, ckpt.data(), Vc, g, tab, &sc, lam, 0);
+        emulate(solve_s3_kernel, blocks, T, Vc, g, tab);
+        emulate(solve_s24_kernel, blocks, T, rc, ckpt.data(), Vc, g, tab, lam);
+    }
+    scal_io[0] = sc.fr[0]; scal_io[1] = sc.fr[1]; scal_io[2] = sc.fr[2];
+    scal_io[3] = sc.corrpx; scal_io[4] = sc.corrpz; scal_io[5] = sc.meanpx;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,127 @@
+"""The y-direction CUDA kernels (rhs_kernel.cu, solve_kernels.cu) run on the CPU.
+
+tests/host_emul/ydir_emul.cpp compiles the kernel SOURCE with g++ (they are one thread per
+wavenumber column, no shared memory / shuffles / atomics) and runs it thread by thread.  This checks,
+without a GPU, (a) the plain flow rhs -> S1 -> S2 -> mean mode -> S3 -> S4 and (b) the fused flow
+(CHB_FUSE: rhs_s1 -> S2(v) -> S3 -> S2(eta)+S4) against the numpy oracle's buildrhs + linsolve
+(dnsdata.f90:611-673, linsolve_blocking.inc:3-107) to the north-star single-step tolerance, 1e-12
+relative.  The GPU parity tests run the same comparisons on the device (tests/test_parity_gpu.py).
+"""
+import ctypes as C
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+from channel_b200 import RK1_rai, RK2_rai, RK3_rai
+from channel_b200.fields import perturbed_laminar
+from oracle.channel_oracle import DnsIn as ODnsIn, Oracle, coriolis_force
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "host_emul", "ydir_emul.cpp")
+BUILD = os.path.join(HERE, "host_emul", "_build")
+CUDA_INC = "/usr/local/cuda/include"
+
+
+def relerr(a, b):
+    n = float(np.abs(b).max())
+    d = float(np.abs(a - b).max())
+    return d / n if n > 0 else d
+
+
+@pytest.fixture(scope="module")
+def emul():
+    if shutil.which("g++") is None or not os.path.exists(os.path.join(CUDA_INC, "cuda_runtime.h")):
+        pytest.skip("needs g++ and the CUDA headers")
+    os.makedirs(BUILD, exist_ok=True)
+    so = os.path.join(BUILD, "libydir_emul.so")
+    deps = [SRC] + [os.path.join(HERE, "..", "channel_b200", "csrc", f)
+                    for f in ("rhs_kernel.cu", "solve_kernels.cu", "solve_device.cuh", "chb_internal.h")]
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-w",
+                               "-I" + CUDA_INC, "-o", so, SRC])
+    lib = C.CDLL(so)
+    dp = C.POINTER(C.c_double)
+    lib.chb_emul_ydir_substep.argtypes = [C.c_int] * 3 + [C.c_double] * 3 + [dp] * 13 + [C.c_double] * 4 + [C.c_int]
+    lib.chb_emul_ydir_substep.restype = C.c_int
+    return lib
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double)) if a is not None else None
+
+
+def run_substep(lib, o, V, P, F, oldrhs, ODE, fused):
+    """one substep of the kernels on copies of the oracle's current state; returns V, oldrhs, rhs, scalars"""
+    ny = o.ny
+    rows = lambda a: np.ascontiguousarray(a[2:ny + 1], dtype=np.float64)
+    bc = np.ascontiguousarray(np.concatenate([np.asarray(getattr(o, n), dtype=np.float64) for n in (
+        "d140", "d14m1", "d240", "d24m1", "d14n", "d14np1", "d24n", "d24np1",
+        "v0bc", "v0m1bc", "vnbc", "vnp1bc", "eta0bc", "eta0m1bc", "etanbc", "etanp1bc")]))
+    y = np.ascontiguousarray(o.y, dtype=np.float64)
+    d0, d1, d2, d4 = rows(o.d0), rows(o.d1), rows(o.d2), rows(o.d4)
+    D0 = np.ascontiguousarray(o.D0mat, dtype=np.float64)
+    V = np.ascontiguousarray(V.copy()); P = np.ascontiguousarray(P); oldrhs = np.ascontiguousarray(oldrhs.copy())
+    F = np.ascontiguousarray(F) if F is not None else None
+    rhs = np.zeros_like(oldrhs)
+    sc = np.array([o.meanpx, o.meanpz, o.meanflowx, o.meanflowz, o.gamma, o.p.u0, o.p.uN,
+                   float(o.CPI), float(o.CPI_type), 0.0])
+    rc = lib.chb_emul_ydir_substep(o.nx, o.ny, o.nz, o.alfa0, o.beta0, o.ni, _dp(y), _dp(d0), _dp(d1), _dp(d2), _dp(d4),
+                                   _dp(bc), _dp(D0), _dp(V.view(np.float64)), _dp(P.view(np.float64)),
+                                   _dp(F.view(np.float64)) if F is not None else None,
+                                   _dp(oldrhs.view(np.float64)), _dp(rhs.view(np.float64)), _dp(sc),
+                                   ODE[0], ODE[1], ODE[2], o.deltat, fused)
+    assert rc == 0
+    return V, oldrhs, rhs, sc
+
+
+CASES = [
+    dict(nx=6, ny=16, nz=5),                                     # smallest: one-and-a-bit checkpoint blocks
+    dict(nx=9, ny=41, nz=7, CPI=False, meanflowx=2.0),           # ny-1 a multiple of 8, constant-flow-rate branch
+    dict(nx=5, ny=30, nz=4, couette=True),                       # Couette walls + coriolis body force
+]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_ydir_kernels_plain_and_fused_match_oracle(emul, case):
+    case = dict(case)
+    couette = case.pop("couette", False)
+    kw = dict(re=1500.0, deltat=2e-3, cflmax=0.0)
+    kw.update(case)
+    if couette:
+        kw.update(CPI=False, u0=-1.0, uN=1.0)
+    p = ODnsIn(**kw)
+    o = Oracle(p)
+    o.V[:] = perturbed_laminar(p.nx, p.ny, p.nz, p.alfa0, p.beta0, p.a, p.ymin, p.ymax, eps=5e-2, couette=couette)
+    if couette:
+        o.set_body_force(coriolis_force(0.02, 9999999.0, 1.0))
+    o.cfl_prepass(); o.outstats()
+    rng = np.random.default_rng(5)
+    o.oldrhs[:, 2:p.ny + 1] = 1e-3 * (rng.standard_normal(o.oldrhs[:, 2:p.ny + 1].shape) + 0j)   # exercise ODE(3)
+    for ODE in (RK1_rai, RK2_rai, RK3_rai):
+        if getattr(o, "_body_force", None) is not None:
+            o._body_force(o)
+        V0 = o.V.copy(); old0 = o.oldrhs.copy()
+        P = o.convolutions(o.V, False)[..., o.izd]
+        mp0 = (o.meanpx, o.meanpz)
+        rhs_ref = o.buildrhs(ODE, False)           # also extends F to the ghost nodes in place
+        F = o.F.copy() if o.F is not None else None
+        o.linsolve(ODE[0] / o.deltat)
+        mp1 = (o.meanpx, o.meanpz)
+        o.meanpx, o.meanpz = mp0                   # the kernels start from the pre-substep scalars
+        sl = slice(2, p.ny + 1)
+        _, _, rhsk, _ = run_substep(emul, o, V0, P, F, old0, ODE, -1)      # rhs_kernel alone
+        for c in range(2):
+            assert relerr(rhsk[c, sl], rhs_ref[c, sl]) < 1e-12, ("rhs", c)
+        for fused in (0, 1):
+            Vk, oldk, rhsk, sc = run_substep(emul, o, V0, P, F, old0, ODE, fused)
+            for c in range(3):
+                assert relerr(Vk[c], o.V[c]) < 1e-12, (fused, "field", c, relerr(Vk[c], o.V[c]))
+            for c in range(2):
+                assert relerr(oldk[c, sl], o.oldrhs[c, sl]) < 1e-12, (fused, "oldrhs", c)
+            assert np.allclose(sc[:3], o.fr, rtol=1e-12, atol=1e-15), (fused, sc[:3], o.fr)
+            assert abs(sc[3] - o.corrpx) <= 1e-11 * max(1.0, abs(o.corrpx))
+            assert abs(sc[5] - mp1[0]) <= 1e-12 * max(1.0, abs(mp1[0]))
+        o.meanpx, o.meanpz = mp1
