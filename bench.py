@@ -136,6 +136,42 @@ def measured_traffic(kernel, nx, ny, nz, world):
     return None, None
 
 
+NVLINK_PEAK_GBS = 900.0   # NVLink 5 per direction and GPU (north_star; B200_PROFILING.md)
+
+
+def nvlink_bytes_per_gpu_step(nx, ny, nz, nzd, world):
+    """bytes one GPU sends (= receives) over NVLink per RK3 step: 3 substeps x
+    (ny+3) planes x its M/P modes x 9 r C (3 velocity components forward, 6 products back) x the
+    (P-1)/P share of every pencil that lives on a peer.  Returns (total, zTOx part, xTOz part)."""
+    M = (nx + 1) * (2 * nz + 1)
+    r = nzd / (2 * nz + 1)
+    per_comp = 3.0 * (M / world) * (ny + 3) * r * C16 * (world - 1) / world
+    return 9.0 * per_comp, 3.0 * per_comp, 6.0 * per_comp
+
+
+def nvlink_report(nx, ny, nz, nzd, world, steps, ms_per_step, kern, direct):
+    """Achieved NVLink GB/s per direction and GPU against 900 GB/s.  Direct mode (default): the pack side
+    of zTOx / xTOz IS the store loop of zfwd / xpass into peer HBM (CUDA IPC), so the transfer time of a
+    transpose is the duration of that kernel (CUDA events); NCCL mode (CHB_P2P=0): the grouped
+    ncclSend/ncclRecv all-to-all ("alltoall" timer, both directions together)."""
+    total, fwd, bwd = nvlink_bytes_per_gpu_step(nx, ny, nz, nzd, world)
+    rep = {"peak_gbs_per_direction": NVLINK_PEAK_GBS, "bytes_per_gpu_step": total,
+           "mode": "direct peer stores fused into zfwd/xpass" if direct else "NCCL grouped send/recv all-to-all",
+           "step": {"gbs": total / (ms_per_step * 1e-3) / 1e9,
+                    "frac": total / (ms_per_step * 1e-3) / 1e9 / NVLINK_PEAK_GBS,
+                    "what": "bytes sent per GPU and step / whole step time (overlap-inclusive)"}}
+    names = ({"zTOx": (["zfwd"], fwd), "xTOz": (["xpass"], bwd)} if direct
+             else {"zTOx+xTOz": (["alltoall"], total)})
+    for k, (ns, b) in names.items():
+        tms = sum(kern[n][0] for n in ns if n in kern) / steps
+        if tms > 0:
+            rep[k] = {"carrier": "+".join(ns), "ms_per_step": tms, "gbs": b / (tms * 1e-3) / 1e9,
+                      "frac": b / (tms * 1e-3) / 1e9 / NVLINK_PEAK_GBS}
+    if "p2p_barrier" in kern:
+        rep["barrier_ms_per_step"] = kern["p2p_barrier"][0] / steps
+    return rep
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -240,8 +276,10 @@ def run_b200(args):
     if rank == 0:
         peak, peak_src = measured_peaks()
         per, step_bytes = algorithmic_bytes(nx, ny, nz, nxd, nzd)
-        fam = {"zfwd": ["zfwd"], "xpass": ["xpass"], "zbwd": ["zbwd"], "rhs": ["rhs"],
-               "solve": ["solve_s1", "solve_s2", "solve_s3", "solve_s4", "solve"]}
+        # fused y-direction flow (CHB_FUSE): rhs_s1 = buildrhs plane loop + first solve sweep (counted under
+        # "rhs"), solve_s24 = eta back-substitution + vetaTOuvw
+        fam = {"zfwd": ["zfwd"], "xpass": ["xpass"], "zbwd": ["zbwd"], "rhs": ["rhs", "rhs_s1"],
+               "solve": ["solve_s1", "solve_s2", "solve_s3", "solve_s4", "solve_s24", "solve"]}
         total_kernel_ms = sum(v[0] for v in kern.values()) or 1.0
         kernels = {}
         for f, names in fam.items():
@@ -292,6 +330,9 @@ def run_b200(args):
                             "chb_get_step_scalars) + chb_download_V, wall clock"},
             "finite": finite,
         }
+        if world > 1:
+            out["nvlink"] = nvlink_report(nx, ny, nz, nzd, world, args.steps, ms_per_step, kern,
+                                          direct=os.environ.get("CHB_P2P", "1") != "0")
         if args.cpu_baseline and world == 1:
             out["cpu_baseline"] = cpu_baseline(w, sample_s=args.cpu_seconds)
         print(json.dumps(out), flush=True)

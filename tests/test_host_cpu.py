@@ -146,3 +146,17 @@ def test_bench_algorithmic_bytes_match_survey():
     per, step = bench.algorithmic_bytes(191, 384, 189, 384, 768)
     assert abs(step - 88e9) / 88e9 < 0.01                   # 88 GB/step at config 2
     assert abs(3 * sum(per.values()) - step) / step < 0.02  # per-kernel rows add up to the step total
+
+
+def test_bench_nvlink_and_hbm_byte_models():
+    """bench.py's byte models reproduce SURVEY.md 8(d): config 4 moves 5.78 TB of HBM traffic per step
+    and 152.6 GB per GPU over NVLink at P=8; config 2 moves 88 GB per step."""
+    import bench
+    _, step4 = bench.algorithmic_bytes(1023, 1024, 1023, 1536, 3072)
+    assert abs(step4 / 1e12 - 5.78) < 0.01
+    _, step2 = bench.algorithmic_bytes(191, 384, 189, 384, 768)
+    assert abs(step2 / 1e9 - 88.0) < 0.5
+    tot, fwd, bwd = bench.nvlink_bytes_per_gpu_step(1023, 1024, 1023, 3072, 8)
+    assert abs(tot / 1e9 - 152.6) < 0.1 and abs(fwd * 2 - bwd) < 1e-6 * bwd
+    rep = bench.nvlink_report(511, 512, 511, 1536, 2, 3, 138.0, {"zfwd": (300.0, 15), "xpass": (500.0, 15)}, True)
+    assert rep["zTOx"]["carrier"] == "zfwd" and 0 < rep["step"]["frac"] < 1
