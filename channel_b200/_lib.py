@@ -57,6 +57,13 @@ SYMBOLS = {
     "chb_device_bytes": (C.c_longlong, [C.c_void_p]),
     "chb_measure_device_peaks": (C.c_int, [c_double_p]),
     "chb_test_fft_lines": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "chb_save_restart_file": (C.c_int, [C.c_void_p, C.c_char_p, C.c_double, C.c_int, C.c_int]),
+    "chb_restart_wait": (C.c_int, [C.c_void_p]),
+    "chb_restart_stats": (C.c_int, [C.c_void_p, c_double_p, c_double_p, c_double_p]),
+    "chb_read_restart_file": (C.c_int, [C.c_void_p, C.c_char_p, c_double_p]),
+    "chb_host_restart_header": (C.c_int, [C.c_int] * 3 + [C.c_double] * 7 + [C.c_void_p]),
+    "chb_host_restart_offset": (C.c_longlong, [C.c_int] * 5),
+    "chb_host_restart_file_bytes": (C.c_longlong, [C.c_int] * 3),
     "chb_host_fft_fit": (C.c_int, [C.c_int]),
     "chb_host_padded_sizes": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "chb_host_setup_tables": (C.c_int, [C.c_int, C.c_double, C.c_double, C.c_double, C.POINTER(HostTables)]),

@@ -143,7 +143,6 @@ void chb_select_lane(chb_handle_s* h, int L) {
 extern "C" int chb_create(chb_handle* out, int nx, int ny, int nz, int nxd, int nzd, double alfa0, double beta0,
                           double ni, double a, double ymin, double ymax, int rank, int nranks, const char* nccl_id,
                           int device) {
-    (void)a; (void)ymin; (void)ymax;
     CHB_REQUIRE(out != nullptr, "chb_create: null handle pointer");
     CHB_REQUIRE(nx >= 1 && ny >= 8 && nz >= 1, "chb_create: need nx>=1, ny>=8, nz>=1");
     CHB_REQUIRE(nxd >= nx + 1 && nxd % 2 == 0, "chb_create: nxd must be even and >= nx+1");
@@ -173,6 +172,8 @@ extern "C" int chb_create(chb_handle* out, int nx, int ny, int nz, int nxd, int 
     const double PI = 3.1415926535897932384626433832795028841971;  // dnsdata.f90:26
     g.dx = PI / (alfa0 * nxd); g.dz = 2.0 * PI / (beta0 * nzd); g.factor = 1.0 / (2.0 * nxd * nzd);  // :124
     h->device = device;
+    h->rio = nullptr;
+    h->grid_a = a; h->grid_ymin = ymin; h->grid_ymax = ymax;
     {
         // lines per z-pass CTA.  zbwd: 2 for the long lines (4 CTAs/SM at nzd = 1536), else 4.  zfwd: 4
         // (a warp's stores into the tiled velocity buffer are 512 contiguous bytes for any value).
@@ -284,6 +285,7 @@ extern "C" int chb_destroy(chb_handle h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     chb_timer_flush(h);
+    chb_restart_destroy(h);
     chb_nccl_destroy(h);
     cudaFree(h->V); cudaFree(h->rhs); cudaFree(h->oldrhs); cudaFree(h->P); cudaFree(h->ckpt);
     if (h->F) cudaFree(h->F);
@@ -351,7 +353,7 @@ extern "C" int chb_set_tables(chb_handle h, const double* y, const double* d0, c
 
 // Fused flow: the deferred plane loop of buildrhs (see chb_internal.h) runs unfused if anything but
 // chb_linsolve(ODE(1)/deltat) touches the handle first.
-static void flush_pending_rhs(chb_handle_s* h) {
+void chb_flush_pending(chb_handle_s* h) {
     if (h && h->rhs_pending) {
         h->rhs_pending = false;
         launch_rhs(h, h->pending_ode, h->pending_deltat);
@@ -364,7 +366,7 @@ static int transfer_V(chb_handle h, double* host, bool upload, bool fortran_layo
     CHB_CUDA_OK(cudaSetDevice(h->device));
     const Geometry& g = h->g;
     const size_t fld = (size_t)g.nyp * g.M;
-    flush_pending_rhs(h);
+    chb_flush_pending(h);
     CHB_CUDA_OK(cudaStreamSynchronize(h->stream));
     for (int c = 0; c < 3; ++c) {
         cplx* dev = field + c * fld;
@@ -410,7 +412,7 @@ static int download_n(chb_handle h, double* host, const cplx* dev, int ncomp) {
     CHB_REQUIRE(h, "null handle");
     CHB_CUDA_OK(cudaSetDevice(h->device));
     const size_t n = (size_t)ncomp * h->g.nyp * h->g.M;
-    flush_pending_rhs(h);
+    chb_flush_pending(h);
     CHB_CUDA_OK(cudaStreamSynchronize(h->stream));
     CHB_CUDA_OK(cudaMemcpy(host, dev, n * sizeof(cplx), cudaMemcpyDeviceToHost));
     return 0;
@@ -472,7 +474,7 @@ extern "C" int chb_set_body_force(chb_handle h) {
     CHB_REQUIRE(h, "null handle");
     if (!h->bf.enabled) return 0;
     CHB_CUDA_OK(cudaSetDevice(h->device));
-    flush_pending_rhs(h);
+    chb_flush_pending(h);
     launch_body_force(h);
     CHB_CUDA_OK(cudaGetLastError());
     return 0;
@@ -508,7 +510,7 @@ static int convolutions_all(chb_handle h, int compute_cfl, bool products) {
 extern "C" int chb_cfl_prepass(chb_handle h) {
     CHB_REQUIRE(h && h->tables_set, "chb_cfl_prepass: tables not set");
     CHB_CUDA_OK(cudaSetDevice(h->device));
-    flush_pending_rhs(h);
+    chb_flush_pending(h);
     if (convolutions_all(h, 1, false)) return 1;
     launch_meanflow_prepass(h);
     CHB_CUDA_OK(cudaGetLastError());
@@ -519,7 +521,7 @@ extern "C" int chb_buildrhs(chb_handle h, const double* ode, double deltat, int 
     CHB_REQUIRE(h && h->tables_set, "chb_buildrhs: tables not set");
     CHB_REQUIRE(deltat > 0.0, "chb_buildrhs: deltat must be > 0");
     CHB_CUDA_OK(cudaSetDevice(h->device));
-    flush_pending_rhs(h);
+    chb_flush_pending(h);
     if (h->bf.enabled) launch_force_ghosts(h);
     if (convolutions_all(h, compute_cfl, true)) return 1;
     if (h->fuse) {
@@ -541,7 +543,7 @@ extern "C" int chb_linsolve(chb_handle h, double lambda) {
         launch_rhs_s1(h, h->pending_ode, h->pending_deltat);
         launch_linsolve_fused(h, lambda);
     } else {
-        flush_pending_rhs(h);
+        chb_flush_pending(h);
         launch_linsolve(h, lambda);
     }
     CHB_CUDA_OK(cudaGetLastError());

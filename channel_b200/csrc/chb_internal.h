@@ -141,6 +141,9 @@ struct chb_handle_s {
     BodyForce bf;
     // multi-GPU
     void* nccl_comm;
+    // restart / snapshot files (restart_io.cu)
+    void* rio;
+    double grid_a, grid_ymin, grid_ymax;   // dns.in a, ymin, ymax: header fields of Dati.cart.out
     // bookkeeping
     long long launches;
     size_t dev_bytes;
@@ -173,6 +176,10 @@ int chb_p2p_setup(chb_handle_s* h, size_t na, size_t nb);   // maps peer Ar/Br/f
 void chb_p2p_teardown(chb_handle_s* h);
 int chb_exchange(chb_handle_s* h, bool a_side);             // completes zTOx (a_side) / xTOz on the lane's stream
 void chb_select_lane(chb_handle_s* h, int lane);            // makes `lane` the one the conv launchers use
+
+// ---- restart_io.cu / chb_api.cu ----
+void chb_restart_destroy(chb_handle_s* h);
+void chb_flush_pending(chb_handle_s* h);   // runs a deferred buildrhs plane loop (fused flow) now
 
 // timing helpers
 struct ScopedKernelTimer {

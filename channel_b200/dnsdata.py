@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import ctypes as C
 import dataclasses
+import os
 import struct
 
 import numpy as np
@@ -317,6 +318,27 @@ class Channel:
             nm = names.raw[i * stride:(i + 1) * stride].split(b"\0")[0].decode()
             out[nm] = (float(ms[i]), int(n[i]))
         return out
+
+    # -- restart / snapshot files (restart_io.cu) --------------------------------------------
+    def save_restart_file(self, path, field: str = "V", async_mode: bool = False):
+        """save_restart_file (dnsdata.f90:821-848) from the device-resident field; collective over ranks."""
+        _lib.check(self.lib.chb_save_restart_file(self.h, os.fsencode(path), self.time, {"V": 0, "F": 1}[field],
+                                                  int(async_mode)), "chb_save_restart_file")
+
+    def restart_wait(self):
+        _lib.check(self.lib.chb_restart_wait(self.h), "chb_restart_wait")
+
+    def restart_stats(self):
+        b, ms, s = C.c_double(), C.c_double(), C.c_double()
+        _lib.check(self.lib.chb_restart_stats(self.h, C.byref(b), C.byref(ms), C.byref(s)), "chb_restart_stats")
+        return dict(bytes=b.value, snapshot_ms=ms.value, total_s=s.value)
+
+    def read_restart_file(self, path):
+        """read_restart_file (dnsdata.f90:677-704): loads this rank's slab, sets and returns `time`."""
+        t = C.c_double()
+        _lib.check(self.lib.chb_read_restart_file(self.h, os.fsencode(path), C.byref(t)), "chb_read_restart_file")
+        self.time = t.value
+        return self.time
 
     def close(self):
         if self.h:

@@ -136,6 +136,33 @@ int chb_get_step_scalars(chb_handle h, double* cfl, double* fr, double* corrpx, 
                          double* meanpx, double* meanpz,
                          double* U_lo, double* U_hi, double* W_lo, double* W_hi);
 
+/* ---- restart / snapshot files ------------------------------------------
+ * Replaces save_restart_file (dnsdata.f90:821-848; call sites dnsdata.f90:885,903,906 and
+ * channel.f90:181) for the device-resident field: writes the reference's Dati.cart.out format
+ * (68-byte header int32 nx,ny,nz + float64 alfa0,beta0,ni,a,ymin,ymax,time, then
+ * V(-1:ny+1,-nz:nz,0:nx,1:3) in Fortran order) without a host copy of V.  Collective: every rank
+ * pwrite()s its x-slab at the offset the reference's MPI-IO subarray view gives it
+ * (mpi_transpose.f90:249-258), rank 0 (has_terminal) also writes the header; all ranks name the same
+ * file.  field = 0 writes V, 1 the body force F (Force.cart.*.out, dnsdata.f90:906).
+ * async_mode = 0: returns when this rank's bytes are written.  async_mode = 1: returns as soon as the
+ * device holds a private copy of the field in file order (a few ms); the PCIe copy and the file
+ * writes continue on a copy stream and a writer thread while the caller goes on time-stepping.  One
+ * snapshot is in flight at a time (a second call first waits for the previous one).  Errors: 4 =
+ * file I/O, 5 = no device memory for the asynchronous snapshot buffer. */
+int chb_save_restart_file(chb_handle h, const char* filename, double time, int field, int async_mode);
+/* Wait for an asynchronous snapshot; returns its error code (0 = written). */
+int chb_restart_wait(chb_handle h);
+/* Last snapshot of this rank: bytes written, device time of the layout transposition (ms), wall time from
+ * the call to the last byte written (s).  Waits for an asynchronous snapshot first. */
+int chb_restart_stats(chb_handle h, double* bytes, double* snapshot_ms, double* total_s);
+/* Replaces read_restart_file (dnsdata.f90:677-704) when the file exists: checks the header against the
+ * handle's nx,ny,nz,alfa0,beta0,ni,a,ymin,ymax (error 3 with the reference's message on mismatch,
+ * dnsdata.f90:696-703), returns `time`, and loads this rank's x-slab into the device field (pread chunks
+ * through pinned buffers overlapped with the PCIe copies, then the layout transposition on the device).
+ * Error 4 if the file cannot be opened: the caller then generates its initial field (dnsdata.f90:705-719)
+ * and uses chb_upload_V. */
+int chb_read_restart_file(chb_handle h, const char* filename, double* time);
+
 /* ---- test / diagnostics accessors (not part of the Fortran binding) ---------- */
 /* RHS left by chb_buildrhs: [2][ny+3][nxB][2nz+1] complex (0=eta, 1=D2v); rows 1..ny-1. */
 int chb_download_rhs(chb_handle h, double* rhs_host);

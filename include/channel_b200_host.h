@@ -39,6 +39,14 @@ int chb_host_decomposition(int nx, int nzd, int nranks, int rank, int* nx0, int*
 long long chb_host_transpose_index(int peer, int ncomp, int comp, int nplanes, int plane, int nzB, int izl,
                                    int nxB, int ixl);
 
+/* Dati.cart.out layout (dnsdata.f90:683-695,830-846; mpi_transpose.f90:249-258), no GPU needed:
+ * the 68-byte header, the byte offset of component c (0..2) of the x-slab that starts at mode nx0, and
+ * the size of the whole file. */
+int chb_host_restart_header(int nx, int ny, int nz, double alfa0, double beta0, double ni, double a,
+                            double ymin, double ymax, double time, unsigned char* out68);
+long long chb_host_restart_offset(int nx, int ny, int nz, int nx0, int c);
+long long chb_host_restart_file_bytes(int nx, int ny, int nz);
+
 /* chb_set_tables with the contents of *t. */
 int chb_host_apply_tables(chb_handle h, const chb_host_tables* t);
 

@@ -61,6 +61,20 @@ def main():
             err = float(np.abs(Vg[c] - ref).max() / np.abs(o.V[c]).max())
             worst = max(worst, err)
             assert err < 1e-11, (rank, (nx, ny, nz), c, err)
+        if not opts:      # one Dati.cart.out written by all ranks at their MPI-IO offsets, read back by all
+            from channel_b200.dnsdata import read_restart_file
+            path = f"/tmp/chb_mgpu_{os.environ.get('MASTER_PORT', '0')}_{nx}.out"
+            ch.save_restart_file(path, async_mode=(nx == 31))
+            ch.restart_wait()
+            dist.barrier()
+            t, Vf = read_restart_file(path, p)
+            assert t == ch.time and np.array_equal(Vf[:, sl], ch.download_V_fortran()), (rank, "restart file")
+            ch.upload_V(np.zeros_like(Vg))
+            ch.read_restart_file(path)
+            assert np.array_equal(ch.download_V(), Vg), (rank, "restart read")
+            dist.barrier()
+            if rank == 0:
+                os.remove(path)
         ch.close()
     dist.barrier()
     if rank == 0:

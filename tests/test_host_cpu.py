@@ -160,3 +160,38 @@ def test_bench_nvlink_and_hbm_byte_models():
     assert abs(tot / 1e9 - 152.6) < 0.1 and abs(fwd * 2 - bwd) < 1e-6 * bwd
     rep = bench.nvlink_report(511, 512, 511, 1536, 2, 3, 138.0, {"zfwd": (300.0, 15), "xpass": (500.0, 15)}, True)
     assert rep["zTOx"]["carrier"] == "zfwd" and 0 < rep["step"]["frac"] < 1
+
+
+def test_restart_file_layout_host_helpers(tmp_path):
+    """Dati.cart.out layout (dnsdata.f90:683-695,830-846): the C helpers of restart_io.cu agree with the
+    Python writer (channel_b200.dnsdata.save_restart_file) and with the way the reference's own
+    utilities read the header (utilities/compare_fields.py:17-18: 3 int32, then 7 float64 at offset 12)."""
+    import struct
+    from channel_b200 import DnsIn
+    from channel_b200.dnsdata import save_restart_file, read_restart_file, HEADER_FMT
+    lib = _lib.load()
+    nx, ny, nz = 5, 8, 3
+    p = DnsIn(nx=nx, ny=ny, nz=nz, re=1234.5)
+    buf = (C.c_ubyte * 68)()
+    assert lib.chb_host_restart_header(nx, ny, nz, p.alfa0, p.beta0, 1.0 / p.re, p.a, p.ymin, p.ymax, 7.25, buf) == 0
+    raw = bytes(buf)
+    assert raw == struct.pack(HEADER_FMT, nx, ny, nz, p.alfa0, p.beta0, 1.0 / p.re, p.a, p.ymin, p.ymax, 7.25)
+    ints = np.frombuffer(raw, dtype=np.int32, count=3); reals = np.frombuffer(raw, dtype=np.float64, count=7, offset=12)
+    assert list(ints) == [nx, ny, nz] and reals[-1] == 7.25 and reals[2] == 1.0 / p.re
+    # offsets: component c of the slab starting at nx0 inside the C-order [3][nx+1][2nz+1][ny+3] array
+    rng = np.random.default_rng(1)
+    V = rng.standard_normal((3, nx + 1, 2 * nz + 1, ny + 3)) + 1j * rng.standard_normal((3, nx + 1, 2 * nz + 1, ny + 3))
+    path = tmp_path / "Dati.cart.out"
+    save_restart_file(path, p, 7.25, V)
+    data = path.read_bytes()
+    assert len(data) == lib.chb_host_restart_file_bytes(nx, ny, nz)
+    for c in range(3):
+        for nx0 in (0, 2, 3):
+            off = lib.chb_host_restart_offset(nx, ny, nz, nx0, c)
+            got = np.frombuffer(data, dtype=np.complex128, count=(2 * nz + 1) * (ny + 3), offset=off)
+            assert np.array_equal(got.reshape(2 * nz + 1, ny + 3), V[c, nx0])
+    t, V2 = read_restart_file(path, p)
+    assert t == 7.25 and np.array_equal(V2, V)
+    with pytest.raises(ValueError):
+        read_restart_file(path, DnsIn(nx=nx, ny=ny, nz=nz, re=999.0))
+    assert lib.chb_save_restart_file(None, b"x", 0.0, 0, 0) != 0 and lib.chb_read_restart_file(None, b"x", None) != 0
