@@ -273,6 +273,31 @@ def run_b200(args):
         e2e_s = float(t.item())
     finite = bool(np.isfinite(last_line).all())
 
+    # ---- optional: snapshot files from the device-resident field ------------
+    snap = None
+    if args.snapshot and world == 1:
+        d = args.snapshot_dir or ("/dev/shm" if os.path.isdir("/dev/shm") else "/tmp")
+        path = os.path.join(d, f"chb_bench_{os.getpid()}.out")
+        try:
+            barrier()
+            t0 = time.perf_counter(); ch.save_restart_file(path, async_mode=False); t_block = time.perf_counter() - t0
+            st_b = ch.restart_stats()
+            ch.stopwatch_begin(); ch.step(stats=False); ch.step(stats=False); ms_2 = ch.stopwatch_end()
+            barrier()
+            t0 = time.perf_counter(); ch.save_restart_file(path, async_mode=True); t_call = time.perf_counter() - t0
+            ch.stopwatch_begin(); ch.step(stats=False); ch.step(stats=False); ms_2a = ch.stopwatch_end()
+            ch.restart_wait(); t_async = time.perf_counter() - t0
+            st_a = ch.restart_stats()
+            snap = {"bytes": st_b["bytes"], "dir": d,
+                    "blocking": {"seconds": t_block, "gbs": st_b["bytes"] / t_block / 1e9,
+                                 "device_transposition_ms": st_b["snapshot_ms"]},
+                    "async": {"call_returns_after_s": t_call, "file_complete_after_s": t_async,
+                              "device_transposition_ms": st_a["snapshot_ms"],
+                              "two_steps_ms_alone": ms_2, "two_steps_ms_while_draining": ms_2a}}
+        finally:
+            if os.path.exists(path):
+                os.remove(path)
+
     if rank == 0:
         peak, peak_src = measured_peaks()
         per, step_bytes = algorithmic_bytes(nx, ny, nz, nxd, nzd)
@@ -330,6 +355,8 @@ def run_b200(args):
                             "chb_get_step_scalars) + chb_download_V, wall clock"},
             "finite": finite,
         }
+        if snap:
+            out["snapshot"] = snap
         if world > 1:
             out["nvlink"] = nvlink_report(nx, ny, nz, nzd, world, args.steps, ms_per_step, kern,
                                           direct=os.environ.get("CHB_P2P", "1") != "0")
@@ -381,6 +408,8 @@ def main():
     ap.add_argument("--workload", default=os.environ.get("CHB_WORKLOAD", DEFAULT_WORKLOAD))
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--snapshot", action="store_true", help="also time chb_save_restart_file (blocking and asynchronous)")
+    ap.add_argument("--snapshot-dir", default=None)
     args = ap.parse_args()
     if args.impl == "reference":
         # each "step" of the reference arm is one bounded sample; keep the whole run to minutes
