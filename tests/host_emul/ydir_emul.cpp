@@ -48,7 +48,7 @@ extern "C" {
 //   oldrhs [2][nyp][M] (in/out), rhs_out [2][nyp][M] (plain flow: the RHS; fused flow: Step1 results).
 // Tables as chb_set_tables receives them.  scal_io: {meanpx, meanpz, meanflowx, meanflowz, gamma, u0, uN,
 // CPI, CPI_type} in; {fr0, fr1, fr2, corrpx, corrpz, meanpx} out.  fused: 0 plain, 1 fused.
-int chb_emul_ydir_substep(int nx, int ny, int nz, double alfa0, double beta0, double ni, const double* y,
+__attribute__((visibility("default"))) int chb_emul_ydir_substep(int nx, int ny, int nz, double alfa0, double beta0, double ni, const double* y,
                           const double* d0, const double* d1, const double* d2, const double* d4,
                           const double* bc5x16, const double* D0mat, double* V, const double* P, const double* F,
                           double* oldrhs, double* rhs_out, double* scal_io, double ode1, double ode2, double ode3,

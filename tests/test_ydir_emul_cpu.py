@@ -41,7 +41,9 @@ def emul():
                     for f in ("rhs_kernel.cu", "solve_kernels.cu", "solve_device.cuh", "chb_internal.h")]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
         subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-w",
-                               "-I" + CUDA_INC, "-o", so, SRC])
+                               # the kernels' host names also exist in libchannel_b200.so (loaded RTLD_GLOBAL by
+                               # other tests): bind this library's references to its own definitions
+                               "-fvisibility=hidden", "-Wl,-Bsymbolic", "-I" + CUDA_INC, "-o", so, SRC])
     lib = C.CDLL(so)
     dp = C.POINTER(C.c_double)
     lib.chb_emul_ydir_substep.argtypes = [C.c_int] * 3 + [C.c_double] * 3 + [dp] * 13 + [C.c_double] * 4 + [C.c_int]
