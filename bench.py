@@ -301,10 +301,8 @@ def run_b200(args):
     if rank == 0:
         peak, peak_src = measured_peaks()
         per, step_bytes = algorithmic_bytes(nx, ny, nz, nxd, nzd)
-        # fused y-direction flow (CHB_FUSE): rhs_s1 = buildrhs plane loop + first solve sweep (counted under
-        # "rhs"), solve_s24 = eta back-substitution + vetaTOuvw
-        fam = {"zfwd": ["zfwd"], "xpass": ["xpass"], "zbwd": ["zbwd"], "rhs": ["rhs", "rhs_s1"],
-               "solve": ["solve_s1", "solve_s2", "solve_s3", "solve_s4", "solve_s24", "solve"]}
+        fam = {"zfwd": ["zfwd"], "xpass": ["xpass"], "zbwd": ["zbwd"], "rhs": ["rhs"],
+               "solve": ["solve_s1", "solve_s2", "solve_s3", "solve_s4", "solve"]}
         total_kernel_ms = sum(v[0] for v in kern.values()) or 1.0
         kernels = {}
         for f, names in fam.items():

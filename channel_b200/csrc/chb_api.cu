@@ -183,9 +183,6 @@ extern "C" int chb_create(chb_handle* out, int nx, int ny, int nz, int nxd, int 
         h->zf_lines_per_cta = e ? atoi(e) : (nzd >= 3072 ? 2 : 4);
         e = getenv("CHB_FFT3");
         h->use_fft3 = (e && atoi(e) == 0) ? 0 : 1;
-        e = getenv("CHB_FUSE");
-        h->fuse = e ? atoi(e) : 0;
-        h->rhs_pending = false;
         // x tiles of the work buffers (transpose_index.h): products 8 wide (128-byte store segments in
         // the x-pass), velocities as wide as the lines of one zfwd CTA
         g.tw = (g.nxB % 8 == 0) ? 3 : ((g.nxB % 4 == 0) ? 2 : 0);
@@ -351,22 +348,12 @@ extern "C" int chb_set_tables(chb_handle h, const double* y, const double* d0, c
     return 0;
 }
 
-// Fused flow: the deferred plane loop of buildrhs (see chb_internal.h) runs unfused if anything but
-// chb_linsolve(ODE(1)/deltat) touches the handle first.
-void chb_flush_pending(chb_handle_s* h) {
-    if (h && h->rhs_pending) {
-        h->rhs_pending = false;
-        launch_rhs(h, h->pending_ode, h->pending_deltat);
-    }
-}
-
 // ---- field transfer --------------------------------------------------------------------------
 static int transfer_V(chb_handle h, double* host, bool upload, bool fortran_layout, cplx* field) {
     CHB_REQUIRE(h, "null handle");
     CHB_CUDA_OK(cudaSetDevice(h->device));
     const Geometry& g = h->g;
     const size_t fld = (size_t)g.nyp * g.M;
-    chb_flush_pending(h);
     CHB_CUDA_OK(cudaStreamSynchronize(h->stream));
     for (int c = 0; c < 3; ++c) {
         cplx* dev = field + c * fld;
@@ -412,7 +399,6 @@ static int download_n(chb_handle h, double* host, const cplx* dev, int ncomp) {
     CHB_REQUIRE(h, "null handle");
     CHB_CUDA_OK(cudaSetDevice(h->device));
     const size_t n = (size_t)ncomp * h->g.nyp * h->g.M;
-    chb_flush_pending(h);
     CHB_CUDA_OK(cudaStreamSynchronize(h->stream));
     CHB_CUDA_OK(cudaMemcpy(host, dev, n * sizeof(cplx), cudaMemcpyDeviceToHost));
     return 0;
@@ -474,7 +460,6 @@ extern "C" int chb_set_body_force(chb_handle h) {
     CHB_REQUIRE(h, "null handle");
     if (!h->bf.enabled) return 0;
     CHB_CUDA_OK(cudaSetDevice(h->device));
-    chb_flush_pending(h);
     launch_body_force(h);
     CHB_CUDA_OK(cudaGetLastError());
     return 0;
@@ -510,7 +495,6 @@ static int convolutions_all(chb_handle h, int compute_cfl, bool products) {
 extern "C" int chb_cfl_prepass(chb_handle h) {
     CHB_REQUIRE(h && h->tables_set, "chb_cfl_prepass: tables not set");
     CHB_CUDA_OK(cudaSetDevice(h->device));
-    chb_flush_pending(h);
     if (convolutions_all(h, 1, false)) return 1;
     launch_meanflow_prepass(h);
     CHB_CUDA_OK(cudaGetLastError());
@@ -521,16 +505,9 @@ extern "C" int chb_buildrhs(chb_handle h, const double* ode, double deltat, int 
     CHB_REQUIRE(h && h->tables_set, "chb_buildrhs: tables not set");
     CHB_REQUIRE(deltat > 0.0, "chb_buildrhs: deltat must be > 0");
     CHB_CUDA_OK(cudaSetDevice(h->device));
-    chb_flush_pending(h);
     if (h->bf.enabled) launch_force_ghosts(h);
     if (convolutions_all(h, compute_cfl, true)) return 1;
-    if (h->fuse) {
-        h->rhs_pending = true;
-        memcpy(h->pending_ode, ode, sizeof(double) * 3);
-        h->pending_deltat = deltat;
-    } else {
-        launch_rhs(h, ode, deltat);
-    }
+    launch_rhs(h, ode, deltat);
     CHB_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -538,14 +515,7 @@ extern "C" int chb_buildrhs(chb_handle h, const double* ode, double deltat, int 
 extern "C" int chb_linsolve(chb_handle h, double lambda) {
     CHB_REQUIRE(h && h->tables_set, "chb_linsolve: tables not set");
     CHB_CUDA_OK(cudaSetDevice(h->device));
-    if (h->rhs_pending && lambda == h->pending_ode[0] / h->pending_deltat) {
-        h->rhs_pending = false;
-        launch_rhs_s1(h, h->pending_ode, h->pending_deltat);
-        launch_linsolve_fused(h, lambda);
-    } else {
-        chb_flush_pending(h);
-        launch_linsolve(h, lambda);
-    }
+    launch_linsolve(h, lambda);
     CHB_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -108,12 +108,6 @@ struct chb_handle_s {
     int chunk_planes;
     int zf_lines_per_cta, zb_lines_per_cta;  // lines per CTA of zfwd / zbwd (CHB_ZF_LPC, CHB_ZB_LPC: 2, 4 or 8)
     int use_fft3;         // register-resident three-stage FFT kernels for the large sizes (CHB_FFT3=0 disables)
-    // fused y-direction flow (CHB_FUSE): chb_buildrhs defers the plane loop of buildrhs to chb_linsolve,
-    // which runs it fused with the first sweep of the banded solves (rhs_s1_kernel) when it is called
-    // with lambda = ODE(1)/deltat; any other use of the handle in between runs the plain rhs kernel first
-    int fuse;
-    bool rhs_pending;
-    double pending_ode[3], pending_deltat;
     cplx* A;        // NCCL mode only: send buffer of zTOx, [peer][3][np][nzB][nxB]
     cplx* Ar;       // z-padded velocity after zTOx, [src rank][3][np][nzB][nxB]
     cplx* B;        // NCCL mode only: send buffer of xTOz
@@ -160,10 +154,8 @@ bool launch_z3_fwd_or_bwd(chb_handle_s* h, int plane0, int nplanes, bool fwd);
 bool launch_x3_pass(chb_handle_s* h, int plane0, int nplanes, int compute_cfl);
 // ---- rhs_kernel.cu ----
 void launch_rhs(chb_handle_s* h, const double* ode, double deltat);
-void launch_rhs_s1(chb_handle_s* h, const double* ode, double deltat);   // fused with S1 of the solve
 // ---- solve_kernels.cu ----
 void launch_linsolve(chb_handle_s* h, double lambda);
-void launch_linsolve_fused(chb_handle_s* h, double lambda);               // after launch_rhs_s1
 void launch_meanflow_prepass(chb_handle_s* h);
 // ---- layout_kernels.cu ----
 void launch_fortran_to_planes(chb_handle_s* h, const cplx* src, cplx* dst, int c, int ix0, int nix);
@@ -177,9 +169,8 @@ void chb_p2p_teardown(chb_handle_s* h);
 int chb_exchange(chb_handle_s* h, bool a_side);             // completes zTOx (a_side) / xTOz on the lane's stream
 void chb_select_lane(chb_handle_s* h, int lane);            // makes `lane` the one the conv launchers use
 
-// ---- restart_io.cu / chb_api.cu ----
+// ---- restart_io.cu ----
 void chb_restart_destroy(chb_handle_s* h);
-void chb_flush_pending(chb_handle_s* h);   // runs a deferred buildrhs plane loop (fused flow) now
 
 // timing helpers
 struct ScopedKernelTimer {

@@ -191,7 +191,6 @@ extern "C" int chb_save_restart_file(chb_handle h, const char* filename, double 
     RestartIO* r = rio_get(h);
     if (!r) return 1;
     if (rio_join(r)) return 1;          // one snapshot in flight at a time
-    chb_flush_pending(h);
     const Geometry& g = h->g;
     const size_t fld = (size_t)g.nyp * g.M;
     const auto t0 = std::chrono::steady_clock::now();
@@ -283,7 +282,6 @@ extern "C" int chb_read_restart_file(chb_handle h, const char* filename, double*
     RestartIO* r = rio_get(h);
     if (!r) return 1;
     if (rio_join(r)) return 1;
-    chb_flush_pending(h);
     const Geometry& g = h->g;
     const int fd = open(filename, O_RDONLY);
     if (fd < 0) {   // the reference generates an initial field instead (dnsdata.f90:705-719): the driver's job

@@ -94,10 +94,9 @@ solve_s1_kernel(cplx* __restrict__ rhs, double* __restrict__ ckpt, Geometry g, D
 template <int COMP>
 __global__ void __launch_bounds__(SOLVE_THREADS)
 solve_s2_kernel(const cplx* __restrict__ rhs, const double* __restrict__ ckpt, cplx* __restrict__ V, Geometry g,
-                DevTables tab, const DevScalars* __restrict__ sc, double lam, int mean_only) {
-    // mean_only: just the column (ix,iz) = (0,0) (fused flow: the other eta columns are solved inside solve_s24)
-    const long long m = mean_only ? (long long)g.nz : (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (m >= g.M || (mean_only && (blockIdx.x != 0 || threadIdx.x != 0))) return;
+                DevTables tab, const DevScalars* __restrict__ sc, double lam) {
+    const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= g.M) return;
     const int ixl = (int)(m / g.nzt);
     const int izp = (int)(m - (long long)ixl * g.nzt);
     const int ix = g.nx0 + ixl, iz = izp - g.nz;
@@ -317,130 +316,6 @@ solve_s4_kernel(cplx* __restrict__ V, Geometry g, DevTables tab) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Fused flow (CHB_FUSE=1): second sweep of the eta solve + second sweep of the compact derivative
-// of v + vetaTOuvw in one ascending march (S2<0> and S4 above).  eta never goes to HBM: each value
-// leaves LeftLU5divStep2 in a register and is combined with vy at once
-// (linsolve_blocking.inc:44-61,99-103).  Reads the Step1 result of eta, its checkpoints and the
-// Step1 result of vy (V comp 3, written by solve_s3), writes u and w: 2.25 C + 2 C per point
-// instead of (2.25 + 1) + (2 + 2).  The mean column is not touched here (single-column S2<0> +
-// mean_mode_kernel on the side stream).
-__global__ void __launch_bounds__(SOLVE_THREADS, 3)
-solve_s24_kernel(const cplx* __restrict__ rhs, const double* __restrict__ ckpt, cplx* __restrict__ V, Geometry g,
-                 DevTables tab, double lam) {
-    const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (m >= g.M) return;
-    const int ixl = (int)(m / g.nzt);
-    const int izp = (int)(m - (long long)ixl * g.nzt);
-    const int ix = g.nx0 + ixl, iz = izp - g.nz;
-    if (ix == 0 && iz == 0) return;
-    const double al = g.alfa0 * ix, be = g.beta0 * iz;
-    const double k2 = al * al + be * be;
-    const int ny = g.ny;
-    const size_t plane = (size_t)g.M, comp = (size_t)g.nyp * plane;
-    const double* bcn = tab.etanbc;
-    const double* bcnp1 = tab.etanp1bc;
-    const double* bc0 = tab.eta0bc;
-    const double* bc0m1 = tab.eta0m1bc;
-    const cplx* __restrict__ xin = rhs + m;          // Step1 result of the eta equation
-    cplx* __restrict__ Vu = V + m;                   // u out
-    cplx* __restrict__ Vw = V + 2 * comp + m;        // vy (after Step1 with D0mat) in, w out
-    cplx d1 = make_double2(0, 0), d2 = d1;           // vy(iy-1), vy(iy-2) of the D0mat Step2 recurrence
-    // u = (ia*vy - ib*eta)/k2, w = (ib*vy + ia*eta)/k2 at node iy, after LeftLU5divStep2 on vy
-    auto emit = [&](int iy, cplx eta, cplx vy) {
-        if (iy >= 1) {  // rows i=0..ny <-> iy=1..ny+1 (rows ny, ny+1 of D0mat are zero)
-            const double* A = tab.D0mat + (size_t)(iy - 1) * 5;
-            const double am2 = __ldg(&A[0]), am1 = __ldg(&A[1]);
-            vy.x -= am2 * d2.x + am1 * d1.x;
-            vy.y -= am2 * d2.y + am1 * d1.y;
-        }
-        d2 = d1;
-        d1 = vy;
-        cplx u, w;
-        u.x = (-al * vy.y + be * eta.y) / k2;
-        u.y = (al * vy.x - be * eta.x) / k2;
-        w.x = (-be * vy.y - al * eta.y) / k2;
-        w.y = (be * vy.x + al * eta.x) / k2;
-        const size_t off = (size_t)(iy + 1) * plane;
-        Vu[off] = u;
-        Vw[off] = w;
-    };
-    const cplx vy_m1 = Vw[0], vy_0 = Vw[plane];
-    cplx v1 = make_double2(0, 0), v2 = v1, v3 = v1;  // eta(i-1), eta(i-2), eta(i-3)
-    for (int i0 = 1; i0 <= ny - 1; i0 += SOLVE_K) {
-        LUState st = {0, 0, 0, 0};
-        if (i0 + SOLVE_K <= ny - 1) {
-            const double* ck = ckpt + ((size_t)((i0 - 1) / SOLVE_K) * 8 + 4) * plane + m;
-            st.l1m2 = ck[0 * plane]; st.l1m1 = ck[1 * plane]; st.l2m2 = ck[2 * plane]; st.l2m1 = ck[3 * plane];
-        }
-        cplx xb[SOLVE_K], yb[SOLVE_K];
-#pragma unroll
-        for (int k = 0; k < SOLVE_K; ++k) {
-            const int iy = i0 + k;
-            xb[k] = (iy <= ny - 1) ? xin[(size_t)(iy + 1) * plane] : make_double2(0.0, 0.0);
-            yb[k] = (iy <= ny - 1) ? Vw[(size_t)(iy + 1) * plane] : make_double2(0.0, 0.0);
-        }
-        double m2[SOLVE_K], m1[SOLVE_K];
-#pragma unroll
-        for (int k = SOLVE_K - 1; k >= 0; --k) {
-            const int iy = i0 + k;
-            m2[k] = m1[k] = 0.0;
-            if (iy <= ny - 1) {
-                Row5 rv, re;
-                build_rows(tab, iy, k2, lam, g.ni, rv, re);
-                if (iy == ny - 1) {
-                    fold_top1(re, bcn, bcnp1);
-                    re.a[3] = re.a[4] = 0.0;
-                } else if (iy == ny - 2) {
-                    fold_top2(re, bcn);
-                    re.a[4] = 0.0;
-                }
-                if (iy == 1) fold_bot1(re, bc0, bc0m1);
-                else if (iy == 2) fold_bot2(re, bc0);
-                double inv, u1, u2;
-                lu_row(re, st, inv, u1, u2);
-                if (iy >= 3) m2[k] = st.l1m2;
-                if (iy >= 2) m1[k] = st.l1m1;
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < SOLVE_K; ++k) {
-            const int iy = i0 + k;
-            if (iy <= ny - 1) {
-                cplx v = xb[k];
-                v.x -= m2[k] * v2.x + m1[k] * v1.x;
-                v.y -= m2[k] * v2.y + m1[k] * v1.y;
-                v3 = v2; v2 = v1; v1 = v;
-                if (iy == 3) {  // bottom closure (linsolve_blocking.inc:51-54), then nodes -1..3 in order
-                    const cplx a1 = v3, a2 = v2, a3 = v1;
-                    cplx vw, vg;
-                    vw.x = (0.0 - (a1.x * bc0[2] + a2.x * bc0[3] + a3.x * bc0[4])) / bc0[1];
-                    vw.y = (0.0 - (a1.y * bc0[2] + a2.y * bc0[3] + a3.y * bc0[4])) / bc0[1];
-                    vg.x = -(vw.x * bc0m1[1] + a1.x * bc0m1[2] + a2.x * bc0m1[3] + a3.x * bc0m1[4]) / bc0m1[0];
-                    vg.y = -(vw.y * bc0m1[1] + a1.y * bc0m1[2] + a2.y * bc0m1[3] + a3.y * bc0m1[4]) / bc0m1[0];
-                    emit(-1, vg, vy_m1);
-                    emit(0, vw, vy_0);
-                    emit(1, a1, yb[0]);   // i0 == 1 here: yb[k] <-> iy = 1 + k
-                    emit(2, a2, yb[1]);
-                    emit(3, a3, yb[2]);
-                } else if (iy > 3) {
-                    emit(iy, v, yb[k]);
-                }
-            }
-        }
-    }
-    {  // top closure (linsolve_blocking.inc:57-60): nodes ny-3..ny-1 = v3,v2,v1
-        cplx vw, vg;
-        vw.x = (0.0 - (v3.x * bcn[0] + v2.x * bcn[1] + v1.x * bcn[2])) / bcn[3];
-        vw.y = (0.0 - (v3.y * bcn[0] + v2.y * bcn[1] + v1.y * bcn[2])) / bcn[3];
-        vg.x = -(v3.x * bcnp1[0] + v2.x * bcnp1[1] + v1.x * bcnp1[2] + vw.x * bcnp1[3]) / bcnp1[4];
-        vg.y = -(v3.y * bcnp1[0] + v2.y * bcnp1[1] + v1.y * bcnp1[2] + vw.y * bcnp1[3]) / bcnp1[4];
-        const cplx vy_n = Vw[(size_t)(ny + 1) * plane], vy_np1 = Vw[(size_t)(ny + 2) * plane];
-        emit(ny, vw, vy_n);
-        emit(ny + 1, vg, vy_np1);
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
 // yintegr (dnsdata.f90:312-324) on a real column f(iy), iy=-1..ny+1, element stride `st`
 __device__ double yintegr_dev(const double* __restrict__ y, const double* f, size_t st, int ny, int imag_part) {
     double II = 0.0;
@@ -567,8 +442,8 @@ void launch_linsolve(chb_handle_s* h, double lam) {
     }
     {
         ScopedKernelTimer tm(h, "solve_s2");
-        solve_s2_kernel<0><<<blocks, SOLVE_THREADS, 0, h->stream>>>(h->rhs, h->ckpt, h->V, g, h->tab, h->sc, lam, 0);
-        solve_s2_kernel<1><<<blocks, SOLVE_THREADS, 0, h->stream>>>(h->rhs, h->ckpt, h->V, g, h->tab, h->sc, lam, 0);
+        solve_s2_kernel<0><<<blocks, SOLVE_THREADS, 0, h->stream>>>(h->rhs, h->ckpt, h->V, g, h->tab, h->sc, lam);
+        solve_s2_kernel<1><<<blocks, SOLVE_THREADS, 0, h->stream>>>(h->rhs, h->ckpt, h->V, g, h->tab, h->sc, lam);
     }
     h->launches += 6;
     // The mean column (0,0) only needs the result of S2 and is skipped by S3/S4: finish it on the
@@ -589,38 +464,6 @@ void launch_linsolve(chb_handle_s* h, double lam) {
         ScopedKernelTimer tm(h, "solve_s4");
         solve_s4_kernel<<<blocks, SOLVE_THREADS, 0, h->stream>>>(h->V, g, h->tab);
     }
-    if (mean_here) {
-        cudaEventRecord(h->ev_join, h->side_stream);
-        cudaStreamWaitEvent(h->stream, h->ev_join, 0);
-    }
-}
-
-// Fused flow: the first sweep already ran inside rhs_s1_kernel (rhs_kernel.cu).
-void launch_linsolve_fused(chb_handle_s* h, double lam) {
-    const Geometry& g = h->g;
-    const int blocks = (int)((g.M + SOLVE_THREADS - 1) / SOLVE_THREADS);
-    const bool mean_here = (g.nx0 == 0);
-    if (mean_here) {   // the mean column: eta Step2 and linsolve_blocking.inc:62-97 on the side stream
-        cudaEventRecord(h->ev_fork, h->stream);
-        cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0);
-        ScopedKernelTimer tm(h, "mean_mode", h->side_stream);
-        solve_s2_kernel<0><<<1, 32, 0, h->side_stream>>>(h->rhs, h->ckpt, h->V, g, h->tab, h->sc, lam, 1);
-        mean_mode_kernel<<<1, 32, 0, h->side_stream>>>(h->V, g, h->tab, h->sc, lam, h->mean_scratch);
-        h->launches += 2;
-    }
-    {
-        ScopedKernelTimer tm(h, "solve_s2");
-        solve_s2_kernel<1><<<blocks, SOLVE_THREADS, 0, h->stream>>>(h->rhs, h->ckpt, h->V, g, h->tab, h->sc, lam, 0);
-    }
-    {
-        ScopedKernelTimer tm(h, "solve_s3");
-        solve_s3_kernel<<<blocks, SOLVE_THREADS, 0, h->stream>>>(h->V, g, h->tab);
-    }
-    {
-        ScopedKernelTimer tm(h, "solve_s24");
-        solve_s24_kernel<<<blocks, SOLVE_THREADS, 0, h->stream>>>(h->rhs, h->ckpt, h->V, g, h->tab, lam);
-    }
-    h->launches += 3;
     if (mean_here) {
         cudaEventRecord(h->ev_join, h->side_stream);
         cudaStreamWaitEvent(h->stream, h->ev_join, 0);

@@ -3,9 +3,8 @@
 //
 // Those kernels are one thread per wavenumber column with no shared memory, shuffles or atomics, so
 // their source is valid host C++ once the CUDA keywords are neutralised; running it here lets the
-// CPU test suite (-m "not gpu") check the kernel logic -- including the fused flow (rhs_s1_kernel,
-// solve_s24_kernel) against the plain one (rhs_kernel, solve_s1..s4) -- against the numpy oracle
-// without a GPU.  It is a checker only: the product path never loads this library.
+// CPU test suite (-m "not gpu") check the kernel logic (rhs_kernel, solve_s1..s4, mean_mode_kernel)
+// against the numpy oracle without a GPU.  It is a checker only: the product path never loads this library.
 #include <cuda_runtime.h>
 
 #include <cmath>
@@ -47,12 +46,12 @@ extern "C" {
 //   V [3][nyp][M] (in: u,v,w; out: u,v,w after linsolve), P [6][nyp][M] products, F [3][nyp][M] or null,
 //   oldrhs [2][nyp][M] (in/out), rhs_out [2][nyp][M] (plain flow: the RHS; fused flow: Step1 results).
 // Tables as chb_set_tables receives them.  scal_io: {meanpx, meanpz, meanflowx, meanflowz, gamma, u0, uN,
-// CPI, CPI_type} in; {fr0, fr1, fr2, corrpx, corrpz, meanpx} out.  fused: 0 plain, 1 fused.
+// CPI, CPI_type} in; {fr0, fr1, fr2, corrpx, corrpz, meanpx} out.  mode: 0 whole substep, -1 rhs_kernel only.
 __attribute__((visibility("default"))) int chb_emul_ydir_substep(int nx, int ny, int nz, double alfa0, double beta0, double ni, const double* y,
                           const double* d0, const double* d1, const double* d2, const double* d4,
                           const double* bc5x16, const double* D0mat, double* V, const double* P, const double* F,
                           double* oldrhs, double* rhs_out, double* scal_io, double ode1, double ode2, double ode3,
-                          double deltat, int fused) {
+                          double deltat, int mode) {
     Geometry g;
     memset(&g, 0, sizeof(g));
     g.nx = nx; g.ny = ny; g.nz = nz;
@@ -94,25 +93,17 @@ __attribute__((visibility("default"))) int chb_emul_ydir_substep(int nx, int ny,
     (void)fld;
     const int T = 128, blocks = (int)((g.M + T - 1) / T);
     const double lam = ode1 / deltat;
-    if (fused <= 0) {
+    {
         if (F) emulate(rhs_kernel<true>, blocks, T, Vc, Pc, Fc, rc, oc, g, tab, &sc, lam, ode2, ode3);
         else emulate(rhs_kernel<false>, blocks, T, Vc, Pc, Fc, rc, oc, g, tab, &sc, lam, ode2, ode3);
-        if (fused < 0) return 0;   // RHS only
+        if (mode < 0) return 0;   // RHS only
         emulate(solve_s1_kernel<0>, blocks, T, rc, ckpt.data(), g, tab, &sc, lam);
         emulate(solve_s1_kernel<1>, blocks, T, rc, ckpt.data(), g, tab, &sc, lam);
-        emulate(solve_s2_kernel<0>, blocks, T, rc, ckpt.data(), Vc, g, tab, &sc, lam, 0);
-        emulate(solve_s2_kernel<1>, blocks, T, rc, ckpt.data(), Vc, g, tab, &sc, lam, 0);
+        emulate(solve_s2_kernel<0>, blocks, T, rc, ckpt.data(), Vc, g, tab, &sc, lam);
+        emulate(solve_s2_kernel<1>, blocks, T, rc, ckpt.data(), Vc, g, tab, &sc, lam);
         emulate(mean_mode_kernel, 1, 32, Vc, g, tab, &sc, lam, scratch.data());
         emulate(solve_s3_kernel, blocks, T, Vc, g, tab);
         emulate(solve_s4_kernel, blocks, T, Vc, g, tab);
-    } else {
-        if (F) emulate(rhs_s1_kernel<true, 2>, blocks, T, Vc, Pc, Fc, rc, oc, ckpt.data(), g, tab, &sc, lam, ode2, ode3);
-        else emulate(rhs_s1_kernel<false, 2>, blocks, T, Vc, Pc, Fc, rc, oc, ckpt.data(), g, tab, &sc, lam, ode2, ode3);
-        emulate(solve_s2_kernel<0>, 1, 32, rc, ckpt.data(), Vc, g, tab, &sc, lam, 1);
-        emulate(mean_mode_kernel, 1, 32, Vc, g, tab, &sc, lam, scratch.data());
-        emulate(solve_s2_kernel<1>, blocks, T, rc, ckpt.data(), Vc, g, tab, &sc, lam, 0);
-        emulate(solve_s3_kernel, blocks, T, Vc, g, tab);
-        emulate(solve_s24_kernel, blocks, T, rc, ckpt.data(), Vc, g, tab, lam);
     }
     scal_io[0] = sc.fr[0]; scal_io[1] = sc.fr[1]; scal_io[2] = sc.fr[2];
     scal_io[3] = sc.corrpx; scal_io[4] = sc.corrpz; scal_io[5] = sc.meanpx;

@@ -118,35 +118,3 @@ def test_fortran_layout_roundtrip():
     assert np.array_equal(ch.download_V(), V0)
     assert np.array_equal(ch.download_V_fortran(), Vf)
 
-
-@pytest.mark.parametrize("fuse", ["1", "2"])
-@pytest.mark.parametrize("nx,ny,nz,couette", [(16, 64, 16, False), (31, 41, 21, False), (15, 32, 10, True)])
-def test_fused_ydir_flow(nx, ny, nz, couette, fuse, monkeypatch):
-    """CHB_FUSE: buildrhs' plane loop fused with the first sweep of the banded solves (rhs_s1_kernel) and
-    the eta back-substitution fused with vetaTOuvw (solve_s24_kernel); same tolerances as the plain flow."""
-    from oracle.channel_oracle import coriolis_force
-    monkeypatch.setenv("CHB_FUSE", fuse)
-    kw = dict(CPI=False, u0=-1.0, uN=1.0) if couette else {}
-    p, o, ch, V0 = make_pair(nx, ny, nz, deltat=0.0, cflmax=1.0, re=2500.0, couette=couette, **kw)
-    if couette:
-        o.set_body_force(coriolis_force(0.02, 9999999.0, 1.0))
-        ch.config_coriolis(0.02, 9999999.0, 1.0)
-    ch.cfl_prepass(); o.cfl_prepass()
-    assert np.allclose(ch.outstats(), o.outstats(), rtol=1e-10, atol=1e-12)
-    lo = o.step(); lg = ch.step()
-    Vg = ch.download_V()
-    for c in range(3):
-        assert relerr(Vg[c], o.V[c]) < 1e-12, ("field after 1 step", c, relerr(Vg[c], o.V[c]))
-    assert np.allclose(lg[1:9], lo[1:9], rtol=1e-9, atol=1e-11), (lg, lo)
-    for i in range(9):
-        lo = o.step(); lg = ch.step()
-        assert np.allclose(lg[1:9], lo[1:9], rtol=1e-8, atol=1e-10), (i, lg, lo)
-    Vg = ch.download_V()
-    for c in range(3):
-        assert relerr(Vg[c], o.V[c]) < 1e-9
-    # a download between buildrhs and linsolve runs the plain rhs kernel instead (same answer)
-    ch.buildrhs(RK1_rai, False); rhs_ref = o.buildrhs(RK1_rai, False)
-    rhs_gpu = ch.download_rhs()
-    sl = slice(2, ny + 1)
-    assert relerr(rhs_gpu[0, sl], rhs_ref[0, sl]) < 1e-11 and relerr(rhs_gpu[1, sl], rhs_ref[1, sl]) < 1e-11
-    ch.close()
