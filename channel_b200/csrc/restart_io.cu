@@ -12,10 +12,12 @@
 // Save pipeline: (1) the device transposes its layout [c][iy][ix][iz] into file order (a tiled 2-D
 // transpose per component) -- blocking mode into the products buffer P, which is dead between
 // time steps; asynchronous mode into a dedicated snapshot buffer, after which the time loop may
-// continue at once; (2) a copy stream drains the snapshot in chunks through two pinned host
-// buffers; (3) the calling thread (blocking) or a writer thread (asynchronous) pwrite()s chunk k
-// while chunk k+1 is in flight over PCIe.  At 1024^3 a snapshot is 103 GB (13 GB per GPU on 8 GPUs):
-// the step time hides it completely in asynchronous mode.
+// continue at once; (2) CHB_IO_THREADS (default 4) host threads drain the snapshot, each with its own
+// copy stream and two pinned buffers: thread w takes chunks w, w+NW, ... and pwrite()s chunk k while
+// its next chunk is in flight over PCIe (one thread's pwrite into the page cache runs at 2-3 GB/s,
+// far below PCIe, so the file side is what needs the parallelism); blocking mode joins them before
+// returning, asynchronous mode leaves them running.  At 1024^3 a snapshot is 103 GB (13 GB per GPU
+// on 8 GPUs): the step time hides it completely in asynchronous mode.  Reading is the mirror image.
 #include <errno.h>
 #include <fcntl.h>
 #include <sys/stat.h>
@@ -33,10 +35,16 @@
 
 #define CHB_RESTART_HEADER_BYTES 68
 
-struct RestartIO {
-    cudaStream_t copy_stream = nullptr;
-    cudaEvent_t snap_done = nullptr, copied[2] = {nullptr, nullptr};
+#define CHB_IO_MAX_THREADS 8
+struct IoLane {   // one host thread's copy stream, events and pinned buffers
+    cudaStream_t stream = nullptr;
+    cudaEvent_t copied[2] = {nullptr, nullptr};
     char* pinned[2] = {nullptr, nullptr};
+};
+struct RestartIO {
+    int nw = 1;
+    IoLane lane[CHB_IO_MAX_THREADS];
+    cudaEvent_t snap_done = nullptr;
     size_t chunk_bytes = 0;
     cplx* snap = nullptr;          // asynchronous mode: device copy of the field in file order
     std::thread worker;
@@ -102,20 +110,27 @@ static RestartIO* rio_get(chb_handle_s* h) {
     if (h->rio) return (RestartIO*)h->rio;
     RestartIO* r = new RestartIO();
     const char* e = getenv("CHB_IO_CHUNK_MB");
-    r->chunk_bytes = (size_t)((e ? atof(e) : 64.0) * 1048576.0);
+    r->chunk_bytes = (size_t)((e ? atof(e) : 32.0) * 1048576.0);
     if (r->chunk_bytes < 4096) r->chunk_bytes = 4096;
     r->chunk_bytes &= ~(size_t)15;
-    bool ok = cudaStreamCreateWithFlags(&r->copy_stream, cudaStreamNonBlocking) == cudaSuccess &&
-              cudaEventCreateWithFlags(&r->snap_done, cudaEventDisableTiming) == cudaSuccess;
-    for (int b = 0; b < 2 && ok; ++b)
-        ok = cudaEventCreateWithFlags(&r->copied[b], cudaEventDisableTiming) == cudaSuccess &&
-             cudaMallocHost((void**)&r->pinned[b], r->chunk_bytes) == cudaSuccess;
-    if (!ok) {
-        chb_set_error(std::string("restart I/O setup: ") + cudaGetErrorString(cudaGetLastError()));
-        delete r;
-        return nullptr;
+    e = getenv("CHB_IO_THREADS");
+    r->nw = e ? atoi(e) : 4;
+    if (r->nw < 1) r->nw = 1;
+    if (r->nw > CHB_IO_MAX_THREADS) r->nw = CHB_IO_MAX_THREADS;
+    bool ok = cudaEventCreateWithFlags(&r->snap_done, cudaEventDisableTiming) == cudaSuccess;
+    for (int w = 0; w < r->nw && ok; ++w) {
+        IoLane& ln = r->lane[w];
+        ok = cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking) == cudaSuccess;
+        for (int b = 0; b < 2 && ok; ++b)
+            ok = cudaEventCreateWithFlags(&ln.copied[b], cudaEventDisableTiming) == cudaSuccess &&
+                 cudaMallocHost((void**)&ln.pinned[b], r->chunk_bytes) == cudaSuccess;
     }
     h->rio = r;
+    if (!ok) {
+        chb_set_error(std::string("restart I/O setup: ") + cudaGetErrorString(cudaGetLastError()));
+        chb_restart_destroy(h);
+        return nullptr;
+    }
     return r;
 }
 
@@ -131,56 +146,78 @@ void chb_restart_destroy(chb_handle_s* h) {
     RestartIO* r = (RestartIO*)h->rio;
     if (!r) return;
     rio_join(r);
-    for (int b = 0; b < 2; ++b) {
-        if (r->pinned[b]) cudaFreeHost(r->pinned[b]);
-        if (r->copied[b]) cudaEventDestroy(r->copied[b]);
+    for (int w = 0; w < CHB_IO_MAX_THREADS; ++w) {
+        IoLane& ln = r->lane[w];
+        for (int b = 0; b < 2; ++b) {
+            if (ln.pinned[b]) cudaFreeHost(ln.pinned[b]);
+            if (ln.copied[b]) cudaEventDestroy(ln.copied[b]);
+        }
+        if (ln.stream) cudaStreamDestroy(ln.stream);
     }
     if (r->snap) cudaFree(r->snap);
     if (r->snap_done) cudaEventDestroy(r->snap_done);
-    if (r->copy_stream) cudaStreamDestroy(r->copy_stream);
     delete r;
     h->rio = nullptr;
 }
 
-// drain `src` (device, file order: [c][ixl][iz][iy]) into the file: chunked D2H on the copy stream
-// through two pinned buffers, chunk k written while chunk k+1 is copied
-static int drain_to_file(chb_handle_s* h, RestartIO* r, const cplx* src, int fd, std::string* err) {
-    const Geometry& g = h->g;
+// The snapshot in chunks that never straddle a component: chunk k -> (offset in the device copy, offset in the file, bytes)
+struct Chunk { size_t dev_off; off_t file_off; size_t n; };
+static bool chunk_at(const Geometry& g, size_t chunk_bytes, size_t k, Chunk* c) {
     const size_t comp_bytes = (size_t)g.nyp * g.M * sizeof(cplx);
-    struct Chunk { size_t src_off; off_t file_off; size_t n; };
-    auto chunk_at = [&](size_t k, Chunk* c) -> bool {   // chunks never straddle a component
-        const size_t per_comp = (comp_bytes + r->chunk_bytes - 1) / r->chunk_bytes;
-        if (k >= 3 * per_comp) return false;
-        const size_t comp = k / per_comp, i = k % per_comp;
-        const size_t o = i * r->chunk_bytes;
-        c->n = (o + r->chunk_bytes <= comp_bytes) ? r->chunk_bytes : comp_bytes - o;
-        c->src_off = comp * comp_bytes + o;
-        c->file_off = (off_t)(chb_host_restart_offset(g.nx, g.ny, g.nz, g.nx0, (int)comp) + (long long)o);
-        return true;
-    };
-    auto issue = [&](size_t k) -> int {
+    const size_t per_comp = (comp_bytes + chunk_bytes - 1) / chunk_bytes;
+    if (k >= 3 * per_comp) return false;
+    const size_t comp = k / per_comp, o = (k % per_comp) * chunk_bytes;
+    c->n = (o + chunk_bytes <= comp_bytes) ? chunk_bytes : comp_bytes - o;
+    c->dev_off = comp * comp_bytes + o;
+    c->file_off = (off_t)(chb_host_restart_offset(g.nx, g.ny, g.nz, g.nx0, (int)comp) + (long long)o);
+    return true;
+}
+
+// host thread w of nw: drain chunks w, w+nw, ... of `src` (device, file order [c][ixl][iz][iy]) into the file;
+// chunk k is written while this thread's next chunk crosses PCIe
+static int drain_lane(chb_handle_s* h, RestartIO* r, int w, const cplx* src, int fd, std::string* err) {
+    cudaSetDevice(h->device);
+    IoLane& ln = r->lane[w];
+    const size_t nw = (size_t)r->nw;
+    auto issue = [&](size_t i) -> int {   // i-th chunk of this lane
         Chunk c;
-        if (!chunk_at(k, &c)) return 0;
-        const int b = (int)(k & 1);
-        if (cudaMemcpyAsync(r->pinned[b], reinterpret_cast<const char*>(src) + c.src_off, c.n, cudaMemcpyDeviceToHost,
-                            r->copy_stream) != cudaSuccess ||
-            cudaEventRecord(r->copied[b], r->copy_stream) != cudaSuccess) {
+        if (!chunk_at(h->g, r->chunk_bytes, w + i * nw, &c)) return 0;
+        const int b = (int)(i & 1);
+        if (cudaMemcpyAsync(ln.pinned[b], reinterpret_cast<const char*>(src) + c.dev_off, c.n, cudaMemcpyDeviceToHost,
+                            ln.stream) != cudaSuccess ||
+            cudaEventRecord(ln.copied[b], ln.stream) != cudaSuccess) {
             *err = std::string("snapshot D2H: ") + cudaGetErrorString(cudaGetLastError());
             return 1;
         }
         return 0;
     };
+    if (cudaStreamWaitEvent(ln.stream, r->snap_done, 0) != cudaSuccess) { *err = "snapshot: cudaStreamWaitEvent failed"; return 1; }
     if (issue(0)) return 1;
     Chunk c;
-    for (size_t k = 0; chunk_at(k, &c); ++k) {
-        if (cudaEventSynchronize(r->copied[k & 1]) != cudaSuccess) {
+    for (size_t i = 0; chunk_at(h->g, r->chunk_bytes, w + i * nw, &c); ++i) {
+        if (cudaEventSynchronize(ln.copied[i & 1]) != cudaSuccess) {
             *err = std::string("snapshot D2H: ") + cudaGetErrorString(cudaGetLastError());
             return 1;
         }
-        if (issue(k + 1)) return 1;     // buffer (k+1)&1 was written to the file in the previous iteration
-        if (write_all(fd, r->pinned[k & 1], c.n, c.file_off, err)) return 1;
+        if (issue(i + 1)) return 1;     // buffer (i+1)&1 went to the file in the previous iteration
+        if (write_all(fd, ln.pinned[i & 1], c.n, c.file_off, err)) return 1;
     }
     return 0;
+}
+
+// all lanes: nw-1 extra threads + the calling one
+static int drain_to_file(chb_handle_s* h, RestartIO* r, const cplx* src, int fd, std::string* err) {
+    std::string errs[CHB_IO_MAX_THREADS];
+    int rcs[CHB_IO_MAX_THREADS] = {0};
+    std::thread th[CHB_IO_MAX_THREADS];
+    for (int w = 1; w < r->nw; ++w) th[w] = std::thread([&, w]() { rcs[w] = drain_lane(h, r, w, src, fd, &errs[w]); });
+    rcs[0] = drain_lane(h, r, 0, src, fd, &errs[0]);
+    int rc = 0;
+    for (int w = 0; w < r->nw; ++w) {
+        if (w) th[w].join();
+        if (rcs[w] && !rc) { rc = rcs[w]; *err = errs[w]; }
+    }
+    return rc;
 }
 
 extern "C" int chb_save_restart_file(chb_handle h, const char* filename, double time, int field, int async_mode) {
@@ -232,7 +269,6 @@ extern "C" int chb_save_restart_file(chb_handle h, const char* filename, double 
     for (int c = 0; c < 3; ++c) launch_planes_to_fortran(h, src + c * fld, dst + c * fld, c, 0, g.nxB);
     CHB_CUDA_OK(cudaEventRecord(e1, h->stream));
     CHB_CUDA_OK(cudaEventRecord(r->snap_done, h->stream));
-    CHB_CUDA_OK(cudaStreamWaitEvent(r->copy_stream, r->snap_done, 0));
     r->bytes = (double)(3 * fld * sizeof(cplx));
 
     // (2)+(3) drain
@@ -308,28 +344,34 @@ extern "C" int chb_read_restart_file(chb_handle h, const char* filename, double*
         close(fd);
         return 4;
     }
-    // pread chunk k into a pinned buffer while chunk k-1 crosses PCIe; stage in P (file order), then transpose
-    const size_t fld = (size_t)g.nyp * g.M, comp_bytes = fld * sizeof(cplx);
+    // thread w: pread its chunk i into a pinned buffer while its chunk i-1 crosses PCIe; staged in P (file order)
+    const size_t fld = (size_t)g.nyp * g.M;
     CHB_CUDA_OK(cudaStreamSynchronize(h->stream));
-    size_t k = 0;
-    for (int c = 0; c < 3; ++c) {
-        const off_t base = (off_t)chb_host_restart_offset(g.nx, g.ny, g.nz, g.nx0, c);
-        for (size_t o = 0; o < comp_bytes; o += r->chunk_bytes, ++k) {
-            const size_t n = (o + r->chunk_bytes <= comp_bytes) ? r->chunk_bytes : comp_bytes - o;
-            const int b = (int)(k & 1);
-            if (k >= 2) CHB_CUDA_OK(cudaEventSynchronize(r->copied[b]));
-            if (read_all(fd, r->pinned[b], n, base + (off_t)o, &err)) { chb_set_error(err); close(fd); return 4; }
-            CHB_CUDA_OK(cudaMemcpyAsync(reinterpret_cast<char*>(h->P) + c * comp_bytes + o, r->pinned[b], n,
-                                        cudaMemcpyHostToDevice, r->copy_stream));
-            CHB_CUDA_OK(cudaEventRecord(r->copied[b], r->copy_stream));
+    std::string errs[CHB_IO_MAX_THREADS];
+    int rcs[CHB_IO_MAX_THREADS] = {0};
+    std::thread th[CHB_IO_MAX_THREADS];
+    auto load_lane = [&](int w) {
+        cudaSetDevice(h->device);
+        IoLane& ln = r->lane[w];
+        Chunk c;
+        for (size_t i = 0; chunk_at(g, r->chunk_bytes, w + i * (size_t)r->nw, &c); ++i) {
+            const int b = (int)(i & 1);
+            if (i >= 2 && cudaEventSynchronize(ln.copied[b]) != cudaSuccess) { rcs[w] = 1; errs[w] = "restart H2D failed"; return; }
+            if (read_all(fd, ln.pinned[b], c.n, c.file_off, &errs[w])) { rcs[w] = 4; return; }
+            if (cudaMemcpyAsync(reinterpret_cast<char*>(h->P) + c.dev_off, ln.pinned[b], c.n, cudaMemcpyHostToDevice,
+                                ln.stream) != cudaSuccess ||
+                cudaEventRecord(ln.copied[b], ln.stream) != cudaSuccess) { rcs[w] = 1; errs[w] = "restart H2D failed"; return; }
         }
-    }
+        if (cudaStreamSynchronize(ln.stream) != cudaSuccess) { rcs[w] = 1; errs[w] = "restart H2D failed"; }
+    };
+    for (int w = 1; w < r->nw; ++w) th[w] = std::thread(load_lane, w);
+    load_lane(0);
+    for (int w = 1; w < r->nw; ++w) th[w].join();
     close(fd);
-    CHB_CUDA_OK(cudaEventRecord(r->snap_done, r->copy_stream));
-    CHB_CUDA_OK(cudaStreamWaitEvent(h->stream, r->snap_done, 0));
+    for (int w = 0; w < r->nw; ++w)
+        if (rcs[w]) { chb_set_error("chb_read_restart_file: " + errs[w]); return rcs[w]; }
     for (int c = 0; c < 3; ++c) launch_fortran_to_planes(h, h->P + c * fld, h->V + c * fld, c, 0, g.nxB);
     CHB_CUDA_OK(cudaStreamSynchronize(h->stream));
-    CHB_CUDA_OK(cudaStreamSynchronize(r->copy_stream));
     CHB_CUDA_OK(cudaGetLastError());
     return 0;
 }

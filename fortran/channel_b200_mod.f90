@@ -116,6 +116,28 @@ MODULE channel_b200
       REAL(C_DOUBLE) :: cfl, fr(3), corrpx, corrpz, meanpx, meanpz, U_lo(5), U_hi(5), W_lo(5), W_hi(5)
       INTEGER(C_INT) :: rc
     END FUNCTION
+    ! restart / snapshot files from the device-resident field (save_restart_file dnsdata.f90:821-848,
+    ! read_restart_file dnsdata.f90:677-704); filename is a NUL-terminated C string: TRIM(filename)//C_NULL_CHAR
+    FUNCTION chb_save_restart_file(h, filename, time, field, async_mode) BIND(C, name="chb_save_restart_file") RESULT(rc)
+      IMPORT :: C_PTR, C_INT, C_DOUBLE, C_CHAR
+      TYPE(C_PTR), VALUE :: h
+      CHARACTER(KIND=C_CHAR) :: filename(*)
+      REAL(C_DOUBLE), VALUE :: time
+      INTEGER(C_INT), VALUE :: field, async_mode
+      INTEGER(C_INT) :: rc
+    END FUNCTION
+    FUNCTION chb_restart_wait(h) BIND(C, name="chb_restart_wait") RESULT(rc)
+      IMPORT :: C_PTR, C_INT
+      TYPE(C_PTR), VALUE :: h
+      INTEGER(C_INT) :: rc
+    END FUNCTION
+    FUNCTION chb_read_restart_file(h, filename, time) BIND(C, name="chb_read_restart_file") RESULT(rc)
+      IMPORT :: C_PTR, C_INT, C_DOUBLE, C_CHAR
+      TYPE(C_PTR), VALUE :: h
+      CHARACTER(KIND=C_CHAR) :: filename(*)
+      REAL(C_DOUBLE) :: time
+      INTEGER(C_INT) :: rc
+    END FUNCTION
   END INTERFACE
 
 CONTAINS
