@@ -263,7 +263,7 @@ extern "C" int chb_create(chb_handle* out, int nx, int ny, int nz, int nxd, int 
     if (dev_alloc(&h->t_y, (size_t)g.nyp) || dev_alloc(&h->t_dy, (size_t)g.nyp) ||
         dev_alloc(&h->t_d0, (size_t)g.nyp * 5) || dev_alloc(&h->t_d1, (size_t)g.nyp * 5) ||
         dev_alloc(&h->t_d2, (size_t)g.nyp * 5) || dev_alloc(&h->t_d4, (size_t)g.nyp * 5) ||
-        dev_alloc(&h->t_D0mat, (size_t)(ny + 1) * 5) || dev_alloc(&h->mean_scratch, (size_t)(ny + 1) * 5 + g.nyp + 8))
+        dev_alloc(&h->t_D0mat, (size_t)(ny + 1) * 5) || dev_alloc(&h->t_rows, (size_t)g.nyp * 25) || dev_alloc(&h->mean_scratch, (size_t)(ny + 1) * 5 + g.nyp + 8))
         return 1;
     if (dev_alloc(&h->sc, 1)) return 1;
     CHB_CUDA_OK(cudaMallocHost((void**)&h->sc_host, sizeof(DevScalars)));
@@ -297,7 +297,7 @@ extern "C" int chb_destroy(chb_handle h) {
     }
     cudaFree(h->Wz); cudaFree(h->Wx); cudaFree(h->Wh); cudaFree(h->rev_z);
     cudaFree(h->t_y); cudaFree(h->t_dy); cudaFree(h->t_d0); cudaFree(h->t_d1); cudaFree(h->t_d2); cudaFree(h->t_d4);
-    cudaFree(h->t_D0mat); cudaFree(h->mean_scratch); cudaFree(h->sc);
+    cudaFree(h->t_D0mat); cudaFree(h->t_rows); cudaFree(h->mean_scratch); cudaFree(h->sc);
     if (h->bf.mask_y) cudaFree(h->bf.mask_y);
     if (h->bf.mask_z) cudaFree(h->bf.mask_z);
     cudaFreeHost(h->sc_host);
@@ -340,6 +340,7 @@ extern "C" int chb_set_tables(chb_handle h, const double* y, const double* d0, c
     DevTables& t = h->tab;
     t.y = h->t_y; t.dy = h->t_dy; t.d0 = h->t_d0; t.d1 = h->t_d1; t.d2 = h->t_d2; t.d4 = h->t_d4;
     t.D0mat = h->t_D0mat;
+    t.rows = h->t_rows;
 #define CP5(name) memcpy(t.name, name, sizeof(double) * 5)
     CP5(d140); CP5(d14m1); CP5(d240); CP5(d24m1); CP5(d14n); CP5(d14np1); CP5(d24n); CP5(d24np1);
     CP5(v0bc); CP5(v0m1bc); CP5(vnbc); CP5(vnp1bc); CP5(eta0bc); CP5(eta0m1bc); CP5(etanbc); CP5(etanp1bc);

@@ -18,6 +18,7 @@ struct DevTables {
     const double* d2;
     const double* d4;
     const double* D0mat;  // [ny+1][5]   after LU5decompStep, row i <-> iy=i+1
+    const double* rows;   // [ny+3][5][5] k2-polynomial coefficients of the D2vmat / etamat rows of this substep (solve_device.cuh)
     double d140[5], d14m1[5], d240[5], d24m1[5], d14n[5], d14np1[5], d24n[5], d24np1[5];
     double v0bc[5], v0m1bc[5], vnbc[5], vnp1bc[5], eta0bc[5], eta0m1bc[5], etanbc[5], etanp1bc[5];
 };
@@ -127,7 +128,7 @@ struct chb_handle_s {
     int* rev_z;     // digit reversal for plan_z
     // tables
     DevTables tab;
-    double *t_y, *t_dy, *t_d0, *t_d1, *t_d2, *t_d4, *t_D0mat;
+    double *t_y, *t_dy, *t_d0, *t_d1, *t_d2, *t_d4, *t_D0mat, *t_rows;
     bool tables_set;
     DevScalars* sc;       // device
     DevScalars* sc_host;  // pinned

@@ -25,6 +25,22 @@ __device__ __forceinline__ void build_rows(const DevTables& tab, int iy, double 
     }
 }
 
+// The same rows from per-substep tables (solve_rows_kernel): with lam fixed during a substep every
+// band entry is a polynomial in k2 whose coefficients depend on (iy, j) only,
+//   D2vmat: lam*(d2 - k2 d0) - ni*(d4 - 2 k2 d2 + k2^2 d0) = Av + k2*(Bv + k2*Cv)
+//   etamat: lam*d0 - ni*(d2 - k2 d0)                       = Ae + k2*Be
+// so a row costs 5 x 2 (v) or 5 x 1 (eta) fused multiply-adds instead of ~12 operations per entry.
+// rows[(iy+1)*25 + j*5 + {0,1,2,3,4}] = Av, Bv, Cv, Ae, Be
+template <int COMP>
+__device__ __forceinline__ void build_row_poly(const double* __restrict__ rows, int iy, double k2, Row5& r) {
+    const double* t = rows + (size_t)(iy + 1) * 25;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+        if (COMP) r.a[j] = __ldg(&t[j * 5 + 0]) + k2 * (__ldg(&t[j * 5 + 1]) + k2 * __ldg(&t[j * 5 + 2]));
+        else r.a[j] = __ldg(&t[j * 5 + 3]) + k2 * __ldg(&t[j * 5 + 4]);
+    }
+}
+
 // applybc_n / applybc_0 on the rows they touch                  dnsdata.f90:458-472
 __device__ __forceinline__ void fold_top1(Row5& r, const double* bcn, const double* bcnp1) {  // row ny-1
     double e = r.a[4];

@@ -19,6 +19,19 @@
 
 #define SOLVE_THREADS 128
 
+// k2-polynomial coefficients of the matrix rows for this substep's lam (solve_device.cuh)
+__global__ void solve_rows_kernel(DevTables tab, double* __restrict__ rows, double lam, double ni, int nyp) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;   // (iy+1)*5 + j
+    if (i >= nyp * 5) return;
+    const double d0 = tab.d0[i], d2 = tab.d2[i], d4 = tab.d4[i];
+    double* t = rows + (size_t)i * 5;
+    t[0] = lam * d2 - ni * d4;
+    t[1] = 2.0 * ni * d2 - lam * d0;
+    t[2] = -ni * d0;
+    t[3] = lam * d0 - ni * d2;
+    t[4] = ni * d0;
+}
+
 // ---------------------------------------------------------------------------------------------
 // COMP = 0: eta equation (etamat), COMP = 1: v equation (D2vmat); blockIdx.y selects nothing, the
 // two components are separate launches of the same grid so that each thread carries one recurrence
@@ -51,9 +64,8 @@ solve_s1_kernel(cplx* __restrict__ rhs, double* __restrict__ ckpt, Geometry g, D
     LUState st = {0, 0, 0, 0};
     cplx x1 = make_double2(0, 0), x2 = x1;  // x(i+1), x(i+2)
     for (int iy = ny - 1; iy >= 1; --iy) {
-        Row5 rv, re;
-        build_rows(tab, iy, k2, lam, g.ni, rv, re);
-        Row5& r = COMP ? rv : re;
+        Row5 r;
+        build_row_poly<COMP>(tab.rows, iy, k2, r);
         const size_t off = (size_t)(iy + 1) * plane;
         cplx b = col[off];
         if (iy == ny - 1) {
@@ -92,7 +104,7 @@ solve_s1_kernel(cplx* __restrict__ rhs, double* __restrict__ ckpt, Geometry g, D
 
 // ---------------------------------------------------------------------------------------------
 template <int COMP>
-__global__ void __launch_bounds__(SOLVE_THREADS)
+__global__ void __launch_bounds__(SOLVE_THREADS, 4)
 solve_s2_kernel(const cplx* __restrict__ rhs, const double* __restrict__ ckpt, cplx* __restrict__ V, Geometry g,
                 DevTables tab, const DevScalars* __restrict__ sc, double lam) {
     const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -137,9 +149,8 @@ solve_s2_kernel(const cplx* __restrict__ rhs, const double* __restrict__ ckpt, c
             const int iy = i0 + k;
             m2[k] = m1[k] = 0.0;
             if (iy <= ny - 1) {
-                Row5 rv, re;
-                build_rows(tab, iy, k2, lam, g.ni, rv, re);
-                Row5& r = COMP ? rv : re;
+                Row5 r;
+                build_row_poly<COMP>(tab.rows, iy, k2, r);
                 if (iy == ny - 1) {
                     fold_top1(r, bcn, bcnp1);
                     r.a[3] = r.a[4] = 0.0;
@@ -288,7 +299,7 @@ solve_s4_kernel(cplx* __restrict__ V, Geometry g, DevTables tab) {
     const int ix = g.nx0 + ixl, iz = izp - g.nz;
     if (ix == 0 && iz == 0) return;
     const double al = g.alfa0 * ix, be = g.beta0 * iz;
-    const double k2 = al * al + be * be;
+    const double rk2 = 1.0 / (al * al + be * be);   // one division per column instead of four per node
     const int ny = g.ny;
     const size_t plane = (size_t)g.M, comp = (size_t)g.nyp * plane;
     cplx b1 = make_double2(0, 0), b2 = b1;
@@ -306,10 +317,10 @@ solve_s4_kernel(cplx* __restrict__ V, Geometry g, DevTables tab) {
         b1 = vy;
         // (ia*vy - ib*eta)/k2 ; (ib*vy + ia*eta)/k2
         cplx u, w;
-        u.x = (-al * vy.y + be * eta.y) / k2;
-        u.y = (al * vy.x - be * eta.x) / k2;
-        w.x = (-be * vy.y - al * eta.y) / k2;
-        w.y = (be * vy.x + al * eta.x) / k2;
+        u.x = (-al * vy.y + be * eta.y) * rk2;
+        u.y = (al * vy.x - be * eta.x) * rk2;
+        w.x = (-be * vy.y - al * eta.y) * rk2;
+        w.y = (be * vy.x + al * eta.x) * rk2;
         V[0 * comp + off] = u;
         V[2 * comp + off] = w;
     }
@@ -435,6 +446,8 @@ __global__ void meanflow_prepass_kernel(cplx* __restrict__ V, Geometry g, DevTab
 void launch_linsolve(chb_handle_s* h, double lam) {
     const Geometry& g = h->g;
     const int blocks = (int)((g.M + SOLVE_THREADS - 1) / SOLVE_THREADS);
+    solve_rows_kernel<<<(g.nyp * 5 + 127) / 128, 128, 0, h->stream>>>(h->tab, h->t_rows, lam, g.ni, g.nyp);
+    h->launches++;
     {
         ScopedKernelTimer tm(h, "solve_s1");
         solve_s1_kernel<0><<<blocks, SOLVE_THREADS, 0, h->stream>>>(h->rhs, h->ckpt, g, h->tab, h->sc, lam);

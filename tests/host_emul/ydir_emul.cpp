@@ -73,6 +73,8 @@ __attribute__((visibility("default"))) int chb_emul_ydir_substep(int nx, int ny,
     tab.y = y; tab.dy = dy.data();
     tab.d0 = full[0].data(); tab.d1 = full[1].data(); tab.d2 = full[2].data(); tab.d4 = full[3].data();
     tab.D0mat = D0mat;
+    std::vector<double> rows((size_t)nyp * 25, 0.0);
+    tab.rows = rows.data();
     double* dst[16] = {tab.d140, tab.d14m1, tab.d240, tab.d24m1, tab.d14n, tab.d14np1, tab.d24n, tab.d24np1,
                        tab.v0bc, tab.v0m1bc, tab.vnbc, tab.vnp1bc, tab.eta0bc, tab.eta0m1bc, tab.etanbc, tab.etanp1bc};
     for (int k = 0; k < 16; ++k) memcpy(dst[k], bc5x16 + 5 * k, sizeof(double) * 5);
@@ -97,6 +99,7 @@ __attribute__((visibility("default"))) int chb_emul_ydir_substep(int nx, int ny,
         if (F) emulate(rhs_kernel<true>, blocks, T, Vc, Pc, Fc, rc, oc, g, tab, &sc, lam, ode2, ode3);
         else emulate(rhs_kernel<false>, blocks, T, Vc, Pc, Fc, rc, oc, g, tab, &sc, lam, ode2, ode3);
         if (mode < 0) return 0;   // RHS only
+        emulate(solve_rows_kernel, (nyp * 5 + 127) / 128, 128, tab, rows.data(), lam, ni, nyp);
         emulate(solve_s1_kernel<0>, blocks, T, rc, ckpt.data(), g, tab, &sc, lam);
         emulate(solve_s1_kernel<1>, blocks, T, rc, ckpt.data(), g, tab, &sc, lam);
         emulate(solve_s2_kernel<0>, blocks, T, rc, ckpt.data(), Vc, g, tab, &sc, lam);
