@@ -16,6 +16,7 @@
 //   lin_v   = sum_j [ODE1/dt*(d2-k2*d0) + ni*(d4-2*k2*d2+k2^2*d0)](j) * v(iy+j)
 //   lin_eta = sum_j [ODE1/dt*d0 + ni*(d2-k2*d0)](j) * (ib*u - ia*w)(iy+j)
 // The mean mode (ix=iz=0) uses the real/imag packing of dnsdata.f90:648-654.
+#include <cstdlib>
 #include "chb_internal.h"
 #include "solve_device.cuh"
 
@@ -25,8 +26,10 @@ struct RhsAcc {
     cplx ev, ee, lv, le;
 };
 
-template <bool HAS_F>
-__global__ void __launch_bounds__(RHS_THREADS)
+// MINB = resident blocks per SM the register allocation is sized for: 3 = 152 registers, no spills;
+// 4 = 128 registers, 16 warps per SM, 56-96 bytes of spills (CHB_RHS_MINB)
+template <bool HAS_F, int MINB>
+__global__ void __launch_bounds__(RHS_THREADS, MINB)
 rhs_kernel(const cplx* __restrict__ V, const cplx* __restrict__ P, const cplx* __restrict__ F, cplx* __restrict__ rhs,
            cplx* __restrict__ oldrhs, Geometry g, DevTables tab, const DevScalars* __restrict__ sc, double ode1_dt,
            double ode2, double ode3) {
@@ -154,13 +157,12 @@ rhs_kernel(const cplx* __restrict__ V, const cplx* __restrict__ P, const cplx* _
 void launch_rhs(chb_handle_s* h, const double* ode, double deltat) {
     const Geometry& g = h->g;
     const int blocks = (int)((g.M + RHS_THREADS - 1) / RHS_THREADS);
+    static const int minb = []() { const char* e = getenv("CHB_RHS_MINB"); return (e && atoi(e) == 4) ? 4 : 3; }();
     ScopedKernelTimer tm(h, "rhs");
-    if (h->bf.enabled)
-        rhs_kernel<true><<<blocks, RHS_THREADS, 0, h->stream>>>(h->V, h->P, h->F, h->rhs, h->oldrhs, g, h->tab, h->sc,
-                                                                ode[0] / deltat, ode[1], ode[2]);
-    else
-        rhs_kernel<false><<<blocks, RHS_THREADS, 0, h->stream>>>(h->V, h->P, nullptr, h->rhs, h->oldrhs, g, h->tab,
-                                                                 h->sc, ode[0] / deltat, ode[1], ode[2]);
+    auto kern = h->bf.enabled ? (minb == 4 ? rhs_kernel<true, 4> : rhs_kernel<true, 3>)
+                              : (minb == 4 ? rhs_kernel<false, 4> : rhs_kernel<false, 3>);
+    kern<<<blocks, RHS_THREADS, 0, h->stream>>>(h->V, h->P, h->bf.enabled ? h->F : nullptr, h->rhs, h->oldrhs, g, h->tab,
+                                               h->sc, ode[0] / deltat, ode[1], ode[2]);
     h->launches++;
 }
 #endif

@@ -96,8 +96,8 @@ __attribute__((visibility("default"))) int chb_emul_ydir_substep(int nx, int ny,
     const int T = 128, blocks = (int)((g.M + T - 1) / T);
     const double lam = ode1 / deltat;
     {
-        if (F) emulate(rhs_kernel<true>, blocks, T, Vc, Pc, Fc, rc, oc, g, tab, &sc, lam, ode2, ode3);
-        else emulate(rhs_kernel<false>, blocks, T, Vc, Pc, Fc, rc, oc, g, tab, &sc, lam, ode2, ode3);
+        if (F) emulate(rhs_kernel<true, 3>, blocks, T, Vc, Pc, Fc, rc, oc, g, tab, &sc, lam, ode2, ode3);
+        else emulate(rhs_kernel<false, 3>, blocks, T, Vc, Pc, Fc, rc, oc, g, tab, &sc, lam, ode2, ode3);
         if (mode < 0) return 0;   // RHS only
         emulate(solve_rows_kernel, (nyp * 5 + 127) / 128, 128, tab, rows.data(), lam, ni, nyp);
         emulate(solve_s1_kernel<0>, blocks, T, rc, ckpt.data(), g, tab, &sc, lam);
