@@ -65,18 +65,38 @@ def _worker(rank, world, port, nx, nz, nzd, ncomp, nplanes, q):
         full = np.concatenate([p_.numpy().view(np.complex128) for p_ in parts], axis=1)
         ref = np.transpose(perturbed_laminar(nx, ny, nz, 0.5, 1.0), (0, 2, 3, 1))
         assert np.abs(full - ref).max() < 1e-18
+        # one Dati.cart.out written by all ranks at the offsets of the MPI-IO view (restart_io.cu's host side)
+        import struct, tempfile
+        path = os.path.join(tempfile.gettempdir(), f"chb_gloo_{port}.out")
+        total = lib.chb_host_restart_file_bytes(nx, ny, nz)
+        fd = os.open(path, os.O_WRONLY | os.O_CREAT, 0o644)
+        os.ftruncate(fd, total)
+        if rank == 0:
+            hdr = (C.c_ubyte * 68)()
+            lib.chb_host_restart_header(nx, ny, nz, 0.5, 1.0, 1e-3, 1.5, 0.0, 2.0, 4.5, hdr)
+            os.pwrite(fd, bytes(hdr), 0)
+        for cc in range(3):
+            os.pwrite(fd, np.ascontiguousarray(slab[cc]).tobytes(), lib.chb_host_restart_offset(nx, ny, nz, nx0, cc))
+        os.close(fd)
+        dist.barrier()
+        raw = open(path, "rb").read()
+        assert len(raw) == total and struct.unpack("<3i7d", raw[:68])[:3] == (nx, ny, nz)
+        assert np.array_equal(np.frombuffer(raw, dtype=np.complex128, offset=68).reshape(full.shape), full)
+        dist.barrier()
+        if rank == 0:
+            os.remove(path)
         dist.destroy_process_group()
         q.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         q.put((rank, repr(e)))
 
 
-@pytest.mark.parametrize("world", [2])
+@pytest.mark.parametrize("world", [2, 4])
 def test_pencil_transpose_block_exchange_gloo(world):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    nx, nz = 7, 3          # nx+1 = 8 modes, nzd = 12: both divisible by 2
+    nx, nz = 7, 3          # nx+1 = 8 modes, nzd = 12: both divisible by 2 and 4
     procs = [ctx.Process(target=_worker, args=(r, world, port, nx, nz, 12, 3, 2, q)) for r in range(world)]
     for p in procs:
         p.start()
