@@ -352,6 +352,9 @@ def run_b200(args):
                     "what": "chb_upload_V (pinned Fortran-layout V) + K x (chb_buildrhs/chb_linsolve x3 + "
                             "chb_get_step_scalars) + chb_download_V, wall clock"},
             "finite": finite,
+            # Runtimedata line of the last timed step (dnsdata.f90:878): time, dudy at both walls (u, w), flow
+            # rate x, meanpx, flow rate z, meanpz, cfl*deltat, deltat -- laminar values 3, 3, 0, 0, 2 expected
+            "runtimedata_last": [float(v) for v in last_line],
         }
         if snap:
             out["snapshot"] = snap
