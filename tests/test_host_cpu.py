@@ -195,3 +195,50 @@ def test_restart_file_layout_host_helpers(tmp_path):
     with pytest.raises(ValueError):
         read_restart_file(path, DnsIn(nx=nx, ny=ny, nz=nz, re=999.0))
     assert lib.chb_save_restart_file(None, b"x", 0.0, 0, 0) != 0 and lib.chb_read_restart_file(None, b"x", None) != 0
+
+
+SHIPPED_DNS_IN = """191       384    189                     ! nx, ny, nz
+0.5       1.0                            ! alfa0 beta0  
+12431                                    ! ni
+1.5       0.0    2.0                     ! a, ymin, ymax
+.TRUE.    1      0.161436                ! CPI, CPItype, gamma
+0.0       0.0                            ! meanpx, meanpz
+0.0       0.0                            ! meanflowx meanflowz
+0.0       0.0                            ! u0 uN
+0.0       1.0    0.0                     ! deltat, cflmax, time
+30       -1      7000        .TRUE.      ! dt_field, dt_save, t_max, time_from_restart
+999999                                  ! nstep
+1                                       ! npy (no. processes y)
+"""
+
+
+def test_cpp_driver_reads_dns_in_and_runtimedata(tmp_path):
+    """channel_b200_run (C++ restatement of PROGRAM channel) parses the repo's shipped dns.in exactly like
+    read_dnsin (dnsdata.f90:98-125) / the Python mirror, and positions an existing Runtimedata like
+    get_record (dnsdata.f90:181-218); --check-input needs no GPU."""
+    import json, subprocess
+    from channel_b200 import read_dnsin
+    from channel_b200.dnsdata import padded_sizes, format_runtimedata
+    exe = os.path.join(os.path.dirname(_lib.LIB_PATH), "channel_b200_run")
+    assert os.path.exists(exe), "build() makes channel_b200/lib/channel_b200_run"
+    (tmp_path / "dns.in").write_text(SHIPPED_DNS_IN)
+    out = json.loads(subprocess.check_output([exe, "--dir", str(tmp_path), "--check-input"], text=True))
+    p = read_dnsin(str(tmp_path / "dns.in"))
+    assert (out["nxd"], out["nzd"]) == padded_sizes(p.nx, p.nz) == (384, 768)
+    for k in ("nx", "ny", "nz", "alfa0", "beta0", "a", "ymin", "ymax", "CPI_type", "gamma", "meanpx", "meanpz", "meanflowx",
+              "meanflowz", "u0", "uN", "deltat", "cflmax", "time", "dt_field", "dt_save", "t_max", "nstep", "npy"):
+        assert out[k] == getattr(p, k), k
+    assert out["ni"] == 1.0 / p.re and bool(out["CPI"]) is p.CPI and bool(out["time_from_restart"]) is p.time_from_restart
+    assert out["rtd_exists"] == 0
+    # Fortran spellings: D exponents, commas, lower-case logicals; restart at time 0.3 inside an existing Runtimedata
+    (tmp_path / "dns.in").write_text(SHIPPED_DNS_IN.replace("12431 ", "1.2431D4").replace(".TRUE.    1", "f, 0,")
+                                     .replace("0.0       1.0    0.0   ", "1.0d-2, 0.0, 0.3"))
+    lines = [format_runtimedata([0.1 * i] + [0.0] * 9 + [0.1]) for i in range(6)]
+    (tmp_path / "Runtimedata").write_text("\n".join(lines) + "\n")
+    out = json.loads(subprocess.check_output([exe, "--dir", str(tmp_path), "--check-input"], text=True))
+    assert out["ni"] == 1.0 / 12431.0 and out["CPI"] == 0 and out["CPI_type"] == 0 and out["deltat"] == 0.01 and out["time"] == 0.3
+    assert out["rtd_exists"] == 1 and out["rtd_found"] == 1 and out["rtd_keep_lines"] == 3 and out["rtd_deltat"] == 0.1
+    # missing values stop the run like a failed list-directed READ
+    (tmp_path / "dns.in").write_text("\n".join(SHIPPED_DNS_IN.splitlines()[:5]))
+    r = subprocess.run([exe, "--dir", str(tmp_path), "--check-input"], capture_output=True, text=True)
+    assert r.returncode != 0 and "expected 12 data lines" in r.stderr
