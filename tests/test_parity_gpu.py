@@ -118,3 +118,27 @@ def test_fortran_layout_roundtrip():
     assert np.array_equal(ch.download_V(), V0)
     assert np.array_equal(ch.download_V_fortran(), Vf)
 
+
+@pytest.mark.parametrize("nx,ny,nz", [(2, 9, 1), (3, 12, 2), (6, 8, 1), (5, 8, 4)])
+def test_minimal_grids(nx, ny, nz):
+    """Smallest sizes the library accepts (ny = 8 is the minimum: two wall rows of each kind plus the
+    interior; nz = 1 gives nzd = 3; odd ny; fewer rows than one checkpoint block of the banded solve)."""
+    p, o, ch, V0 = make_pair(nx, ny, nz, deltat=1e-3, cflmax=0.0, re=500.0)
+    ch.cfl_prepass(); o.cfl_prepass()
+    assert np.allclose(ch.outstats(), o.outstats(), rtol=1e-11, atol=1e-13)
+    for i in range(2):
+        lo = o.step(); lg = ch.step()
+        assert np.allclose(lg[1:9], lo[1:9], rtol=1e-9, atol=1e-11), (i, lg, lo)
+    Vg = ch.download_V()
+    for c in range(3):
+        assert relerr(Vg[c], o.V[c]) < 1e-11, (c, relerr(Vg[c], o.V[c]))
+    ch.close()
+
+
+def test_rejected_sizes_report_errors():
+    """Sizes outside the library's domain fail loudly at chb_create (no fallback): ny < 8, odd nxd."""
+    from channel_b200 import Channel, DnsIn, _lib
+    with pytest.raises(_lib.ChannelB200Error, match="ny>=8"):
+        Channel(DnsIn(nx=4, ny=7, nz=4))
+    with pytest.raises(_lib.ChannelB200Error, match="nxd must be even"):
+        Channel(DnsIn(nx=1, ny=8, nz=1))           # nxd = 3(nx+1)/2 = 3
