@@ -210,3 +210,93 @@ def test_oracles_reproduce_golden_fixtures(path):
         for k in range(3):
             assert rel(V1[k], g["V1"][k]) <= tol and rel(Vend[k], g["Vend"][k]) <= tol * 10
         assert np.allclose(np.array(lines), g["lines"], rtol=max(tol * 100, 1e-15), atol=1e-11 if tol else 0)
+
+
+def test_fd_tables_match_the_references_matlab_formulation():
+    """The reference carries a second, independently written implementation of its compact-FD tables:
+    matlab-interface/base/compute_derivatives.m:18-79 (grid: init_dns.m:24, walls==2), which solves the same
+    5x5 moment systems with MATLAB's pivoted `M\\t` instead of the Fortran's unpivoted LUdecomp / LLUdiv
+    (rbmat.f90:60-76,201-215).  Restated here with numpy.linalg.solve and compared with the oracle's
+    (dnsdata.f90:241-286 order of operations) and the C++ host tables: a cross-check of the restatement
+    against the reference's own alternative formulation (the wall rows of d1/d2 are the d14*/d24* stencils)."""
+    from channel_b200.dnsdata import Tables
+    ny, a, ymin, ymax = 48, 1.5, 0.0, 2.0
+    o = Oracle(DnsIn(nx=2, ny=ny, nz=2))
+    y = 0.5 * (1 + np.tanh(a * (2 * np.arange(-1, ny + 2) / ny - 1)) / np.tanh(a)) * (ymax - ymin) + ymin   # init_dns.m:24
+    assert np.allclose(y, o.y, rtol=0, atol=1e-15)
+    d = {k: np.zeros((ny + 3, 5)) for k in ("d0", "d1", "d2", "d4")}
+    for iY in range(1, ny):                                     # compute_derivatives.m:18-54
+        iy = iY + 1                                             # 0-based row of node iY
+        dyv = y[iy - 2:iy + 3] - y[iy]
+        M = np.array([[dyv[j] ** (4 - i) for j in range(5)] for i in range(5)])
+        t = np.zeros(5); t[0] = 24
+        d4 = np.linalg.solve(M, t)
+        M0 = np.array([[(5 - i) * (6 - i) * (7 - i) * (8 - i) * dyv[j] ** (4 - i) for j in range(5)] for i in range(5)])
+        t = np.array([np.sum(d4 * dyv ** (8 - i)) for i in range(5)])
+        d0 = np.linalg.solve(M0, t)
+        t = np.zeros(5)
+        for i in range(3):
+            t[i] = np.sum(d0 * (4 - i) * (3 - i) * dyv ** (2 - i))
+        d2 = np.linalg.solve(M, t)
+        t = np.zeros(5)
+        for i in range(4):
+            t[i] = np.sum(d0 * (4 - i) * dyv ** (3 - i))
+        d1 = np.linalg.solve(M, t)
+        d["d4"][iy], d["d0"][iy], d["d2"][iy], d["d1"][iy] = d4, d0, d2, d1
+    def wall(node, base):                                       # compute_derivatives.m:55-90
+        dyv = y[base:base + 5] - y[node]
+        M = np.array([[dyv[j] ** (4 - i) for j in range(5)] for i in range(5)])
+        t1 = np.zeros(5); t1[3] = 1
+        t2 = np.zeros(5); t2[2] = 2
+        return np.linalg.solve(M, t1), np.linalg.solve(M, t2)
+    ref_wall = {"d140": wall(1, 0)[0], "d240": wall(1, 0)[1], "d14m1": wall(0, 0)[0], "d24m1": wall(0, 0)[1],
+                "d14n": wall(ny + 1, ny - 2)[0], "d24n": wall(ny + 1, ny - 2)[1],
+                "d14np1": wall(ny + 2, ny - 2)[0], "d24np1": wall(ny + 2, ny - 2)[1]}
+    host = Tables(ny, a, ymin, ymax)
+    rel = lambda x, r: np.abs(x - r).max() / np.abs(r).max()
+    for k in ("d0", "d1", "d2", "d4"):
+        for iy in range(2, ny + 1):
+            assert rel(getattr(o, k)[iy], d[k][iy]) < 1e-9, (k, iy, rel(getattr(o, k)[iy], d[k][iy]))
+            assert rel(getattr(host, k)[iy - 2], d[k][iy]) < 1e-9, ("host", k, iy)
+    for k, r in ref_wall.items():
+        assert rel(np.asarray(getattr(o, k)), r) < 1e-9, (k, rel(np.asarray(getattr(o, k)), r))
+        assert rel(np.asarray(getattr(host, k)), r) < 1e-9, ("host", k)
+
+
+def test_transform_conventions_match_the_references_plane_ift():
+    """matlab-interface/base/plane_ift.m is the reference's own statement of the spectral -> physical
+    transform of a plane: z-modes (-nz..nz) stored as (0..nz, -nz..-1) in a zero-padded line of nzd, ifft along
+    z, 'symmetric' ifft of logical length 2 nxd along x, times 2 nzd nxd (i.e. unnormalised, sign +).  The
+    nonlinear term of the oracle must equal: physical fields by plane_ift -> pointwise products ->
+    the adjoint-convention forward transforms written as explicit DFT sums (sign -, dnsdata.f90:124 factor
+    1/(2 nxd nzd)) -> modes 0..nx, -nz..nz (mpi_transpose.f90:99-106, izd dnsdata.f90:156)."""
+    nx, ny, nz = 3, 8, 2
+    o = Oracle(DnsIn(nx=nx, ny=ny, nz=nz))
+    nxd, nzd = o.nxd, o.nzd
+    V = perturbed_laminar(nx, ny, nz, o.alfa0, o.beta0, eps=0.3, seed=3)
+    ref = o.convolutions(V, False)[..., o.izd]                       # [6, ny+3, nx+1, 2nz+1]
+
+    def plane_ift(A):                                                # A[ix 0..nx, iz+nz] -> real [2nxd, nzd]
+        out = np.zeros((2 * nxd, nzd), complex)
+        out[0:nx + 1, nzd - nz:nzd] = A[:, 0:nz]                     # plane_ift.m:11-13
+        out[0:nx + 1, 0:nz + 1] = A[:, nz:2 * nz + 1]
+        out[0:nx + 1] = np.fft.ifft(out[0:nx + 1], axis=1)           # :16-18 (MATLAB ifft = 1/N sum X e^{+i...})
+        herm = np.zeros((2 * nxd, nzd), complex)                     # :21 'symmetric': the lower half is the conjugate mirror
+        herm[0:nx + 1] = out[0:nx + 1]
+        herm[0] = herm[0].real
+        for k in range(1, nx + 1):
+            herm[2 * nxd - k] = np.conj(herm[k])
+        phys = np.fft.ifft(herm, axis=0) * (2 * nzd * nxd)
+        assert np.abs(phys.imag).max() < 1e-12 * max(1.0, np.abs(phys.real).max())
+        return phys.real
+
+    x = np.arange(2 * nxd); z = np.arange(nzd)
+    Ex = np.exp(-2j * np.pi * np.outer(np.arange(nx + 1), x) / (2 * nxd))                 # forward in x, modes 0..nx
+    kz = np.arange(-nz, nz + 1)
+    Ez = np.exp(-2j * np.pi * np.outer(z, kz) / nzd)                                      # forward in z, modes -nz..nz
+    pairs = [(0, 0), (1, 1), (2, 2), (0, 1), (1, 2), (0, 2)]                              # uu vv ww uv vw uw (dnsdata.f90:581-584)
+    for iy in (0, 3, ny + 2):
+        phys = [plane_ift(V[c, iy]) for c in range(3)]
+        for k, (a, b) in enumerate(pairs):
+            P = Ex @ (phys[a] * phys[b] * o.factor) @ Ez
+            assert np.abs(P - ref[k, iy]).max() <= 1e-13 * max(1e-30, np.abs(ref[k]).max()), (iy, k)
