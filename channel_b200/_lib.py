@@ -37,6 +37,7 @@ SYMBOLS = {
     "chb_set_forcing": (C.c_int, [C.c_void_p] + [C.c_double] * 4 + [C.c_int, C.c_int, C.c_double]),
     "chb_cfl_prepass": (C.c_int, [C.c_void_p]),
     "chb_set_body_force_linear": (C.c_int, [C.c_void_p, C.c_int, c_double_p, c_double_p, c_double_p, C.c_int]),
+    "chb_set_body_force_linear_yz": (C.c_int, [C.c_void_p, C.c_int, c_double_p, c_double_p, C.c_int]),
     "chb_set_body_force": (C.c_int, [C.c_void_p]),
     "chb_buildrhs": (C.c_int, [C.c_void_p, c_double_p, C.c_double, C.c_int]),
     "chb_linsolve": (C.c_int, [C.c_void_p, C.c_double]),

@@ -6,7 +6,8 @@
 // outputs (Runtimedata, Dati.cart.out, Dati.cart.<n>.out at the dt_field / dt_save cadence of outstats).
 // One process = one GPU = npx 1 (the multi-GPU path is driven through the Fortran shim or torchrun).
 //
-//   channel_b200_run [--dir D] [--coriolis] [--device N] [--check-input]
+//   channel_b200_run [--dir D] [--bodyforce coriolis|am_f1|am_butterfly] [--device N] [--check-input]
+//   (the body force is a compile-time choice in the reference: -Dbodyforce + an #include of one of body_forces/*/*.inc)
 //
 // --check-input parses dns.in (and Runtimedata, if any) and prints what the run would use, without a GPU.
 #include <cerrno>
@@ -191,14 +192,21 @@ struct Run {
 int main(int argc, char** argv) {
     std::string dir = "./";
     bool coriolis = false, check_input = false;
+    std::string am;   // "am_f1" | "am_butterfly"
     int device = 0;
     for (int i = 1; i < argc; ++i) {
         const std::string a = argv[i];
         if (a == "--dir" && i + 1 < argc) { dir = argv[++i]; if (dir.back() != '/') dir += '/'; }
         else if (a == "--coriolis") coriolis = true;
+        else if (a == "--bodyforce" && i + 1 < argc) {
+            const std::string b = argv[++i];
+            if (b == "coriolis") coriolis = true;
+            else if (b == "am_f1" || b == "am_butterfly") am = b;
+            else die("--bodyforce: coriolis, am_f1 or am_butterfly");
+        }
         else if (a == "--device" && i + 1 < argc) device = atoi(argv[++i]);
         else if (a == "--check-input") check_input = true;
-        else die("usage: channel_b200_run [--dir D] [--coriolis] [--device N] [--check-input]");
+        else die("usage: channel_b200_run [--dir D] [--bodyforce coriolis|am_f1|am_butterfly] [--device N] [--check-input]");
     }
     Run r;
     r.dir = dir;
@@ -311,6 +319,32 @@ int main(int argc, char** argv) {
         for (int iz = -p.nz; iz <= p.nz; ++iz) mz[iz + p.nz] = std::abs(iz) <= iz_thr ? 1.0 : 0.0;
         const double A[9] = {0, -omega2, 0, omega2, 0, 0, 0, 0, 0};                      // F1 = -2Ro v, F2 = +2Ro u (coriolis.inc:29-41)
         check(chb_set_body_force_linear(r.h, 1, A, my.data(), mz.data(), 0), "chb_set_body_force_linear");
+        check(chb_set_body_force(r.h), "chb_set_body_force");
+        r.bodyforce = true;
+    }
+
+    if (!am.empty()) {   // am_f1.inc / am_butterfly.inc with the hard-coded parameters of am_pardec.inc:1
+        const double lambdaz_f = 500.0, amp = 1000.0, PI = 3.1415926535897932384626433832795028841971;
+        const int iz_f = (int)std::lround((2.0 * PI / lambdaz_f) / (p.beta0 / 1000.0));
+        printf(" Using bodyforce, %s\n", am == "am_f1" ? "am_f1 (suppression of superposition)"
+                                                       : "am_buttefly (suppression of superposition + small scales)");
+        const int nzt = 2 * p.nz + 1;
+        std::vector<double> m((size_t)(ny + 3) * nzt, 0.0);
+        for (int i = 0; i < ny + 3; ++i) {
+            const double yp = (r.y[i] > 1 ? p.ymax - r.y[i] : r.y[i]) * 1000.0;
+            for (int iz = -p.nz; iz <= p.nz; ++iz) {
+                bool on;
+                if (am == "am_f1") {
+                    const double lzp = iz == 0 ? 1e10 : 2 * PI / (p.beta0 * std::abs(iz)) * 1000;
+                    on = std::abs(iz) <= iz_f && lzp > 2.3 * yp * yp;
+                } else {
+                    on = std::abs(iz) <= iz_f ? yp <= 60 : yp > 60;
+                }
+                m[(size_t)i * nzt + iz + p.nz] = on ? 1.0 : 0.0;
+            }
+        }
+        const double A[9] = {-amp, 0, 0, 0, -amp, 0, 0, 0, -amp};
+        check(chb_set_body_force_linear_yz(r.h, 1, A, m.data(), 1), "chb_set_body_force_linear_yz");
         check(chb_set_body_force(r.h), "chb_set_body_force");
         r.bodyforce = true;
     }

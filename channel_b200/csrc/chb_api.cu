@@ -300,6 +300,7 @@ extern "C" int chb_destroy(chb_handle h) {
     cudaFree(h->t_D0mat); cudaFree(h->t_rows); cudaFree(h->mean_scratch); cudaFree(h->sc);
     if (h->bf.mask_y) cudaFree(h->bf.mask_y);
     if (h->bf.mask_z) cudaFree(h->bf.mask_z);
+    if (h->bf.mask_yz) cudaFree(h->bf.mask_yz);
     cudaFreeHost(h->sc_host);
     cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join);
     cudaStreamDestroy(h->side_stream);
@@ -441,20 +442,40 @@ extern "C" int chb_set_forcing(chb_handle h, double meanpx, double meanpz, doubl
 }
 
 // ---- body force ------------------------------------------------------------------------------
+static int set_body_force_common(chb_handle h, int enable, const double* A, int exclude_mean) {
+    CHB_CUDA_OK(cudaSetDevice(h->device));
+    h->bf.enabled = enable;
+    if (!enable) return 0;
+    memcpy(h->bf.A, A, sizeof(double) * 9);
+    h->bf.exclude_mean = exclude_mean;
+    if (!h->F && dev_alloc(&h->F, (size_t)3 * h->g.nyp * h->g.M)) return 1;
+    return 0;
+}
 extern "C" int chb_set_body_force_linear(chb_handle h, int enable, const double* A, const double* mask_y,
                                          const double* mask_z, int exclude_mean) {
     CHB_REQUIRE(h, "null handle");
-    CHB_CUDA_OK(cudaSetDevice(h->device));
-    const Geometry& g = h->g;
-    h->bf.enabled = enable;
+    CHB_REQUIRE(!enable || (A && mask_y && mask_z), "chb_set_body_force_linear: null argument");
+    if (set_body_force_common(h, enable, A, exclude_mean)) return 1;
     if (!enable) return 0;
-    CHB_REQUIRE(A && mask_y && mask_z, "chb_set_body_force_linear: null argument");
-    memcpy(h->bf.A, A, sizeof(double) * 9);
-    h->bf.exclude_mean = exclude_mean;
-    if (!h->F && dev_alloc(&h->F, (size_t)3 * g.nyp * g.M)) return 1;
+    const Geometry& g = h->g;
     if (!h->bf.mask_y && (dev_alloc(&h->bf.mask_y, (size_t)g.nyp) || dev_alloc(&h->bf.mask_z, (size_t)g.nzt))) return 1;
     CHB_CUDA_OK(cudaMemcpy(h->bf.mask_y, mask_y, sizeof(double) * g.nyp, cudaMemcpyHostToDevice));
     CHB_CUDA_OK(cudaMemcpy(h->bf.mask_z, mask_z, sizeof(double) * g.nzt, cudaMemcpyHostToDevice));
+    if (h->bf.mask_yz) {   // back to the separable form
+        cudaFree(h->bf.mask_yz);
+        h->bf.mask_yz = nullptr;
+    }
+    return 0;
+}
+extern "C" int chb_set_body_force_linear_yz(chb_handle h, int enable, const double* A, const double* mask_yz,
+                                            int exclude_mean) {
+    CHB_REQUIRE(h, "null handle");
+    CHB_REQUIRE(!enable || (A && mask_yz), "chb_set_body_force_linear_yz: null argument");
+    if (set_body_force_common(h, enable, A, exclude_mean)) return 1;
+    if (!enable) return 0;
+    const Geometry& g = h->g;
+    if (!h->bf.mask_yz && dev_alloc(&h->bf.mask_yz, (size_t)g.nyp * g.nzt)) return 1;
+    CHB_CUDA_OK(cudaMemcpy(h->bf.mask_yz, mask_yz, sizeof(double) * g.nyp * g.nzt, cudaMemcpyHostToDevice));
     return 0;
 }
 extern "C" int chb_set_body_force(chb_handle h) {

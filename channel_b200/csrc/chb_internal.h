@@ -55,6 +55,7 @@ struct BodyForce {
     double A[9];
     double* mask_y;  // [ny+3]
     double* mask_z;  // [2nz+1]
+    double* mask_yz; // [ny+3][2nz+1] or null: general mask(iy,iz), used instead of mask_y*mask_z
     int exclude_mean;
 };
 

@@ -231,6 +231,37 @@ class Channel:
         A = np.zeros((3, 3)); A[1, 0] = omega2; A[0, 1] = -omega2
         self.config_body_force_linear(A, my, mz, exclude_mean=False)
 
+    def config_body_force_linear_yz(self, A, mask_yz, exclude_mean=False):
+        """general mask(iy, iz), shape (ny+3, 2nz+1)"""
+        A = np.ascontiguousarray(A, np.float64).reshape(9)
+        m = np.ascontiguousarray(mask_yz, np.float64)
+        assert m.shape == (self.ny + 3, 2 * self.nz + 1)
+        _lib.check(self.lib.chb_set_body_force_linear_yz(self.h, 1, _dp(A), _dp(m), int(exclude_mean)),
+                   "chb_set_body_force_linear_yz")
+        self.bodyforce = True
+        self.set_body_force()
+
+    def _am_pieces(self, lambdaz_f):
+        iz_f = int(np.rint((2.0 * np.pi / lambdaz_f) / (self.p.beta0 / 1000.0)))      # am_f1.inc:7
+        yp = np.where(self.y > 1, self.p.ymax - self.y, self.y) * 1000.0              # am_f1.inc:20
+        iz = np.arange(-self.nz, self.nz + 1)
+        return iz_f, yp, iz
+
+    def config_am_f1(self, lambdaz_f=500.0, amp=1000.0):
+        """body_forces/am_f1/am_f1.inc: F = -amp V where lambda_z+ > 2.3 (y+)^2 and |iz| <= iz_f, mean mode excluded."""
+        iz_f, yp, iz = self._am_pieces(lambdaz_f)
+        with np.errstate(divide="ignore"):
+            lzp = np.where(iz == 0, 1e10, 2 * np.pi / (self.p.beta0 * np.abs(iz)) * 1000)
+        mask = (lzp[None, :] > 2.3 * yp[:, None] ** 2) & (np.abs(iz) <= iz_f)[None, :]
+        self.config_body_force_linear_yz(-amp * np.eye(3), mask.astype(np.float64), exclude_mean=True)
+
+    def config_am_butterfly(self, lambdaz_f=500.0, amp=1000.0):
+        """body_forces/am_butterfly/am_butterfly.inc: two boxes, (|iz| <= iz_f, y+ <= 60) and (|iz| > iz_f, y+ > 60)."""
+        iz_f, yp, iz = self._am_pieces(lambdaz_f)
+        inner = (np.abs(iz) <= iz_f)[None, :]
+        mask = (inner & (yp <= 60)[:, None]) | (~inner & (yp > 60)[:, None])
+        self.config_body_force_linear_yz(-amp * np.eye(3), mask.astype(np.float64), exclude_mean=True)
+
     def set_body_force(self):
         _lib.check(self.lib.chb_set_body_force(self.h), "chb_set_body_force")
 

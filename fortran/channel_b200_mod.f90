@@ -90,6 +90,14 @@ MODULE channel_b200
       REAL(C_DOUBLE) :: A(9), mask_y(*), mask_z(*)
       INTEGER(C_INT) :: rc
     END FUNCTION
+    FUNCTION chb_set_body_force_linear_yz(h, enable, A, mask_yz, exclude_mean) &
+        BIND(C, name="chb_set_body_force_linear_yz") RESULT(rc)
+      IMPORT :: C_PTR, C_INT, C_DOUBLE
+      TYPE(C_PTR), VALUE :: h
+      INTEGER(C_INT), VALUE :: enable, exclude_mean
+      REAL(C_DOUBLE) :: A(9), mask_yz(*)      ! mask_yz(iz+nz+1 + (2nz+1)*(iy+1)): row-major (iy, iz)
+      INTEGER(C_INT) :: rc
+    END FUNCTION
     FUNCTION chb_set_body_force(h) BIND(C, name="chb_set_body_force") RESULT(rc)
       IMPORT :: C_PTR, C_INT
       TYPE(C_PTR), VALUE :: h

@@ -100,7 +100,7 @@ int chb_set_forcing(chb_handle h, double meanpx, double meanpz, double meanflowx
 int chb_cfl_prepass(chb_handle h);
 
 /* Body force, device path for the masked linear forces the reference ships
- * (body_forces/coriolis/coriolis.inc:29-41, am_f1.inc, am_butterfly.inc):
+ * (body_forces/coriolis/coriolis.inc:29-41; the am hooks use the _yz variant below):
  *   F_r(iy,iz,ix) = sum_c A[r][c] * mask(iy,|iz| or iz) * V_c(iy,iz,ix)
  * A is 3x3 row-major; mask_y[ny+3] and mask_z[2nz+1] are 0/1 factors whose product
  * is the mask; exclude_mean!=0 leaves F(:,0,0,:) untouched.  Entries outside the
@@ -108,6 +108,11 @@ int chb_cfl_prepass(chb_handle h);
  * enable=0 switches the body force off (bodyforce undefined, header.h:29). */
 int chb_set_body_force_linear(chb_handle h, int enable, const double* A, const double* mask_y,
                               const double* mask_z, int exclude_mean);
+/* Same with a general 0/1 (or weighting) mask over (iy, iz), row-major mask_yz[(ny+3)][(2nz+1)]: the am_f1
+ * and am_butterfly hooks, whose active region couples y and z (am_f1.inc:13-28: lambda_z+ > 2.3 (y+)^2;
+ * am_butterfly.inc:11-29: two boxes).  Replaces a separable mask set before, and vice versa. */
+int chb_set_body_force_linear_yz(chb_handle h, int enable, const double* A, const double* mask_yz,
+                                 int exclude_mean);
 /* set_body_force() call sites channel.f90:129-131,142-144,155-157. */
 int chb_set_body_force(chb_handle h);
 

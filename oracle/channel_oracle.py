@@ -637,3 +637,44 @@ def coriolis_force(omega2: float, kz_cutoff: float, y_threshold_bot: float):
             zeichen = 2 * pc - 3
             o.F[pc - 1][ymask, :, zs] = zeichen * omega2 * o.V[c - 1][ymask, :, zs]
     return fn
+
+
+def _am_masks(o: Oracle, lambdaz_f: float):
+    """shared pieces of the am hooks: iz_f (config_body_force, am_f1.inc:7) and y+ of every node (:20)."""
+    iz_f = int(np.rint((2.0 * np.pi / lambdaz_f) / (o.beta0 / 1000.0)))
+    yp = np.where(o.y > 1, o.p.ymax - o.y, o.y) * 1000.0
+    return iz_f, yp
+
+
+def am_f1_force(lambdaz_f: float = 500.0, amp: float = 1000.0):
+    """body_forces/am_f1/am_f1.inc:13-28 (parameters am_pardec.inc:1): F = -amp V where
+    lambda_z+ > 2.3 (y+)^2, |iz| <= iz_f, except the mean mode."""
+    def fn(o: Oracle):
+        if o.F is None:
+            o.F = np.zeros_like(o.V)
+        iz_f, yp = _am_masks(o, lambdaz_f)
+        for iz in range(-min(iz_f, o.nz), min(iz_f, o.nz) + 1):
+            lzp = 1e10 if iz == 0 else 2 * np.pi / (o.beta0 * abs(iz)) * 1000
+            ym = lzp > 2.3 * yp ** 2
+            for ix in range(o.nx + 1):
+                if ix == 0 and iz == 0:
+                    continue
+                o.F[:, ym, ix, iz + o.nz] = -amp * o.V[:, ym, ix, iz + o.nz]
+    return fn
+
+
+def am_butterfly_force(lambdaz_f: float = 500.0, amp: float = 1000.0):
+    """body_forces/am_butterfly/am_butterfly.inc:11-29: F = -amp V for (|iz| <= iz_f, y+ <= 60, not the mean
+    mode) and for (|iz| > iz_f, y+ > 60)."""
+    def fn(o: Oracle):
+        if o.F is None:
+            o.F = np.zeros_like(o.V)
+        iz_f, yp = _am_masks(o, lambdaz_f)
+        for iz in range(-o.nz, o.nz + 1):
+            ym = (yp <= 60) if abs(iz) <= iz_f else (yp > 60)
+            for ix in range(o.nx + 1):
+                if abs(iz) <= iz_f and ix == 0 and iz == 0:
+                    continue
+                o.F[:, ym, ix, iz + o.nz] = -amp * o.V[:, ym, ix, iz + o.nz]
+    return fn
+

@@ -26,6 +26,21 @@ static inline void __syncthreads() {}
 #define CHB_HOST_EMUL 1
 #include "../../channel_b200/csrc/rhs_kernel.cu"
 #include "../../channel_b200/csrc/solve_kernels.cu"
+#include "../../channel_b200/csrc/bodyforce_kernels.cu"
+
+// run `kern(args...)` for every thread of a (gx, gy) grid of 1-D blocks
+template <class K, class... Args>
+static void emulate2(K kern, int gx, int gy, int threads, Args... args) {
+    e_blockDim = dim3(threads, 1, 1);
+    e_gridDim = dim3(gx, gy, 1);
+    for (int by = 0; by < gy; ++by)
+        for (int bx = 0; bx < gx; ++bx)
+            for (int t = 0; t < threads; ++t) {
+                e_blockIdx = make_uint3(bx, by, 0);
+                e_threadIdx = make_uint3(t, 0, 0);
+                kern(args...);
+            }
+}
 
 // run `kern(args...)` for every thread of a 1-D grid
 template <class K, class... Args>
@@ -110,6 +125,40 @@ __attribute__((visibility("default"))) int chb_emul_ydir_substep(int nx, int ny,
     }
     scal_io[0] = sc.fr[0]; scal_io[1] = sc.fr[1]; scal_io[2] = sc.fr[2];
     scal_io[3] = sc.corrpx; scal_io[4] = sc.corrpz; scal_io[5] = sc.meanpx;
+    return 0;
+}
+
+// set_body_force (body_force_kernel) followed, if ghosts != 0, by the ghost-node extension of buildrhs
+// (force_ghost_kernel, dnsdata.f90:616-629).  V, F: [3][nyp][M] device layout; masks as chb_set_body_force_linear
+// (mask_yz null) or chb_set_body_force_linear_yz (mask_yz set); d4: [(ny-1)][5] as chb_set_tables receives it.
+__attribute__((visibility("default"))) int chb_emul_body_force(int nx, int ny, int nz, const double* V, double* F,
+                                                               const double* A, const double* mask_y, const double* mask_z,
+                                                               const double* mask_yz, int exclude_mean, int ghosts,
+                                                               const double* d4) {
+    Geometry g;
+    memset(&g, 0, sizeof(g));
+    g.nx = nx; g.ny = ny; g.nz = nz;
+    g.nyp = ny + 3; g.nzt = 2 * nz + 1;
+    g.nranks = 1; g.nxN = nx; g.nxB = nx + 1;
+    g.M = (long long)g.nxB * g.nzt;
+    BodyForce bf;
+    memset(&bf, 0, sizeof(bf));
+    bf.enabled = 1;
+    memcpy(bf.A, A, sizeof(double) * 9);
+    bf.mask_y = const_cast<double*>(mask_y);
+    bf.mask_z = const_cast<double*>(mask_z);
+    bf.mask_yz = const_cast<double*>(mask_yz);
+    bf.exclude_mean = exclude_mean;
+    emulate2(body_force_kernel, (int)((g.M + 255) / 256), g.nyp, 256, reinterpret_cast<const cplx*>(V),
+             reinterpret_cast<cplx*>(F), g, bf);
+    if (ghosts) {
+        std::vector<double> full((size_t)g.nyp * 5, 0.0);
+        memcpy(&full[10], d4, sizeof(double) * 5 * (ny - 1));
+        DevTables tab;
+        memset(&tab, 0, sizeof(tab));
+        tab.d4 = full.data();
+        emulate(force_ghost_kernel, (int)((g.M + 255) / 256), 256, reinterpret_cast<cplx*>(F), g, tab);
+    }
     return 0;
 }
 

@@ -142,3 +142,29 @@ def test_rejected_sizes_report_errors():
         Channel(DnsIn(nx=4, ny=7, nz=4))
     with pytest.raises(_lib.ChannelB200Error, match="nxd must be even"):
         Channel(DnsIn(nx=1, ny=8, nz=1))           # nxd = 3(nx+1)/2 = 3
+
+
+@pytest.mark.parametrize("hook", ["am_f1", "am_butterfly"])
+def test_am_body_forces(hook):
+    """body_forces/am_f1/am_f1.inc and am_butterfly/am_butterfly.inc: F = -amp V inside a region of the (y, z-mode)
+    plane that is not a product of ranges (chb_set_body_force_linear_yz)."""
+    from oracle.channel_oracle import am_butterfly_force, am_f1_force
+    p, o, ch, V0 = make_pair(15, 32, 10, deltat=2e-3, cflmax=0.0, re=1500.0)
+    if hook == "am_f1":
+        o.set_body_force(am_f1_force(2000.0, 10.0)); ch.config_am_f1(2000.0, 10.0)
+    else:
+        o.set_body_force(am_butterfly_force(2000.0, 10.0)); ch.config_am_butterfly(2000.0, 10.0)
+    ch.cfl_prepass(); o.cfl_prepass(); ch.outstats(); o.outstats()
+    for i in range(3):
+        l_o = o.step(); l_g = ch.step()
+        assert np.allclose(l_g[1:9], l_o[1:9], rtol=1e-9, atol=1e-11), (i, l_g, l_o)
+    Vg = ch.download_V()
+    for c in range(3):
+        assert relerr(Vg[c], o.V[c]) < 1e-11
+    F = ch.download_F()
+    assert relerr(F, o.F) < 1e-12 and np.abs(F).max() > 0
+    # back to a separable mask on the same handle (coriolis) and off again
+    ch.config_coriolis(0.02, 9999999.0, 1.0)
+    ch.step()
+    assert np.isfinite(ch.download_V().view(np.float64)).all()
+    ch.close()

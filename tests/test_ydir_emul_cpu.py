@@ -16,7 +16,7 @@ import pytest
 
 from channel_b200 import RK1_rai, RK2_rai, RK3_rai
 from channel_b200.fields import perturbed_laminar
-from oracle.channel_oracle import DnsIn as ODnsIn, Oracle, coriolis_force
+from oracle.channel_oracle import DnsIn as ODnsIn, Oracle, am_butterfly_force, am_f1_force, coriolis_force
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "host_emul", "ydir_emul.cpp")
@@ -37,7 +37,7 @@ def emul():
     os.makedirs(BUILD, exist_ok=True)
     so = os.path.join(BUILD, "libydir_emul.so")
     deps = [SRC] + [os.path.join(HERE, "..", "channel_b200", "csrc", f)
-                    for f in ("rhs_kernel.cu", "solve_kernels.cu", "solve_device.cuh", "chb_internal.h")]
+                    for f in ("rhs_kernel.cu", "solve_kernels.cu", "bodyforce_kernels.cu", "solve_device.cuh", "chb_internal.h")]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
         subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-w",
                                # the kernels' host names also exist in libchannel_b200.so (loaded RTLD_GLOBAL by
@@ -47,6 +47,8 @@ def emul():
     dp = C.POINTER(C.c_double)
     lib.chb_emul_ydir_substep.argtypes = [C.c_int] * 3 + [C.c_double] * 3 + [dp] * 13 + [C.c_double] * 4 + [C.c_int]
     lib.chb_emul_ydir_substep.restype = C.c_int
+    lib.chb_emul_body_force.argtypes = [C.c_int] * 3 + [dp] * 6 + [C.c_int, C.c_int, dp]
+    lib.chb_emul_body_force.restype = C.c_int
     return lib
 
 
@@ -126,3 +128,58 @@ def test_ydir_kernels_match_oracle(emul, case):
             assert abs(sc[3] - o.corrpx) <= 1e-11 * max(1.0, abs(o.corrpx))
             assert abs(sc[5] - mp1[0]) <= 1e-12 * max(1.0, abs(mp1[0]))
         o.meanpx, o.meanpz = mp1
+
+
+@pytest.mark.parametrize("hook", ["coriolis", "am_f1", "am_butterfly", "am_f1_wide"])
+def test_body_force_kernels_match_the_reference_hooks(emul, hook):
+    """body_force_kernel / force_ghost_kernel (bodyforce_kernels.cu) with the masks channel_b200.dnsdata builds,
+    against the oracle's restatement of body_forces/*/*.inc and of the ghost extension dnsdata.f90:616-629."""
+    from channel_b200.dnsdata import Channel
+
+    class Masks:                       # Channel's mask builders without a handle (no GPU here)
+        _am_pieces = Channel._am_pieces
+        config_am_f1 = Channel.config_am_f1
+        config_am_butterfly = Channel.config_am_butterfly
+        config_coriolis = Channel.config_coriolis
+
+        def config_body_force_linear(self, A, my, mz, exclude_mean=False):
+            self.got = dict(A=A, my=my, mz=mz, myz=None, ex=exclude_mean)
+
+        def config_body_force_linear_yz(self, A, myz, exclude_mean=False):
+            self.got = dict(A=A, my=None, mz=None, myz=myz, ex=exclude_mean)
+
+    nx, ny, nz = 5, 32, 7
+    p = ODnsIn(nx=nx, ny=ny, nz=nz, re=1000.0)
+    o = Oracle(p)
+    rng = np.random.default_rng(11)
+    o.V[:] = rng.standard_normal(o.V.shape) + 1j * rng.standard_normal(o.V.shape)
+    m = Masks(); m.p = p; m.y = o.y; m.nz = nz; m.ny = ny
+    if hook == "coriolis":
+        fn = coriolis_force(0.02, 3.0, 0.4); m.config_coriolis(0.02, 3.0, 0.4)
+    elif hook == "am_f1":
+        fn = am_f1_force(2000.0, 10.0); m.config_am_f1(2000.0, 10.0)
+    elif hook == "am_f1_wide":         # iz_f = 13 > nz: every stored z-mode is inside the |iz| <= iz_f range
+        fn = am_f1_force(500.0, 1000.0); m.config_am_f1(500.0, 1000.0)
+    else:
+        fn = am_butterfly_force(2000.0, 10.0); m.config_am_butterfly(2000.0, 10.0)
+    F0 = 0.1 * (rng.standard_normal(o.V.shape) + 0j)       # entries outside the mask keep their previous value
+    o.F = F0.copy()
+    fn(o)
+    g = m.got
+    c = lambda a: np.ascontiguousarray(a, dtype=np.float64) if a is not None else None
+    A, my, mz, myz = c(np.asarray(g["A"]).reshape(9)), c(g["my"]), c(g["mz"]), c(g["myz"])
+    V = np.ascontiguousarray(o.V); F = np.ascontiguousarray(F0.copy())
+    d4 = np.ascontiguousarray(o.d4[2:ny + 1], dtype=np.float64)
+    assert emul.chb_emul_body_force(nx, ny, nz, _dp(V.view(np.float64)), _dp(F.view(np.float64)), _dp(A), _dp(my), _dp(mz),
+                                    _dp(myz), int(g["ex"]), 0, _dp(d4)) == 0
+    assert np.array_equal(F, o.F)
+    assert (F != F0).any() and (F == F0).any()
+    # ghost extension at the start of buildrhs
+    Fo = o.F
+    Fo[:, 0:2] = 0
+    Fo[:, 0] = -o._D(o.d4, Fo, 1) / o.d4[2, 0]
+    Fo[:, ny + 1:ny + 3] = 0
+    Fo[:, ny + 2] = -o._D(o.d4, Fo, ny - 1) / o.d4[ny, 4]
+    assert emul.chb_emul_body_force(nx, ny, nz, _dp(V.view(np.float64)), _dp(F.view(np.float64)), _dp(A), _dp(my), _dp(mz),
+                                    _dp(myz), int(g["ex"]), 1, _dp(d4)) == 0
+    assert relerr(F, Fo) < 1e-13
