@@ -135,7 +135,12 @@ rhs_kernel(const cplx* __restrict__ V, const cplx* __restrict__ P, const cplx* _
                 ee.x += mpx;
                 ee.y += mpz;
             }
-            const cplx oe = oldrhs[0 * comp + oo], ov = oldrhs[1 * comp + oo];
+            // RK substep 1 has ODE(3) = 0 (RK1_rai, dnsdata.f90:70): the previous explicit term is not read
+            cplx oe = make_double2(0.0, 0.0), ov = oe;
+            if (ode3 != 0.0) {
+                oe = oldrhs[0 * comp + oo];
+                ov = oldrhs[1 * comp + oo];
+            }
             cplx re, rv;
             re.x = acc[0].le.x + ode2 * ee.x - ode3 * oe.x;
             re.y = acc[0].le.y + ode2 * ee.y - ode3 * oe.y;
