@@ -25,7 +25,7 @@
 __global__ void __launch_bounds__(CONV_THREADS)
 zfwd_kernel(const cplx* __restrict__ V, PeerPtrs Aw, Geometry g, FftPlan pl, const cplx* __restrict__ W,
             const int* __restrict__ rev, int plane0, int np, int tx, int line_stride) {
-    extern __shared__ cplx smem[];
+    CHB_DYN_SMEM(cplx, smem);
     const int ixl0 = blockIdx.x * tx;
     const int pli = blockIdx.y;
     const int c = blockIdx.z;
@@ -58,7 +58,7 @@ zfwd_kernel(const cplx* __restrict__ V, PeerPtrs Aw, Geometry g, FftPlan pl, con
 __global__ void __launch_bounds__(CONV_THREADS)
 zbwd_kernel(const cplx* __restrict__ Br, cplx* __restrict__ P, Geometry g, FftPlan pl, const cplx* __restrict__ W,
             const int* __restrict__ rev, int plane0, int np, int tx, int line_stride) {
-    extern __shared__ cplx smem[];
+    CHB_DYN_SMEM(cplx, smem);
     const int ixl0 = blockIdx.x * tx;
     const int pli = blockIdx.y;
     const int c = blockIdx.z;  // product index 0..5
@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(CONV_THREADS)
 xpass_kernel(const cplx* __restrict__ Ar, PeerPtrs Bw, Geometry g, FftPlan pl, const cplx* __restrict__ W,
              const cplx* __restrict__ Wh, const double* __restrict__ dy, DevScalars* sc, int plane0, int np, int lx,
              int line_stride, int compute_cfl) {
-    extern __shared__ cplx smem[];
+    CHB_DYN_SMEM(cplx, smem);
     __shared__ double red[CONV_THREADS / 32];
     const int izl0 = blockIdx.x * lx;
     const int pli = blockIdx.y;
@@ -272,7 +272,7 @@ template <int S, bool DIF>
 __global__ void __launch_bounds__(CONV_THREADS)
 test_fft_kernel(cplx* data, FftPlan pl, const cplx* __restrict__ W, const int* __restrict__ rev, int nlines, int lpb,
                 int line_stride) {
-    extern __shared__ cplx smem[];
+    CHB_DYN_SMEM(cplx, smem);
     const int l0 = blockIdx.x * lpb;
     const int nl = min(lpb, nlines - l0);
     const int n = pl.n;

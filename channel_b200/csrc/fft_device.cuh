@@ -15,6 +15,14 @@
 
 typedef double2 cplx;
 
+// dynamic shared memory of a kernel; tests/host_emul/cta_emul.hpp supplies the buffer when the kernel
+// source is compiled for the CPU
+#ifdef CHB_HOST_EMUL
+#define CHB_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(cta_emul::g_dyn_smem)
+#else
+#define CHB_DYN_SMEM(type, name) extern __shared__ type name[]
+#endif
+
 #define CHB_MAX_PASSES 10
 struct FftPlan {
     int n;

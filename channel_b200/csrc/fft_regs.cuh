@@ -178,6 +178,18 @@ __device__ __forceinline__ void dif_stage_b(cplx* x, const cplx* wc, bool c_nonz
     if (c_nonzero) static_for<G::B - 1>([&](auto i) { x[i + 1] = cmul(x[i + 1], wc[i + 1]); });
 }
 
+#ifdef CHB_HOST_EMUL
+// tests/host_emul: the asynchronous copies become plain copies done by the issuing thread (every use is followed by
+// a __syncthreads() before other threads read the data), the mbarrier becomes a no-op.
+#include <cstring>
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int) { *bar = 0; }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long*, unsigned) {}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long*) { memcpy(dst, src, bytes); }
+__device__ __forceinline__ void mbar_wait(unsigned long long*, unsigned) {}
+__device__ __forceinline__ void bulk_prefetch_l2(const void*, unsigned) {}
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) { memcpy(dst, src, 16); }
+__device__ __forceinline__ void cp_async_wait_all() {}
+#else
 // ---- TMA 1-D bulk copy global -> shared with mbarrier completion (cp.async.bulk, SASS UBLKCP) ----
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
@@ -214,3 +226,4 @@ __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+#endif   // CHB_HOST_EMUL

@@ -47,7 +47,7 @@ xpass4_kernel(const cplx* __restrict__ Ar, const __grid_constant__ PeerPtrs Bw, 
     constexpr int LB = A * BCP;        // complex per buffer
     constexpr int NB = A * C;          // stage-B butterflies per transform
     static_assert(T % C == 0 && NB % C == 0, "stage-B twiddle must be a per-thread constant");
-    extern __shared__ cplx smem[];
+    CHB_DYN_SMEM(cplx, smem);
     const int tl = threadIdx.x % T, l = threadIdx.x / T;
     const int izl = blockIdx.x * LPC + l;
     const int pli = blockIdx.y;
@@ -229,6 +229,7 @@ xpass4_kernel(const cplx* __restrict__ Ar, const __grid_constant__ PeerPtrs Bw, 
     }
 }
 
+#ifndef CHB_HOST_EMUL   // tests/host_emul compiles the kernel above with g++ and runs it on CPU threads
 template <class G, int LPC, int MINB>
 static bool launch_x4(chb_handle_s* h, int plane0, int nplanes, int compute_cfl) {
     constexpr int T = G::N / G::C;
@@ -256,3 +257,4 @@ bool launch_x3_pass(chb_handle_s* h, int plane0, int nplanes, int compute_cfl) {
         default: return false;
     }
 }
+#endif

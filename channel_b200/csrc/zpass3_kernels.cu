@@ -35,7 +35,7 @@ template <class G, int LPC, int TPL, int MINB>
 __global__ void __launch_bounds__(LPC * TPL, MINB)
 zfwd4_kernel(const cplx* __restrict__ V, PeerPtrs Aw, Geometry g, const cplx* __restrict__ W, int plane0, int np,
              int LS) {
-    extern __shared__ cplx smem[];
+    CHB_DYN_SMEM(cplx, smem);
     constexpr int BCP = G::BC + 1;
     static_assert(TPL % G::C == 0, "stage-B twiddle must be a per-thread constant");
     const int tl = threadIdx.x % TPL, wl = threadIdx.x / TPL;
@@ -120,7 +120,7 @@ template <class G, int LPC, int TPL, int MINB>
 __global__ void __launch_bounds__(LPC * TPL, MINB)
 zbwd4_kernel(const cplx* __restrict__ Br, cplx* __restrict__ P, Geometry g, const cplx* __restrict__ W, int plane0, int np,
              int LS) {
-    extern __shared__ cplx smem[];
+    CHB_DYN_SMEM(cplx, smem);
     constexpr int BCP = G::BC + 1;
     static_assert(TPL % G::C == 0, "stage-B twiddle must be a per-thread constant");
     const int tl = threadIdx.x % TPL, wl = threadIdx.x / TPL;

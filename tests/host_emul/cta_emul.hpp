@@ -1,0 +1,83 @@
+// cta_emul.hpp - test infrastructure: run a CUDA kernel's SOURCE on the CPU, one OS thread per CUDA thread
+// of a thread block, `__syncthreads()` = a pthread barrier, shared memory = a process-wide buffer (one
+// block runs at a time).  Enough of the CUDA surface for the FFT-pass kernels of channel_b200/csrc
+// (blockIdx/threadIdx, dynamic and static shared memory, __ldg, warp shuffles, atomicMax on a 64-bit word);
+// TMA / cp.async / mbarrier are replaced by plain copies where a kernel uses them (CHB_HOST_EMUL branches in
+// fft_regs.cuh).  It checks kernel LOGIC (indexing, twiddles, layouts, barriers between phases) before a GPU
+// minute is spent; it says nothing about performance and the product never loads it.
+#pragma once
+#include <cuda_runtime.h>
+#include <pthread.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+namespace cta_emul {
+inline thread_local uint3 t_threadIdx, t_blockIdx;
+inline dim3 g_blockDim, g_gridDim;
+inline pthread_barrier_t g_block_barrier;
+inline std::vector<pthread_barrier_t> g_warp_barrier;
+inline double g_warp_buf[64][32];                 // [warp][lane] exchange buffer for shuffles (blocks of <= 2048 threads)
+alignas(16) inline unsigned char g_dyn_smem[232448];   // 227 KB of dynamic shared memory
+}  // namespace cta_emul
+
+#define blockIdx cta_emul::t_blockIdx
+#define threadIdx cta_emul::t_threadIdx
+#define blockDim cta_emul::g_blockDim
+#define gridDim cta_emul::g_gridDim
+#undef __launch_bounds__
+#define __launch_bounds__(...)
+#define __grid_constant__
+#define __shared__ static
+#define CHB_EMUL_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(cta_emul::g_dyn_smem)
+
+template <class T>
+static inline T __ldg(const T* p) { return *p; }
+static inline void __syncthreads() { pthread_barrier_wait(&cta_emul::g_block_barrier); }
+static inline double __shfl_xor_sync(unsigned, double v, int o) {
+    const int tid = cta_emul::t_threadIdx.x, w = tid >> 5, l = tid & 31;
+    cta_emul::g_warp_buf[w][l] = v;
+    pthread_barrier_wait(&cta_emul::g_warp_barrier[w]);
+    const double r = cta_emul::g_warp_buf[w][l ^ o];
+    pthread_barrier_wait(&cta_emul::g_warp_barrier[w]);
+    return r;
+}
+static inline long long __double_as_longlong(double d) { long long r; memcpy(&r, &d, 8); return r; }
+static inline unsigned long long atomicMax(unsigned long long* a, unsigned long long v) {
+    auto* p = reinterpret_cast<std::atomic<unsigned long long>*>(a);
+    unsigned long long old = p->load();
+    while (old < v && !p->compare_exchange_weak(old, v)) {}
+    return old;
+}
+
+namespace cta_emul {
+// run kern(args...) for every block of a (gx, gy, gz) grid of 1-D blocks of `threads` threads (a multiple of 32)
+template <class K, class... Args>
+void launch(K kern, dim3 grid, int threads, Args... args) {
+    if (threads % 32 != 0 || threads > 2048) { fprintf(stderr, "cta_emul: block size %d\n", threads); abort(); }
+    g_blockDim = dim3(threads, 1, 1);
+    g_gridDim = grid;
+    pthread_barrier_init(&g_block_barrier, nullptr, threads);
+    g_warp_barrier.resize(threads / 32);
+    for (auto& b : g_warp_barrier) pthread_barrier_init(&b, nullptr, 32);
+    for (unsigned bz = 0; bz < grid.z; ++bz)
+        for (unsigned by = 0; by < grid.y; ++by)
+            for (unsigned bx = 0; bx < grid.x; ++bx) {
+                std::vector<std::thread> th;
+                th.reserve(threads);
+                for (int t = 0; t < threads; ++t)
+                    th.emplace_back([=]() {
+                        t_blockIdx = make_uint3(bx, by, bz);
+                        t_threadIdx = make_uint3(t, 0, 0);
+                        kern(args...);
+                    });
+                for (auto& x : th) x.join();
+            }
+    for (auto& b : g_warp_barrier) pthread_barrier_destroy(&b);
+    pthread_barrier_destroy(&g_block_barrier);
+}
+}  // namespace cta_emul

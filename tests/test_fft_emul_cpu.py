@@ -1,0 +1,82 @@
+"""The x-pass kernel of the nonlinear term (xpass3_kernels.cu) run on the CPU.
+
+tests/host_emul/fft_emul.cpp compiles the kernel SOURCE with g++ and runs each thread block on OS threads
+(cta_emul.hpp: __syncthreads = barrier, shared memory = a buffer).  For a few z-lines of each specialised
+size (nxd = 384, 768, 1536) the result - zero-padded c2r, CFL, six products * factor, r2c, modes 0..nx in the
+tiled work-buffer layout - is compared with numpy's FFT (ffts.f90:72-75 conventions, dnsdata.f90:535-588).
+The GPU tests (tests/test_fft3_gpu.py) check the same kernels on the device; this one needs no GPU and is
+where a new kernel variant is proven before it is measured."""
+import ctypes as C
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "host_emul", "fft_emul.cpp")
+BUILD = os.path.join(HERE, "host_emul", "_build")
+CUDA_INC = "/usr/local/cuda/include"
+
+
+@pytest.fixture(scope="module")
+def emul():
+    if shutil.which("g++") is None or not os.path.exists(os.path.join(CUDA_INC, "cuda_runtime.h")):
+        pytest.skip("needs g++ and the CUDA headers")
+    os.makedirs(BUILD, exist_ok=True)
+    so = os.path.join(BUILD, "libfft_emul.so")
+    csrc = os.path.join(HERE, "..", "channel_b200", "csrc")
+    deps = [SRC, os.path.join(HERE, "host_emul", "cta_emul.hpp")] + [
+        os.path.join(csrc, f) for f in ("xpass3_kernels.cu", "fft_regs.cuh", "fft_device.cuh", "chb_internal.h", "transpose_index.h")]
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-w", "-pthread",
+                               "-fvisibility=hidden", "-Wl,-Bsymbolic", "-I" + CUDA_INC, "-o", so, SRC])
+    lib = C.CDLL(so)
+    dp = C.POINTER(C.c_double)
+    lib.chb_emul_xpass.argtypes = [C.c_int] * 6 + [C.c_double] * 2 + [C.c_int, dp, dp, dp, C.c_int, dp]
+    lib.chb_emul_xpass.restype = C.c_int
+    return lib
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def xpass_reference(A, nx, nxd, nzd, alfa0, beta0, dy, ny, compute_cfl):
+    """A: [3][np][nzB][nx+1] -> products [6][np][nzB][nx+1], cfl"""
+    _, npl, nzB, _ = A.shape
+    X = np.zeros((3, npl, nzB, nxd + 1), complex)
+    X[..., :nx + 1] = A                                               # zero padding in x, dnsdata.f90:535
+    R = np.fft.irfft(X, n=2 * nxd, axis=-1) * (2 * nxd)               # RFT, unnormalised, sign +
+    factor = 1.0 / (2.0 * nxd * nzd)                                  # dnsdata.f90:124
+    dx = np.pi / (alfa0 * nxd); dz = 2 * np.pi / (beta0 * nzd)
+    cfl = 0.0
+    if compute_cfl:
+        for pli in range(npl):
+            iy = pli - 1
+            if 1 <= iy <= ny - 1:
+                s = np.abs(R[0, pli]) / dx + np.abs(R[1, pli]) / dy[iy + 1] + np.abs(R[2, pli]) / dz
+                cfl = max(cfl, float(s.max()))
+    pairs = [(0, 0), (1, 1), (2, 2), (0, 1), (1, 2), (0, 2)]          # dnsdata.f90:581-584
+    P = np.stack([R[a] * R[b] * factor for a, b in pairs])
+    return np.fft.rfft(P, axis=-1)[..., :nx + 1], cfl                 # HFT, sign -, keep 0..nx
+
+
+@pytest.mark.parametrize("nx,nxd,tw", [(255, 384, 3), (255, 384, 0), (511, 768, 3), (1023, 1536, 3), (300, 768, 0)])
+def test_xpass_kernel_on_cpu_threads(emul, nx, nxd, tw):
+    ny, nzd, nzB, npl = 6, 6, 2, 3            # planes iy = -1, 0, 1: the CFL expression sees iy = 1 only
+    rng = np.random.default_rng(nx + tw)
+    A = rng.standard_normal((3, npl, nzB, nx + 1)) + 1j * rng.standard_normal((3, npl, nzB, nx + 1))
+    dy = np.linspace(0.01, 0.03, ny + 3)
+    ref, cfl_ref = xpass_reference(A, nx, nxd, nzd, 0.5, 1.0, dy, ny, True)
+    Ar = np.ascontiguousarray(A)
+    Br = np.zeros((6, npl, (nx + 1) >> tw, nzB, 1 << tw), complex)
+    cfl = C.c_double()
+    rc = emul.chb_emul_xpass(nx, ny, nzB, npl, nxd, nzd, 0.5, 1.0, tw, _dp(Ar.view(np.float64)), _dp(Br.view(np.float64)),
+                             _dp(dy), 1, C.byref(cfl))
+    assert rc == 0
+    got = np.transpose(Br, (0, 1, 3, 2, 4)).reshape(6, npl, nzB, nx + 1)      # [p][plane][z row][x tile][x in tile] -> x
+    scale = np.abs(ref).max()
+    assert np.abs(got - ref).max() <= 1e-13 * scale, np.abs(got - ref).max() / scale
+    assert abs(cfl.value - cfl_ref) <= 1e-13 * cfl_ref
