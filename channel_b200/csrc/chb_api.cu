@@ -183,6 +183,8 @@ extern "C" int chb_create(chb_handle* out, int nx, int ny, int nz, int nxd, int 
         h->zf_lines_per_cta = e ? atoi(e) : (nzd >= 3072 ? 2 : 4);
         e = getenv("CHB_FFT3");
         h->use_fft3 = (e && atoi(e) == 0) ? 0 : 1;
+        e = getenv("CHB_XPASS_SPLIT");
+        h->xpass_split = e ? atoi(e) : 0;
         // x tiles of the work buffers (transpose_index.h): products 8 wide (128-byte store segments in
         // the x-pass), velocities as wide as the lines of one zfwd CTA
         g.tw = (g.nxB % 8 == 0) ? 3 : ((g.nxB % 4 == 0) ? 2 : 0);

@@ -30,15 +30,26 @@ static void run_x4(const cplx* Ar, cplx* Br, const Geometry& g, const cplx* W, c
                      compute_cfl);
 }
 
+template <class G, int MINB>
+static void run_x5(const cplx* Ar, cplx* Br, const Geometry& g, const cplx* W, const cplx* Wh, const double* dy, DevScalars* sc,
+                   int np, int compute_cfl) {
+    PeerPtrs Bw;
+    memset(&Bw, 0, sizeof(Bw));
+    Bw.p[0] = Br;
+    constexpr int T = 2 * (G::N / G::C);
+    cta_emul::launch(xpass5_kernel<G, MINB, false>, dim3(g.nzB, np, 1), T, Ar, Bw, g, W, Wh, dy, sc, 0, np, compute_cfl);
+}
+
 extern "C" {
 
 // One chunk of `np` planes, single rank: Ar = velocities after the z pass, row-major [3][np][nzB][nx+1];
 // Br = products for the backward z pass in the tiled layout of transpose_index.h (tile width 2^tw),
 // [6][np][(nx+1) >> tw][nzB][1 << tw]; dy[ny+3]; cfl_out = max of the CFL expression (dnsdata.f90:552-556).
-// Planes are iy = -1 .. np-2 (plane0 = 0).  Returns 2 if no specialised kernel exists for nxd.
+// Planes are iy = -1 .. np-2 (plane0 = 0).  variant 0: xpass4 (one thread per innermost butterfly position),
+// 1: xpass5 (two threads per position; nxd = 1536).  Returns 2 if no such kernel exists for nxd.
 __attribute__((visibility("default"))) int chb_emul_xpass(int nx, int ny, int nzB, int np, int nxd, int nzd, double alfa0,
                                                           double beta0, int tw, const double* Ar, double* Br,
-                                                          const double* dy, int compute_cfl, double* cfl_out) {
+                                                          const double* dy, int compute_cfl, double* cfl_out, int variant) {
     Geometry g;
     memset(&g, 0, sizeof(g));
     g.nx = nx; g.ny = ny; g.nxd = nxd; g.nzd = nzd;
@@ -56,6 +67,10 @@ __attribute__((visibility("default"))) int chb_emul_xpass(int nx, int ny, int nz
     cplx* B = reinterpret_cast<cplx*>(Br);
     const cplx* Wc = reinterpret_cast<const cplx*>(W.data());
     const cplx* Whc = reinterpret_cast<const cplx*>(Wh.data());
+    if (variant == 1) {
+        if (nxd != 1536) return 2;
+        run_x5<Fft3<1536, 12, 16, 8>, 1>(A, B, g, Wc, Whc, dy, &sc, np, compute_cfl);
+    } else
     switch (nxd) {
         case 384: run_x4<Fft3<384, 12, 8, 4>, 1, 6>(A, B, g, Wc, Whc, dy, &sc, np, compute_cfl); break;
         case 768: run_x4<Fft3<768, 12, 16, 4>, 1, 3>(A, B, g, Wc, Whc, dy, &sc, np, compute_cfl); break;

@@ -34,7 +34,7 @@ def emul():
                                "-fvisibility=hidden", "-Wl,-Bsymbolic", "-I" + CUDA_INC, "-o", so, SRC])
     lib = C.CDLL(so)
     dp = C.POINTER(C.c_double)
-    lib.chb_emul_xpass.argtypes = [C.c_int] * 6 + [C.c_double] * 2 + [C.c_int, dp, dp, dp, C.c_int, dp]
+    lib.chb_emul_xpass.argtypes = [C.c_int] * 6 + [C.c_double] * 2 + [C.c_int, dp, dp, dp, C.c_int, dp, C.c_int]
     lib.chb_emul_xpass.restype = C.c_int
     return lib
 
@@ -63,8 +63,9 @@ def xpass_reference(A, nx, nxd, nzd, alfa0, beta0, dy, ny, compute_cfl):
     return np.fft.rfft(P, axis=-1)[..., :nx + 1], cfl                 # HFT, sign -, keep 0..nx
 
 
-@pytest.mark.parametrize("nx,nxd,tw", [(255, 384, 3), (255, 384, 0), (511, 768, 3), (1023, 1536, 3), (300, 768, 0)])
-def test_xpass_kernel_on_cpu_threads(emul, nx, nxd, tw):
+@pytest.mark.parametrize("nx,nxd,tw,variant", [(255, 384, 3, 0), (255, 384, 0, 0), (511, 768, 3, 0), (1023, 1536, 3, 0),
+                                               (300, 768, 0, 0), (1023, 1536, 3, 1), (703, 1536, 2, 1)])
+def test_xpass_kernel_on_cpu_threads(emul, nx, nxd, tw, variant):
     ny, nzd, nzB, npl = 6, 6, 2, 3            # planes iy = -1, 0, 1: the CFL expression sees iy = 1 only
     rng = np.random.default_rng(nx + tw)
     A = rng.standard_normal((3, npl, nzB, nx + 1)) + 1j * rng.standard_normal((3, npl, nzB, nx + 1))
@@ -74,7 +75,7 @@ def test_xpass_kernel_on_cpu_threads(emul, nx, nxd, tw):
     Br = np.zeros((6, npl, (nx + 1) >> tw, nzB, 1 << tw), complex)
     cfl = C.c_double()
     rc = emul.chb_emul_xpass(nx, ny, nzB, npl, nxd, nzd, 0.5, 1.0, tw, _dp(Ar.view(np.float64)), _dp(Br.view(np.float64)),
-                             _dp(dy), 1, C.byref(cfl))
+                             _dp(dy), 1, C.byref(cfl), variant)
     assert rc == 0
     got = np.transpose(Br, (0, 1, 3, 2, 4)).reshape(6, npl, nzB, nx + 1)      # [p][plane][z row][x tile][x in tile] -> x
     scale = np.abs(ref).max()
