@@ -72,24 +72,3 @@ def test_fft3_matches_generic_kernels(monkeypatch):
     for k in range(6):
         assert relerr(out["1"][0][k], out["0"][0][k]) < 1e-13
     assert abs(out["1"][1] - out["0"][1]) <= 1e-13 * out["0"][1]
-
-
-def test_xpass_split_variant_nxd1536(monkeypatch):
-    """CHB_XPASS_SPLIT=1: xpass5 (two threads per innermost butterfly position, 12 instead of 6 warps per SM at
-    nxd = 1536) must give the products of the default kernel to rounding; also checked against numpy on the CPU
-    emulator (tests/test_fft_emul_cpu.py)."""
-    out = {}
-    for flag in ("0", "1"):
-        monkeypatch.setenv("CHB_XPASS_SPLIT", flag)
-        p, o, ch, V0 = make_pair(1023, 8, 3, eps=5e-2)
-        ch.cfl_prepass(); ch.get_step_scalars()
-        ch.buildrhs(RK1_rai, True)
-        out[flag] = (ch.download_products(), ch.get_step_scalars()["cfl"])
-        if flag == "1":
-            Pref = o.convolutions(o.V, False)[..., o.izd]
-            for k in range(6):
-                assert relerr(out[flag][0][k], Pref[k]) < 1e-12, ("product vs oracle", k)
-        ch.close()
-    for k in range(6):
-        assert relerr(out["1"][0][k], out["0"][0][k]) < 1e-13
-    assert abs(out["1"][1] - out["0"][1]) <= 1e-13 * out["0"][1]
