@@ -185,6 +185,7 @@ zbwd4_kernel(const cplx* __restrict__ Br, cplx* __restrict__ P, Geometry g, cons
     }
 }
 
+#ifndef CHB_HOST_EMUL   // tests/host_emul compiles the kernels above with g++ and runs them on CPU threads
 template <class G, int LPC, int TPL, int MINB>
 static bool launch_z4(chb_handle_s* h, int plane0, int nplanes, bool fwd) {
     constexpr int BCP = G::BC + 1;
@@ -227,3 +228,4 @@ bool launch_z3_fwd_or_bwd(chb_handle_s* h, int plane0, int nplanes, bool fwd) {
         default: return false;
     }
 }
+#endif

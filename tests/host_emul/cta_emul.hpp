@@ -15,6 +15,9 @@
 #include <cstring>
 #include <thread>
 #include <vector>
+#include <algorithm>
+using std::max;
+using std::min;
 
 namespace cta_emul {
 inline thread_local uint3 t_threadIdx, t_blockIdx;

@@ -8,6 +8,7 @@
 
 #define CHB_HOST_EMUL 1
 #include "../../channel_b200/csrc/xpass3_kernels.cu"
+#include "../../channel_b200/csrc/zpass3_kernels.cu"
 
 static std::vector<double> twiddle_table(int count, int denom) {   // as chb_api.cu: exp(+2 pi i e / denom)
     std::vector<double> w(2 * (size_t)count);
@@ -38,6 +39,23 @@ static void run_x5(const cplx* Ar, cplx* Br, const Geometry& g, const cplx* W, c
     Bw.p[0] = Br;
     constexpr int T = 2 * (G::N / G::C);
     cta_emul::launch(xpass5_kernel<G, MINB, false>, dim3(g.nzB, np, 1), T, Ar, Bw, g, W, Wh, dy, sc, 0, np, compute_cfl);
+}
+
+template <class G, int LPC, int TPL, int MINB>
+static void run_z4(bool fwd, const cplx* in, cplx* out, const Geometry& g, const cplx* W, int np) {
+    constexpr int BCP = G::BC + 1;
+    int LS = G::A * BCP;
+    const int want = (LPC == 8) ? 1 : (LPC == 4 ? 2 : 4);       // as launch_z4 (zpass3_kernels.cu)
+    while (LS % 8 != want) ++LS;
+    if ((size_t)LPC * LS * sizeof(cplx) > sizeof(cta_emul::g_dyn_smem)) abort();
+    if (fwd) {
+        PeerPtrs Aw;
+        memset(&Aw, 0, sizeof(Aw));
+        Aw.p[0] = out;
+        cta_emul::launch(zfwd4_kernel<G, LPC, TPL, MINB>, dim3(g.nxB / LPC, np, 3), LPC * TPL, in, Aw, g, W, 0, np, LS);
+    } else {
+        cta_emul::launch(zbwd4_kernel<G, LPC, TPL, MINB>, dim3(g.nxB / LPC, np, 6), LPC * TPL, in, out, g, W, 0, np, LS);
+    }
 }
 
 extern "C" {
@@ -80,6 +98,42 @@ __attribute__((visibility("default"))) int chb_emul_xpass(int nx, int ny, int nz
     double c;
     memcpy(&c, &sc.cfl_bits, sizeof(double));
     if (cfl_out) *cfl_out = c;
+    return 0;
+}
+
+// z passes of one chunk of `np` planes (plane0 = 0, so ny+3 must equal np), single rank, nzB = nzd.
+//   fwd != 0: in = V [3][np][nxB][2nz+1] -> out = velocity work buffer (transpose_index.h, tile width 2^twa or
+//             row-major [3][np][nzd][nxB] for twa < 0)
+//   fwd == 0: in = products work buffer (tile width 2^tw) -> out = P [6][np][nxB][2nz+1]
+// lpc = lines per CTA (the variants chb_create selects from).  Returns 2 if that kernel does not exist.
+__attribute__((visibility("default"))) int chb_emul_zpass(int fwd, int nxB, int nz, int nzd, int np, int lpc, int tw, int twa,
+                                                          const double* in, double* out) {
+    Geometry g;
+    memset(&g, 0, sizeof(g));
+    g.nz = nz; g.nzd = nzd; g.nzt = 2 * nz + 1;
+    g.ny = np - 3; g.nyp = np;
+    g.rank = 0; g.nranks = 1;
+    g.nx = nxB - 1; g.nx0 = 0; g.nxN = nxB - 1; g.nxB = nxB;
+    g.nz0 = 0; g.nzN = nzd - 1; g.nzB = nzd;
+    g.M = (long long)nxB * g.nzt;
+    g.tw = tw; g.twa = twa;
+    if (nxB % lpc != 0) return 2;
+    std::vector<double> W = twiddle_table(nzd, nzd);
+    const cplx* Wc = reinterpret_cast<const cplx*>(W.data());
+    const cplx* I = reinterpret_cast<const cplx*>(in);
+    cplx* O = reinterpret_cast<cplx*>(out);
+    const bool f = fwd != 0;
+    switch (nzd * 16 + lpc) {     // as launch_z3_fwd_or_bwd
+        case 768 * 16 + 2: run_z4<Fft3<768, 12, 8, 8>, 2, 64, 8>(f, I, O, g, Wc, np); break;
+        case 768 * 16 + 4: run_z4<Fft3<768, 12, 8, 8>, 4, 64, 4>(f, I, O, g, Wc, np); break;
+        case 768 * 16 + 8: run_z4<Fft3<768, 12, 8, 8>, 8, 32, 2>(f, I, O, g, Wc, np); break;
+        case 1536 * 16 + 2: run_z4<Fft3<1536, 12, 16, 8>, 2, 64, 4>(f, I, O, g, Wc, np); break;
+        case 1536 * 16 + 4: run_z4<Fft3<1536, 12, 16, 8>, 4, 64, 2>(f, I, O, g, Wc, np); break;
+        case 1536 * 16 + 8: run_z4<Fft3<1536, 12, 16, 8>, 8, 32, 1>(f, I, O, g, Wc, np); break;
+        case 3072 * 16 + 2: run_z4<Fft3<3072, 12, 16, 16>, 2, 64, 2>(f, I, O, g, Wc, np); break;
+        case 3072 * 16 + 4: run_z4<Fft3<3072, 12, 16, 16>, 4, 64, 1>(f, I, O, g, Wc, np); break;
+        default: return 2;
+    }
     return 0;
 }
 

@@ -1,4 +1,4 @@
-"""The x-pass kernel of the nonlinear term (xpass3_kernels.cu) run on the CPU.
+"""The FFT-pass kernels of the nonlinear term (xpass3_kernels.cu, zpass3_kernels.cu) run on the CPU.
 
 tests/host_emul/fft_emul.cpp compiles the kernel SOURCE with g++ and runs each thread block on OS threads
 (cta_emul.hpp: __syncthreads = barrier, shared memory = a buffer).  For a few z-lines of each specialised
@@ -28,7 +28,7 @@ def emul():
     so = os.path.join(BUILD, "libfft_emul.so")
     csrc = os.path.join(HERE, "..", "channel_b200", "csrc")
     deps = [SRC, os.path.join(HERE, "host_emul", "cta_emul.hpp")] + [
-        os.path.join(csrc, f) for f in ("xpass3_kernels.cu", "fft_regs.cuh", "fft_device.cuh", "chb_internal.h", "transpose_index.h")]
+        os.path.join(csrc, f) for f in ("xpass3_kernels.cu", "zpass3_kernels.cu", "fft_regs.cuh", "fft_device.cuh", "chb_internal.h", "transpose_index.h")]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
         subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-w", "-pthread",
                                "-fvisibility=hidden", "-Wl,-Bsymbolic", "-I" + CUDA_INC, "-o", so, SRC])
@@ -36,6 +36,8 @@ def emul():
     dp = C.POINTER(C.c_double)
     lib.chb_emul_xpass.argtypes = [C.c_int] * 6 + [C.c_double] * 2 + [C.c_int, dp, dp, dp, C.c_int, dp, C.c_int]
     lib.chb_emul_xpass.restype = C.c_int
+    lib.chb_emul_zpass.argtypes = [C.c_int] * 8 + [dp, dp]
+    lib.chb_emul_zpass.restype = C.c_int
     return lib
 
 
@@ -81,3 +83,41 @@ def test_xpass_kernel_on_cpu_threads(emul, nx, nxd, tw, variant):
     scale = np.abs(ref).max()
     assert np.abs(got - ref).max() <= 1e-13 * scale, np.abs(got - ref).max() / scale
     assert abs(cfl.value - cfl_ref) <= 1e-13 * cfl_ref
+
+
+def _tiled(a, tw):
+    """[..., z row, x] -> work-buffer layout [..., x tile, z row, x in tile] (transpose_index.h)"""
+    *lead, nz_, nx_ = a.shape
+    return np.ascontiguousarray(np.moveaxis(a.reshape(*lead, nz_, nx_ >> tw, 1 << tw), -2, -3))
+
+
+@pytest.mark.parametrize("nz,nzd,lpc", [(255, 768, 4), (255, 768, 2), (255, 768, 8), (511, 1536, 4), (511, 1536, 2),
+                                        (511, 1536, 8), (1023, 3072, 2), (1023, 3072, 4), (300, 768, 4)])
+def test_zpass_kernels_on_cpu_threads(emul, nz, nzd, lpc):
+    """zfwd4: zero-pad in z + backward FFT + zTOx pack (dnsdata.f90:504-510, ffts.f90:71, mpi_transpose.f90:64-71);
+    zbwd4: xTOz unpack + forward FFT + truncation through izd (ffts.f90:70, dnsdata.f90:609), incl. the TMA /
+    cp.async staging replaced by plain copies."""
+    nxB, npl = 8, 3
+    nzt = 2 * nz + 1
+    rng = np.random.default_rng(nz + lpc)
+    V = rng.standard_normal((3, npl, nxB, nzt)) + 1j * rng.standard_normal((3, npl, nxB, nzt))
+    Z = np.zeros((3, npl, nxB, nzd), complex)
+    Z[..., 0:nz + 1] = V[..., nz:]
+    Z[..., nzd - nz:] = V[..., :nz]
+    ref = np.fft.ifft(Z, axis=-1) * nzd                                # [3][np][x][z]
+    for twa in (-1, {2: 1, 4: 2, 8: 3}[lpc]):
+        out = np.zeros((3, npl, nzd, nxB), complex)
+        assert emul.chb_emul_zpass(1, nxB, nz, nzd, npl, lpc, 3, twa, _dp(np.ascontiguousarray(V).view(np.float64)),
+                                   _dp(out.view(np.float64))) == 0
+        want = np.swapaxes(ref, -1, -2)                                # [3][np][z][x]
+        want = want if twa < 0 else _tiled(want, twa).reshape(out.shape)
+        assert np.abs(out - want).max() <= 1e-13 * np.abs(ref).max(), (twa, np.abs(out - want).max())
+    # backward pass: products in the tiled buffer -> spectral, truncated
+    B = rng.standard_normal((6, npl, nzd, nxB)) + 1j * rng.standard_normal((6, npl, nzd, nxB))
+    F = np.fft.fft(np.swapaxes(B, -1, -2), axis=-1)                    # [6][np][x][k]
+    refP = np.concatenate([F[..., nzd - nz:], F[..., :nz + 1]], axis=-1)
+    for tw in sorted({0, {2: 1, 4: 2, 8: 3}[lpc], 3}):
+        P = np.zeros((6, npl, nxB, nzt), complex)
+        assert emul.chb_emul_zpass(0, nxB, nz, nzd, npl, lpc, tw, -1, _dp(_tiled(B, tw).view(np.float64)),
+                                   _dp(P.view(np.float64))) == 0
+        assert np.abs(P - refP).max() <= 1e-13 * np.abs(refP).max(), (tw, np.abs(P - refP).max())
