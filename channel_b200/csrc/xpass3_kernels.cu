@@ -231,9 +231,10 @@ xpass4_kernel(const cplx* __restrict__ Ar, const __grid_constant__ PeerPtrs Bw, 
 }
 
 // ---------------------------------------------------------------------------------------------
-// xpass5: the same pass with TWO threads per innermost butterfly position (T = 2 M/C threads per line), for
-// the sizes whose six line buffers leave room for one CTA per SM only (M = 1536: 148.6 KB): twice the
-// resident warps at the same shared memory.  The flattened task loops of the outer stages take the extra
+// xpass5: the same pass with TWO threads per innermost butterfly position (T = 2 M/C threads per line): for
+// M = 1536, whose six line buffers (148.6 KB) leave room for one CTA per SM only, twice the resident warps at
+// the same shared memory (12 instead of 6); for M = 768, two CTAs of 12 warps at 85 registers instead of three
+// of 6 warps at 96.  The flattened task loops of the outer stages take the extra
 // threads as they are; in the innermost stage both threads of a position run the radix-C butterflies of u, v, w
 // (duplicated: 3 of the 9 innermost butterflies per position) and then one forms uu, vv, ww and the other
 // uv, vw, uw.  Because two threads now read the same u, v, w entries that the products overwrite in place, a
@@ -252,7 +253,7 @@ xpass5_kernel(const cplx* __restrict__ Ar, const __grid_constant__ PeerPtrs Bw, 
     constexpr int LB = A * BCP;        // complex per buffer
     constexpr int NB = A * C;          // stage-B butterflies per transform
     static_assert(T % C == 0 && NB % C == 0, "stage-B twiddle must be a per-thread constant");
-    static_assert(C != 4, "the swizzled layout of the C = 4 kernels is not needed here");
+    static_assert(TP % 32 == 0, "the two halves of a line must be whole warps");
     CHB_DYN_SMEM(cplx, smem);
     const int tl = threadIdx.x % T, l = threadIdx.x / T;
     const int izl = blockIdx.x * LPC + l;
@@ -335,7 +336,8 @@ xpass5_kernel(const cplx* __restrict__ Ar, const __grid_constant__ PeerPtrs Bw, 
     // ---- backward stage C -> physical space -> CFL, products -> forward stage C --------------
     {
         const int pos = tl % TP, half = tl / TP;      // half is warp-uniform (TP is a multiple of 32)
-        const int ka = pos % A, kb = pos / A;
+        // C = 4: consecutive lanes = consecutive kb (see sig); else consecutive ka
+        const int ka = (C == 4) ? pos / B : pos % A, kb = (C == 4) ? pos % B : pos / A;
         cplx* base = S + ka * BCP;
         int sc_[C];
         static_for<C>([&](auto c_) { constexpr int c = decltype(c_)::value; sc_[c] = sig(kb * C + c); });
@@ -476,6 +478,7 @@ static bool launch_x5(chb_handle_s* h, int plane0, int nplanes, int compute_cfl)
 // ---------------------------------------------------------------------------------------------
 bool launch_x3_pass(chb_handle_s* h, int plane0, int nplanes, int compute_cfl) {
     if (h->xpass_split && h->g.nxd == 1536) return launch_x5<Fft3<1536, 12, 16, 8>, 1>(h, plane0, nplanes, compute_cfl);
+    if (h->xpass_split && h->g.nxd == 768) return launch_x5<Fft3<768, 12, 16, 4>, 2>(h, plane0, nplanes, compute_cfl);
     switch (h->g.nxd) {
         case 384: return launch_x4<Fft3<384, 12, 8, 4>, 1, 6>(h, plane0, nplanes, compute_cfl);
         case 768: return launch_x4<Fft3<768, 12, 16, 4>, 1, 3>(h, plane0, nplanes, compute_cfl);

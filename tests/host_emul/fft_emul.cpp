@@ -64,7 +64,7 @@ extern "C" {
 // Br = products for the backward z pass in the tiled layout of transpose_index.h (tile width 2^tw),
 // [6][np][(nx+1) >> tw][nzB][1 << tw]; dy[ny+3]; cfl_out = max of the CFL expression (dnsdata.f90:552-556).
 // Planes are iy = -1 .. np-2 (plane0 = 0).  variant 0: xpass4 (one thread per innermost butterfly position),
-// 1: xpass5 (two threads per position; nxd = 1536).  Returns 2 if no such kernel exists for nxd.
+// 1: xpass5 (two threads per position; nxd = 768, 1536).  Returns 2 if no such kernel exists for nxd.
 __attribute__((visibility("default"))) int chb_emul_xpass(int nx, int ny, int nzB, int np, int nxd, int nzd, double alfa0,
                                                           double beta0, int tw, const double* Ar, double* Br,
                                                           const double* dy, int compute_cfl, double* cfl_out, int variant) {
@@ -86,8 +86,9 @@ __attribute__((visibility("default"))) int chb_emul_xpass(int nx, int ny, int nz
     const cplx* Wc = reinterpret_cast<const cplx*>(W.data());
     const cplx* Whc = reinterpret_cast<const cplx*>(Wh.data());
     if (variant == 1) {
-        if (nxd != 1536) return 2;
-        run_x5<Fft3<1536, 12, 16, 8>, 1>(A, B, g, Wc, Whc, dy, &sc, np, compute_cfl);
+        if (nxd == 1536) run_x5<Fft3<1536, 12, 16, 8>, 1>(A, B, g, Wc, Whc, dy, &sc, np, compute_cfl);
+        else if (nxd == 768) run_x5<Fft3<768, 12, 16, 4>, 2>(A, B, g, Wc, Whc, dy, &sc, np, compute_cfl);
+        else return 2;
     } else
     switch (nxd) {
         case 384: run_x4<Fft3<384, 12, 8, 4>, 1, 6>(A, B, g, Wc, Whc, dy, &sc, np, compute_cfl); break;

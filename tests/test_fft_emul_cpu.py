@@ -66,7 +66,8 @@ def xpass_reference(A, nx, nxd, nzd, alfa0, beta0, dy, ny, compute_cfl):
 
 
 @pytest.mark.parametrize("nx,nxd,tw,variant", [(255, 384, 3, 0), (255, 384, 0, 0), (511, 768, 3, 0), (1023, 1536, 3, 0),
-                                               (300, 768, 0, 0), (1023, 1536, 3, 1), (703, 1536, 2, 1)])
+                                               (300, 768, 0, 0), (1023, 1536, 3, 1), (703, 1536, 2, 1),
+                                               (511, 768, 3, 1), (300, 768, 0, 1)])
 def test_xpass_kernel_on_cpu_threads(emul, nx, nxd, tw, variant):
     ny, nzd, nzB, npl = 6, 6, 2, 3            # planes iy = -1, 0, 1: the CFL expression sees iy = 1 only
     rng = np.random.default_rng(nx + tw)

@@ -9,14 +9,15 @@ from tests.helpers import make_pair, relerr
 
 pytestmark = pytest.mark.gpu
 
-def test_xpass_split_variant_nxd1536(monkeypatch):
-    """CHB_XPASS_SPLIT=1: xpass5 (two threads per innermost butterfly position, 12 instead of 6 warps per SM at
-    nxd = 1536) must give the products of the default kernel to rounding; also checked against numpy on the CPU
-    emulator (tests/test_fft_emul_cpu.py)."""
+@pytest.mark.parametrize("nx,ny,nz", [(1023, 8, 3), (511, 8, 4)])
+def test_xpass_split_variant(nx, ny, nz, monkeypatch):
+    """CHB_XPASS_SPLIT=1: xpass5 (two threads per innermost butterfly position: 12 instead of 6 warps per SM at
+    nxd = 1536, two CTAs of 12 warps instead of three of 6 at nxd = 768) must give the products of the default
+    kernel to rounding; also checked against numpy on the CPU emulator (tests/test_fft_emul_cpu.py)."""
     out = {}
     for flag in ("0", "1"):
         monkeypatch.setenv("CHB_XPASS_SPLIT", flag)
-        p, o, ch, V0 = make_pair(1023, 8, 3, eps=5e-2)
+        p, o, ch, V0 = make_pair(nx, ny, nz, eps=5e-2)
         ch.cfl_prepass(); ch.get_step_scalars()
         ch.buildrhs(RK1_rai, True)
         out[flag] = (ch.download_products(), ch.get_step_scalars()["cfl"])
