@@ -31,7 +31,10 @@ __device__ __forceinline__ void z_twiddle_seq(cplx* x, cplx w1) {
 // zfwd4 / zbwd4: the same three stages with TPL (a multiple of 32) threads per line and
 // block-wide barriers between stages, sized so that MINB CTAs are resident per SM: while one CTA
 // waits for its lines to arrive from HBM another one computes.
-template <class G, int LPC, int TPL, int MINB>
+// DIRECT (experimental, CHB_ZF_DIRECT=1, proven on the CPU emulator, not yet measured): stage A reads its inputs
+// straight from global memory (a warp reads 512 contiguous bytes per radix digit) instead of through the TMA
+// staging copy: two of the six shared-memory passes per point disappear, the load latency moves into the threads.
+template <class G, int LPC, int TPL, int MINB, bool DIRECT = false>
 __global__ void __launch_bounds__(LPC * TPL, MINB)
 zfwd4_kernel(const cplx* __restrict__ V, PeerPtrs Aw, Geometry g, const cplx* __restrict__ W, int plane0, int np,
              int LS) {
@@ -47,28 +50,33 @@ zfwd4_kernel(const cplx* __restrict__ V, PeerPtrs Aw, Geometry g, const cplx* __
     {   // ---- stage A, line-major; the V line is staged by TMA bulk copies into the in-place layout
         const cplx* __restrict__ src = V + (((size_t)comp * g.nyp + iyp) * g.nxB + ixl0 + wl) * g.nzt;
         cplx* sm = smem + wl * LS;
-        if (tl == 0) {
-            mbar_init(&mbar[wl], 1);
-            mbar_expect_tx(&mbar[wl], (unsigned)(g.nzt * sizeof(cplx)));
-            for (int a = 0; a < G::A; ++a) {
-                const int lo = a * G::BC, hi = lo + G::BC - 1;
-                const int h1 = min(hi, nz);                    // rows 1..nz+1        <- V(iy,0:nz)
-                if (h1 >= lo) bulk_g2s(sm + a * BCP, src + nz + lo, (unsigned)((h1 - lo + 1) * sizeof(cplx)), &mbar[wl]);
-                const int l2 = max(lo, G::N - nz);             // rows nzd-nz+1..nzd  <- V(iy,-nz:-1)
-                if (hi >= l2)
-                    bulk_g2s(sm + a * BCP + (l2 - lo), src + (l2 - (G::N - nz)), (unsigned)((hi - l2 + 1) * sizeof(cplx)),
-                             &mbar[wl]);
+        if constexpr (!DIRECT) {
+            if (tl == 0) {
+                mbar_init(&mbar[wl], 1);
+                mbar_expect_tx(&mbar[wl], (unsigned)(g.nzt * sizeof(cplx)));
+                for (int a = 0; a < G::A; ++a) {
+                    const int lo = a * G::BC, hi = lo + G::BC - 1;
+                    const int h1 = min(hi, nz);                    // rows 1..nz+1        <- V(iy,0:nz)
+                    if (h1 >= lo) bulk_g2s(sm + a * BCP, src + nz + lo, (unsigned)((h1 - lo + 1) * sizeof(cplx)), &mbar[wl]);
+                    const int l2 = max(lo, G::N - nz);             // rows nzd-nz+1..nzd  <- V(iy,-nz:-1)
+                    if (hi >= l2)
+                        bulk_g2s(sm + a * BCP + (l2 - lo), src + (l2 - (G::N - nz)), (unsigned)((hi - l2 + 1) * sizeof(cplx)),
+                                 &mbar[wl]);
+                }
             }
+            __syncthreads();
+            mbar_wait(&mbar[wl], 0);
         }
-        __syncthreads();
-        mbar_wait(&mbar[wl], 0);
 #pragma unroll 1
         for (int t1 = tl; t1 < G::BC; t1 += TPL) {
             cplx x[G::A];
             static_for<G::A>([&](auto a_) {
                 constexpr int a = decltype(a_)::value;
                 const int n = a * G::BC + t1;
-                x[a] = (n <= nz || n >= G::N - nz) ? sm[a * BCP + t1] : make_double2(0.0, 0.0);
+                if constexpr (DIRECT)
+                    x[a] = (n <= nz) ? __ldg(src + nz + n) : ((n >= G::N - nz) ? __ldg(src + (n - (G::N - nz))) : make_double2(0.0, 0.0));
+                else
+                    x[a] = (n <= nz || n >= G::N - nz) ? sm[a * BCP + t1] : make_double2(0.0, 0.0);
             });
             Dft<G::A, +1>::run(x);
             if (t1 != 0) z_twiddle_seq<G::A>(x, ctw<+1>(W, t1));
@@ -196,10 +204,11 @@ static bool launch_z4(chb_handle_s* h, int plane0, int nplanes, bool fwd) {
     if (h->g.nxB % LPC != 0) return false;
     dim3 grid(h->g.nxB / LPC, nplanes, fwd ? 3 : 6);
     if (fwd) {
-        cudaFuncSetAttribute(zfwd4_kernel<G, LPC, TPL, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(zfwd4_kernel<G, LPC, TPL, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        auto kern = h->zf_direct ? zfwd4_kernel<G, LPC, TPL, MINB, true> : zfwd4_kernel<G, LPC, TPL, MINB, false>;
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         ScopedKernelTimer tm(h, "zfwd", h->cstream);
-        zfwd4_kernel<G, LPC, TPL, MINB><<<grid, LPC * TPL, smem, h->cstream>>>(h->V, h->Aw, h->g, h->Wz, plane0, h->chunk_planes, LS);
+        kern<<<grid, LPC * TPL, smem, h->cstream>>>(h->V, h->Aw, h->g, h->Wz, plane0, h->chunk_planes, LS);
     } else {
         cudaFuncSetAttribute(zbwd4_kernel<G, LPC, TPL, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(zbwd4_kernel<G, LPC, TPL, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);

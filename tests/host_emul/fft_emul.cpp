@@ -42,7 +42,7 @@ static void run_x5(const cplx* Ar, cplx* Br, const Geometry& g, const cplx* W, c
 }
 
 template <class G, int LPC, int TPL, int MINB>
-static void run_z4(bool fwd, const cplx* in, cplx* out, const Geometry& g, const cplx* W, int np) {
+static void run_z4(int fwd, const cplx* in, cplx* out, const Geometry& g, const cplx* W, int np) {
     constexpr int BCP = G::BC + 1;
     int LS = G::A * BCP;
     const int want = (LPC == 8) ? 1 : (LPC == 4 ? 2 : 4);       // as launch_z4 (zpass3_kernels.cu)
@@ -52,7 +52,10 @@ static void run_z4(bool fwd, const cplx* in, cplx* out, const Geometry& g, const
         PeerPtrs Aw;
         memset(&Aw, 0, sizeof(Aw));
         Aw.p[0] = out;
-        cta_emul::launch(zfwd4_kernel<G, LPC, TPL, MINB>, dim3(g.nxB / LPC, np, 3), LPC * TPL, in, Aw, g, W, 0, np, LS);
+        if (fwd == 2)   // DIRECT: stage A reads global memory
+            cta_emul::launch(zfwd4_kernel<G, LPC, TPL, MINB, true>, dim3(g.nxB / LPC, np, 3), LPC * TPL, in, Aw, g, W, 0, np, LS);
+        else
+            cta_emul::launch(zfwd4_kernel<G, LPC, TPL, MINB, false>, dim3(g.nxB / LPC, np, 3), LPC * TPL, in, Aw, g, W, 0, np, LS);
     } else {
         cta_emul::launch(zbwd4_kernel<G, LPC, TPL, MINB>, dim3(g.nxB / LPC, np, 6), LPC * TPL, in, out, g, W, 0, np, LS);
     }
@@ -103,7 +106,7 @@ __attribute__((visibility("default"))) int chb_emul_xpass(int nx, int ny, int nz
 }
 
 // z passes of one chunk of `np` planes (plane0 = 0, so ny+3 must equal np), single rank, nzB = nzd.
-//   fwd != 0: in = V [3][np][nxB][2nz+1] -> out = velocity work buffer (transpose_index.h, tile width 2^twa or
+//   fwd = 1 (TMA-staged stage A) or 2 (direct global loads): in = V [3][np][nxB][2nz+1] -> out = velocity work buffer (transpose_index.h, tile width 2^twa or
 //             row-major [3][np][nzd][nxB] for twa < 0)
 //   fwd == 0: in = products work buffer (tile width 2^tw) -> out = P [6][np][nxB][2nz+1]
 // lpc = lines per CTA (the variants chb_create selects from).  Returns 2 if that kernel does not exist.
@@ -123,7 +126,7 @@ __attribute__((visibility("default"))) int chb_emul_zpass(int fwd, int nxB, int 
     const cplx* Wc = reinterpret_cast<const cplx*>(W.data());
     const cplx* I = reinterpret_cast<const cplx*>(in);
     cplx* O = reinterpret_cast<cplx*>(out);
-    const bool f = fwd != 0;
+    const int f = fwd;
     switch (nzd * 16 + lpc) {     // as launch_z3_fwd_or_bwd
         case 768 * 16 + 2: run_z4<Fft3<768, 12, 8, 8>, 2, 64, 8>(f, I, O, g, Wc, np); break;
         case 768 * 16 + 4: run_z4<Fft3<768, 12, 8, 8>, 4, 64, 4>(f, I, O, g, Wc, np); break;

@@ -106,9 +106,9 @@ def test_zpass_kernels_on_cpu_threads(emul, nz, nzd, lpc):
     Z[..., 0:nz + 1] = V[..., nz:]
     Z[..., nzd - nz:] = V[..., :nz]
     ref = np.fft.ifft(Z, axis=-1) * nzd                                # [3][np][x][z]
-    for twa in (-1, {2: 1, 4: 2, 8: 3}[lpc]):
+    for twa, mode in ((-1, 1), ({2: 1, 4: 2, 8: 3}[lpc], 1), (-1, 2), ({2: 1, 4: 2, 8: 3}[lpc], 2)):   # mode 2 = DIRECT stage A
         out = np.zeros((3, npl, nzd, nxB), complex)
-        assert emul.chb_emul_zpass(1, nxB, nz, nzd, npl, lpc, 3, twa, _dp(np.ascontiguousarray(V).view(np.float64)),
+        assert emul.chb_emul_zpass(mode, nxB, nz, nzd, npl, lpc, 3, twa, _dp(np.ascontiguousarray(V).view(np.float64)),
                                    _dp(out.view(np.float64))) == 0
         want = np.swapaxes(ref, -1, -2)                                # [3][np][z][x]
         want = want if twa < 0 else _tiled(want, twa).reshape(out.shape)
