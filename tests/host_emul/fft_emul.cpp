@@ -121,7 +121,7 @@ __attribute__((visibility("default"))) int chb_emul_zpass(int fwd, int nxB, int 
     g.nz0 = 0; g.nzN = nzd - 1; g.nzB = nzd;
     g.M = (long long)nxB * g.nzt;
     g.tw = tw; g.twa = twa;
-    if (nxB % lpc != 0) return 2;
+    if (nxB % (lpc & 1023) != 0) return 2;
     std::vector<double> W = twiddle_table(nzd, nzd);
     const cplx* Wc = reinterpret_cast<const cplx*>(W.data());
     const cplx* I = reinterpret_cast<const cplx*>(in);
@@ -136,6 +136,7 @@ __attribute__((visibility("default"))) int chb_emul_zpass(int fwd, int nxB, int 
         case 1536 * 16 + 8: run_z4<Fft3<1536, 12, 16, 8>, 8, 32, 1>(f, I, O, g, Wc, np); break;
         case 3072 * 16 + 2: run_z4<Fft3<3072, 12, 16, 16>, 2, 64, 2>(f, I, O, g, Wc, np); break;
         case 3072 * 16 + 4: run_z4<Fft3<3072, 12, 16, 16>, 4, 64, 1>(f, I, O, g, Wc, np); break;
+        case 3072 * 16 + 2 + 1024: run_z4<Fft3<3072, 12, 16, 16>, 2, 128, 2>(f, I, O, g, Wc, np); break;   // lpc = 2 + 1024: TPL = 128
         default: return 2;
     }
     return 0;

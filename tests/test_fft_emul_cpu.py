@@ -93,13 +93,15 @@ def _tiled(a, tw):
 
 
 @pytest.mark.parametrize("nz,nzd,lpc", [(255, 768, 4), (255, 768, 2), (255, 768, 8), (511, 1536, 4), (511, 1536, 2),
-                                        (511, 1536, 8), (1023, 3072, 2), (1023, 3072, 4), (300, 768, 4)])
+                                        (511, 1536, 8), (1023, 3072, 2), (1023, 3072, 4), (300, 768, 4),
+                                        (1023, 3072, 2 + 1024)])     # + 1024: the 128-threads-per-line variant
 def test_zpass_kernels_on_cpu_threads(emul, nz, nzd, lpc):
     """zfwd4: zero-pad in z + backward FFT + zTOx pack (dnsdata.f90:504-510, ffts.f90:71, mpi_transpose.f90:64-71);
     zbwd4: xTOz unpack + forward FFT + truncation through izd (ffts.f90:70, dnsdata.f90:609), incl. the TMA /
     cp.async staging replaced by plain copies."""
     nxB, npl = 8, 3
     nzt = 2 * nz + 1
+    lpc_code, lpc = lpc, lpc & 1023
     rng = np.random.default_rng(nz + lpc)
     V = rng.standard_normal((3, npl, nxB, nzt)) + 1j * rng.standard_normal((3, npl, nxB, nzt))
     Z = np.zeros((3, npl, nxB, nzd), complex)
@@ -108,7 +110,7 @@ def test_zpass_kernels_on_cpu_threads(emul, nz, nzd, lpc):
     ref = np.fft.ifft(Z, axis=-1) * nzd                                # [3][np][x][z]
     for twa, mode in ((-1, 1), ({2: 1, 4: 2, 8: 3}[lpc], 1), (-1, 2), ({2: 1, 4: 2, 8: 3}[lpc], 2)):   # mode 2 = DIRECT stage A
         out = np.zeros((3, npl, nzd, nxB), complex)
-        assert emul.chb_emul_zpass(mode, nxB, nz, nzd, npl, lpc, 3, twa, _dp(np.ascontiguousarray(V).view(np.float64)),
+        assert emul.chb_emul_zpass(mode, nxB, nz, nzd, npl, lpc_code, 3, twa, _dp(np.ascontiguousarray(V).view(np.float64)),
                                    _dp(out.view(np.float64))) == 0
         want = np.swapaxes(ref, -1, -2)                                # [3][np][z][x]
         want = want if twa < 0 else _tiled(want, twa).reshape(out.shape)
@@ -119,6 +121,6 @@ def test_zpass_kernels_on_cpu_threads(emul, nz, nzd, lpc):
     refP = np.concatenate([F[..., nzd - nz:], F[..., :nz + 1]], axis=-1)
     for tw in sorted({0, {2: 1, 4: 2, 8: 3}[lpc], 3}):
         P = np.zeros((6, npl, nxB, nzt), complex)
-        assert emul.chb_emul_zpass(0, nxB, nz, nzd, npl, lpc, tw, -1, _dp(_tiled(B, tw).view(np.float64)),
+        assert emul.chb_emul_zpass(0, nxB, nz, nzd, npl, lpc_code, tw, -1, _dp(_tiled(B, tw).view(np.float64)),
                                    _dp(P.view(np.float64))) == 0
         assert np.abs(P - refP).max() <= 1e-13 * np.abs(refP).max(), (tw, np.abs(P - refP).max())
