@@ -185,8 +185,8 @@ extern "C" int chb_create(chb_handle* out, int nx, int ny, int nz, int nxd, int 
         h->use_fft3 = (e && atoi(e) == 0) ? 0 : 1;
         e = getenv("CHB_ZF_DIRECT");
         h->zf_direct = e ? atoi(e) : 0;
-        e = getenv("CHB_Z_TPL128");
-        h->z_tpl128 = e ? atoi(e) : 0;
+        e = getenv("CHB_Z_TPL");
+        h->z_tpl = e ? atoi(e) : 0;
         e = getenv("CHB_XPASS_SPLIT");
         h->xpass_split = e ? atoi(e) : 0;
         // x tiles of the work buffers (transpose_index.h): products 8 wide (128-byte store segments in

@@ -111,7 +111,7 @@ struct chb_handle_s {
     int zf_lines_per_cta, zb_lines_per_cta;  // lines per CTA of zfwd / zbwd (CHB_ZF_LPC, CHB_ZB_LPC: 2, 4 or 8)
     int use_fft3;         // register-resident three-stage FFT kernels for the large sizes (CHB_FFT3=0 disables)
     int zf_direct;        // CHB_ZF_DIRECT=1: zfwd4 stage A reads global memory directly (no TMA staging); experimental
-    int z_tpl128;         // CHB_Z_TPL128=1: 128 threads per line in the z passes at nzd = 3072; experimental
+    int z_tpl;            // CHB_Z_TPL=128|96: threads per line of the z passes at nzd = 1536 / 3072 (default 64); experimental
     int xpass_split;      // CHB_XPASS_SPLIT=1: xpass5 (two threads per innermost butterfly position) at nxd = 1536; experimental
     cplx* A;        // NCCL mode only: send buffer of zTOx, [peer][3][np][nzB][nxB]
     cplx* Ar;       // z-padded velocity after zTOx, [src rank][3][np][nzB][nxB]

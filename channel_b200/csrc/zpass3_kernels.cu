@@ -225,9 +225,14 @@ static bool launch_z4(chb_handle_s* h, int plane0, int nplanes, bool fwd) {
 bool launch_z3_fwd_or_bwd(chb_handle_s* h, int plane0, int nplanes, bool fwd) {
     if (h->g.nz < 2) return false;
     const int lpc = fwd ? h->zf_lines_per_cta : h->zb_lines_per_cta;
-    // experimental (CHB_Z_TPL128=1, proven on the CPU emulator, not yet measured): 128 threads per line at
-    // nzd = 3072, i.e. 16 instead of 8 resident warps per SM (two CTAs of two lines), at a 128-register cap
-    if (h->z_tpl128 && h->g.nzd == 3072 && lpc == 2) return launch_z4<Fft3<3072, 12, 16, 16>, 2, 128, 2>(h, plane0, nplanes, fwd);
+    // experimental (CHB_Z_TPL=128 | 96, proven on the CPU emulator, not yet measured): more threads per line, i.e. more
+    // resident warps per SM at the same shared memory, with two lines per CTA:
+    //   nzd = 3072: 128 threads/line, 2 CTAs/SM -> 16 warps (default 8), 128 registers, 0 / 8 bytes of spills
+    //   nzd = 1536: 128 threads/line, 3 CTAs/SM -> 24 warps (default 16), 80 registers, no spills
+    //               96 threads/line, 4 CTAs/SM -> 24 warps, 80 registers, no spills
+    if (h->z_tpl == 128 && lpc == 2 && h->g.nzd == 3072) return launch_z4<Fft3<3072, 12, 16, 16>, 2, 128, 2>(h, plane0, nplanes, fwd);
+    if (h->z_tpl == 128 && lpc == 2 && h->g.nzd == 1536) return launch_z4<Fft3<1536, 12, 16, 8>, 2, 128, 3>(h, plane0, nplanes, fwd);
+    if (h->z_tpl == 96 && lpc == 2 && h->g.nzd == 1536) return launch_z4<Fft3<1536, 12, 16, 8>, 2, 96, 4>(h, plane0, nplanes, fwd);
     switch (h->g.nzd * 16 + lpc) {
         case 768 * 16 + 2: return launch_z4<Fft3<768, 12, 8, 8>, 2, 64, 8>(h, plane0, nplanes, fwd);
         case 768 * 16 + 4: return launch_z4<Fft3<768, 12, 8, 8>, 4, 64, 4>(h, plane0, nplanes, fwd);

@@ -137,6 +137,8 @@ __attribute__((visibility("default"))) int chb_emul_zpass(int fwd, int nxB, int 
         case 3072 * 16 + 2: run_z4<Fft3<3072, 12, 16, 16>, 2, 64, 2>(f, I, O, g, Wc, np); break;
         case 3072 * 16 + 4: run_z4<Fft3<3072, 12, 16, 16>, 4, 64, 1>(f, I, O, g, Wc, np); break;
         case 3072 * 16 + 2 + 1024: run_z4<Fft3<3072, 12, 16, 16>, 2, 128, 2>(f, I, O, g, Wc, np); break;   // lpc = 2 + 1024: TPL = 128
+        case 1536 * 16 + 2 + 1024: run_z4<Fft3<1536, 12, 16, 8>, 2, 128, 3>(f, I, O, g, Wc, np); break;
+        case 1536 * 16 + 2 + 2048: run_z4<Fft3<1536, 12, 16, 8>, 2, 96, 4>(f, I, O, g, Wc, np); break;      // + 2048: TPL = 96
         default: return 2;
     }
     return 0;

@@ -94,7 +94,8 @@ def _tiled(a, tw):
 
 @pytest.mark.parametrize("nz,nzd,lpc", [(255, 768, 4), (255, 768, 2), (255, 768, 8), (511, 1536, 4), (511, 1536, 2),
                                         (511, 1536, 8), (1023, 3072, 2), (1023, 3072, 4), (300, 768, 4),
-                                        (1023, 3072, 2 + 1024)])     # + 1024: the 128-threads-per-line variant
+                                        (1023, 3072, 2 + 1024), (511, 1536, 2 + 1024),       # + 1024: 128 threads per line
+                                        (511, 1536, 2 + 2048)])                              # + 2048: 96 threads per line
 def test_zpass_kernels_on_cpu_threads(emul, nz, nzd, lpc):
     """zfwd4: zero-pad in z + backward FFT + zTOx pack (dnsdata.f90:504-510, ffts.f90:71, mpi_transpose.f90:64-71);
     zbwd4: xTOz unpack + forward FFT + truncation through izd (ffts.f90:70, dnsdata.f90:609), incl. the TMA /

@@ -52,22 +52,23 @@ def test_zfwd_direct_variant(nx, ny, nz, monkeypatch):
     assert abs(out["1"][1] - out["0"][1]) <= 1e-13 * out["0"][1]
 
 
-def test_zpass_128_threads_per_line_nzd3072(monkeypatch):
-    """CHB_Z_TPL128=1: the z passes at nzd = 3072 with 128 instead of 64 threads per line (16 instead of 8 resident
-    warps per SM at a 128-register cap, no spills); same products as the default kernels."""
+@pytest.mark.parametrize("nx,ny,nz,tpl", [(7, 8, 1023, "128"), (15, 8, 511, "128"), (15, 8, 511, "96")])
+def test_zpass_threads_per_line_variants(nx, ny, nz, tpl, monkeypatch):
+    """CHB_Z_TPL=128|96: the z passes at nzd = 3072 / 1536 with more threads per line (16 instead of 8, 24 instead of
+    16 resident warps per SM, no spills); same products as the default kernels."""
     out = {}
-    for flag in ("0", "1"):
-        monkeypatch.setenv("CHB_Z_TPL128", flag)
+    for flag in ("0", tpl):
+        monkeypatch.setenv("CHB_Z_TPL", flag)
         monkeypatch.setenv("CHB_ZF_LPC", "2"); monkeypatch.setenv("CHB_ZB_LPC", "2")
-        p, o, ch, V0 = make_pair(7, 8, 1023, eps=5e-2)
+        p, o, ch, V0 = make_pair(nx, ny, nz, eps=5e-2)
         ch.cfl_prepass(); ch.get_step_scalars()
         ch.buildrhs(RK1_rai, True)
         out[flag] = (ch.download_products(), ch.get_step_scalars()["cfl"])
-        if flag == "1":
+        if flag != "0":
             Pref = o.convolutions(o.V, False)[..., o.izd]
             for k in range(6):
                 assert relerr(out[flag][0][k], Pref[k]) < 1e-12, ("product vs oracle", k)
         ch.close()
     for k in range(6):
-        assert relerr(out["1"][0][k], out["0"][0][k]) < 1e-13
-    assert abs(out["1"][1] - out["0"][1]) <= 1e-13 * out["0"][1]
+        assert relerr(out[tpl][0][k], out["0"][0][k]) < 1e-13
+    assert abs(out[tpl][1] - out["0"][1]) <= 1e-13 * out["0"][1]
