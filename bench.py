@@ -136,6 +136,7 @@ def measured_traffic(kernel, nx, ny, nz, world):
     return None, None
 
 
+FP64_PEAK_TFLOPS = 33.8   # measured FP64 FMA ceiling of one B200 (profiles/README.md, round 1 stage a)
 NVLINK_PEAK_GBS = 900.0   # NVLink 5 per direction and GPU (north_star; B200_PROFILING.md)
 
 
@@ -325,6 +326,16 @@ def run_b200(args):
         ach = bytes_per_launch / (tms / nl * 1e-3) / 1e9
         tpp, tsrc = measured_traffic(dom, nx, ny, nz, world)
         traffic = tpp * (ny + 3) * 3 * args.steps / nl if (tpp and dom in ("zfwd", "xpass", "zbwd")) else None
+        # the x-pass is bound by the FP64 pipe and the shared-memory crossbar, not by HBM: report its
+        # nominal FFT flops (5 M log2 M per complex transform of the half-length M = nxd, 3 c2r + 6 r2c per z-line,
+        # plus ~10 flops per point and transform for the split / merge passes) against the measured FP64 ceiling
+        fp64 = None
+        if "xpass" in kernels:
+            flops_line = 9 * (5.0 * nxd * np.log2(nxd) + 10.0 * nxd) + 12.0 * 2 * nxd
+            lines_step = 3.0 * (nzd / world) * (ny + 3)
+            tf = flops_line * lines_step / (kernels["xpass"]["ms_per_step"] * 1e-3) / 1e12
+            fp64 = {"kernel": "xpass", "nominal_tflops": tf, "peak_tflops": FP64_PEAK_TFLOPS, "frac": tf / FP64_PEAK_TFLOPS,
+                    "peak_source": "chb_measure_device_peaks on B200, profiles/README.md (33.8 TFLOP/s FMA)"}
         out = {
             "metric": "rk3_timesteps_per_s", "value": 1000.0 / ms_per_step, "unit": "steps/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
@@ -339,7 +350,7 @@ def run_b200(args):
                        "device_bytes_per_gpu": ch.device_bytes()},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
                          "frac": ach / peak, "traffic": traffic, "traffic_source": tsrc, "peak_source": peak_src,
-                         "bytes_per_launch": bytes_per_launch, "launches": nl},
+                         "bytes_per_launch": bytes_per_launch, "launches": nl, "fp64": fp64},
             "step_roofline": {"bytes_per_step": step_bytes, "achieved": step_bytes / (ms_per_step * 1e-3) / 1e9,
                               "peak": peak * world, "unit": "GB/s",
                               "frac": step_bytes / (ms_per_step * 1e-3) / 1e9 / (peak * world)},
