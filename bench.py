@@ -333,7 +333,7 @@ def run_b200(args):
         if "xpass" in kernels:
             flops_line = 9 * (5.0 * nxd * np.log2(nxd) + 10.0 * nxd) + 12.0 * 2 * nxd
             lines_step = 3.0 * (nzd / world) * (ny + 3)
-            tf = flops_line * lines_step / (kernels["xpass"]["ms_per_step"] * 1e-3) / 1e12
+            tf = float(flops_line * lines_step / (kernels["xpass"]["ms_per_step"] * 1e-3) / 1e12)
             fp64 = {"kernel": "xpass", "nominal_tflops": tf, "peak_tflops": FP64_PEAK_TFLOPS, "frac": tf / FP64_PEAK_TFLOPS,
                     "peak_source": "chb_measure_device_peaks on B200, profiles/README.md (33.8 TFLOP/s FMA)"}
         out = {
