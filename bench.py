@@ -182,6 +182,87 @@ def measured_peaks():
 
 
 # ---------------------------------------------------------------------------------------------
+def build_report(args, w, nx, ny, nz, nxd, nzd, world, couette, ms_per_step, kern, launches, clocks, e2e_s, vbytes,
+                 dev_bytes, finite, last_line, snap):
+    """The JSON line of the B200 arm from the measurements (pure: no GPU needed, unit-tested on the CPU).
+    kern: {timer name: (total ms over the timed steps, launches)} from chb_timing_report."""
+    dof = 3 * (2 * nx + 1) * (2 * nz + 1) * ny          # README.md:26 convention
+    peak, peak_src = measured_peaks()
+    per, step_bytes = algorithmic_bytes(nx, ny, nz, nxd, nzd)
+    fam = {"zfwd": ["zfwd"], "xpass": ["xpass"], "zbwd": ["zbwd"], "rhs": ["rhs"],
+           "solve": ["solve_s1", "solve_s2", "solve_s3", "solve_s4", "solve"]}
+    total_kernel_ms = sum(v[0] for v in kern.values()) or 1.0
+    kernels = {}
+    for f, names in fam.items():
+        tms = sum(kern[n][0] for n in names if n in kern)
+        if tms <= 0:
+            continue
+        bytes_total = per[f] / world * 3 * args.steps     # per rank, 3 substeps per step
+        kernels[f] = {"ms_per_step": tms / args.steps, "share": tms / total_kernel_ms,
+                      "gbs": bytes_total / (tms * 1e-3) / 1e9,
+                      "frac": bytes_total / (tms * 1e-3) / 1e9 / peak}
+    for n in kern:
+        if n.startswith("solve_"):
+            kernels["solve"].setdefault("parts_ms_per_step", {})[n] = kern[n][0] / args.steps
+        if not any(n in names for names in fam.values()):
+            kernels[n] = {"ms_per_step": kern[n][0] / args.steps, "share": kern[n][0] / total_kernel_ms}
+    dom = max((k for k in kernels if "gbs" in kernels[k]), key=lambda k: kernels[k]["ms_per_step"])
+    nl = sum(kern[n][1] for n in fam[dom] if n in kern)
+    tms = sum(kern[n][0] for n in fam[dom] if n in kern)
+    bytes_per_launch = per[dom] / world * 3 * args.steps / nl
+    ach = bytes_per_launch / (tms / nl * 1e-3) / 1e9
+    tpp, tsrc = measured_traffic(dom, nx, ny, nz, world)
+    traffic = tpp * (ny + 3) * 3 * args.steps / nl if (tpp and dom in ("zfwd", "xpass", "zbwd")) else None
+    # the x-pass is bound by the FP64 pipe and the shared-memory crossbar, not by HBM (DESIGN.md 3): report its
+    # nominal FFT flops (5 M log2 M per complex transform of the half-length M = nxd, 3 c2r + 6 r2c per z-line,
+    # plus ~10 flops per point and transform for the split / merge passes) against the measured FP64 ceiling
+    fp64 = None
+    if "xpass" in kernels:
+        flops_line = 9 * (5.0 * nxd * np.log2(nxd) + 10.0 * nxd) + 12.0 * 2 * nxd
+        lines_step = 3.0 * (nzd / world) * (ny + 3)
+        tf = float(flops_line * lines_step / (kernels["xpass"]["ms_per_step"] * 1e-3) / 1e12)
+        fp64 = {"kernel": "xpass", "nominal_tflops": tf, "peak_tflops": FP64_PEAK_TFLOPS, "frac": tf / FP64_PEAK_TFLOPS,
+                "peak_source": "chb_measure_device_peaks on B200, profiles/README.md (33.8 TFLOP/s FMA)"}
+    out = {
+        "metric": "rk3_timesteps_per_s", "value": 1000.0 / ms_per_step, "unit": "steps/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "ns_per_dof_step": ms_per_step * 1e6 / dof,
+        "config": {"workload": f"{w['name']}: turbulent-channel grid nx,ny,nz={nx},{ny},{nz} "
+                               f"(nxd,nzd={nxd},{nzd}), perturbed laminar "
+                               f"{'Couette+coriolis' if couette else 'Poiseuille, CPI'} field, FP64, cflmax=1",
+                   "dof": dof, "decomposition": f"x-pencils over {world} GPU(s), npy=1",
+                   "l2": "state (%.1f GB/GPU) far larger than the 126 MB L2; no flush needed" % (dev_bytes / 1e9),
+                   "device_bytes_per_gpu": dev_bytes},
+        "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
+                     "frac": ach / peak, "traffic": traffic, "traffic_source": tsrc, "peak_source": peak_src,
+                     "bytes_per_launch": bytes_per_launch, "launches": nl, "fp64": fp64},
+        "step_roofline": {"bytes_per_step": step_bytes, "achieved": step_bytes / (ms_per_step * 1e-3) / 1e9,
+                          "peak": peak * world, "unit": "GB/s",
+                          "frac": step_bytes / (ms_per_step * 1e-3) / 1e9 / (peak * world)},
+        "kernels": kernels,
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "e2e": {"value": args.steps / e2e_s, "unit": "steps/s",
+                "h2d_bytes_per_step": vbytes * world / args.steps,
+                "d2h_bytes_per_step": vbytes * world / args.steps + 8 * 40,
+                "what": "chb_upload_V (pinned Fortran-layout V) + K x (chb_buildrhs/chb_linsolve x3 + "
+                        "chb_get_step_scalars) + chb_download_V, wall clock"},
+        "finite": finite,
+        # Runtimedata line of the last timed step (dnsdata.f90:878): time, dudy at both walls (u, w), flow
+        # rate x, meanpx, flow rate z, meanpz, cfl*deltat, deltat -- laminar values 3, 3, 0, 0, 2 expected
+        "runtimedata_last": [float(v) for v in last_line],
+    }
+    if snap:
+        out["snapshot"] = snap
+    if world > 1:
+        out["nvlink"] = nvlink_report(nx, ny, nz, nzd, world, args.steps, ms_per_step, kern,
+                                      direct=os.environ.get("CHB_P2P", "1") != "0")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -300,78 +381,8 @@ def run_b200(args):
                 os.remove(path)
 
     if rank == 0:
-        peak, peak_src = measured_peaks()
-        per, step_bytes = algorithmic_bytes(nx, ny, nz, nxd, nzd)
-        fam = {"zfwd": ["zfwd"], "xpass": ["xpass"], "zbwd": ["zbwd"], "rhs": ["rhs"],
-               "solve": ["solve_s1", "solve_s2", "solve_s3", "solve_s4", "solve"]}
-        total_kernel_ms = sum(v[0] for v in kern.values()) or 1.0
-        kernels = {}
-        for f, names in fam.items():
-            tms = sum(kern[n][0] for n in names if n in kern)
-            if tms <= 0:
-                continue
-            bytes_total = per[f] / world * 3 * args.steps     # per rank, 3 substeps per step
-            kernels[f] = {"ms_per_step": tms / args.steps, "share": tms / total_kernel_ms,
-                          "gbs": bytes_total / (tms * 1e-3) / 1e9,
-                          "frac": bytes_total / (tms * 1e-3) / 1e9 / peak}
-        for n in kern:
-            if n.startswith("solve_"):
-                kernels["solve"].setdefault("parts_ms_per_step", {})[n] = kern[n][0] / args.steps
-            if not any(n in names for names in fam.values()):
-                kernels[n] = {"ms_per_step": kern[n][0] / args.steps, "share": kern[n][0] / total_kernel_ms}
-        dom = max((k for k in kernels if "gbs" in kernels[k]), key=lambda k: kernels[k]["ms_per_step"])
-        nl = sum(kern[n][1] for n in fam[dom] if n in kern)
-        tms = sum(kern[n][0] for n in fam[dom] if n in kern)
-        bytes_per_launch = per[dom] / world * 3 * args.steps / nl
-        ach = bytes_per_launch / (tms / nl * 1e-3) / 1e9
-        tpp, tsrc = measured_traffic(dom, nx, ny, nz, world)
-        traffic = tpp * (ny + 3) * 3 * args.steps / nl if (tpp and dom in ("zfwd", "xpass", "zbwd")) else None
-        # the x-pass is bound by the FP64 pipe and the shared-memory crossbar, not by HBM: report its
-        # nominal FFT flops (5 M log2 M per complex transform of the half-length M = nxd, 3 c2r + 6 r2c per z-line,
-        # plus ~10 flops per point and transform for the split / merge passes) against the measured FP64 ceiling
-        fp64 = None
-        if "xpass" in kernels:
-            flops_line = 9 * (5.0 * nxd * np.log2(nxd) + 10.0 * nxd) + 12.0 * 2 * nxd
-            lines_step = 3.0 * (nzd / world) * (ny + 3)
-            tf = float(flops_line * lines_step / (kernels["xpass"]["ms_per_step"] * 1e-3) / 1e12)
-            fp64 = {"kernel": "xpass", "nominal_tflops": tf, "peak_tflops": FP64_PEAK_TFLOPS, "frac": tf / FP64_PEAK_TFLOPS,
-                    "peak_source": "chb_measure_device_peaks on B200, profiles/README.md (33.8 TFLOP/s FMA)"}
-        out = {
-            "metric": "rk3_timesteps_per_s", "value": 1000.0 / ms_per_step, "unit": "steps/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "ns_per_dof_step": ms_per_step * 1e6 / dof,
-            "config": {"workload": f"{w['name']}: turbulent-channel grid nx,ny,nz={nx},{ny},{nz} "
-                                   f"(nxd,nzd={nxd},{nzd}), perturbed laminar "
-                                   f"{'Couette+coriolis' if couette else 'Poiseuille, CPI'} field, FP64, cflmax=1",
-                       "dof": dof, "decomposition": f"x-pencils over {world} GPU(s), npy=1",
-                       "l2": "state (%.1f GB/GPU) far larger than the 126 MB L2; no flush needed" % (ch.device_bytes() / 1e9),
-                       "device_bytes_per_gpu": ch.device_bytes()},
-            "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
-                         "frac": ach / peak, "traffic": traffic, "traffic_source": tsrc, "peak_source": peak_src,
-                         "bytes_per_launch": bytes_per_launch, "launches": nl, "fp64": fp64},
-            "step_roofline": {"bytes_per_step": step_bytes, "achieved": step_bytes / (ms_per_step * 1e-3) / 1e9,
-                              "peak": peak * world, "unit": "GB/s",
-                              "frac": step_bytes / (ms_per_step * 1e-3) / 1e9 / (peak * world)},
-            "kernels": kernels,
-            "gpu_launches": launches,
-            "clocks": clocks,
-            "e2e": {"value": args.steps / e2e_s, "unit": "steps/s",
-                    "h2d_bytes_per_step": vbytes * world / args.steps,
-                    "d2h_bytes_per_step": vbytes * world / args.steps + 8 * 40,
-                    "what": "chb_upload_V (pinned Fortran-layout V) + K x (chb_buildrhs/chb_linsolve x3 + "
-                            "chb_get_step_scalars) + chb_download_V, wall clock"},
-            "finite": finite,
-            # Runtimedata line of the last timed step (dnsdata.f90:878): time, dudy at both walls (u, w), flow
-            # rate x, meanpx, flow rate z, meanpz, cfl*deltat, deltat -- laminar values 3, 3, 0, 0, 2 expected
-            "runtimedata_last": [float(v) for v in last_line],
-        }
-        if snap:
-            out["snapshot"] = snap
-        if world > 1:
-            out["nvlink"] = nvlink_report(nx, ny, nz, nzd, world, args.steps, ms_per_step, kern,
-                                          direct=os.environ.get("CHB_P2P", "1") != "0")
+        out = build_report(args, w, nx, ny, nz, nxd, nzd, world, couette, ms_per_step, kern, launches, clocks, e2e_s, vbytes,
+                           ch.device_bytes(), finite, last_line, snap)
         if args.cpu_baseline and world == 1:
             out["cpu_baseline"] = cpu_baseline(w, sample_s=args.cpu_seconds)
         print(json.dumps(out), flush=True)

@@ -242,3 +242,40 @@ def test_cpp_driver_reads_dns_in_and_runtimedata(tmp_path):
     (tmp_path / "dns.in").write_text("\n".join(SHIPPED_DNS_IN.splitlines()[:5]))
     r = subprocess.run([exe, "--dir", str(tmp_path), "--check-input"], capture_output=True, text=True)
     assert r.returncode != 0 and "expected 12 data lines" in r.stderr
+
+
+@pytest.mark.parametrize("world", [1, 2, 8])
+def test_bench_report_assembly(world):
+    """bench.build_report (the JSON line of the B200 arm) from synthetic measurements: every key of the driver
+    contract is there and the numbers are consistent; no GPU involved."""
+    import json, types
+    import bench
+    args = types.SimpleNamespace(steps=4, warmup=3, cpu_baseline=False, cpu_seconds=1.0)
+    w = bench.parse_workload("3")
+    nx, ny, nz, nxd, nzd = 511, 512, 511, 768, 1536
+    ms = 225.8 / world
+    kern = {"zfwd": (21.8 * 4 / world, 60), "xpass": (76.1 * 4 / world, 60), "zbwd": (46.5 * 4 / world, 60),
+            "rhs": (38.1 * 4 / world, 12), "solve_s1": (12.0 * 4 / world, 24), "solve_s2": (16.3 * 4 / world, 24),
+            "solve_s3": (5.9 * 4 / world, 12), "solve_s4": (8.6 * 4 / world, 12), "mean_mode": (13.4 * 4, 12)}
+    if world > 1:
+        kern["p2p_barrier"] = (0.8, 120)
+    out = bench.build_report(args, w, nx, ny, nz, nxd, nzd, world, False, ms, kern, 288 * 4, {"sm_mhz": 1860, "sm_max_mhz": 1965,
+                             "reasons": [], "samples": 9}, 1.39, 3 * 16 * 512 // world * 1023 * 515, 58e9 / world, True,
+                             np.arange(11.0), None)
+    if world > 1:
+        out["nvlink"] = bench.nvlink_report(nx, ny, nz, nzd, world, args.steps, ms, kern, direct=True)
+    line = json.loads(json.dumps(out))
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "roofline", "e2e", "gpu_launches", "clocks"):
+        assert k in line, k
+    assert line["n_gpus"] == world and line["dtype"] == "f64" and "workload" in line["config"] and "model" not in line["config"]
+    assert abs(line["value"] - 1000.0 / ms) < 1e-9 and line["vs_baseline"] is None
+    r = line["roofline"]
+    assert r["bound"] == "hbm" and r["kernel"] == "xpass" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
+    assert 0.3 < r["frac"] < 0.4 and 0.3 < r["fp64"]["frac"] < 0.45          # the measured round-1 numbers: 0.35 and 0.39
+    assert abs(line["step_roofline"]["frac"] - 0.488) < 0.01
+    assert set(line["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"}
+    assert line["kernels"]["solve"]["parts_ms_per_step"]["solve_s2"] == pytest.approx(16.3 / world)
+    assert line["runtimedata_last"] == list(map(float, range(11)))
+    if world > 1:
+        assert line["nvlink"]["zTOx"]["carrier"] == "zfwd" and line["nvlink"]["barrier_ms_per_step"] == pytest.approx(0.2)
