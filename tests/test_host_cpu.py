@@ -279,3 +279,24 @@ def test_bench_report_assembly(world):
     assert line["runtimedata_last"] == list(map(float, range(11)))
     if world > 1:
         assert line["nvlink"]["zTOx"]["carrier"] == "zfwd" and line["nvlink"]["barrier_ms_per_step"] == pytest.approx(0.2)
+
+
+def test_bench_reference_arm_runs_on_the_cpu():
+    """`bench.py --impl reference` (the CPU arm the driver runs next to the B200 arm): one JSON line with the same
+    metric / unit, "impl": "reference", its own cpu_baseline description and a zero-copy e2e."""
+    import json, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--workload", "1", "--steps", "1",
+                        "--warmup", "0", "--cpu-seconds", "1"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "rk3_timesteps_per_s" and d["unit"] == "steps/s" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # other ranks of a torchrun launch exit without work and without output
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2")
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2"], env=env,
+                       capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0 and r.stdout.strip() == ""
