@@ -12,7 +12,7 @@
 static thread_local std::string g_err;
 void chb_set_error(const std::string& s) { g_err = s; }
 extern "C" const char* chb_last_error(void) { return g_err.c_str(); }
-extern "C" int chb_version(void) { return 1000; }
+extern "C" int chb_version(void) { return 1001; }   // 1001: restart files, body-force mask(iy,iz)
 
 #define CHB_REQUIRE(cond, msg)  \
     do {                        \
