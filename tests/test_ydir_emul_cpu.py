@@ -84,6 +84,7 @@ CASES = [
     dict(nx=6, ny=16, nz=5),                                     # smallest: one-and-a-bit checkpoint blocks
     dict(nx=9, ny=41, nz=7, CPI=False, meanflowx=2.0),           # ny-1 a multiple of 8, constant-flow-rate branch
     dict(nx=5, ny=30, nz=4, couette=True),                       # Couette walls + coriolis body force
+    dict(nx=4, ny=24, nz=6, alfa0=0.8, beta0=1.7, a=2.0, ymin=-1.0, ymax=1.0, CPI=True, CPI_type=0, gamma=0.3),   # another box, grid stretching and CPI law
 ]
 
 
