@@ -74,12 +74,12 @@ def test_zpass_threads_per_line_variants(nx, ny, nz, tpl, monkeypatch):
     assert abs(out[tpl][1] - out["0"][1]) <= 1e-13 * out["0"][1]
 
 
-def test_other_box_and_stretching():
-    """A parity case away from the defaults every other test uses: alfa0, beta0, the wall-normal box [-1, 1], the
-    stretching parameter a and the CPI law (type 0).  (Not an experimental kernel; it lives here because it was
+def test_other_wavenumbers_stretching_and_cpi_law():
+    """A parity case away from the defaults every other test uses: alfa0, beta0, the stretching parameter a and the
+    CPI law (type 0); another wall-normal box is covered on the CPU (tests/test_ydir_emul_cpu.py).  (Not an experimental kernel; it lives here because it was
     added when no GPU was left in the round to run it.)"""
-    p, o, ch, V0 = make_pair(19, 40, 13, deltat=0.0, cflmax=0.8, re=1800.0, alfa0=0.8, beta0=1.7, a=2.0, ymin=-1.0,
-                             ymax=1.0, CPI=True, CPI_type=0, gamma=0.3)
+    p, o, ch, V0 = make_pair(19, 40, 13, deltat=0.0, cflmax=0.8, re=1800.0, alfa0=0.8, beta0=1.7, a=2.0,
+                             CPI=True, CPI_type=0, gamma=0.3)
     ch.cfl_prepass(); o.cfl_prepass()
     assert np.allclose(ch.outstats(), o.outstats(), rtol=1e-10, atol=1e-12)
     for i in range(5):
