@@ -242,7 +242,7 @@ class Channel:
         self.set_body_force()
 
     def _am_pieces(self, lambdaz_f):
-        iz_f = int(np.rint((2.0 * np.pi / lambdaz_f) / (self.p.beta0 / 1000.0)))      # am_f1.inc:7
+        iz_f = int(np.floor((2.0 * np.pi / lambdaz_f) / (self.p.beta0 / 1000.0) + 0.5))   # NINT, am_f1.inc:7
         yp = np.where(self.y > 1, self.p.ymax - self.y, self.y) * 1000.0              # am_f1.inc:20
         iz = np.arange(-self.nz, self.nz + 1)
         return iz_f, yp, iz

@@ -42,6 +42,7 @@ def load():
     lib.co_fft_lines.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p]
     lib.co_set_coriolis.argtypes = [C.c_void_p] + [C.c_double] * 3
     lib.co_set_body_force.argtypes = [C.c_void_p]
+    lib.co_set_am.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double]
     lib.co_buildrhs.argtypes = [C.c_void_p, _dp, C.c_int]
     lib.co_linsolve.argtypes = [C.c_void_p, C.c_double]
     lib.co_cfl_prepass.argtypes = [C.c_void_p]
@@ -99,6 +100,11 @@ class COracle:
 
     def set_coriolis(self, omega2, kz_cutoff, y_threshold_bot):
         self.lib.co_set_coriolis(self.h, omega2, kz_cutoff, y_threshold_bot)
+        self.lib.co_set_body_force(self.h)
+
+    def set_am(self, which, lambdaz_f, amp):
+        """which = "am_f1" | "am_butterfly" (body_forces/am_f1/am_f1.inc, am_butterfly/am_butterfly.inc)"""
+        self.lib.co_set_am(self.h, {"am_f1": 2, "am_butterfly": 3}[which], lambdaz_f, amp)
         self.lib.co_set_body_force(self.h)
 
     def cfl_prepass(self):

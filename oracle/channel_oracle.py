@@ -641,7 +641,7 @@ def coriolis_force(omega2: float, kz_cutoff: float, y_threshold_bot: float):
 
 def _am_masks(o: Oracle, lambdaz_f: float):
     """shared pieces of the am hooks: iz_f (config_body_force, am_f1.inc:7) and y+ of every node (:20)."""
-    iz_f = int(np.rint((2.0 * np.pi / lambdaz_f) / (o.beta0 / 1000.0)))
+    iz_f = int(np.floor((2.0 * np.pi / lambdaz_f) / (o.beta0 / 1000.0) + 0.5))   # NINT
     yp = np.where(o.y > 1, o.p.ymax - o.y, o.y) * 1000.0
     return iz_f, yp
 

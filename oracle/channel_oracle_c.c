@@ -164,8 +164,10 @@ typedef struct {
     cplx* wh;                 /* exp(+i pi k / nxd), k=0..nxd */
     int nthreads;
     cplx** work;              /* per-thread FFT work, 3*max(nzd,nxd+1) */
-    /* coriolis body force (body_forces/coriolis/coriolis.inc) */
+    /* body force: 1 = coriolis (body_forces/coriolis/coriolis.inc), 2 = am_f1, 3 = am_butterfly */
     int bodyforce;
+    double am_amp;
+    int am_iz_f;
     double omega2;
     int iz_thr;
     double y_thr_bot, y_thr_top;
@@ -554,20 +556,49 @@ void co_set_coriolis(co_state* st, double omega2, double kz_cutoff, double y_thr
     st->iz_thr = thr < st->nz ? thr : st->nz;
     if (!st->F) st->F = (cplx*)calloc((size_t)3 * (st->nx + 1) * st->nzt * st->nyp, sizeof(cplx));
 }
-void co_set_body_force(co_state* st) { /* coriolis.inc:29-41 */
+/* config_body_force of body_forces/am_f1/am_f1.inc:4-10 and am_butterfly/am_butterfly.inc:4-9; which = 2 | 3 */
+void co_set_am(co_state* st, int which, double lambdaz_f, double amp) {
+    st->bodyforce = which;
+    st->am_amp = amp;
+    st->am_iz_f = (int)lround((2.0 * M_PI / lambdaz_f) / (st->beta0 / 1000.0));
+    if (!st->F) st->F = (cplx*)calloc((size_t)3 * (st->nx + 1) * st->nzt * st->nyp, sizeof(cplx));
+}
+void co_set_body_force(co_state* st) {
     if (!st->bodyforce) return;
+    if (st->bodyforce == 1) { /* coriolis.inc:29-41 */
 #pragma omp parallel for
-    for (int ix = 0; ix <= st->nx; ++ix)
-        for (int iz = -st->iz_thr; iz <= st->iz_thr; ++iz)
-            for (int iy = -1; iy <= st->ny + 1; ++iy) {
-                if (YY(st, iy) <= st->y_thr_bot || YY(st, iy) >= st->y_thr_top) {
-                    for (int c = 1; c <= 2; ++c) {
-                        const int pc = c % 2 + 1;
-                        const int zeichen = 2 * pc - 3;
-                        st->F[IDXV(st, pc - 1, ix, iz + st->nz, iy + 1)] = zeichen * st->omega2 * st->V[IDXV(st, c - 1, ix, iz + st->nz, iy + 1)];
+        for (int ix = 0; ix <= st->nx; ++ix)
+            for (int iz = -st->iz_thr; iz <= st->iz_thr; ++iz)
+                for (int iy = -1; iy <= st->ny + 1; ++iy) {
+                    if (YY(st, iy) <= st->y_thr_bot || YY(st, iy) >= st->y_thr_top) {
+                        for (int c = 1; c <= 2; ++c) {
+                            const int pc = c % 2 + 1;
+                            const int zeichen = 2 * pc - 3;
+                            st->F[IDXV(st, pc - 1, ix, iz + st->nz, iy + 1)] = zeichen * st->omega2 * st->V[IDXV(st, c - 1, ix, iz + st->nz, iy + 1)];
+                        }
                     }
                 }
-            }
+        return;
+    }
+    /* am_f1.inc:13-28 (loop over |iz| <= iz_f, condition lambda_z+ > 2.3 (y+)^2) and am_butterfly.inc:11-29 (all iz,
+     * two boxes); both F = -amp V, the mean mode excluded where the hooks exclude it */
+    const int izlim = st->bodyforce == 2 ? (st->am_iz_f < st->nz ? st->am_iz_f : st->nz) : st->nz;
+#pragma omp parallel for
+    for (int ix = 0; ix <= st->nx; ++ix)
+        for (int iV = 0; iV < 3; ++iV)
+            for (int iz = -izlim; iz <= izlim; ++iz)
+                for (int iy = -1; iy <= st->ny + 1; ++iy) {
+                    const double y = YY(st, iy);
+                    const double yp = (y > 1 ? st->ymax - y : y) * 1000;
+                    int on;
+                    if (st->bodyforce == 2) {
+                        const double lzp = iz == 0 ? 1e10 : 2 * M_PI / (st->beta0 * abs(iz)) * 1000;
+                        on = (lzp > 2.3 * yp * yp) && !(ix == 0 && iz == 0);
+                    } else {
+                        on = (abs(iz) <= st->am_iz_f && yp <= 60 && !(ix == 0 && iz == 0)) || (abs(iz) > st->am_iz_f && yp > 60);
+                    }
+                    if (on) st->F[IDXV(st, iV, ix, iz + st->nz, iy + 1)] = -st->am_amp * st->V[IDXV(st, iV, ix, iz + st->nz, iy + 1)];
+                }
 }
 
 /* dnsdata.f90:611-673.  max_iters < 0: the whole plane loop; otherwise stop after that many

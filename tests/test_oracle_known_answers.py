@@ -8,7 +8,8 @@ import numpy as np
 import pytest
 
 from channel_b200.fields import perturbed_laminar
-from oracle.channel_oracle import DnsIn, Oracle, RK1_rai, RK2_rai, RK3_rai, coriolis_force, padded_sizes
+from oracle.channel_oracle import (DnsIn, Oracle, RK1_rai, RK2_rai, RK3_rai, am_butterfly_force, am_f1_force,
+                                   coriolis_force, padded_sizes)
 from oracle.c_oracle import COracle, fft_lines
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -300,3 +301,24 @@ def test_transform_conventions_match_the_references_plane_ift():
         for k, (a, b) in enumerate(pairs):
             P = Ex @ (phys[a] * phys[b] * o.factor) @ Ez
             assert np.abs(P - ref[k, iy]).max() <= 1e-13 * max(1e-30, np.abs(ref[k]).max()), (iy, k)
+
+
+@pytest.mark.parametrize("hook", ["am_f1", "am_butterfly"])
+def test_c_and_numpy_restatements_agree_on_the_am_hooks(hook):
+    """body_forces/am_f1/am_f1.inc and am_butterfly/am_butterfly.inc in both restatements (numpy: masks over whole
+    arrays; C: the hooks' own loop nests), three RK3 steps."""
+    nx, ny, nz = 9, 32, 7
+    p = DnsIn(nx=nx, ny=ny, nz=nz, re=1500.0, deltat=2e-3, cflmax=0.0)
+    o = Oracle(p); c = COracle(p)
+    V0 = perturbed_laminar(nx, ny, nz, p.alfa0, p.beta0, eps=1e-2)
+    o.V[:] = V0; c.set_V(V0)
+    o.set_body_force((am_f1_force if hook == "am_f1" else am_butterfly_force)(2000.0, 10.0)); c.set_am(hook, 2000.0, 10.0)
+    o.cfl_prepass(); c.cfl_prepass()
+    assert np.allclose(o.outstats(), c.outstats(), rtol=1e-12, atol=1e-13)
+    for _ in range(3):
+        lo = o.step(); lc = c.step()
+        assert np.allclose(lo, lc, rtol=1e-9, atol=1e-11)
+    Vc = c.get_V()
+    for k in range(3):
+        assert rel(Vc[k], o.V[k]) < 1e-11
+    assert np.abs(o.F).max() > 0
