@@ -38,6 +38,8 @@ SYMBOLS = {
     "chb_cfl_prepass": (C.c_int, [C.c_void_p]),
     "chb_set_body_force_linear": (C.c_int, [C.c_void_p, C.c_int, c_double_p, c_double_p, c_double_p, C.c_int]),
     "chb_set_body_force_linear_yz": (C.c_int, [C.c_void_p, C.c_int, c_double_p, c_double_p, C.c_int]),
+    "chb_upload_F": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "chb_download_F": (C.c_int, [C.c_void_p, C.c_void_p]),
     "chb_set_body_force": (C.c_int, [C.c_void_p]),
     "chb_buildrhs": (C.c_int, [C.c_void_p, c_double_p, C.c_double, C.c_int]),
     "chb_linsolve": (C.c_int, [C.c_void_p, C.c_double]),

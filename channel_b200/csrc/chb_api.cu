@@ -398,6 +398,20 @@ extern "C" int chb_upload_V(chb_handle h, const double* V) { return transfer_V(h
 extern "C" int chb_download_V(chb_handle h, double* V) { return transfer_V(h, V, false, true, h ? h->V : nullptr); }
 extern "C" int chb_upload_V_planes(chb_handle h, const double* V) { return transfer_V(h, const_cast<double*>(V), true, false, h ? h->V : nullptr); }
 extern "C" int chb_download_V_planes(chb_handle h, double* V) { return transfer_V(h, V, false, false, h ? h->V : nullptr); }
+// Generic body-force path (chb_set_body_force_host): the caller evaluates its own set_body_force hook
+// on the host (chb_download_V, its Fortran code) and hands the result over; chb_set_body_force is then a no-op and
+// buildrhs uses F as it is (ghost extension dnsdata.f90:616-629 included).  Host layout = Fortran F(-1:ny+1,-nz:nz,nx0:nxN,1:3).
+extern "C" int chb_upload_F(chb_handle h, const double* F) {
+    CHB_REQUIRE(h && F, "chb_upload_F: null argument");
+    CHB_CUDA_OK(cudaSetDevice(h->device));
+    if (!h->F && dev_alloc(&h->F, (size_t)3 * h->g.nyp * h->g.M)) return 1;
+    h->bf.enabled = 2;   // external: chb_set_body_force does not recompute F
+    return transfer_V(h, const_cast<double*>(F), true, true, h->F);
+}
+extern "C" int chb_download_F(chb_handle h, double* F) {
+    CHB_REQUIRE(h && h->F, "chb_download_F: body force not enabled");
+    return transfer_V(h, F, false, true, h->F);
+}
 extern "C" int chb_download_F_planes(chb_handle h, double* F) {
     CHB_REQUIRE(h && h->F, "chb_download_F_planes: body force not enabled");
     return transfer_V(h, F, false, false, h->F);
@@ -486,7 +500,7 @@ extern "C" int chb_set_body_force_linear_yz(chb_handle h, int enable, const doub
 }
 extern "C" int chb_set_body_force(chb_handle h) {
     CHB_REQUIRE(h, "null handle");
-    if (!h->bf.enabled) return 0;
+    if (!h->bf.enabled || h->bf.enabled == 2) return 0;   // 2: F comes from the host (chb_upload_F)
     CHB_CUDA_OK(cudaSetDevice(h->device));
     launch_body_force(h);
     CHB_CUDA_OK(cudaGetLastError());

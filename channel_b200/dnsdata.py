@@ -262,6 +262,18 @@ class Channel:
         mask = (inner & (yp <= 60)[:, None]) | (~inner & (yp > 60)[:, None])
         self.config_body_force_linear_yz(-amp * np.eye(3), mask.astype(np.float64), exclude_mean=True)
 
+    def upload_F_fortran(self, Ff):
+        """generic body-force path: F evaluated on the host, Fortran layout [c][ix][iz][iy] (chb_upload_F)"""
+        Ff = np.ascontiguousarray(Ff, dtype=np.complex128)
+        assert Ff.shape == (3, self.nxB, 2 * self.nz + 1, self.ny + 3)
+        _lib.check(self.lib.chb_upload_F(self.h, Ff.ctypes.data), "chb_upload_F")
+        self.bodyforce = True
+
+    def download_F_fortran(self):
+        Ff = np.empty((3, self.nxB, 2 * self.nz + 1, self.ny + 3), np.complex128)
+        _lib.check(self.lib.chb_download_F(self.h, Ff.ctypes.data), "chb_download_F")
+        return Ff
+
     def set_body_force(self):
         _lib.check(self.lib.chb_set_body_force(self.h), "chb_set_body_force")
 

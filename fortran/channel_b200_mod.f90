@@ -98,6 +98,12 @@ MODULE channel_b200
       REAL(C_DOUBLE) :: A(9), mask_yz(*)      ! mask_yz(iz+nz+1 + (2nz+1)*(iy+1)): row-major (iy, iz)
       INTEGER(C_INT) :: rc
     END FUNCTION
+    FUNCTION chb_upload_F(h, F) BIND(C, name="chb_upload_F") RESULT(rc)   ! F(-1:ny+1,-nz:nz,nx0:nxN,1:3) from a host-side hook
+      IMPORT :: C_PTR, C_INT, C_DOUBLE_COMPLEX
+      TYPE(C_PTR), VALUE :: h
+      COMPLEX(C_DOUBLE_COMPLEX) :: F(*)
+      INTEGER(C_INT) :: rc
+    END FUNCTION
     FUNCTION chb_set_body_force(h) BIND(C, name="chb_set_body_force") RESULT(rc)
       IMPORT :: C_PTR, C_INT
       TYPE(C_PTR), VALUE :: h

@@ -113,6 +113,12 @@ int chb_set_body_force_linear(chb_handle h, int enable, const double* A, const d
  * am_butterfly.inc:11-29: two boxes).  Replaces a separable mask set before, and vice versa. */
 int chb_set_body_force_linear_yz(chb_handle h, int enable, const double* A, const double* mask_yz,
                                  int exclude_mean);
+/* Generic path for arbitrary set_body_force hooks that are not masked linear maps: the caller evaluates its hook on
+ * the host (chb_download_V, its own code) and uploads the result before chb_buildrhs; chb_set_body_force is then a
+ * no-op.  Host layout = Fortran F(-1:ny+1,-nz:nz,nx0:nxN,1:3); chb_download_F returns the field in the same layout
+ * (Force.cart.<n>.out, dnsdata.f90:905-906).  Slow by construction (two PCIe crossings per RK substep). */
+int chb_upload_F(chb_handle h, const double* F_host);
+int chb_download_F(chb_handle h, double* F_host);
 /* set_body_force() call sites channel.f90:129-131,142-144,155-157. */
 int chb_set_body_force(chb_handle h);
 

@@ -89,3 +89,32 @@ def test_other_wavenumbers_stretching_and_cpi_law():
     for c in range(3):
         assert relerr(Vg[c], o.V[c]) < 1e-10
     ch.close()
+
+
+def test_host_side_body_force_hook_matches_device_path():
+    """chb_upload_F: a set_body_force hook evaluated on the host (here the coriolis hook in numpy on the downloaded
+    Fortran-layout field) gives the same run as the masked linear device path."""
+    from channel_b200 import RK2_rai, RK3_rai
+    p, o, ch, V0 = make_pair(15, 32, 10, deltat=2e-3, cflmax=0.0, re=1500.0, couette=True, CPI=False, u0=-1.0, uN=1.0)
+    p2, o2, ch2, _ = make_pair(15, 32, 10, deltat=2e-3, cflmax=0.0, re=1500.0, couette=True, CPI=False, u0=-1.0, uN=1.0)
+    ch.config_coriolis(0.02, 9999999.0, 1.0)
+    ymask = (ch.y <= 1.0) | (ch.y >= p.ymax - 1.0)
+    Ff = np.zeros((3, ch2.nxB, 2 * p.nz + 1, p.ny + 3), complex)
+
+    def host_hook():                                  # body_forces/coriolis/coriolis.inc:29-41 on the host
+        Vf = ch2.download_V_fortran()
+        Ff[0][..., ymask] = -0.02 * Vf[1][..., ymask]
+        Ff[1][..., ymask] = 0.02 * Vf[0][..., ymask]
+        ch2.upload_F_fortran(Ff)
+
+    host_hook()
+    for c in (ch, ch2):
+        c.cfl_prepass(); c.outstats()
+    for _ in range(2):
+        for k, RK in enumerate((RK1_rai, RK2_rai, RK3_rai)):
+            ch.set_body_force(); host_hook()
+            for c in (ch, ch2):
+                c.buildrhs(RK, k == 2); c.linsolve(RK[0] / c.deltat)
+    assert np.array_equal(ch.download_V(), ch2.download_V())
+    assert np.array_equal(ch.download_F(), np.transpose(ch2.download_F_fortran(), (0, 3, 1, 2)))
+    ch.close(); ch2.close()
