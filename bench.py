@@ -254,6 +254,13 @@ def build_report(args, w, nx, ny, nz, nxd, nzd, world, couette, ms_per_step, ker
         # rate x, meanpx, flow rate z, meanpz, cfl*deltat, deltat -- laminar values 3, 3, 0, 0, 2 expected
         "runtimedata_last": [float(v) for v in last_line],
     }
+    if world > 1:
+        # with P > 1 the step is bounded by max(HBM time, NVLink time), both per GPU
+        nv_total, _, _ = nvlink_bytes_per_gpu_step(nx, ny, nz, nzd, world)
+        t_hbm = step_bytes / world / (peak * 1e9) * 1e3
+        t_nvl = nv_total / (NVLINK_PEAK_GBS * 1e9) * 1e3
+        out["step_roofline"].update({"hbm_ms": t_hbm, "nvlink_ms": t_nvl, "roofline_ms": max(t_hbm, t_nvl),
+                                     "frac_of_max_hbm_nvlink": max(t_hbm, t_nvl) / ms_per_step})
     if snap:
         out["snapshot"] = snap
     if world > 1:

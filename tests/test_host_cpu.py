@@ -279,6 +279,10 @@ def test_bench_report_assembly(world):
     assert line["runtimedata_last"] == list(map(float, range(11)))
     if world > 1:
         assert line["nvlink"]["zTOx"]["carrier"] == "zfwd" and line["nvlink"]["barrier_ms_per_step"] == pytest.approx(0.2)
+        sr = line["step_roofline"]
+        assert sr["roofline_ms"] == max(sr["hbm_ms"], sr["nvlink_ms"]) and 0 < sr["frac_of_max_hbm_nvlink"] < 1
+        if world == 8:
+            assert sr["nvlink_ms"] > sr["hbm_ms"]          # NVLink overtakes HBM from P = 4 on
 
 
 def test_bench_reference_arm_runs_on_the_cpu():
