@@ -187,6 +187,9 @@ extern "C" int chb_create(chb_handle* out, int nx, int ny, int nz, int nxd, int 
         h->zf_direct = e ? atoi(e) : 0;
         e = getenv("CHB_Z_TPL");
         h->z_tpl = e ? atoi(e) : 0;
+        e = getenv("CHB_RHS_CHUNKED");
+        h->rhs_chunked = e ? atoi(e) : 0;
+        h->rhs_state = nullptr;
         e = getenv("CHB_XPASS_SPLIT");
         h->xpass_split = e ? atoi(e) : 0;
         // x tiles of the work buffers (transpose_index.h): products 8 wide (128-byte store segments in
@@ -271,6 +274,7 @@ extern "C" int chb_create(chb_handle* out, int nx, int ny, int nz, int nxd, int 
         dev_alloc(&h->t_d2, (size_t)g.nyp * 5) || dev_alloc(&h->t_d4, (size_t)g.nyp * 5) ||
         dev_alloc(&h->t_D0mat, (size_t)(ny + 1) * 5) || dev_alloc(&h->t_rows, (size_t)g.nyp * 25) || dev_alloc(&h->mean_scratch, (size_t)(ny + 1) * 5 + g.nyp + 8))
         return 1;
+    if (h->rhs_chunked && dev_alloc(&h->rhs_state, (size_t)32 * g.M)) return 1;
     if (dev_alloc(&h->sc, 1)) return 1;
     CHB_CUDA_OK(cudaMallocHost((void**)&h->sc_host, sizeof(DevScalars)));
     memset(h->sc_host, 0, sizeof(DevScalars));
@@ -292,6 +296,7 @@ extern "C" int chb_destroy(chb_handle h) {
     chb_nccl_destroy(h);
     cudaFree(h->V); cudaFree(h->rhs); cudaFree(h->oldrhs); cudaFree(h->P); cudaFree(h->ckpt);
     if (h->F) cudaFree(h->F);
+    if (h->rhs_state) cudaFree(h->rhs_state);
     if (h->p2p) chb_p2p_teardown(h);
     for (int L = 0; L < h->nlanes; ++L) {
         Lane& ln = h->lane[L];
@@ -508,7 +513,9 @@ extern "C" int chb_set_body_force(chb_handle h) {
 }
 
 // ---- the hot path ----------------------------------------------------------------------------
-static int convolutions_all(chb_handle h, int compute_cfl, bool products) {
+// rhs_ode != null (chunked RHS assembly, experimental): after the backward z pass of every chunk the plane loop of
+// buildrhs runs for that chunk's planes on the main stream, concurrently with the next chunk's passes on the lane stream
+static int convolutions_all(chb_handle h, int compute_cfl, bool products, const double* rhs_ode = nullptr, double rhs_deltat = 0.0) {
     const Geometry& g = h->g;
     const int np = h->chunk_planes;
     // fork: the lanes start after everything queued on the main stream (V complete)
@@ -524,6 +531,12 @@ static int convolutions_all(chb_handle h, int compute_cfl, bool products) {
         // xTOz, mpi_transpose.f90:88-117; in direct mode the barrier also frees Ar for the next chunk
         if ((products || h->p2p) && chb_exchange(h, false)) return 1;
         if (products) launch_zbwd(h, p0, n);
+        if (products && rhs_ode) {
+            Lane& ln = h->lane[h->cur_lane];
+            CHB_CUDA_OK(cudaEventRecord(ln.done, ln.stream));
+            CHB_CUDA_OK(cudaStreamWaitEvent(h->stream, ln.done, 0));
+            launch_rhs_chunk(h, rhs_ode, rhs_deltat, p0, n, h->stream);
+        }
     }
     // join
     for (int L = 0; L < h->nlanes; ++L) {
@@ -548,8 +561,12 @@ extern "C" int chb_buildrhs(chb_handle h, const double* ode, double deltat, int 
     CHB_REQUIRE(deltat > 0.0, "chb_buildrhs: deltat must be > 0");
     CHB_CUDA_OK(cudaSetDevice(h->device));
     if (h->bf.enabled) launch_force_ghosts(h);
-    if (convolutions_all(h, compute_cfl, true)) return 1;
-    launch_rhs(h, ode, deltat);
+    if (h->rhs_chunked) {
+        if (convolutions_all(h, compute_cfl, true, ode, deltat)) return 1;
+    } else {
+        if (convolutions_all(h, compute_cfl, true)) return 1;
+        launch_rhs(h, ode, deltat);
+    }
     CHB_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -112,6 +112,8 @@ struct chb_handle_s {
     int use_fft3;         // register-resident three-stage FFT kernels for the large sizes (CHB_FFT3=0 disables)
     int zf_direct;        // CHB_ZF_DIRECT=1: zfwd4 stage A reads global memory directly (no TMA staging); experimental
     int z_tpl;            // CHB_Z_TPL=128|96: threads per line of the z passes at nzd = 1536 / 3072 (default 64); experimental
+    int rhs_chunked;      // CHB_RHS_CHUNKED=1: rhs_kernel per chunk of planes right after its zbwd; experimental
+    double* rhs_state;    // [32][M] accumulators carried between the chunks
     int xpass_split;      // CHB_XPASS_SPLIT=1: xpass5 (two threads per innermost butterfly position) at nxd = 1536; experimental
     cplx* A;        // NCCL mode only: send buffer of zTOx, [peer][3][np][nzB][nxB]
     cplx* Ar;       // z-padded velocity after zTOx, [src rank][3][np][nzB][nxB]
@@ -159,6 +161,7 @@ bool launch_z3_fwd_or_bwd(chb_handle_s* h, int plane0, int nplanes, bool fwd);
 bool launch_x3_pass(chb_handle_s* h, int plane0, int nplanes, int compute_cfl);
 // ---- rhs_kernel.cu ----
 void launch_rhs(chb_handle_s* h, const double* ode, double deltat);
+void launch_rhs_chunk(chb_handle_s* h, const double* ode, double deltat, int plane0, int nplanes, cudaStream_t st);
 // ---- solve_kernels.cu ----
 void launch_linsolve(chb_handle_s* h, double lambda);
 void launch_meanflow_prepass(chb_handle_s* h);

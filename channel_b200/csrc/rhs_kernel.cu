@@ -28,11 +28,15 @@ struct RhsAcc {
 
 // MINB = resident blocks per SM the register allocation is sized for: 3 = 152 registers, no spills;
 // 4 = 128 registers, 16 warps per SM, 56-96 bytes of spills (CHB_RHS_MINB)
-template <bool HAS_F, int MINB>
+// CHUNKED (experimental, CHB_RHS_CHUNKED=1): the march covers the input planes ip0..ip1 only and carries the four
+// partially accumulated output planes to the next launch through `state` ([32][M] doubles), so that the plane loop
+// of buildrhs can follow the convolutions chunk by chunk (and run under the transposes of the next chunk) instead
+// of waiting for all planes.  Same operations in the same order: bit-identical to the single march.
+template <bool HAS_F, int MINB, bool CHUNKED = false>
 __global__ void __launch_bounds__(RHS_THREADS, MINB)
 rhs_kernel(const cplx* __restrict__ V, const cplx* __restrict__ P, const cplx* __restrict__ F, cplx* __restrict__ rhs,
            cplx* __restrict__ oldrhs, Geometry g, DevTables tab, const DevScalars* __restrict__ sc, double ode1_dt,
-           double ode2, double ode3) {
+           double ode2, double ode3, int ip0, int ip1, double* __restrict__ state) {
     const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= g.M) return;
     const int ixl = (int)(m / g.nzt);
@@ -59,8 +63,21 @@ rhs_kernel(const cplx* __restrict__ V, const cplx* __restrict__ P, const cplx* _
         mpx = sc->meanpx;
         mpz = sc->meanpz;
     }
+    if constexpr (CHUNKED) {
+        if (ip0 > -1) {   // resume: the four output planes ip0-2 .. ip0+1 are partially accumulated
+            const double* st = state + m;
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                acc[s].ev = make_double2(st[(8 * s + 0) * plane], st[(8 * s + 1) * plane]);
+                acc[s].ee = make_double2(st[(8 * s + 2) * plane], st[(8 * s + 3) * plane]);
+                acc[s].lv = make_double2(st[(8 * s + 4) * plane], st[(8 * s + 5) * plane]);
+                acc[s].le = make_double2(st[(8 * s + 6) * plane], st[(8 * s + 7) * plane]);
+            }
+        }
+    }
+    const int ip_first = CHUNKED ? ip0 : -1, ip_last = CHUNKED ? ip1 : ny + 1;
 
-    for (int ip = -1; ip <= ny + 1; ++ip) {
+    for (int ip = ip_first; ip <= ip_last; ++ip) {
         const size_t off = (size_t)(ip + 1) * plane + m;
         const cplx p1 = P[0 * comp + off], p2 = P[1 * comp + off], p3 = P[2 * comp + off];
         const cplx p4 = P[3 * comp + off], p5 = P[4 * comp + off], p6 = P[5 * comp + off];
@@ -155,10 +172,34 @@ rhs_kernel(const cplx* __restrict__ V, const cplx* __restrict__ P, const cplx* _
         for (int s = 0; s < 4; ++s) acc[s] = acc[s + 1];
         acc[4].ev = acc[4].ee = acc[4].lv = acc[4].le = make_double2(0.0, 0.0);
     }
+    if constexpr (CHUNKED) {
+        if (ip1 < ny + 1) {
+            double* st = state + m;
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                st[(8 * s + 0) * plane] = acc[s].ev.x; st[(8 * s + 1) * plane] = acc[s].ev.y;
+                st[(8 * s + 2) * plane] = acc[s].ee.x; st[(8 * s + 3) * plane] = acc[s].ee.y;
+                st[(8 * s + 4) * plane] = acc[s].lv.x; st[(8 * s + 5) * plane] = acc[s].lv.y;
+                st[(8 * s + 6) * plane] = acc[s].le.x; st[(8 * s + 7) * plane] = acc[s].le.y;
+            }
+        }
+    }
 }
 
 
 #ifndef CHB_HOST_EMUL   // tests/host_emul compiles the kernel above with g++ and runs it thread by thread
+// one chunk of input planes [plane0, plane0 + nplanes) (plane index = iy + 1), on stream `st`; chunks must be
+// launched in ascending order on the same stream (the carried accumulators)
+void launch_rhs_chunk(chb_handle_s* h, const double* ode, double deltat, int plane0, int nplanes, cudaStream_t st) {
+    const Geometry& g = h->g;
+    const int blocks = (int)((g.M + RHS_THREADS - 1) / RHS_THREADS);
+    ScopedKernelTimer tm(h, "rhs", st);
+    auto kern = h->bf.enabled ? rhs_kernel<true, 3, true> : rhs_kernel<false, 3, true>;
+    kern<<<blocks, RHS_THREADS, 0, st>>>(h->V, h->P, h->bf.enabled ? h->F : nullptr, h->rhs, h->oldrhs, g, h->tab, h->sc,
+                                         ode[0] / deltat, ode[1], ode[2], plane0 - 1, plane0 + nplanes - 2, h->rhs_state);
+    h->launches++;
+}
+
 void launch_rhs(chb_handle_s* h, const double* ode, double deltat) {
     const Geometry& g = h->g;
     const int blocks = (int)((g.M + RHS_THREADS - 1) / RHS_THREADS);
@@ -167,7 +208,7 @@ void launch_rhs(chb_handle_s* h, const double* ode, double deltat) {
     auto kern = h->bf.enabled ? (minb == 4 ? rhs_kernel<true, 4> : rhs_kernel<true, 3>)
                               : (minb == 4 ? rhs_kernel<false, 4> : rhs_kernel<false, 3>);
     kern<<<blocks, RHS_THREADS, 0, h->stream>>>(h->V, h->P, h->bf.enabled ? h->F : nullptr, h->rhs, h->oldrhs, g, h->tab,
-                                               h->sc, ode[0] / deltat, ode[1], ode[2]);
+                                               h->sc, ode[0] / deltat, ode[1], ode[2], 0, 0, nullptr);
     h->launches++;
 }
 #endif

@@ -61,7 +61,7 @@ extern "C" {
 //   V [3][nyp][M] (in: u,v,w; out: u,v,w after linsolve), P [6][nyp][M] products, F [3][nyp][M] or null,
 //   oldrhs [2][nyp][M] (in/out), rhs_out [2][nyp][M] (plain flow: the RHS; fused flow: Step1 results).
 // Tables as chb_set_tables receives them.  scal_io: {meanpx, meanpz, meanflowx, meanflowz, gamma, u0, uN,
-// CPI, CPI_type} in; {fr0, fr1, fr2, corrpx, corrpz, meanpx} out.  mode: 0 whole substep, -1 rhs_kernel only.
+// CPI, CPI_type} in; {fr0, fr1, fr2, corrpx, corrpz, meanpx} out.  mode: 0 whole substep, -1 rhs_kernel only, 2 / -2 the same with the chunked rhs march.
 __attribute__((visibility("default"))) int chb_emul_ydir_substep(int nx, int ny, int nz, double alfa0, double beta0, double ni, const double* y,
                           const double* d0, const double* d1, const double* d2, const double* d4,
                           const double* bc5x16, const double* D0mat, double* V, const double* P, const double* F,
@@ -111,8 +111,17 @@ __attribute__((visibility("default"))) int chb_emul_ydir_substep(int nx, int ny,
     const int T = 128, blocks = (int)((g.M + T - 1) / T);
     const double lam = ode1 / deltat;
     {
-        if (F) emulate(rhs_kernel<true, 3>, blocks, T, Vc, Pc, Fc, rc, oc, g, tab, &sc, lam, ode2, ode3);
-        else emulate(rhs_kernel<false, 3>, blocks, T, Vc, Pc, Fc, rc, oc, g, tab, &sc, lam, ode2, ode3);
+        if (mode == 2 || mode == -2) {   // chunked march with carried accumulators: uneven chunks of input planes
+            std::vector<double> state((size_t)32 * g.M, 0.0);
+            const int cuts[5] = {-1, 2, 3, ny / 2, ny + 2};    // chunks [-1,1], [2,2], [3,ny/2-1], [ny/2, ny+1]
+            for (int c = 0; c < 4; ++c) {
+                if (F) emulate(rhs_kernel<true, 3, true>, blocks, T, Vc, Pc, Fc, rc, oc, g, tab, &sc, lam, ode2, ode3, cuts[c], cuts[c + 1] - 1, state.data());
+                else emulate(rhs_kernel<false, 3, true>, blocks, T, Vc, Pc, Fc, rc, oc, g, tab, &sc, lam, ode2, ode3, cuts[c], cuts[c + 1] - 1, state.data());
+            }
+        } else {
+            if (F) emulate(rhs_kernel<true, 3>, blocks, T, Vc, Pc, Fc, rc, oc, g, tab, &sc, lam, ode2, ode3, 0, 0, (double*)nullptr);
+            else emulate(rhs_kernel<false, 3>, blocks, T, Vc, Pc, Fc, rc, oc, g, tab, &sc, lam, ode2, ode3, 0, 0, (double*)nullptr);
+        }
         if (mode < 0) return 0;   // RHS only
         emulate(solve_rows_kernel, (nyp * 5 + 127) / 128, 128, tab, rows.data(), lam, ni, nyp);
         emulate(solve_s1_kernel<0>, blocks, T, rc, ckpt.data(), g, tab, &sc, lam);

@@ -119,7 +119,10 @@ def test_ydir_kernels_match_oracle(emul, case):
         _, _, rhsk, _ = run_substep(emul, o, V0, P, F, old0, ODE, -1)      # rhs_kernel alone
         for c in range(2):
             assert relerr(rhsk[c, sl], rhs_ref[c, sl]) < 1e-12, ("rhs", c)
-        for fused in (0,):
+        _, old_c, rhs_c, _ = run_substep(emul, o, V0, P, F, old0, ODE, -2)     # chunked march: bit-identical
+        _, old_1, _, _ = run_substep(emul, o, V0, P, F, old0, ODE, -1)
+        assert np.array_equal(rhs_c, rhsk) and np.array_equal(old_c, old_1)
+        for fused in (0, 2):
             Vk, oldk, rhsk, sc = run_substep(emul, o, V0, P, F, old0, ODE, fused)
             for c in range(3):
                 assert relerr(Vk[c], o.V[c]) < 1e-12, (fused, "field", c, relerr(Vk[c], o.V[c]))
