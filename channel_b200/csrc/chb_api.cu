@@ -272,7 +272,7 @@ extern "C" int chb_create(chb_handle* out, int nx, int ny, int nz, int nxd, int 
     if (dev_alloc(&h->t_y, (size_t)g.nyp) || dev_alloc(&h->t_dy, (size_t)g.nyp) ||
         dev_alloc(&h->t_d0, (size_t)g.nyp * 5) || dev_alloc(&h->t_d1, (size_t)g.nyp * 5) ||
         dev_alloc(&h->t_d2, (size_t)g.nyp * 5) || dev_alloc(&h->t_d4, (size_t)g.nyp * 5) ||
-        dev_alloc(&h->t_D0mat, (size_t)(ny + 1) * 5) || dev_alloc(&h->t_rows, (size_t)g.nyp * 25) || dev_alloc(&h->mean_scratch, (size_t)(ny + 1) * 5 + g.nyp + 8))
+        dev_alloc(&h->t_D0mat, (size_t)(ny + 1) * 5) || dev_alloc(&h->t_rows, (size_t)g.nyp * 25) || dev_alloc(&h->mean_scratch, (size_t)(ny + 1) * 5 + 3 * g.nyp + 8))
         return 1;
     if (h->rhs_chunked && dev_alloc(&h->rhs_state, (size_t)32 * g.M)) return 1;
     if (dev_alloc(&h->sc, 1)) return 1;

@@ -360,73 +360,99 @@ __device__ void store_wall_columns(cplx* V, DevScalars* sc, const Geometry& g, s
     }
 }
 
-// mean column (0,0) after S2: linsolve_blocking.inc:62-97.  Single thread; scratch holds the
-// factorised eta00mat [ny+1][5] and ucor [ny+3].
-__global__ void mean_mode_kernel(cplx* __restrict__ V, Geometry g, DevTables tab, DevScalars* sc, double lam,
-                                 double* __restrict__ scratch) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    const int ny = g.ny, nz = g.nz;
+// mean column (0,0) after S2: linsolve_blocking.inc:62-97.  One block: the strided accesses to the column (one
+// 16-byte element per plane of M columns) are spread over the threads, the recurrences (factorisation of
+// etamat(0,0), the ucor solve, the three y-integrals, in the reference's order of operations) run on thread 0 over
+// contiguous copies.  scratch: eta00mat [ny+1][5], ucor [ny+3], U [ny+3], W [ny+3].
+#define MEAN_THREADS 128
+__global__ void __launch_bounds__(MEAN_THREADS)
+mean_mode_kernel(cplx* __restrict__ V, Geometry g, DevTables tab, DevScalars* sc, double lam, double* __restrict__ scratch) {
+    if (blockIdx.x != 0) return;
+    const int ny = g.ny, nz = g.nz, nyp = g.nyp;
+    const int tid = threadIdx.x, nth = blockDim.x;
     const size_t plane = (size_t)g.M, comp = (size_t)g.nyp * plane;
     const size_t m00 = (size_t)nz;  // ixl=0, izp=nz
-    double* A = scratch;                       // [ny+1][5]
-    double* ucor = scratch + (size_t)(ny + 1) * 5;  // [ny+3], index iy+1
+    double* A = scratch;                             // [ny+1][5]
+    double* ucor = scratch + (size_t)(ny + 1) * 5;   // [ny+3], index iy+1
+    double* U = ucor + nyp;                          // Re eta -> u(0,0)
+    double* W = U + nyp;                             // Im eta -> w(0,0)
     // V(:,0,0,3) = Im eta ; V(:,0,0,1) = Re eta            :63-64
-    for (int i = 0; i < ny + 3; ++i) {
+    for (int i = tid; i < nyp; i += nth) {
         const cplx e = V[0 * comp + (size_t)i * plane + m00];
         V[2 * comp + (size_t)i * plane + m00] = make_double2(e.y, 0.0);
         V[0 * comp + (size_t)i * plane + m00] = make_double2(e.x, 0.0);
+        U[i] = e.x;
+        W[i] = e.y;
     }
-    // etamat(0,0), factorised again (k2 = 0)
-    LUState st = {0, 0, 0, 0};
-    for (int i = 0; i < 5; ++i) { A[(size_t)(ny - 1) * 5 + i] = 0.0; A[(size_t)ny * 5 + i] = 0.0; }
-    for (int iy = ny - 1; iy >= 1; --iy) {
-        Row5 rv, re;
-        build_rows(tab, iy, 0.0, lam, g.ni, rv, re);
-        if (iy == ny - 1) { fold_top1(re, tab.etanbc, tab.etanp1bc); re.a[3] = re.a[4] = 0.0; }
-        else if (iy == ny - 2) { fold_top2(re, tab.etanbc); re.a[4] = 0.0; }
-        if (iy == 1) fold_bot1(re, tab.eta0bc, tab.eta0m1bc);
-        else if (iy == 2) fold_bot2(re, tab.eta0bc);
-        double inv, u1, u2;
-        lu_row(re, st, inv, u1, u2);
-        double* r = A + (size_t)(iy - 1) * 5;
-        r[0] = st.l1m2; r[1] = st.l1m1; r[2] = inv; r[3] = u1; r[4] = u2;
+    __syncthreads();
+    if (tid == 0) {
+        // etamat(0,0), factorised again (k2 = 0)
+        LUState st = {0, 0, 0, 0};
+        for (int i = 0; i < 5; ++i) { A[(size_t)(ny - 1) * 5 + i] = 0.0; A[(size_t)ny * 5 + i] = 0.0; }
+        for (int iy = ny - 1; iy >= 1; --iy) {
+            Row5 rv, re;
+            build_rows(tab, iy, 0.0, lam, g.ni, rv, re);
+            if (iy == ny - 1) { fold_top1(re, tab.etanbc, tab.etanp1bc); re.a[3] = re.a[4] = 0.0; }
+            else if (iy == ny - 2) { fold_top2(re, tab.etanbc); re.a[4] = 0.0; }
+            if (iy == 1) fold_bot1(re, tab.eta0bc, tab.eta0m1bc);
+            else if (iy == 2) fold_bot2(re, tab.eta0bc);
+            double inv, u1, u2;
+            lu_row(re, st, inv, u1, u2);
+            double* r = A + (size_t)(iy - 1) * 5;
+            r[0] = st.l1m2; r[1] = st.l1m1; r[2] = inv; r[3] = u1; r[4] = u2;
+        }
+        A[0] = A[1] = 0.0;  // rbparmat_blocking.f90:45
+        A[5] = 0.0;
+        // ucor: rhs 1 on rows 1..ny-1                                :65-68
+        for (int i = 0; i < ny + 3; ++i) ucor[i] = 0.0;
+        for (int iy = 1; iy <= ny - 1; ++iy) ucor[iy + 1] = 1.0;
+        for (int iy = ny - 1; iy >= 1; --iy) {
+            const double* r = A + (size_t)(iy - 1) * 5;
+            ucor[iy + 1] = (ucor[iy + 1] - (r[3] * ucor[iy + 2] + r[4] * ucor[iy + 3])) * r[2];
+        }
+        for (int iy = 1; iy <= ny + 1; ++iy) {
+            const double* r = A + (size_t)(iy - 1) * 5;
+            ucor[iy + 1] = ucor[iy + 1] - (r[0] * ucor[iy - 1] + r[1] * ucor[iy]);
+        }
+        {
+            const double* e0bc = tab.eta0bc; const double* e0m1 = tab.eta0m1bc;
+            const double* enbc = tab.etanbc; const double* enp1 = tab.etanp1bc;
+            ucor[1] = -(ucor[2] * e0bc[2] + ucor[3] * e0bc[3] + ucor[4] * e0bc[4]) / e0bc[1];                      // :70
+            ucor[0] = -(ucor[1] * e0m1[1] + ucor[2] * e0m1[2] + ucor[3] * e0m1[3] + ucor[4] * e0m1[4]) / e0m1[0];  // :71
+            ucor[ny + 1] = -(ucor[ny - 2] * enbc[0] + ucor[ny - 1] * enbc[1] + ucor[ny] * enbc[2]) / enbc[3];      // :74
+            ucor[ny + 2] = -(ucor[ny - 2] * enp1[0] + ucor[ny - 1] * enp1[1] + ucor[ny] * enp1[2] + ucor[ny + 1] * enp1[3]) / enp1[4];  // :75
+        }
+        sc->fr[0] = yintegr_dev(tab.y, U, 1, ny, 0);  // :77
+        sc->fr[1] = yintegr_dev(tab.y, W, 1, ny, 0);
+        sc->fr[2] = yintegr_dev(tab.y, ucor, 1, ny, 0);
+        if (fabs(sc->meanflowx) > 1.0e-7 && !sc->CPI) sc->corrpx = (sc->meanflowx - sc->fr[0]) / sc->fr[2];   // :79-82
+        if (fabs(sc->meanflowz) > 1.0e-7 && !sc->CPI) sc->corrpz = (sc->meanflowz - sc->fr[1]) / sc->fr[2];   // :83-86
     }
-    A[0] = A[1] = 0.0;  // rbparmat_blocking.f90:45
-    A[5] = 0.0;
-    // ucor: rhs 1 on rows 1..ny-1                                :65-68
-    for (int i = 0; i < ny + 3; ++i) ucor[i] = 0.0;
-    for (int iy = 1; iy <= ny - 1; ++iy) ucor[iy + 1] = 1.0;
-    for (int iy = ny - 1; iy >= 1; --iy) {
-        const double* r = A + (size_t)(iy - 1) * 5;
-        ucor[iy + 1] = (ucor[iy + 1] - (r[3] * ucor[iy + 2] + r[4] * ucor[iy + 3])) * r[2];
+    __syncthreads();
+    if (fabs(sc->meanflowx) > 1.0e-7 && !sc->CPI) {
+        const double c = sc->corrpx;
+        for (int i = tid; i < nyp; i += nth) {
+            U[i] += c * ucor[i];
+            V[0 * comp + (size_t)i * plane + m00].x = U[i];
+        }
     }
-    for (int iy = 1; iy <= ny + 1; ++iy) {
-        const double* r = A + (size_t)(iy - 1) * 5;
-        ucor[iy + 1] = ucor[iy + 1] - (r[0] * ucor[iy - 1] + r[1] * ucor[iy]);
+    if (fabs(sc->meanflowz) > 1.0e-7 && !sc->CPI) {
+        const double c = sc->corrpz;
+        for (int i = tid; i < nyp; i += nth) {
+            W[i] += c * ucor[i];
+            V[2 * comp + (size_t)i * plane + m00].x = W[i];
+        }
     }
-    {
-        const double* e0bc = tab.eta0bc; const double* e0m1 = tab.eta0m1bc;
-        const double* enbc = tab.etanbc; const double* enp1 = tab.etanp1bc;
-        ucor[1] = -(ucor[2] * e0bc[2] + ucor[3] * e0bc[3] + ucor[4] * e0bc[4]) / e0bc[1];                      // :70
-        ucor[0] = -(ucor[1] * e0m1[1] + ucor[2] * e0m1[2] + ucor[3] * e0m1[3] + ucor[4] * e0m1[4]) / e0m1[0];  // :71
-        ucor[ny + 1] = -(ucor[ny - 2] * enbc[0] + ucor[ny - 1] * enbc[1] + ucor[ny] * enbc[2]) / enbc[3];      // :74
-        ucor[ny + 2] = -(ucor[ny - 2] * enp1[0] + ucor[ny - 1] * enp1[1] + ucor[ny] * enp1[2] + ucor[ny + 1] * enp1[3]) / enp1[4];  // :75
+    __syncthreads();
+    if (tid == 0) {
+        cpi_update(sc, g.ni);
+        for (int i = 0; i < 5; ++i) {   // what outstats reads (dnsdata.f90:866-870)
+            sc->U_lo[i] = U[i];
+            sc->W_lo[i] = W[i];
+            sc->U_hi[i] = U[ny - 2 + i];
+            sc->W_hi[i] = W[ny - 2 + i];
+        }
     }
-    const double* Ucol = reinterpret_cast<const double*>(V + 0 * comp + m00);
-    const double* Wcol = reinterpret_cast<const double*>(V + 2 * comp + m00);
-    sc->fr[0] = yintegr_dev(tab.y, Ucol, 2 * plane, ny, 0);  // :77
-    sc->fr[1] = yintegr_dev(tab.y, Wcol, 2 * plane, ny, 0);
-    sc->fr[2] = yintegr_dev(tab.y, ucor, 1, ny, 0);
-    if (fabs(sc->meanflowx) > 1.0e-7 && !sc->CPI) {            // :79-82
-        sc->corrpx = (sc->meanflowx - sc->fr[0]) / sc->fr[2];
-        for (int i = 0; i < ny + 3; ++i) V[0 * comp + (size_t)i * plane + m00].x += sc->corrpx * ucor[i];
-    }
-    if (fabs(sc->meanflowz) > 1.0e-7 && !sc->CPI) {            // :83-86
-        sc->corrpz = (sc->meanflowz - sc->fr[1]) / sc->fr[2];
-        for (int i = 0; i < ny + 3; ++i) V[2 * comp + (size_t)i * plane + m00].x += sc->corrpz * ucor[i];
-    }
-    cpi_update(sc, g.ni);
-    store_wall_columns(V, sc, g, m00);
 }
 
 // channel.f90:101-115: flow rates of the initial mean profile and CPI meanpx
@@ -466,7 +492,7 @@ void launch_linsolve(chb_handle_s* h, double lam) {
         cudaEventRecord(h->ev_fork, h->stream);
         cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0);
         ScopedKernelTimer tm(h, "mean_mode", h->side_stream);
-        mean_mode_kernel<<<1, 32, 0, h->side_stream>>>(h->V, g, h->tab, h->sc, lam, h->mean_scratch);
+        mean_mode_kernel<<<1, MEAN_THREADS, 0, h->side_stream>>>(h->V, g, h->tab, h->sc, lam, h->mean_scratch);
         h->launches++;
     }
     {

@@ -1,58 +1,29 @@
-// ydir_emul.cpp - test infrastructure: the y-direction CUDA kernels (rhs_kernel.cu, solve_kernels.cu)
-// compiled with g++ and run thread by thread on the CPU.
+// ydir_emul.cpp - test infrastructure: the y-direction CUDA kernels (rhs_kernel.cu, solve_kernels.cu,
+// bodyforce_kernels.cu) compiled with g++ and run on CPU threads (cta_emul.hpp).
 //
 // Those kernels are one thread per wavenumber column with no shared memory, shuffles or atomics, so
 // their source is valid host C++ once the CUDA keywords are neutralised; running it here lets the
 // CPU test suite (-m "not gpu") check the kernel logic (rhs_kernel, solve_s1..s4, mean_mode_kernel)
 // against the numpy oracle without a GPU.  It is a checker only: the product path never loads this library.
-#include <cuda_runtime.h>
+#include "cta_emul.hpp"
 
 #include <cmath>
 #include <cstring>
 #include <vector>
-
-static uint3 e_blockIdx, e_threadIdx;
-static dim3 e_blockDim, e_gridDim;
-#define blockIdx e_blockIdx
-#define threadIdx e_threadIdx
-#define blockDim e_blockDim
-#define gridDim e_gridDim
-template <class T>
-static inline T __ldg(const T* p) { return *p; }
-static inline void __syncthreads() {}
-#undef __launch_bounds__
-#define __launch_bounds__(...)
 
 #define CHB_HOST_EMUL 1
 #include "../../channel_b200/csrc/rhs_kernel.cu"
 #include "../../channel_b200/csrc/solve_kernels.cu"
 #include "../../channel_b200/csrc/bodyforce_kernels.cu"
 
-// run `kern(args...)` for every thread of a (gx, gy) grid of 1-D blocks
-template <class K, class... Args>
-static void emulate2(K kern, int gx, int gy, int threads, Args... args) {
-    e_blockDim = dim3(threads, 1, 1);
-    e_gridDim = dim3(gx, gy, 1);
-    for (int by = 0; by < gy; ++by)
-        for (int bx = 0; bx < gx; ++bx)
-            for (int t = 0; t < threads; ++t) {
-                e_blockIdx = make_uint3(bx, by, 0);
-                e_threadIdx = make_uint3(t, 0, 0);
-                kern(args...);
-            }
-}
-
-// run `kern(args...)` for every thread of a 1-D grid
+// run kern(args...) on a 1-D grid of 1-D blocks (cta_emul.hpp: one OS thread per CUDA thread, real barriers)
 template <class K, class... Args>
 static void emulate(K kern, int blocks, int threads, Args... args) {
-    e_blockDim = dim3(threads, 1, 1);
-    e_gridDim = dim3(blocks, 1, 1);
-    for (int b = 0; b < blocks; ++b)
-        for (int t = 0; t < threads; ++t) {
-            e_blockIdx = make_uint3(b, 0, 0);
-            e_threadIdx = make_uint3(t, 0, 0);
-            kern(args...);
-        }
+    cta_emul::launch(kern, dim3(blocks, 1, 1), threads, args...);
+}
+template <class K, class... Args>
+static void emulate2(K kern, int gx, int gy, int threads, Args... args) {
+    cta_emul::launch(kern, dim3(gx, gy, 1), threads, args...);
 }
 
 extern "C" {
@@ -61,7 +32,7 @@ extern "C" {
 //   V [3][nyp][M] (in: u,v,w; out: u,v,w after linsolve), P [6][nyp][M] products, F [3][nyp][M] or null,
 //   oldrhs [2][nyp][M] (in/out), rhs_out [2][nyp][M] (plain flow: the RHS; fused flow: Step1 results).
 // Tables as chb_set_tables receives them.  scal_io: {meanpx, meanpz, meanflowx, meanflowz, gamma, u0, uN,
-// CPI, CPI_type} in; {fr0, fr1, fr2, corrpx, corrpz, meanpx} out.  mode: 0 whole substep, -1 rhs_kernel only, 2 / -2 the same with the chunked rhs march.
+// CPI, CPI_type} in; {fr0, fr1, fr2, corrpx, corrpz, meanpx} and, from index 10, U_lo, U_hi, W_lo, W_hi (5 each) out; 30 doubles.  mode: 0 whole substep, -1 rhs_kernel only, 2 / -2 the same with the chunked rhs march.
 __attribute__((visibility("default"))) int chb_emul_ydir_substep(int nx, int ny, int nz, double alfa0, double beta0, double ni, const double* y,
                           const double* d0, const double* d1, const double* d2, const double* d4,
                           const double* bc5x16, const double* D0mat, double* V, const double* P, const double* F,
@@ -101,7 +72,7 @@ __attribute__((visibility("default"))) int chb_emul_ydir_substep(int nx, int ny,
 
     const size_t fld = (size_t)nyp * g.M;
     std::vector<double> ckpt((size_t)((ny - 1) / CHB_SOLVE_K + 1) * 8 * g.M, 0.0);
-    std::vector<double> scratch((size_t)(ny + 1) * 5 + nyp + 8, 0.0);
+    std::vector<double> scratch((size_t)(ny + 1) * 5 + 3 * nyp + 8, 0.0);
     cplx* Vc = reinterpret_cast<cplx*>(V);
     const cplx* Pc = reinterpret_cast<const cplx*>(P);
     const cplx* Fc = reinterpret_cast<const cplx*>(F);
@@ -128,12 +99,15 @@ __attribute__((visibility("default"))) int chb_emul_ydir_substep(int nx, int ny,
         emulate(solve_s1_kernel<1>, blocks, T, rc, ckpt.data(), g, tab, &sc, lam);
         emulate(solve_s2_kernel<0>, blocks, T, rc, ckpt.data(), Vc, g, tab, &sc, lam);
         emulate(solve_s2_kernel<1>, blocks, T, rc, ckpt.data(), Vc, g, tab, &sc, lam);
-        emulate(mean_mode_kernel, 1, 32, Vc, g, tab, &sc, lam, scratch.data());
+        emulate(mean_mode_kernel, 1, MEAN_THREADS, Vc, g, tab, &sc, lam, scratch.data());
         emulate(solve_s3_kernel, blocks, T, Vc, g, tab);
         emulate(solve_s4_kernel, blocks, T, Vc, g, tab);
     }
     scal_io[0] = sc.fr[0]; scal_io[1] = sc.fr[1]; scal_io[2] = sc.fr[2];
     scal_io[3] = sc.corrpx; scal_io[4] = sc.corrpz; scal_io[5] = sc.meanpx;
+    for (int i = 0; i < 5; ++i) {   // the wall values outstats reads (dnsdata.f90:866-870)
+        scal_io[10 + i] = sc.U_lo[i]; scal_io[15 + i] = sc.U_hi[i]; scal_io[20 + i] = sc.W_lo[i]; scal_io[25 + i] = sc.W_hi[i];
+    }
     return 0;
 }
 

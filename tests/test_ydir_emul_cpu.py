@@ -36,10 +36,10 @@ def emul():
         pytest.skip("needs g++ and the CUDA headers")
     os.makedirs(BUILD, exist_ok=True)
     so = os.path.join(BUILD, "libydir_emul.so")
-    deps = [SRC] + [os.path.join(HERE, "..", "channel_b200", "csrc", f)
+    deps = [SRC, os.path.join(HERE, "host_emul", "cta_emul.hpp")] + [os.path.join(HERE, "..", "channel_b200", "csrc", f)
                     for f in ("rhs_kernel.cu", "solve_kernels.cu", "bodyforce_kernels.cu", "solve_device.cuh", "chb_internal.h")]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
-        subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-w",
+        subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-w", "-pthread",
                                # the kernels' host names also exist in libchannel_b200.so (loaded RTLD_GLOBAL by
                                # other tests): bind this library's references to its own definitions
                                "-fvisibility=hidden", "-Wl,-Bsymbolic", "-I" + CUDA_INC, "-o", so, SRC])
@@ -70,7 +70,7 @@ def run_substep(lib, o, V, P, F, oldrhs, ODE, fused):
     F = np.ascontiguousarray(F) if F is not None else None
     rhs = np.zeros_like(oldrhs)
     sc = np.array([o.meanpx, o.meanpz, o.meanflowx, o.meanflowz, o.gamma, o.p.u0, o.p.uN,
-                   float(o.CPI), float(o.CPI_type), 0.0])
+                   float(o.CPI), float(o.CPI_type), 0.0] + [0.0] * 20)
     rc = lib.chb_emul_ydir_substep(o.nx, o.ny, o.nz, o.alfa0, o.beta0, o.ni, _dp(y), _dp(d0), _dp(d1), _dp(d2), _dp(d4),
                                    _dp(bc), _dp(D0), _dp(V.view(np.float64)), _dp(P.view(np.float64)),
                                    _dp(F.view(np.float64)) if F is not None else None,
@@ -131,6 +131,10 @@ def test_ydir_kernels_match_oracle(emul, case):
             assert np.allclose(sc[:3], o.fr, rtol=1e-12, atol=1e-15), (fused, sc[:3], o.fr)
             assert abs(sc[3] - o.corrpx) <= 1e-11 * max(1.0, abs(o.corrpx))
             assert abs(sc[5] - mp1[0]) <= 1e-12 * max(1.0, abs(mp1[0]))
+            ny_, nz_ = p.ny, p.nz                      # wall values of the mean column, as outstats reads them
+            for k, ref in ((10, o.V[0, 0:5, 0, nz_].real), (15, o.V[0, ny_ - 2:ny_ + 3, 0, nz_].real),
+                           (20, o.V[2, 0:5, 0, nz_].real), (25, o.V[2, ny_ - 2:ny_ + 3, 0, nz_].real)):
+                assert np.allclose(sc[k:k + 5], ref, rtol=1e-11, atol=1e-13), (fused, k)
         o.meanpx, o.meanpz = mp1
 
 
