@@ -144,4 +144,58 @@ __attribute__((visibility("default"))) int chb_emul_zpass(int fwd, int nxB, int 
     return 0;
 }
 
+// The whole nonlinear term of one plane on P emulated ranks with the direct-store transposes (CHB_P2P=1): rank r owns
+// x-modes [r nxB, (r+1) nxB) and z-lines [r nzB, (r+1) nzB); zfwd of every rank stores into the owners' velocity
+// buffers, xpass of every rank into the owners' product buffers (PeerPtrs = the other ranks' buffers, as CUDA IPC
+// maps them), zbwd reads its own.  nx = 255 (nxd = 384), nz = 255 (nzd = 768), one plane (iy = 1 of ny = 8), the
+// default lines-per-CTA (zfwd 4, zbwd 4) and tile widths chb_create would choose.
+//   V: [P][3][1][nxB][2nz+1] per-rank slabs -> Pout: [P][6][1][nxB][2nz+1]
+__attribute__((visibility("default"))) int chb_emul_convolutions_multi(int P, const double* V, double* Pout) {
+    const int nx = 255, nz = 255, nxd = 384, nzd = 768, np = 1;
+    if ((nx + 1) % P || nzd % P || P > CHB_MAX_RANKS) return 2;
+    const int nxB = (nx + 1) / P, nzB = nzd / P, nzt = 2 * nz + 1;
+    const size_t na = (size_t)3 * np * nzd * nxB, nb = (size_t)6 * np * nzd * nxB, nv = (size_t)np * nxB * nzt;
+    std::vector<std::vector<cplx>> Ar(P, std::vector<cplx>(na)), Br(P, std::vector<cplx>(nb));
+    std::vector<double> Wz = twiddle_table(nzd, nzd), Wx = twiddle_table(nxd, nxd), Wh = twiddle_table(nxd, 2 * nxd);
+    std::vector<double> dy(16, 1.0);
+    auto geom = [&](int r) {
+        Geometry g;
+        memset(&g, 0, sizeof(g));
+        g.nx = nx; g.ny = 8; g.nz = nz; g.nxd = nxd; g.nzd = nzd; g.nyp = np; g.nzt = nzt;
+        g.rank = r; g.nranks = P;
+        chb_decompose(nx + 1, nzd, P, r, &g.nx0, &g.nxN, &g.nz0, &g.nzN);
+        g.nxB = nxB; g.nzB = nzB; g.M = (long long)nxB * nzt;
+        const double PI = 3.1415926535897932384626433832795028841971;
+        g.alfa0 = 0.5; g.beta0 = 1.0; g.dx = PI / (0.5 * nxd); g.dz = 2.0 * PI / nzd; g.factor = 1.0 / (2.0 * nxd * nzd);
+        g.tw = (nxB % 8 == 0) ? 3 : ((nxB % 4 == 0) ? 2 : 0);     // as chb_create
+        g.twa = (P > 1 && nxB % 4 == 0) ? 2 : -1;                  // width of a zfwd CTA (4 lines)
+        return g;
+    };
+    PeerPtrs Aw, Bw;
+    memset(&Aw, 0, sizeof(Aw)); memset(&Bw, 0, sizeof(Bw));
+    for (int q = 0; q < P; ++q) { Aw.p[q] = Ar[q].data(); Bw.p[q] = Br[q].data(); }
+    typedef Fft3<768, 12, 8, 8> GZ;
+    typedef Fft3<384, 12, 8, 4> GX;
+    constexpr int LPC = 4, TPL = 64;
+    int LS = GZ::A * (GZ::BC + 1);
+    while (LS % 8 != 2) ++LS;
+    DevScalars sc;
+    memset(&sc, 0, sizeof(sc));
+    for (int r = 0; r < P; ++r)   // z-pad + backward z FFT + zTOx into the owners' buffers
+        cta_emul::launch(zfwd4_kernel<GZ, LPC, TPL, 4, false>, dim3(nxB / LPC, np, 3), LPC * TPL,
+                         reinterpret_cast<const cplx*>(V) + (size_t)r * 3 * nv, Aw, geom(r), reinterpret_cast<const cplx*>(Wz.data()), 0, np, LS);
+    for (int r = 0; r < P; ++r) { // x pass on the z-lines of rank r, xTOz into the owners' buffers
+        if (P > 1)
+            cta_emul::launch(xpass4_kernel<GX, 1, 6, true>, dim3(nzB, np, 1), GX::N / GX::C, (const cplx*)Ar[r].data(), Bw, geom(r),
+                             reinterpret_cast<const cplx*>(Wx.data()), reinterpret_cast<const cplx*>(Wh.data()), (const double*)dy.data(), &sc, 0, np, 0);
+        else
+            cta_emul::launch(xpass4_kernel<GX, 1, 6, false>, dim3(nzB, np, 1), GX::N / GX::C, (const cplx*)Ar[r].data(), Bw, geom(r),
+                             reinterpret_cast<const cplx*>(Wx.data()), reinterpret_cast<const cplx*>(Wh.data()), (const double*)dy.data(), &sc, 0, np, 0);
+    }
+    for (int r = 0; r < P; ++r)   // forward z FFT + truncation
+        cta_emul::launch(zbwd4_kernel<GZ, LPC, TPL, 4>, dim3(nxB / LPC, np, 6), LPC * TPL, (const cplx*)Br[r].data(),
+                         reinterpret_cast<cplx*>(Pout) + (size_t)r * 6 * nv, geom(r), reinterpret_cast<const cplx*>(Wz.data()), 0, np, LS);
+    return 0;
+}
+
 }  // extern "C"

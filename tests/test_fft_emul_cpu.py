@@ -38,6 +38,8 @@ def emul():
     lib.chb_emul_xpass.restype = C.c_int
     lib.chb_emul_zpass.argtypes = [C.c_int] * 8 + [dp, dp]
     lib.chb_emul_zpass.restype = C.c_int
+    lib.chb_emul_convolutions_multi.argtypes = [C.c_int, dp, dp]
+    lib.chb_emul_convolutions_multi.restype = C.c_int
     return lib
 
 
@@ -125,3 +127,30 @@ def test_zpass_kernels_on_cpu_threads(emul, nz, nzd, lpc):
         assert emul.chb_emul_zpass(0, nxB, nz, nzd, npl, lpc_code, tw, -1, _dp(_tiled(B, tw).view(np.float64)),
                                    _dp(P.view(np.float64))) == 0
         assert np.abs(P - refP).max() <= 1e-13 * np.abs(refP).max(), (tw, np.abs(P - refP).max())
+
+
+@pytest.mark.parametrize("P", [1, 2, 8])
+def test_nonlinear_term_on_emulated_ranks(emul, P):
+    """zfwd -> (direct-store zTOx) -> xpass -> (direct-store xTOz) -> zbwd for one plane on P emulated ranks, each
+    storing straight into the owners' buffers the way the GPUs do over NVLink (mpi_transpose.f90:50-117,214-215):
+    the per-rank products must equal the single-domain numpy result, for every P (transpose invariance)."""
+    nx, nz, nxd, nzd = 255, 255, 384, 768
+    nzt = 2 * nz + 1
+    rng = np.random.default_rng(17)
+    V = rng.standard_normal((3, nx + 1, nzt)) + 1j * rng.standard_normal((3, nx + 1, nzt))
+    Z = np.zeros((3, nx + 1, nzd), complex)
+    Z[..., :nz + 1] = V[..., nz:]; Z[..., nzd - nz:] = V[..., :nz]
+    Z = np.fft.ifft(Z, axis=-1) * nzd
+    X = np.zeros((3, nxd + 1, nzd), complex); X[:, :nx + 1] = Z
+    R = np.fft.irfft(X, n=2 * nxd, axis=1) * (2 * nxd)
+    f = 1.0 / (2.0 * nxd * nzd)
+    pairs = [(0, 0), (1, 1), (2, 2), (0, 1), (1, 2), (0, 2)]
+    Pp = np.stack([R[a] * R[b] * f for a, b in pairs])
+    H = np.fft.fft(np.fft.rfft(Pp, axis=1)[:, :nx + 1], axis=-1)
+    ref = np.concatenate([H[..., nzd - nz:], H[..., :nz + 1]], axis=-1)            # [6][nx+1][2nz+1]
+    nxB = (nx + 1) // P
+    Vr = np.ascontiguousarray(np.stack([V[:, r * nxB:(r + 1) * nxB] for r in range(P)])[:, :, None])   # [P][3][1][nxB][nzt]
+    out = np.zeros((P, 6, 1, nxB, nzt), complex)
+    assert emul.chb_emul_convolutions_multi(P, _dp(Vr.view(np.float64)), _dp(out.view(np.float64))) == 0
+    got = np.concatenate([out[r, :, 0] for r in range(P)], axis=1)
+    assert np.abs(got - ref).max() <= 1e-13 * np.abs(ref).max(), np.abs(got - ref).max() / np.abs(ref).max()
