@@ -187,6 +187,8 @@ extern "C" int chb_create(chb_handle* out, int nx, int ny, int nz, int nxd, int 
         h->zf_direct = e ? atoi(e) : 0;
         e = getenv("CHB_Z_TPL");
         h->z_tpl = e ? atoi(e) : 0;
+        e = getenv("CHB_SOLVE_PF");
+        h->solve_pf = e ? atoi(e) : 0;
         e = getenv("CHB_RHS_CHUNKED");
         h->rhs_chunked = e ? atoi(e) : 0;
         h->rhs_state = nullptr;

@@ -112,6 +112,7 @@ struct chb_handle_s {
     int use_fft3;         // register-resident three-stage FFT kernels for the large sizes (CHB_FFT3=0 disables)
     int zf_direct;        // CHB_ZF_DIRECT=1: zfwd4 stage A reads global memory directly (no TMA staging); experimental
     int z_tpl;            // CHB_Z_TPL=128|96: threads per line of the z passes at nzd = 1536 / 3072 (default 64); experimental
+    int solve_pf;         // CHB_SOLVE_PF=1: S1 / S3 / S4 with eight rows of loads in flight per thread; experimental
     int rhs_chunked;      // CHB_RHS_CHUNKED=1: rhs_kernel per chunk of planes right after its zbwd; experimental
     double* rhs_state;    // [32][M] accumulators carried between the chunks
     int xpass_split;      // CHB_XPASS_SPLIT=1: xpass5 (two threads per innermost butterfly position) at nxd = 1536; experimental

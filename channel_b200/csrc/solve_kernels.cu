@@ -36,7 +36,10 @@ __global__ void solve_rows_kernel(DevTables tab, double* __restrict__ rows, doub
 // COMP = 0: eta equation (etamat), COMP = 1: v equation (D2vmat); blockIdx.y selects nothing, the
 // two components are separate launches of the same grid so that each thread carries one recurrence
 // (half the registers, twice the resident warps).
-template <int COMP>
+// PF (experimental, CHB_SOLVE_PF=1): the loads of the next PF rows are issued before the rows are processed (as S2
+// does with its blocks), so that a thread keeps PF instead of one or two 16-byte loads in flight: for the
+// strong-scaled runs, where a GPU has too few columns to hide the latency with threads alone.
+template <int COMP, int PF = 1>
 __global__ void __launch_bounds__(SOLVE_THREADS)
 solve_s1_kernel(cplx* __restrict__ rhs, double* __restrict__ ckpt, Geometry g, DevTables tab,
                 const DevScalars* __restrict__ sc, double lam) {
@@ -63,11 +66,10 @@ solve_s1_kernel(cplx* __restrict__ rhs, double* __restrict__ ckpt, Geometry g, D
     cplx* __restrict__ col = rhs + COMP * comp + m;
     LUState st = {0, 0, 0, 0};
     cplx x1 = make_double2(0, 0), x2 = x1;  // x(i+1), x(i+2)
-    for (int iy = ny - 1; iy >= 1; --iy) {
+    auto row = [&](int iy, cplx b) {
         Row5 r;
         build_row_poly<COMP>(tab.rows, iy, k2, r);
         const size_t off = (size_t)(iy + 1) * plane;
-        cplx b = col[off];
         if (iy == ny - 1) {
             fold_top1(r, bcn, bcnp1);
             if (COMP == 0) b.x -= r.a[3] * bcn_eta / tab.etanbc[3];  // linsolve_blocking.inc:40
@@ -99,6 +101,18 @@ solve_s1_kernel(cplx* __restrict__ rhs, double* __restrict__ ckpt, Geometry g, D
             double* ck = ckpt + ((size_t)((iy - 1) / SOLVE_K - 1) * 8 + (COMP ? 0 : 4)) * plane + m;
             ck[0 * plane] = st.l1m2; ck[1 * plane] = st.l1m1; ck[2 * plane] = st.l2m2; ck[3 * plane] = st.l2m1;
         }
+    };
+    if constexpr (PF > 1) {
+        for (int i0 = ny - 1; i0 >= 1; i0 -= PF) {
+            cplx bb[PF];
+#pragma unroll
+            for (int k = 0; k < PF; ++k) bb[k] = (i0 - k >= 1) ? col[(size_t)(i0 - k + 1) * plane] : make_double2(0.0, 0.0);
+#pragma unroll
+            for (int k = 0; k < PF; ++k)
+                if (i0 - k >= 1) row(i0 - k, bb[k]);
+        }
+    } else {
+        for (int iy = ny - 1; iy >= 1; --iy) row(iy, col[(size_t)(iy + 1) * plane]);
     }
 }
 
@@ -220,6 +234,7 @@ __device__ __forceinline__ cplx stencil5(const double* c, cplx a0, cplx a1, cplx
 }
 
 // S3: vy (before Step2) -> V comp 3
+template <int PF = 1>
 __global__ void __launch_bounds__(SOLVE_THREADS)
 solve_s3_kernel(cplx* __restrict__ V, Geometry g, DevTables tab) {
     const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -249,7 +264,7 @@ solve_s3_kernel(cplx* __restrict__ V, Geometry g, DevTables tab) {
     }
     cplx x1 = make_double2(0, 0), x2 = x1;
     // window w0..w4 = v(iy-2..iy+2); currently holds ny-3..ny+1 = window of iy = ny-1
-    for (int iy = ny - 1; iy >= 1; --iy) {
+    auto row = [&](int iy) {
         const int ti = (iy + 1) * 5;
         double c[5];
 #pragma unroll
@@ -282,14 +297,33 @@ solve_s3_kernel(cplx* __restrict__ V, Geometry g, DevTables tab) {
         x2 = x1;
         x1 = x;
         out[(size_t)(iy + 1) * plane] = x;
-        // slide the window down
-        w4 = w3; w3 = w2; w2 = w1; w1 = w0;
-        if (iy - 3 >= -1) w0 = VAT(iy - 3);
+    };
+    if constexpr (PF > 1) {
+        for (int i0 = ny - 1; i0 >= 1; i0 -= PF) {
+            cplx nb[PF];   // the values that enter the window after rows i0, i0-1, ...
+#pragma unroll
+            for (int k = 0; k < PF; ++k) nb[k] = (i0 - k >= 1 && i0 - k - 3 >= -1) ? VAT(i0 - k - 3) : make_double2(0.0, 0.0);
+#pragma unroll
+            for (int k = 0; k < PF; ++k)
+                if (i0 - k >= 1) {
+                    row(i0 - k);
+                    w4 = w3; w3 = w2; w2 = w1; w1 = w0;
+                    w0 = nb[k];
+                }
+        }
+    } else {
+        for (int iy = ny - 1; iy >= 1; --iy) {
+            row(iy);
+            // slide the window down
+            w4 = w3; w3 = w2; w2 = w1; w1 = w0;
+            if (iy - 3 >= -1) w0 = VAT(iy - 3);
+        }
     }
 #undef VAT
 }
 
 // S4: Step2 with D0mat, then u,w
+template <int PF = 1>
 __global__ void __launch_bounds__(SOLVE_THREADS)
 solve_s4_kernel(cplx* __restrict__ V, Geometry g, DevTables tab) {
     const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -303,10 +337,8 @@ solve_s4_kernel(cplx* __restrict__ V, Geometry g, DevTables tab) {
     const int ny = g.ny;
     const size_t plane = (size_t)g.M, comp = (size_t)g.nyp * plane;
     cplx b1 = make_double2(0, 0), b2 = b1;
-    for (int iy = -1; iy <= ny + 1; ++iy) {
+    auto row = [&](int iy, cplx vy, const cplx eta) {
         const size_t off = (size_t)(iy + 1) * plane + m;
-        cplx vy = V[2 * comp + off];
-        const cplx eta = V[0 * comp + off];
         if (iy >= 1) {  // rows i=0..ny <-> iy=1..ny+1 (rows ny, ny+1 of D0mat are zero)
             const double* A = tab.D0mat + (size_t)(iy - 1) * 5;
             const double am2 = __ldg(&A[0]), am1 = __ldg(&A[1]);
@@ -323,6 +355,26 @@ solve_s4_kernel(cplx* __restrict__ V, Geometry g, DevTables tab) {
         w.y = (be * vy.x + al * eta.x) * rk2;
         V[0 * comp + off] = u;
         V[2 * comp + off] = w;
+    };
+    if constexpr (PF > 1) {
+        for (int i0 = -1; i0 <= ny + 1; i0 += PF) {
+            cplx vyb[PF], etab[PF];
+#pragma unroll
+            for (int k = 0; k < PF; ++k) {
+                const bool in = i0 + k <= ny + 1;
+                const size_t off = (size_t)(i0 + k + 1) * plane + m;
+                vyb[k] = in ? V[2 * comp + off] : make_double2(0.0, 0.0);
+                etab[k] = in ? V[0 * comp + off] : make_double2(0.0, 0.0);
+            }
+#pragma unroll
+            for (int k = 0; k < PF; ++k)
+                if (i0 + k <= ny + 1) row(i0 + k, vyb[k], etab[k]);
+        }
+    } else {
+        for (int iy = -1; iy <= ny + 1; ++iy) {
+            const size_t off = (size_t)(iy + 1) * plane + m;
+            row(iy, V[2 * comp + off], V[0 * comp + off]);
+        }
     }
 }
 
@@ -474,10 +526,16 @@ void launch_linsolve(chb_handle_s* h, double lam) {
     const int blocks = (int)((g.M + SOLVE_THREADS - 1) / SOLVE_THREADS);
     solve_rows_kernel<<<(g.nyp * 5 + 127) / 128, 128, 0, h->stream>>>(h->tab, h->t_rows, lam, g.ni, g.nyp);
     h->launches++;
+    const bool pf = h->solve_pf != 0;   // experimental: eight rows of loads in flight per thread in S1 / S3 / S4
     {
         ScopedKernelTimer tm(h, "solve_s1");
-        solve_s1_kernel<0><<<blocks, SOLVE_THREADS, 0, h->stream>>>(h->rhs, h->ckpt, g, h->tab, h->sc, lam);
-        solve_s1_kernel<1><<<blocks, SOLVE_THREADS, 0, h->stream>>>(h->rhs, h->ckpt, g, h->tab, h->sc, lam);
+        if (pf) {
+            solve_s1_kernel<0, 8><<<blocks, SOLVE_THREADS, 0, h->stream>>>(h->rhs, h->ckpt, g, h->tab, h->sc, lam);
+            solve_s1_kernel<1, 8><<<blocks, SOLVE_THREADS, 0, h->stream>>>(h->rhs, h->ckpt, g, h->tab, h->sc, lam);
+        } else {
+            solve_s1_kernel<0><<<blocks, SOLVE_THREADS, 0, h->stream>>>(h->rhs, h->ckpt, g, h->tab, h->sc, lam);
+            solve_s1_kernel<1><<<blocks, SOLVE_THREADS, 0, h->stream>>>(h->rhs, h->ckpt, g, h->tab, h->sc, lam);
+        }
     }
     {
         ScopedKernelTimer tm(h, "solve_s2");
@@ -497,11 +555,13 @@ void launch_linsolve(chb_handle_s* h, double lam) {
     }
     {
         ScopedKernelTimer tm(h, "solve_s3");
-        solve_s3_kernel<<<blocks, SOLVE_THREADS, 0, h->stream>>>(h->V, g, h->tab);
+        if (pf) solve_s3_kernel<8><<<blocks, SOLVE_THREADS, 0, h->stream>>>(h->V, g, h->tab);
+        else solve_s3_kernel<1><<<blocks, SOLVE_THREADS, 0, h->stream>>>(h->V, g, h->tab);
     }
     {
         ScopedKernelTimer tm(h, "solve_s4");
-        solve_s4_kernel<<<blocks, SOLVE_THREADS, 0, h->stream>>>(h->V, g, h->tab);
+        if (pf) solve_s4_kernel<8><<<blocks, SOLVE_THREADS, 0, h->stream>>>(h->V, g, h->tab);
+        else solve_s4_kernel<1><<<blocks, SOLVE_THREADS, 0, h->stream>>>(h->V, g, h->tab);
     }
     if (mean_here) {
         cudaEventRecord(h->ev_join, h->side_stream);

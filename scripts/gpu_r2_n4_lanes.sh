@@ -13,5 +13,6 @@ run lanes2 CHB_LANES=2
 run lanes2_w4 CHB_LANES=2 CHB_WORK_GB=4
 run lanes2_w2 CHB_LANES=2 CHB_WORK_GB=2
 run lanes1_w4 CHB_WORK_GB=4
+run solvepf CHB_SOLVE_PF=1
 run rhschunk_w4 CHB_RHS_CHUNKED=1 CHB_WORK_GB=4
 run rhschunk_lanes2_w4 CHB_RHS_CHUNKED=1 CHB_LANES=2 CHB_WORK_GB=4

@@ -19,6 +19,7 @@ run c3_zfdirect 3 CHB_ZF_DIRECT=1
 run c3_ztpl128 3 CHB_Z_TPL=128 CHB_ZF_LPC=2 CHB_ZB_LPC=2
 run c3_ztpl96 3 CHB_Z_TPL=96 CHB_ZF_LPC=2 CHB_ZB_LPC=2
 run c3_zb128_only 3 CHB_Z_TPL=128 CHB_ZB_LPC=2
+run c3_solvepf 3 CHB_SOLVE_PF=1
 run c3_rhschunk 3 CHB_RHS_CHUNKED=1
 run c3_rhschunk_lanes2 3 CHB_RHS_CHUNKED=1 CHB_LANES=2
 run c4shape_default 1023,16,1023 A=1

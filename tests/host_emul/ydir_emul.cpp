@@ -32,7 +32,7 @@ extern "C" {
 //   V [3][nyp][M] (in: u,v,w; out: u,v,w after linsolve), P [6][nyp][M] products, F [3][nyp][M] or null,
 //   oldrhs [2][nyp][M] (in/out), rhs_out [2][nyp][M] (plain flow: the RHS; fused flow: Step1 results).
 // Tables as chb_set_tables receives them.  scal_io: {meanpx, meanpz, meanflowx, meanflowz, gamma, u0, uN,
-// CPI, CPI_type} in; {fr0, fr1, fr2, corrpx, corrpz, meanpx} and, from index 10, U_lo, U_hi, W_lo, W_hi (5 each) out; 30 doubles.  mode: 0 whole substep, -1 rhs_kernel only, 2 / -2 the same with the chunked rhs march.
+// CPI, CPI_type} in; {fr0, fr1, fr2, corrpx, corrpz, meanpx} and, from index 10, U_lo, U_hi, W_lo, W_hi (5 each) out; 30 doubles.  mode: 0 whole substep, -1 rhs_kernel only, 2 / -2 the same with the chunked rhs march, 3 the whole substep with the prefetching S1 / S3 / S4.
 __attribute__((visibility("default"))) int chb_emul_ydir_substep(int nx, int ny, int nz, double alfa0, double beta0, double ni, const double* y,
                           const double* d0, const double* d1, const double* d2, const double* d4,
                           const double* bc5x16, const double* D0mat, double* V, const double* P, const double* F,
@@ -95,13 +95,23 @@ __attribute__((visibility("default"))) int chb_emul_ydir_substep(int nx, int ny,
         }
         if (mode < 0) return 0;   // RHS only
         emulate(solve_rows_kernel, (nyp * 5 + 127) / 128, 128, tab, rows.data(), lam, ni, nyp);
-        emulate(solve_s1_kernel<0>, blocks, T, rc, ckpt.data(), g, tab, &sc, lam);
-        emulate(solve_s1_kernel<1>, blocks, T, rc, ckpt.data(), g, tab, &sc, lam);
+        if (mode == 3) {   // S1 / S3 / S4 with eight rows of loads in flight per thread
+            emulate(solve_s1_kernel<0, 8>, blocks, T, rc, ckpt.data(), g, tab, &sc, lam);
+            emulate(solve_s1_kernel<1, 8>, blocks, T, rc, ckpt.data(), g, tab, &sc, lam);
+        } else {
+            emulate(solve_s1_kernel<0, 1>, blocks, T, rc, ckpt.data(), g, tab, &sc, lam);
+            emulate(solve_s1_kernel<1, 1>, blocks, T, rc, ckpt.data(), g, tab, &sc, lam);
+        }
         emulate(solve_s2_kernel<0>, blocks, T, rc, ckpt.data(), Vc, g, tab, &sc, lam);
         emulate(solve_s2_kernel<1>, blocks, T, rc, ckpt.data(), Vc, g, tab, &sc, lam);
         emulate(mean_mode_kernel, 1, MEAN_THREADS, Vc, g, tab, &sc, lam, scratch.data());
-        emulate(solve_s3_kernel, blocks, T, Vc, g, tab);
-        emulate(solve_s4_kernel, blocks, T, Vc, g, tab);
+        if (mode == 3) {
+            emulate(solve_s3_kernel<8>, blocks, T, Vc, g, tab);
+            emulate(solve_s4_kernel<8>, blocks, T, Vc, g, tab);
+        } else {
+            emulate(solve_s3_kernel<1>, blocks, T, Vc, g, tab);
+            emulate(solve_s4_kernel<1>, blocks, T, Vc, g, tab);
+        }
     }
     scal_io[0] = sc.fr[0]; scal_io[1] = sc.fr[1]; scal_io[2] = sc.fr[2];
     scal_io[3] = sc.corrpx; scal_io[4] = sc.corrpz; scal_io[5] = sc.meanpx;

@@ -122,8 +122,13 @@ def test_ydir_kernels_match_oracle(emul, case):
         _, old_c, rhs_c, _ = run_substep(emul, o, V0, P, F, old0, ODE, -2)     # chunked march: bit-identical
         _, old_1, _, _ = run_substep(emul, o, V0, P, F, old0, ODE, -1)
         assert np.array_equal(rhs_c, rhsk) and np.array_equal(old_c, old_1)
-        for fused in (0, 2):
+        V_default = None
+        for fused in (0, 2, 3):          # 0: default kernels, 2: chunked rhs march, 3: prefetching S1 / S3 / S4
             Vk, oldk, rhsk, sc = run_substep(emul, o, V0, P, F, old0, ODE, fused)
+            if fused == 0:
+                V_default = Vk
+            else:
+                assert np.array_equal(Vk, V_default), fused      # same operations in the same order
             for c in range(3):
                 assert relerr(Vk[c], o.V[c]) < 1e-12, (fused, "field", c, relerr(Vk[c], o.V[c]))
             for c in range(2):

@@ -137,3 +137,18 @@ def test_chunked_rhs_assembly(lanes, monkeypatch):
         ch.close()
     assert np.array_equal(out["1"][0], out["0"][0])
     assert np.array_equal(out["1"][1], out["0"][1])
+
+
+def test_prefetching_solve_sweeps(monkeypatch):
+    """CHB_SOLVE_PF=1: S1 / S3 / S4 issue the loads of the next eight rows before processing them; the arithmetic and
+    its order are unchanged, so the fields are bit-identical to the default kernels."""
+    out = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("CHB_SOLVE_PF", flag)
+        p, o, ch, V0 = make_pair(31, 49, 21, deltat=0.0, cflmax=1.0, re=3000.0)     # ny - 1 = 48 rows, ny + 3 = 52 planes
+        ch.cfl_prepass(); ch.outstats()
+        lines = [ch.step() for _ in range(3)]
+        out[flag] = (ch.download_V(), np.array(lines))
+        ch.close()
+    assert np.array_equal(out["1"][0], out["0"][0])
+    assert np.array_equal(out["1"][1], out["0"][1])
