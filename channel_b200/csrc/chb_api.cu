@@ -140,6 +140,9 @@ void chb_select_lane(chb_handle_s* h, int L) {
 }
 
 // ---- create / destroy ---------------------------------------------------------------------
+static int create_impl(chb_handle_s* h, int nx, int ny, int nz, int nxd, int nzd, double alfa0, double beta0, double ni,
+                       double a, double ymin, double ymax, int rank, int nranks, const char* nccl_id, int device);
+
 extern "C" int chb_create(chb_handle* out, int nx, int ny, int nz, int nxd, int nzd, double alfa0, double beta0,
                           double ni, double a, double ymin, double ymax, int rank, int nranks, const char* nccl_id,
                           int device) {
@@ -155,7 +158,22 @@ extern "C" int chb_create(chb_handle* out, int nx, int ny, int nz, int nxd, int 
     CHB_CUDA_OK(cudaGetDeviceCount(&ndev));
     CHB_REQUIRE(ndev > 0, "chb_create: no CUDA device (this library has no CPU fallback)");
     CHB_CUDA_OK(cudaSetDevice(device));
-    chb_handle_s* h = new chb_handle_s();
+    chb_handle_s* h = new chb_handle_s();   // value-initialised: every pointer, stream and event starts out null
+    h->device = device;
+    const int rc = create_impl(h, nx, ny, nz, nxd, nzd, alfa0, beta0, ni, a, ymin, ymax, rank, nranks, nccl_id, device);
+    if (rc) {   // release whatever was allocated before the failure; keep the error text of the failure
+        const std::string err = g_err;
+        chb_destroy(h);
+        g_err = err;
+        *out = nullptr;
+        return rc;
+    }
+    *out = h;
+    return 0;
+}
+
+static int create_impl(chb_handle_s* h, int nx, int ny, int nz, int nxd, int nzd, double alfa0, double beta0, double ni,
+                       double a, double ymin, double ymax, int rank, int nranks, const char* nccl_id, int device) {
     g_alloc_bytes = 0;
     h->sw0 = h->sw1 = nullptr;
     memset(&h->g, 0, sizeof(h->g));
@@ -285,7 +303,6 @@ extern "C" int chb_create(chb_handle* out, int nx, int ny, int nz, int nxd, int 
     if (h->p2p && chb_p2p_setup(h, 0, 0)) return 1;
     CHB_CUDA_OK(cudaDeviceSynchronize());
     h->dev_bytes = g_alloc_bytes;
-    *out = h;
     return 0;
 }
 
@@ -305,8 +322,8 @@ extern "C" int chb_destroy(chb_handle h) {
         if (ln.A) cudaFree(ln.A);
         if (ln.B) cudaFree(ln.B);
         cudaFree(ln.Ar); cudaFree(ln.Br); cudaFree(ln.flags);
-        cudaEventDestroy(ln.done);
-        cudaStreamDestroy(ln.stream);
+        if (ln.done) cudaEventDestroy(ln.done);
+        if (ln.stream) cudaStreamDestroy(ln.stream);
     }
     cudaFree(h->Wz); cudaFree(h->Wx); cudaFree(h->Wh); cudaFree(h->rev_z);
     cudaFree(h->t_y); cudaFree(h->t_dy); cudaFree(h->t_d0); cudaFree(h->t_d1); cudaFree(h->t_d2); cudaFree(h->t_d4);
@@ -314,10 +331,14 @@ extern "C" int chb_destroy(chb_handle h) {
     if (h->bf.mask_y) cudaFree(h->bf.mask_y);
     if (h->bf.mask_z) cudaFree(h->bf.mask_z);
     if (h->bf.mask_yz) cudaFree(h->bf.mask_yz);
-    cudaFreeHost(h->sc_host);
-    cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join);
-    cudaStreamDestroy(h->side_stream);
-    cudaStreamDestroy(h->stream);
+    if (h->sc_host) cudaFreeHost(h->sc_host);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->sw0) cudaEventDestroy(h->sw0);
+    if (h->sw1) cudaEventDestroy(h->sw1);
+    if (h->side_stream) cudaStreamDestroy(h->side_stream);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    cudaGetLastError();   // a handle torn down half-built must not leave an error behind for the next call
     delete h;
     return 0;
 }
