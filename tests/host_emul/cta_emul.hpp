@@ -67,19 +67,22 @@ void launch(K kern, dim3 grid, int threads, Args... args) {
     pthread_barrier_init(&g_block_barrier, nullptr, threads);
     g_warp_barrier.resize(threads / 32);
     for (auto& b : g_warp_barrier) pthread_barrier_init(&b, nullptr, 32);
-    for (unsigned bz = 0; bz < grid.z; ++bz)
-        for (unsigned by = 0; by < grid.y; ++by)
-            for (unsigned bx = 0; bx < grid.x; ++bx) {
-                std::vector<std::thread> th;
-                th.reserve(threads);
-                for (int t = 0; t < threads; ++t)
-                    th.emplace_back([=]() {
+    // one OS thread per CUDA thread of a block, created once per launch; the blocks of the grid run one after the
+    // other (a barrier between them: shared memory is reused)
+    std::vector<std::thread> th;
+    th.reserve(threads);
+    for (int t = 0; t < threads; ++t)
+        th.emplace_back([=]() {
+            t_threadIdx = make_uint3(t, 0, 0);
+            for (unsigned bz = 0; bz < grid.z; ++bz)
+                for (unsigned by = 0; by < grid.y; ++by)
+                    for (unsigned bx = 0; bx < grid.x; ++bx) {
                         t_blockIdx = make_uint3(bx, by, bz);
-                        t_threadIdx = make_uint3(t, 0, 0);
                         kern(args...);
-                    });
-                for (auto& x : th) x.join();
-            }
+                        pthread_barrier_wait(&g_block_barrier);
+                    }
+        });
+    for (auto& x : th) x.join();
     for (auto& b : g_warp_barrier) pthread_barrier_destroy(&b);
     pthread_barrier_destroy(&g_block_barrier);
 }
