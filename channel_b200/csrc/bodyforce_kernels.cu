@@ -65,16 +65,16 @@ __global__ void force_ghost_kernel(cplx* __restrict__ F, Geometry g, DevTables t
     }
 }
 
-#ifndef CHB_HOST_EMUL   // tests/host_emul compiles the kernels above with g++ and runs them thread by thread
+#if !defined(CHB_HOST_EMUL) || defined(CHB_HOST_EMUL_FULL)   // the kernel-only emulation harnesses (tests/host_emul) stop here
 void launch_body_force(chb_handle_s* h) {
     const Geometry& g = h->g;
     dim3 grid((unsigned)((g.M + 255) / 256), g.nyp);
-    body_force_kernel<<<grid, 256, 0, h->stream>>>(h->V, h->F, g, h->bf);
+    CHB_LAUNCH(grid, 256, 0, h->stream, body_force_kernel)(h->V, h->F, g, h->bf);
     h->launches++;
 }
 void launch_force_ghosts(chb_handle_s* h) {
     const Geometry& g = h->g;
-    force_ghost_kernel<<<(unsigned)((g.M + 255) / 256), 256, 0, h->stream>>>(h->F, g, h->tab);
+    CHB_LAUNCH((unsigned)((g.M + 255) / 256), 256, 0, h->stream, force_ghost_kernel)(h->F, g, h->tab);
     h->launches++;
 }
 #endif

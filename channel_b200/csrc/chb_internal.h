@@ -181,6 +181,16 @@ void chb_select_lane(chb_handle_s* h, int lane);            // makes `lane` the 
 // ---- restart_io.cu ----
 void chb_restart_destroy(chb_handle_s* h);
 
+// Kernel launch.  The device build expands to the <<< >>> syntax; tests/host_emul builds the same sources with g++
+// and routes launches to the CTA emulator (test infrastructure, never part of the product library).  The kernel
+// goes last so that template arguments with commas need no parentheses:
+//   CHB_LAUNCH(grid, block, smem_bytes, stream, kernel<args>)(kernel arguments);
+#ifdef CHB_HOST_EMUL
+#define CHB_LAUNCH(grid, block, smem, stream, ...) cta_emul::launcher(__VA_ARGS__, grid, block)
+#else
+#define CHB_LAUNCH(grid, block, smem, stream, ...) __VA_ARGS__<<<grid, block, smem, stream>>>
+#endif
+
 // timing helpers
 struct ScopedKernelTimer {
     chb_handle_s* h;

@@ -232,7 +232,7 @@ void launch_zfwd(chb_handle_s* h, int plane0, int nplanes) {
     cudaFuncSetAttribute(zfwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dim3 grid((h->g.nxB + tx - 1) / tx, nplanes, 3);
     ScopedKernelTimer tm(h, "zfwd", h->cstream);
-    zfwd_kernel<<<grid, CONV_THREADS, smem, h->cstream>>>(h->V, h->Aw, h->g, h->plan_z, h->Wz, h->rev_z, plane0,
+    CHB_LAUNCH(grid, CONV_THREADS, smem, h->cstream, zfwd_kernel)(h->V, h->Aw, h->g, h->plan_z, h->Wz, h->rev_z, plane0,
                                                          h->chunk_planes, tx, ls);
     h->launches++;
 }
@@ -245,7 +245,7 @@ void launch_zbwd(chb_handle_s* h, int plane0, int nplanes) {
     cudaFuncSetAttribute(zbwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dim3 grid((h->g.nxB + tx - 1) / tx, nplanes, 6);
     ScopedKernelTimer tm(h, "zbwd", h->cstream);
-    zbwd_kernel<<<grid, CONV_THREADS, smem, h->cstream>>>(h->Br, h->P, h->g, h->plan_z, h->Wz, h->rev_z, plane0,
+    CHB_LAUNCH(grid, CONV_THREADS, smem, h->cstream, zbwd_kernel)(h->Br, h->P, h->g, h->plan_z, h->Wz, h->rev_z, plane0,
                                                          h->chunk_planes, tx, ls);
     h->launches++;
 }
@@ -260,7 +260,7 @@ void launch_xpass(chb_handle_s* h, int plane0, int nplanes, int compute_cfl) {
     cudaFuncSetAttribute(xpass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dim3 grid(h->g.nzB / lx, nplanes);
     ScopedKernelTimer tm(h, "xpass", h->cstream);
-    xpass_kernel<<<grid, CONV_THREADS, smem, h->cstream>>>(h->Ar, h->Bw, h->g, h->plan_x, h->Wx, h->Wh, h->t_dy, h->sc,
+    CHB_LAUNCH(grid, CONV_THREADS, smem, h->cstream, xpass_kernel)(h->Ar, h->Bw, h->g, h->plan_x, h->Wx, h->Wh, h->t_dy, h->sc,
                                                           plane0, h->chunk_planes, lx, ls, compute_cfl);
     h->launches++;
 }
@@ -296,7 +296,7 @@ int launch_test_fft(const FftPlan& pl, const cplx* W, const int* rev, cplx* data
     const int grid = (nlines + lpb - 1) / lpb;
 #define RUN(S, DIF)                                                                                          \
     cudaFuncSetAttribute(test_fft_kernel<S, DIF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
-    test_fft_kernel<S, DIF><<<grid, CONV_THREADS, smem>>>(data, pl, W, rev, nlines, lpb, ls)
+    CHB_LAUNCH(grid, CONV_THREADS, smem, 0, test_fft_kernel<S, DIF>)(data, pl, W, rev, nlines, lpb, ls)
     if (sign == 1) { RUN(+1, true); }
     else if (sign == -1) { RUN(-1, true); }
     else if (sign == 2) { RUN(+1, false); }

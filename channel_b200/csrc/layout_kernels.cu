@@ -48,12 +48,12 @@ __global__ void transpose_planes_to_cols(const cplx* __restrict__ src, cplx* __r
 void launch_fortran_to_planes(chb_handle_s* h, const cplx* src, cplx* dst, int, int, int) {
     const long long ncols = h->g.M;
     dim3 grid((unsigned)((ncols + TILE - 1) / TILE), (h->g.nyp + TILE - 1) / TILE), block(TILE, 8);
-    transpose_cols_to_planes<<<grid, block, 0, h->stream>>>(src, dst, ncols, h->g.nyp);
+    CHB_LAUNCH(grid, block, 0, h->stream, transpose_cols_to_planes)(src, dst, ncols, h->g.nyp);
     h->launches++;
 }
 void launch_planes_to_fortran(chb_handle_s* h, const cplx* src, cplx* dst, int, int, int) {
     const long long ncols = h->g.M;
     dim3 grid((unsigned)((ncols + TILE - 1) / TILE), (h->g.nyp + TILE - 1) / TILE), block(TILE, 8);
-    transpose_planes_to_cols<<<grid, block, 0, h->stream>>>(src, dst, ncols, h->g.nyp);
+    CHB_LAUNCH(grid, block, 0, h->stream, transpose_planes_to_cols)(src, dst, ncols, h->g.nyp);
     h->launches++;
 }

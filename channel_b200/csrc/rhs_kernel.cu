@@ -187,7 +187,7 @@ rhs_kernel(const cplx* __restrict__ V, const cplx* __restrict__ P, const cplx* _
 }
 
 
-#ifndef CHB_HOST_EMUL   // tests/host_emul compiles the kernel above with g++ and runs it thread by thread
+#if !defined(CHB_HOST_EMUL) || defined(CHB_HOST_EMUL_FULL)   // the kernel-only emulation harnesses (tests/host_emul) stop here
 // one chunk of input planes [plane0, plane0 + nplanes) (plane index = iy + 1), on stream `st`; chunks must be
 // launched in ascending order on the same stream (the carried accumulators)
 void launch_rhs_chunk(chb_handle_s* h, const double* ode, double deltat, int plane0, int nplanes, cudaStream_t st) {
@@ -195,7 +195,7 @@ void launch_rhs_chunk(chb_handle_s* h, const double* ode, double deltat, int pla
     const int blocks = (int)((g.M + RHS_THREADS - 1) / RHS_THREADS);
     ScopedKernelTimer tm(h, "rhs", st);
     auto kern = h->bf.enabled ? rhs_kernel<true, 3, true> : rhs_kernel<false, 3, true>;
-    kern<<<blocks, RHS_THREADS, 0, st>>>(h->V, h->P, h->bf.enabled ? h->F : nullptr, h->rhs, h->oldrhs, g, h->tab, h->sc,
+    CHB_LAUNCH(blocks, RHS_THREADS, 0, st, kern)(h->V, h->P, h->bf.enabled ? h->F : nullptr, h->rhs, h->oldrhs, g, h->tab, h->sc,
                                          ode[0] / deltat, ode[1], ode[2], plane0 - 1, plane0 + nplanes - 2, h->rhs_state);
     h->launches++;
 }
@@ -207,7 +207,7 @@ void launch_rhs(chb_handle_s* h, const double* ode, double deltat) {
     ScopedKernelTimer tm(h, "rhs");
     auto kern = h->bf.enabled ? (minb == 4 ? rhs_kernel<true, 4> : rhs_kernel<true, 3>)
                               : (minb == 4 ? rhs_kernel<false, 4> : rhs_kernel<false, 3>);
-    kern<<<blocks, RHS_THREADS, 0, h->stream>>>(h->V, h->P, h->bf.enabled ? h->F : nullptr, h->rhs, h->oldrhs, g, h->tab,
+    CHB_LAUNCH(blocks, RHS_THREADS, 0, h->stream, kern)(h->V, h->P, h->bf.enabled ? h->F : nullptr, h->rhs, h->oldrhs, g, h->tab,
                                                h->sc, ode[0] / deltat, ode[1], ode[2], 0, 0, nullptr);
     h->launches++;
 }

@@ -520,27 +520,27 @@ __global__ void meanflow_prepass_kernel(cplx* __restrict__ V, Geometry g, DevTab
     store_wall_columns(V, sc, g, m00);
 }
 
-#ifndef CHB_HOST_EMUL   // tests/host_emul compiles the kernels above with g++ and runs them thread by thread
+#if !defined(CHB_HOST_EMUL) || defined(CHB_HOST_EMUL_FULL)   // the kernel-only emulation harnesses (tests/host_emul) stop here
 void launch_linsolve(chb_handle_s* h, double lam) {
     const Geometry& g = h->g;
     const int blocks = (int)((g.M + SOLVE_THREADS - 1) / SOLVE_THREADS);
-    solve_rows_kernel<<<(g.nyp * 5 + 127) / 128, 128, 0, h->stream>>>(h->tab, h->t_rows, lam, g.ni, g.nyp);
+    CHB_LAUNCH((g.nyp * 5 + 127) / 128, 128, 0, h->stream, solve_rows_kernel)(h->tab, h->t_rows, lam, g.ni, g.nyp);
     h->launches++;
     const bool pf = h->solve_pf != 0;   // experimental: eight rows of loads in flight per thread in S1 / S3 / S4
     {
         ScopedKernelTimer tm(h, "solve_s1");
         if (pf) {
-            solve_s1_kernel<0, 8><<<blocks, SOLVE_THREADS, 0, h->stream>>>(h->rhs, h->ckpt, g, h->tab, h->sc, lam);
-            solve_s1_kernel<1, 8><<<blocks, SOLVE_THREADS, 0, h->stream>>>(h->rhs, h->ckpt, g, h->tab, h->sc, lam);
+            CHB_LAUNCH(blocks, SOLVE_THREADS, 0, h->stream, solve_s1_kernel<0, 8>)(h->rhs, h->ckpt, g, h->tab, h->sc, lam);
+            CHB_LAUNCH(blocks, SOLVE_THREADS, 0, h->stream, solve_s1_kernel<1, 8>)(h->rhs, h->ckpt, g, h->tab, h->sc, lam);
         } else {
-            solve_s1_kernel<0><<<blocks, SOLVE_THREADS, 0, h->stream>>>(h->rhs, h->ckpt, g, h->tab, h->sc, lam);
-            solve_s1_kernel<1><<<blocks, SOLVE_THREADS, 0, h->stream>>>(h->rhs, h->ckpt, g, h->tab, h->sc, lam);
+            CHB_LAUNCH(blocks, SOLVE_THREADS, 0, h->stream, solve_s1_kernel<0>)(h->rhs, h->ckpt, g, h->tab, h->sc, lam);
+            CHB_LAUNCH(blocks, SOLVE_THREADS, 0, h->stream, solve_s1_kernel<1>)(h->rhs, h->ckpt, g, h->tab, h->sc, lam);
         }
     }
     {
         ScopedKernelTimer tm(h, "solve_s2");
-        solve_s2_kernel<0><<<blocks, SOLVE_THREADS, 0, h->stream>>>(h->rhs, h->ckpt, h->V, g, h->tab, h->sc, lam);
-        solve_s2_kernel<1><<<blocks, SOLVE_THREADS, 0, h->stream>>>(h->rhs, h->ckpt, h->V, g, h->tab, h->sc, lam);
+        CHB_LAUNCH(blocks, SOLVE_THREADS, 0, h->stream, solve_s2_kernel<0>)(h->rhs, h->ckpt, h->V, g, h->tab, h->sc, lam);
+        CHB_LAUNCH(blocks, SOLVE_THREADS, 0, h->stream, solve_s2_kernel<1>)(h->rhs, h->ckpt, h->V, g, h->tab, h->sc, lam);
     }
     h->launches += 6;
     // The mean column (0,0) only needs the result of S2 and is skipped by S3/S4: finish it on the
@@ -550,18 +550,18 @@ void launch_linsolve(chb_handle_s* h, double lam) {
         cudaEventRecord(h->ev_fork, h->stream);
         cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0);
         ScopedKernelTimer tm(h, "mean_mode", h->side_stream);
-        mean_mode_kernel<<<1, MEAN_THREADS, 0, h->side_stream>>>(h->V, g, h->tab, h->sc, lam, h->mean_scratch);
+        CHB_LAUNCH(1, MEAN_THREADS, 0, h->side_stream, mean_mode_kernel)(h->V, g, h->tab, h->sc, lam, h->mean_scratch);
         h->launches++;
     }
     {
         ScopedKernelTimer tm(h, "solve_s3");
-        if (pf) solve_s3_kernel<8><<<blocks, SOLVE_THREADS, 0, h->stream>>>(h->V, g, h->tab);
-        else solve_s3_kernel<1><<<blocks, SOLVE_THREADS, 0, h->stream>>>(h->V, g, h->tab);
+        if (pf) CHB_LAUNCH(blocks, SOLVE_THREADS, 0, h->stream, solve_s3_kernel<8>)(h->V, g, h->tab);
+        else CHB_LAUNCH(blocks, SOLVE_THREADS, 0, h->stream, solve_s3_kernel<1>)(h->V, g, h->tab);
     }
     {
         ScopedKernelTimer tm(h, "solve_s4");
-        if (pf) solve_s4_kernel<8><<<blocks, SOLVE_THREADS, 0, h->stream>>>(h->V, g, h->tab);
-        else solve_s4_kernel<1><<<blocks, SOLVE_THREADS, 0, h->stream>>>(h->V, g, h->tab);
+        if (pf) CHB_LAUNCH(blocks, SOLVE_THREADS, 0, h->stream, solve_s4_kernel<8>)(h->V, g, h->tab);
+        else CHB_LAUNCH(blocks, SOLVE_THREADS, 0, h->stream, solve_s4_kernel<1>)(h->V, g, h->tab);
     }
     if (mean_here) {
         cudaEventRecord(h->ev_join, h->side_stream);
@@ -571,7 +571,7 @@ void launch_linsolve(chb_handle_s* h, double lam) {
 
 void launch_meanflow_prepass(chb_handle_s* h) {
     if (h->g.nx0 != 0) return;
-    meanflow_prepass_kernel<<<1, 32, 0, h->stream>>>(h->V, h->g, h->tab, h->sc);
+    CHB_LAUNCH(1, 32, 0, h->stream, meanflow_prepass_kernel)(h->V, h->g, h->tab, h->sc);
     h->launches++;
 }
 #endif

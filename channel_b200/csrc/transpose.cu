@@ -211,7 +211,7 @@ int chb_exchange(chb_handle_s* h, bool a_side) {
         FlagPtrs fp;
         for (int q = 0; q < g.nranks; ++q) fp.p[q] = h->peer_flags[q];
         ScopedKernelTimer tm(h, "p2p_barrier", h->cstream);
-        p2p_barrier_kernel<<<1, 32, 0, h->cstream>>>(fp, h->flags, g.rank, g.nranks, ++h->lane[h->cur_lane].epoch);
+        CHB_LAUNCH(1, 32, 0, h->cstream, p2p_barrier_kernel)(fp, h->flags, g.rank, g.nranks, ++h->lane[h->cur_lane].epoch);
         h->launches++;
         return 0;
     }

@@ -441,7 +441,7 @@ xpass5_kernel(const cplx* __restrict__ Ar, const __grid_constant__ PeerPtrs Bw, 
     }
 }
 
-#ifndef CHB_HOST_EMUL   // tests/host_emul compiles the kernel above with g++ and runs it on CPU threads
+#if !defined(CHB_HOST_EMUL) || defined(CHB_HOST_EMUL_FULL)   // the kernel-only emulation harnesses (tests/host_emul) stop here
 template <class G, int LPC, int MINB>
 static bool launch_x4(chb_handle_s* h, int plane0, int nplanes, int compute_cfl) {
     constexpr int T = G::N / G::C;
@@ -453,7 +453,7 @@ static bool launch_x4(chb_handle_s* h, int plane0, int nplanes, int compute_cfl)
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     dim3 grid(h->g.nzB / LPC, nplanes);
     ScopedKernelTimer tm(h, "xpass", h->cstream);
-    kern<<<grid, LPC * T, smem, h->cstream>>>(h->Ar, h->Bw, h->g, h->Wx, h->Wh, h->t_dy, h->sc, plane0, h->chunk_planes,
+    CHB_LAUNCH(grid, LPC * T, smem, h->cstream, kern)(h->Ar, h->Bw, h->g, h->Wx, h->Wh, h->t_dy, h->sc, plane0, h->chunk_planes,
                                              compute_cfl);
     h->launches++;
     return true;
@@ -470,7 +470,7 @@ static bool launch_x5(chb_handle_s* h, int plane0, int nplanes, int compute_cfl)
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     dim3 grid(h->g.nzB, nplanes);
     ScopedKernelTimer tm(h, "xpass", h->cstream);
-    kern<<<grid, T, smem, h->cstream>>>(h->Ar, h->Bw, h->g, h->Wx, h->Wh, h->t_dy, h->sc, plane0, h->chunk_planes, compute_cfl);
+    CHB_LAUNCH(grid, T, smem, h->cstream, kern)(h->Ar, h->Bw, h->g, h->Wx, h->Wh, h->t_dy, h->sc, plane0, h->chunk_planes, compute_cfl);
     h->launches++;
     return true;
 }

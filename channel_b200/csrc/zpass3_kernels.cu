@@ -193,7 +193,7 @@ zbwd4_kernel(const cplx* __restrict__ Br, cplx* __restrict__ P, Geometry g, cons
     }
 }
 
-#ifndef CHB_HOST_EMUL   // tests/host_emul compiles the kernels above with g++ and runs them on CPU threads
+#if !defined(CHB_HOST_EMUL) || defined(CHB_HOST_EMUL_FULL)   // the kernel-only emulation harnesses (tests/host_emul) stop here
 template <class G, int LPC, int TPL, int MINB>
 static bool launch_z4(chb_handle_s* h, int plane0, int nplanes, bool fwd) {
     constexpr int BCP = G::BC + 1;
@@ -208,12 +208,12 @@ static bool launch_z4(chb_handle_s* h, int plane0, int nplanes, bool fwd) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         ScopedKernelTimer tm(h, "zfwd", h->cstream);
-        kern<<<grid, LPC * TPL, smem, h->cstream>>>(h->V, h->Aw, h->g, h->Wz, plane0, h->chunk_planes, LS);
+        CHB_LAUNCH(grid, LPC * TPL, smem, h->cstream, kern)(h->V, h->Aw, h->g, h->Wz, plane0, h->chunk_planes, LS);
     } else {
         cudaFuncSetAttribute(zbwd4_kernel<G, LPC, TPL, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(zbwd4_kernel<G, LPC, TPL, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         ScopedKernelTimer tm(h, "zbwd", h->cstream);
-        zbwd4_kernel<G, LPC, TPL, MINB><<<grid, LPC * TPL, smem, h->cstream>>>(h->Br, h->P, h->g, h->Wz, plane0, h->chunk_planes, LS);
+        CHB_LAUNCH(grid, LPC * TPL, smem, h->cstream, zbwd4_kernel<G, LPC, TPL, MINB>)(h->Br, h->P, h->g, h->Wz, plane0, h->chunk_planes, LS);
     }
     h->launches++;
     return true;

@@ -16,11 +16,14 @@
 #include <thread>
 #include <vector>
 #include <algorithm>
+#include <math.h>
+#include <cmath>
 using std::max;
 using std::min;
 
 namespace cta_emul {
 inline thread_local uint3 t_threadIdx, t_blockIdx;
+inline thread_local int t_linear_tid;
 inline dim3 g_blockDim, g_gridDim;
 inline pthread_barrier_t g_block_barrier;
 inline std::vector<pthread_barrier_t> g_warp_barrier;
@@ -42,7 +45,7 @@ template <class T>
 static inline T __ldg(const T* p) { return *p; }
 static inline void __syncthreads() { pthread_barrier_wait(&cta_emul::g_block_barrier); }
 static inline double __shfl_xor_sync(unsigned, double v, int o) {
-    const int tid = cta_emul::t_threadIdx.x, w = tid >> 5, l = tid & 31;
+    const int tid = cta_emul::t_linear_tid, w = tid >> 5, l = tid & 31;
     cta_emul::g_warp_buf[w][l] = v;
     pthread_barrier_wait(&cta_emul::g_warp_barrier[w]);
     const double r = cta_emul::g_warp_buf[w][l ^ o];
@@ -57,12 +60,20 @@ static inline unsigned long long atomicMax(unsigned long long* a, unsigned long 
     return old;
 }
 
+// cuda_runtime.h declares this convenience overload for nvcc only
+template <class T>
+static inline cudaError_t cudaFuncSetAttribute(T* /*kernel*/, cudaFuncAttribute, int) { return cudaSuccess; }
+static inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+static inline void __threadfence_system() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+static inline void __nanosleep(unsigned) { std::this_thread::yield(); }
+
 namespace cta_emul {
-// run kern(args...) for every block of a (gx, gy, gz) grid of 1-D blocks of `threads` threads (a multiple of 32)
+// run kern(args...) for every block of the grid; blocks of up to 2048 threads (a multiple of 32), 1-D to 3-D
 template <class K, class... Args>
-void launch(K kern, dim3 grid, int threads, Args... args) {
+void launch(K kern, dim3 grid, dim3 block, Args... args) {
+    const int threads = (int)(block.x * block.y * block.z);
     if (threads % 32 != 0 || threads > 2048) { fprintf(stderr, "cta_emul: block size %d\n", threads); abort(); }
-    g_blockDim = dim3(threads, 1, 1);
+    g_blockDim = block;
     g_gridDim = grid;
     pthread_barrier_init(&g_block_barrier, nullptr, threads);
     g_warp_barrier.resize(threads / 32);
@@ -73,7 +84,8 @@ void launch(K kern, dim3 grid, int threads, Args... args) {
     th.reserve(threads);
     for (int t = 0; t < threads; ++t)
         th.emplace_back([=]() {
-            t_threadIdx = make_uint3(t, 0, 0);
+            t_threadIdx = make_uint3(t % block.x, (t / block.x) % block.y, t / (block.x * block.y));
+            t_linear_tid = t;
             for (unsigned bz = 0; bz < grid.z; ++bz)
                 for (unsigned by = 0; by < grid.y; ++by)
                     for (unsigned bx = 0; bx < grid.x; ++bx) {
@@ -86,4 +98,17 @@ void launch(K kern, dim3 grid, int threads, Args... args) {
     for (auto& b : g_warp_barrier) pthread_barrier_destroy(&b);
     pthread_barrier_destroy(&g_block_barrier);
 }
+template <class K, class... Args>
+void launch(K kern, dim3 grid, int threads, Args... args) { launch(kern, grid, dim3(threads, 1, 1), args...); }
+
+// CHB_LAUNCH(grid, block, smem, stream, kernel)(args...) of the product sources in the emulation build
+template <class K>
+struct Launcher {
+    K kern;
+    dim3 grid, block;
+    template <class... Args>
+    void operator()(Args... args) const { launch(kern, grid, block, args...); }
+};
+template <class K, class G, class B>
+Launcher<K> launcher(K kern, G grid, B block) { return Launcher<K>{kern, dim3(grid), dim3(block)}; }
 }  // namespace cta_emul

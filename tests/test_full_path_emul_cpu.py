@@ -1,0 +1,55 @@
+"""The whole C ABI path on the CPU: tests/host_emul/build_full_emul.sh compiles the library's OWN sources (chb_api.cu,
+every launcher and kernel, restart_io.cu, host_tables.cpp) with g++, runs the kernels on the CTA emulator
+(cta_emul.hpp) and replaces the CUDA runtime by host memory (fake_cudart.cpp).  A few `-m gpu` tests are then run,
+unchanged, against that build in a subprocess (tests/host_emul/run_gpu_tests_emulated.py).
+
+This is test infrastructure: it checks the host logic and the kernel logic of the product sources end to end
+(handle creation and destruction, launch order and arguments, work-buffer layouts between the passes, restart
+files) before a GPU minute is spent.  The product never loads the emulated build; the real `-m gpu` run on a
+B200 is what counts for parity and the only place where performance exists."""
+import os
+import shutil
+import subprocess
+import sys
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+EMUL = os.path.join(HERE, "host_emul")
+LIB = os.path.join(EMUL, "_build", "libchannel_b200_emul.so")
+
+
+@pytest.fixture(scope="module")
+def emulated_library():
+    if shutil.which("g++") is None or not os.path.exists("/usr/local/cuda/include/cuda_runtime.h"):
+        pytest.skip("needs g++ and the CUDA headers")
+    csrc = os.path.join(ROOT, "channel_b200", "csrc")
+    deps = [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".cu", ".cuh", ".h", ".cpp"))]
+    deps += [os.path.join(EMUL, f) for f in ("cta_emul.hpp", "fake_cudart.cpp", "emul_prelude.hpp", "build_full_emul.sh")]
+    if not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in deps):
+        subprocess.check_call(["sh", os.path.join(EMUL, "build_full_emul.sh")], stdout=subprocess.DEVNULL)
+    return LIB
+
+
+def run_emulated(args, timeout=900):
+    r = subprocess.run([sys.executable, os.path.join(EMUL, "run_gpu_tests_emulated.py")] + args, cwd=ROOT,
+                       capture_output=True, text=True, timeout=timeout)
+    return r.returncode, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+def test_parity_and_layout_tests_on_the_emulated_library(emulated_library):
+    """One RK3 step against the oracle on two of the minimal grids, the rejected sizes and the Fortran-layout round
+    trip, through chb_create ... chb_destroy of the emulated build."""
+    rc, out = run_emulated(["tests/test_parity_gpu.py", "-x", "-q", "-k",
+                            "minimal_grids and (2-9-1 or 5-8-4) or rejected_sizes or fortran_layout"])
+    assert rc == 0, out
+    assert " passed" in out and "failed" not in out
+
+
+def test_restart_files_on_the_emulated_library(emulated_library):
+    """Snapshot files (blocking and asynchronous, ragged chunks) and the restart read with its header check: the
+    writer threads, the chunk arithmetic and the byte layout, on host memory."""
+    rc, out = run_emulated(["tests/test_restart_io_gpu.py", "-x", "-q", "-k", "byte_identical and 7-16-5 or roundtrip_and_header"])
+    assert rc == 0, out
+    assert " passed" in out and "failed" not in out
