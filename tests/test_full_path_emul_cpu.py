@@ -53,3 +53,38 @@ def test_restart_files_on_the_emulated_library(emulated_library):
     rc, out = run_emulated(["tests/test_restart_io_gpu.py", "-x", "-q", "-k", "byte_identical and 7-16-5 or roundtrip_and_header"])
     assert rc == 0, out
     assert " passed" in out and "failed" not in out
+
+
+def test_cpp_driver_on_the_emulated_library(emulated_library, tmp_path):
+    """channel_main.cpp (the C++ restatement of PROGRAM channel) linked against the emulated build: a run from dns.in
+    alone writes Runtimedata, the dt_field snapshot and the final Dati.cart.out; a second run restarts from them."""
+    import numpy as np
+    exe = os.path.join(EMUL, "_build", "channel_b200_run_emul")
+    src = os.path.join(ROOT, "channel_b200", "csrc", "channel_main.cpp")
+    if not os.path.exists(exe) or os.path.getmtime(src) > os.path.getmtime(exe) or os.path.getmtime(LIB) > os.path.getmtime(exe):
+        subprocess.check_call(["g++", "-O1", "-std=c++17", "-w", "-o", exe, src, "-L" + os.path.dirname(LIB), "-lchannel_b200_emul",
+                               "-Wl,-rpath," + os.path.dirname(LIB), "-pthread"])
+    (tmp_path / "dns.in").write_text("""7 16 5   ! nx ny nz
+0.5 1.0
+1500
+1.5 0.0 2.0
+.FALSE. 1 0.161436
+0.002 0.0
+0.0 0.0
+0.0 0.0
+0.05 0.0 0.0
+0.12 -1 1000 .TRUE.
+3
+1
+""")
+    r = subprocess.run([exe, "--dir", str(tmp_path)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    rtd = np.array([[float(x) for x in l.split()] for l in open(tmp_path / "Runtimedata") if l.strip()])
+    assert rtd.shape == (4, 11) and np.isfinite(rtd).all()
+    assert np.allclose(rtd[:, 0], [0.0, 0.05, 0.10, 0.15]) and abs(rtd[-1, 5] - 2.0) < 1e-3      # time, flow rate of the parabola
+    size = 68 + 16 * 3 * 8 * 11 * 19
+    assert os.path.getsize(tmp_path / "Dati.cart.out") == size and os.path.getsize(tmp_path / "Dati.cart.1.out") == size
+    r = subprocess.run([exe, "--dir", str(tmp_path)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "starting from time" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    rtd2 = np.array([[float(x) for x in l.split()] for l in open(tmp_path / "Runtimedata") if l.strip()])
+    assert rtd2.shape == (3 + 1 + 3, 11) and np.array_equal(rtd2[:3], rtd[:3]) and np.all(np.diff(rtd2[:, 0]) > 0)
