@@ -64,6 +64,9 @@ SYMBOLS = {
     "chb_restart_wait": (C.c_int, [C.c_void_p]),
     "chb_restart_stats": (C.c_int, [C.c_void_p, c_double_p, c_double_p, c_double_p]),
     "chb_read_restart_file": (C.c_int, [C.c_void_p, C.c_char_p, c_double_p]),
+    "chb_set_convvel": (C.c_int, [C.c_void_p, C.c_int]),
+    "chb_get_convvel": (C.c_int, [C.c_void_p, c_double_p, C.POINTER(C.c_longlong)]),
+    "chb_save_convvel_file": (C.c_int, [C.c_void_p, C.c_char_p]),
     "chb_host_restart_header": (C.c_int, [C.c_int] * 3 + [C.c_double] * 7 + [C.c_void_p]),
     "chb_host_restart_offset": (C.c_longlong, [C.c_int] * 5),
     "chb_host_restart_file_bytes": (C.c_longlong, [C.c_int] * 3),

@@ -6,7 +6,7 @@
 // outputs (Runtimedata, Dati.cart.out, Dati.cart.<n>.out at the dt_field / dt_save cadence of outstats).
 // One process = one GPU = npx 1 (the multi-GPU path is driven through the Fortran shim or torchrun).
 //
-//   channel_b200_run [--dir D] [--bodyforce coriolis|am_f1|am_butterfly] [--device N] [--check-input]
+//   channel_b200_run [--dir D] [--bodyforce coriolis|am_f1|am_butterfly] [--convvel] [--device N] [--check-input]
 //   (the body force is a compile-time choice in the reference: -Dbodyforce + an #include of one of body_forces/*/*.inc)
 //
 // --check-input parses dns.in (and Runtimedata, if any) and prints what the run would use, without a GPU.
@@ -140,7 +140,7 @@ struct Run {
     std::vector<double> y, d0, d1, d2, d4, D0mat;
     double time = 0, time0 = 0, deltat = 0, ni = 0;
     int istep = 0, ifield = 0;
-    bool prev_was_close = false, bodyforce = false;
+    bool prev_was_close = false, bodyforce = false, convvel = false;
     FILE* rtd = nullptr;
     std::string dir;
 
@@ -177,6 +177,10 @@ struct Run {
                     printf(" Writing Force.cart.%s.out at time %g\n", n.c_str(), time);
                     save("Force.cart." + n + ".out", 1);
                 }
+                if (convvel) {   // dnsdata.f90:908-913
+                    printf(" Writing Convvel.cart.%s.out at time %g\n", n.c_str(), time);
+                    check(chb_save_convvel_file(h, (dir + "Convvel.cart." + n + ".out").c_str()), "chb_save_convvel_file");
+                }
                 prev_was_close = false;
             } else {
                 prev_was_close = true;
@@ -191,7 +195,7 @@ struct Run {
 
 int main(int argc, char** argv) {
     std::string dir = "./";
-    bool coriolis = false, check_input = false;
+    bool coriolis = false, check_input = false, r_convvel = false;
     std::string am;   // "am_f1" | "am_butterfly"
     int device = 0;
     for (int i = 1; i < argc; ++i) {
@@ -206,7 +210,8 @@ int main(int argc, char** argv) {
         }
         else if (a == "--device" && i + 1 < argc) device = atoi(argv[++i]);
         else if (a == "--check-input") check_input = true;
-        else die("usage: channel_b200_run [--dir D] [--bodyforce coriolis|am_f1|am_butterfly] [--device N] [--check-input]");
+        else if (a == "--convvel") r_convvel = true;
+        else die("usage: channel_b200_run [--dir D] [--bodyforce coriolis|am_f1|am_butterfly] [--convvel] [--device N] [--check-input]");
     }
     Run r;
     r.dir = dir;
@@ -347,6 +352,11 @@ int main(int argc, char** argv) {
         check(chb_set_body_force_linear_yz(r.h, 1, A, m.data(), 1), "chb_set_body_force_linear_yz");
         check(chb_set_body_force(r.h), "chb_set_body_force");
         r.bodyforce = true;
+    }
+
+    if (r_convvel) {   // #define convvel (header.h:44)
+        check(chb_set_convvel(r.h, 1), "chb_set_convvel");
+        r.convvel = true;
     }
 
     // Compute CFL, flow rate, CPI (channel.f90:95-115), first Runtimedata line

@@ -316,6 +316,8 @@ extern "C" int chb_destroy(chb_handle h) {
     cudaFree(h->V); cudaFree(h->rhs); cudaFree(h->oldrhs); cudaFree(h->P); cudaFree(h->ckpt);
     if (h->F) cudaFree(h->F);
     if (h->rhs_state) cudaFree(h->rhs_state);
+    if (h->cv_Vold) cudaFree(h->cv_Vold);
+    if (h->cv_uconv) cudaFree(h->cv_uconv);
     if (h->p2p) chb_p2p_teardown(h);
     for (int L = 0; L < h->nlanes; ++L) {
         Lane& ln = h->lane[L];
@@ -538,7 +540,10 @@ extern "C" int chb_set_body_force(chb_handle h) {
 // ---- the hot path ----------------------------------------------------------------------------
 // rhs_ode != null (chunked RHS assembly, experimental): after the backward z pass of every chunk the plane loop of
 // buildrhs runs for that chunk's planes on the main stream, concurrently with the next chunk's passes on the lane stream
-static int convolutions_all(chb_handle h, int compute_cfl, bool products, const double* rhs_ode = nullptr, double rhs_deltat = 0.0) {
+static int convolutions_all(chb_handle h, int compute_cfl, bool products, const double* rhs_ode = nullptr, double rhs_deltat = 0.0,
+                            double deltat = 0.0) {
+    // the first sweep of buildrhs after an outstats also feeds the convection-velocity diagnostic (dnsdata.f90:515-531)
+    const bool convvel = products && h->cv_enabled && h->cv_compute;
     const Geometry& g = h->g;
     const int np = h->chunk_planes;
     // fork: the lanes start after everything queued on the main stream (V complete)
@@ -550,6 +555,7 @@ static int convolutions_all(chb_handle h, int compute_cfl, bool products, const 
         chb_select_lane(h, c % h->nlanes);
         launch_zfwd(h, p0, n);                       // stores straight into the x-side owner's buffer
         if (chb_exchange(h, true)) return 1;         // zTOx, mpi_transpose.f90:50-83
+        if (convvel) launch_convvel(h, p0, n, deltat);
         launch_xpass(h, p0, n, compute_cfl);
         // xTOz, mpi_transpose.f90:88-117; in direct mode the barrier also frees Ar for the next chunk
         if ((products || h->p2p) && chb_exchange(h, false)) return 1;
@@ -560,6 +566,10 @@ static int convolutions_all(chb_handle h, int compute_cfl, bool products, const 
             CHB_CUDA_OK(cudaStreamWaitEvent(h->stream, ln.done, 0));
             launch_rhs_chunk(h, rhs_ode, rhs_deltat, p0, n, h->stream);
         }
+    }
+    if (convvel) {   // IF (iy==nyN+2 .AND. compute_convvel): convvel_cnt=convvel_cnt+1; compute_convvel=.FALSE.   :546-549
+        h->cv_cnt += 1;
+        h->cv_compute = 0;
     }
     // join
     for (int L = 0; L < h->nlanes; ++L) {
@@ -585,9 +595,9 @@ extern "C" int chb_buildrhs(chb_handle h, const double* ode, double deltat, int 
     CHB_CUDA_OK(cudaSetDevice(h->device));
     if (h->bf.enabled) launch_force_ghosts(h);
     if (h->rhs_chunked) {
-        if (convolutions_all(h, compute_cfl, true, ode, deltat)) return 1;
+        if (convolutions_all(h, compute_cfl, true, ode, deltat, deltat)) return 1;
     } else {
-        if (convolutions_all(h, compute_cfl, true)) return 1;
+        if (convolutions_all(h, compute_cfl, true, nullptr, 0.0, deltat)) return 1;
         launch_rhs(h, ode, deltat);
     }
     CHB_CUDA_OK(cudaGetLastError());
@@ -627,6 +637,7 @@ extern "C" int chb_get_step_scalars(chb_handle h, double* cfl, double* fr, doubl
     }
     if (pull_scalars(h)) return 1;
     chb_timer_flush(h);
+    if (h->cv_enabled) h->cv_compute = 1;   // compute_convvel=.TRUE.   dnsdata.f90:858-860
     DevScalars* s = h->sc_host;
     double c;
     memcpy(&c, &s->cfl_bits, sizeof(double));

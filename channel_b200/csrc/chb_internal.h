@@ -143,6 +143,11 @@ struct chb_handle_s {
     BodyForce bf;
     // multi-GPU
     void* nccl_comm;
+    // convection-velocity diagnostic (convvel.cu; #ifdef convvel of the reference)
+    int cv_enabled, cv_compute;   // compute: set by chb_get_step_scalars (outstats), consumed by the next buildrhs sweep
+    long long cv_cnt;             // convvel_cnt
+    cplx* cv_Vold;                // Voldz  [3][ny+3][nzd][nxB]
+    double* cv_uconv;             // uconv  [3][ny+3][nzd][nxB]
     // restart / snapshot files (restart_io.cu)
     void* rio;
     double grid_a, grid_ymin, grid_ymax;   // dns.in a, ymin, ymax: header fields of Dati.cart.out
@@ -178,6 +183,8 @@ void chb_p2p_teardown(chb_handle_s* h);
 int chb_exchange(chb_handle_s* h, bool a_side);             // completes zTOx (a_side) / xTOz on the lane's stream
 void chb_select_lane(chb_handle_s* h, int lane);            // makes `lane` the one the conv launchers use
 
+// ---- convvel.cu ----
+void launch_convvel(chb_handle_s* h, int plane0, int nplanes, double deltat);
 // ---- restart_io.cu ----
 void chb_restart_destroy(chb_handle_s* h);
 

@@ -383,6 +383,20 @@ class Channel:
         self.time = t.value
         return self.time
 
+    # -- convection-velocity diagnostic (convvel.cu; #ifdef convvel of the reference) -----------------
+    def enable_convvel(self, on: bool = True):
+        _lib.check(self.lib.chb_set_convvel(self.h, int(on)), "chb_set_convvel")
+
+    def get_convvel(self):
+        """(uconv [3][ny+3][nx+1][nzd] as save_convvel_file orders it, convvel_cnt)"""
+        u = np.empty((3, self.ny + 3, self.nx + 1, self.nzd))
+        n = C.c_longlong()
+        _lib.check(self.lib.chb_get_convvel(self.h, _dp(u), C.byref(n)), "chb_get_convvel")
+        return u, n.value
+
+    def save_convvel_file(self, path):
+        _lib.check(self.lib.chb_save_convvel_file(self.h, os.fsencode(path)), "chb_save_convvel_file")
+
     def close(self):
         if self.h:
             self.lib.chb_destroy(self.h)

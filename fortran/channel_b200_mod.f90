@@ -152,6 +152,19 @@ MODULE channel_b200
       REAL(C_DOUBLE) :: time
       INTEGER(C_INT) :: rc
     END FUNCTION
+    ! convection-velocity diagnostic (#ifdef convvel): arm once, save at the dt_field cadence of outstats
+    FUNCTION chb_set_convvel(h, enable) BIND(C, name="chb_set_convvel") RESULT(rc)
+      IMPORT :: C_PTR, C_INT
+      TYPE(C_PTR), VALUE :: h
+      INTEGER(C_INT), VALUE :: enable
+      INTEGER(C_INT) :: rc
+    END FUNCTION
+    FUNCTION chb_save_convvel_file(h, filename) BIND(C, name="chb_save_convvel_file") RESULT(rc)
+      IMPORT :: C_PTR, C_INT, C_CHAR
+      TYPE(C_PTR), VALUE :: h
+      CHARACTER(KIND=C_CHAR) :: filename(*)
+      INTEGER(C_INT) :: rc
+    END FUNCTION
   END INTERFACE
 
 CONTAINS

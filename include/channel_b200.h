@@ -174,6 +174,18 @@ int chb_restart_stats(chb_handle h, double* bytes, double* snapshot_ms, double* 
  * and uses chb_upload_V. */
 int chb_read_restart_file(chb_handle h, const char* filename, double* time);
 
+/* ---- convection-velocity diagnostic (the reference's #ifdef convvel) -------------------------
+ * chb_set_convvel(h, 1) allocates Voldz and uconv (dnsdata.f90:141-143) and arms the diagnostic: the first chb_buildrhs
+ * after every chb_get_step_scalars (= after every outstats, dnsdata.f90:858-860) then compares the z-transformed
+ * velocities with those of the previous such sweep and accumulates cu = Im(conj(ust) dtu)/(ix alfa0 |ust|^2) into uconv
+ * (dnsdata.f90:515-531,546-549).  chb_get_convvel returns uconv as [3][ny+3][nx+1][nzd] float64 (the order
+ * save_convvel_file writes, dnsdata.f90:792-816) and convvel_cnt; chb_save_convvel_file does what outstats does at
+ * the dt_field cadence (dnsdata.f90:908-913): uconv/convvel_cnt to the file, then uconv = 0, convvel_cnt = 0.
+ * One GPU only in this version (error 2 otherwise). */
+int chb_set_convvel(chb_handle h, int enable);
+int chb_get_convvel(chb_handle h, double* uconv_host, long long* count);
+int chb_save_convvel_file(chb_handle h, const char* filename);
+
 /* ---- test / diagnostics accessors (not part of the Fortran binding) ---------- */
 /* RHS left by chb_buildrhs: [2][ny+3][nxB][2nz+1] complex (0=eta, 1=D2v); rows 1..ny-1. */
 int chb_download_rhs(chb_handle h, double* rhs_host);

@@ -162,6 +162,10 @@ class Oracle:
         self.V = np.zeros((3, ny + 3, nx + 1, 2 * nz + 1), np.complex128)
         self.oldrhs = np.zeros((2, ny + 3, nx + 1, 2 * nz + 1), np.complex128)  # [eta,d2v]; A.7: zero
         self.F = None          # body force (same shape as V) or None
+        # convection-velocity diagnostic (#ifdef convvel, dnsdata.f90:84-89,141-143): off unless enable_convvel()
+        self.convvel = False
+        self.Voldz = None; self.uconv = None
+        self.convvel_cnt = -1; self.compute_convvel = False
         self.cfl = 0.0
         self.fr = np.zeros(3)
         self.corrpx = 0.0
@@ -345,6 +349,17 @@ class Oracle:
         Z[..., 0:nz + 1] = V[..., nz:2 * nz + 1]           # :504
         Z[..., nzd - nz:nzd] = V[..., 0:nz]                 # :505
         Z = _ifft_u(Z, axis=-1)                             # :510  IFT
+        if self.convvel and self.compute_convvel:           # :515-531, all planes of this sweep; then :546-549
+            if self.convvel_cnt > -1:
+                ix0 = np.arange(self.nx + 1, dtype=np.float64)[None, None, :, None]
+                dtu = (Z - self.Voldz) / self.deltat
+                ust = 0.5 * (Z + self.Voldz)
+                with np.errstate(divide="ignore", invalid="ignore"):
+                    cu = (np.conj(ust) * dtu).imag / (ix0 * self.alfa0 * (ust * np.conj(ust)).real)
+                self.uconv[:, :, 1:, :] += cu[:, :, 1:, :]  # IF (ix0>0)
+            self.Voldz = Z.copy()
+            self.convvel_cnt += 1
+            self.compute_convvel = False
         X = np.zeros((3, ny + 3, nxd + 1, nzd), np.complex128)
         X[:, :, 0:nx + 1, :] = Z                            # :533 zTOx, :535 zero pad
         R = _irfft_u(X, n=2 * nxd, axis=2)                  # :535  RFT -> [3, ny+3, 2nxd, nzd]
@@ -596,6 +611,8 @@ class Oracle:
     def outstats(self):
         """dnsdata.f90:853-880: returns the Runtimedata line (11 columns)."""
         ny, nz = self.ny, self.nz
+        if self.convvel:
+            self.compute_convvel = True                     # :858-860
         runtime_global = self.cfl
         self.cfl = 0.0
         if self.cflmax > 0:
@@ -607,6 +624,20 @@ class Oracle:
                          self.fr[0] + self.corrpx * self.fr[2], self.meanpx + self.corrpx,
                          self.fr[1] + self.corrpz * self.fr[2], self.meanpz + self.corrpz,
                          runtime_global * self.deltat, self.deltat])
+
+    def enable_convvel(self):
+        """#define convvel: Voldz / uconv(1:nzd, 1:nxB, iy, 1:3), here [3, ny+3, nx+1, nzd] (dnsdata.f90:141-143)."""
+        self.convvel = True
+        shape = (3, self.ny + 3, self.nx + 1, self.nzd)
+        self.Voldz = np.zeros(shape, np.complex128); self.uconv = np.zeros(shape)
+        self.convvel_cnt = -1; self.compute_convvel = False
+
+    def convvel_file_bytes(self):
+        """what outstats writes at the dt_field cadence (dnsdata.f90:908-913, save_convvel_file :792-816):
+        uconv / convvel_cnt as float64 [iV][iy+1][ix][iz_d], no header; then uconv = 0, convvel_cnt = 0."""
+        out = (self.uconv / self.convvel_cnt).astype(np.float64).tobytes()
+        self.uconv[:] = 0; self.convvel_cnt = 0
+        return out
 
     def set_body_force(self, fn):
         """fn(oracle) fills self.F from self.V (body_forces/*.inc hooks)."""

@@ -57,12 +57,14 @@ def test_restart_files_on_the_emulated_library(emulated_library):
 
 def test_experimental_variants_on_the_emulated_library(emulated_library):
     """Two of the not-yet-measured variants through the C ABI of the emulated build: xpass5 at nxd = 768 against the
-    default kernel and the oracle, and the host-side body-force path (chb_upload_F).  The others
+    default kernel and the oracle, the host-side body-force path (chb_upload_F) and the convection-velocity
+    diagnostic (convvel.cu).  The others
     (tests/test_zz_experimental_gpu.py, 13 tests) take a quarter of an hour on the emulator and are run by hand:
     python tests/host_emul/run_gpu_tests_emulated.py tests/test_zz_experimental_gpu.py"""
-    rc, out = run_emulated(["tests/test_zz_experimental_gpu.py", "-x", "-q", "-k", "host_side_body_force or (xpass_split and 511-8-4)"])
+    rc, out = run_emulated(["tests/test_zz_experimental_gpu.py", "-x", "-q", "-k",
+                            "host_side_body_force or (xpass_split and 511-8-4) or convection_velocity"])
     assert rc == 0, out
-    assert "2 passed" in out and "failed" not in out
+    assert "3 passed" in out and "failed" not in out
 
 
 def test_cpp_driver_on_the_emulated_library(emulated_library, tmp_path):

@@ -152,3 +152,36 @@ def test_prefetching_solve_sweeps(monkeypatch):
         ch.close()
     assert np.array_equal(out["1"][0], out["0"][0])
     assert np.array_equal(out["1"][1], out["0"][1])
+
+
+def test_convection_velocity_diagnostic(tmp_path):
+    """The reference's #ifdef convvel branch of convolutions (dnsdata.f90:515-531,546-549,858-860): uconv and its count
+    against the oracle's restatement, and Convvel.cart.<n>.out (save_convvel_file :792-816, outstats :908-913).  cu
+    divides by |ust|^2, so entries whose velocity is at rounding level (0/0 in the reference too) are left out."""
+    p, o, ch, V0 = make_pair(15, 24, 10, deltat=0.0, cflmax=1.0, re=2500.0, eps=5e-2)
+    o.enable_convvel(); ch.enable_convvel()
+    ch.cfl_prepass(); o.cfl_prepass()
+    ch.outstats(); o.outstats()
+    for _ in range(3):
+        o.step(); ch.step()
+    ug, cnt = ch.get_convvel()
+    assert cnt == o.convvel_cnt == 2                          # the first sweep only stores Voldz
+    # (where the velocity vanishes - the wall planes - the reference divides 0 by 0: NaN or rounding noise, not compared)
+    amp = np.abs(o.Voldz)
+    ok = (amp > 1e-5 * amp.max()) & np.isfinite(o.uconv)
+    ok[:, :, 0, :] = False                                    # ix = 0 is never accumulated
+    assert ok.sum() > 1000
+    assert np.abs(ug[ok] - o.uconv[ok]).max() <= 1e-7 * np.abs(o.uconv[ok]).max()
+    assert np.all(ug[:, :, 0, :] == 0)
+    path = tmp_path / "Convvel.cart.1.out"
+    ch.save_convvel_file(path)
+    raw = np.fromfile(path, dtype=np.float64)
+    assert raw.size == ug.size and np.array_equal(raw.reshape(ug.shape), ug / cnt, equal_nan=True)
+    u2, c2 = ch.get_convvel()
+    assert c2 == 0 and np.all(u2 == 0)                        # uconv=0; convvel_cnt=0 after the file
+    o.step(); ch.step()
+    assert ch.get_convvel()[1] == 1
+    Vg = ch.download_V()                                      # the diagnostic does not touch the solution
+    for c in range(3):
+        assert relerr(Vg[c], o.V[c]) < 1e-10
+    ch.close()
