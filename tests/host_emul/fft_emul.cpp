@@ -38,7 +38,7 @@ static void run_x5(const cplx* Ar, cplx* Br, const Geometry& g, const cplx* W, c
     memset(&Bw, 0, sizeof(Bw));
     Bw.p[0] = Br;
     constexpr int T = 2 * (G::N / G::C);
-    cta_emul::launch(xpass5_kernel<G, MINB, false>, dim3(g.nzB, np, 1), T, Ar, Bw, g, W, Wh, dy, sc, 0, np, compute_cfl);
+    cta_emul::launch(xpass4_kernel<G, 1, MINB, false, 2>, dim3(g.nzB, np, 1), T, Ar, Bw, g, W, Wh, dy, sc, 0, np, compute_cfl);
 }
 
 template <class G, int LPC, int TPL, int MINB>
@@ -67,7 +67,7 @@ extern "C" {
 // Br = products for the backward z pass in the tiled layout of transpose_index.h (tile width 2^tw),
 // [6][np][(nx+1) >> tw][nzB][1 << tw]; dy[ny+3]; cfl_out = max of the CFL expression (dnsdata.f90:552-556).
 // Planes are iy = -1 .. np-2 (plane0 = 0).  variant 0: xpass4 (one thread per innermost butterfly position),
-// 1: xpass5 (two threads per position; nxd = 768, 1536).  Returns 2 if no such kernel exists for nxd.
+// 1: the split x-pass (two threads per position; nxd = 768, 1536).  Returns 2 if no such kernel exists for nxd.
 __attribute__((visibility("default"))) int chb_emul_xpass(int nx, int ny, int nzB, int np, int nxd, int nzd, double alfa0,
                                                           double beta0, int tw, const double* Ar, double* Br,
                                                           const double* dy, int compute_cfl, double* cfl_out, int variant) {

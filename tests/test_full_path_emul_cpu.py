@@ -56,7 +56,7 @@ def test_restart_files_on_the_emulated_library(emulated_library):
 
 
 def test_experimental_variants_on_the_emulated_library(emulated_library):
-    """Two of the not-yet-measured variants through the C ABI of the emulated build: xpass5 at nxd = 768 against the
+    """Two of the not-yet-measured variants through the C ABI of the emulated build: the split x-pass at nxd = 768 against the
     default kernel and the oracle, the host-side body-force path (chb_upload_F) and the convection-velocity
     diagnostic (convvel.cu).  The others
     (tests/test_zz_experimental_gpu.py, 13 tests) take a quarter of an hour on the emulator and are run by hand:

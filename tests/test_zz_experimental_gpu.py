@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 
 @pytest.mark.parametrize("nx,ny,nz", [(1023, 8, 3), (511, 8, 4)])
 def test_xpass_split_variant(nx, ny, nz, monkeypatch):
-    """CHB_XPASS_SPLIT=1: xpass5 (two threads per innermost butterfly position: 12 instead of 6 warps per SM at
+    """CHB_XPASS_SPLIT=1: the split x-pass (two threads per innermost butterfly position: 12 instead of 6 warps per SM at
     nxd = 1536, two CTAs of 12 warps instead of three of 6 at nxd = 768) must give the products of the default
     kernel to rounding; also checked against numpy on the CPU emulator (tests/test_fft_emul_cpu.py)."""
     out = {}
