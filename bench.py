@@ -234,7 +234,9 @@ def build_report(args, w, nx, ny, nz, nxd, nzd, world, couette, ms_per_step, ker
                                f"{'Couette+coriolis' if couette else 'Poiseuille, CPI'} field, FP64, cflmax=1",
                    "dof": dof, "decomposition": f"x-pencils over {world} GPU(s), npy=1",
                    "l2": "state (%.1f GB/GPU) far larger than the 126 MB L2; no flush needed" % (dev_bytes / 1e9),
-                   "device_bytes_per_gpu": dev_bytes},
+                   "device_bytes_per_gpu": dev_bytes,
+                   # library switches set in the environment; empty = every default
+                   "switches": {k: v for k, v in sorted(os.environ.items()) if k.startswith("CHB_") and k != "CHB_WORKLOAD"}},
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
                      "frac": ach / peak, "traffic": traffic, "traffic_source": tsrc, "peak_source": peak_src,
                      "bytes_per_launch": bytes_per_launch, "launches": nl, "fp64": fp64},
