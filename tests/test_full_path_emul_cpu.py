@@ -100,3 +100,37 @@ def test_cpp_driver_on_the_emulated_library(emulated_library, tmp_path):
     assert r.returncode == 0 and "starting from time" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
     rtd2 = np.array([[float(x) for x in l.split()] for l in open(tmp_path / "Runtimedata") if l.strip()])
     assert rtd2.shape == (3 + 1 + 3, 11) and np.array_equal(rtd2[:3], rtd[:3]) and np.all(np.diff(rtd2[:, 0]) > 0)
+
+
+BENCH_ON_EMULATION = r'''
+import sys, json, io, contextlib
+sys.path.insert(0, sys.argv[1])
+import channel_b200._lib as L
+L.LIB_PATH = sys.argv[2]
+import torch
+torch.cuda.is_available = lambda: True            # the emulated build has no device: stand-ins for the three torch.cuda calls
+torch.cuda.set_device = lambda *a, **k: None
+torch.cuda.synchronize = lambda *a, **k: None
+torch.Tensor.pin_memory = lambda self, *a, **k: self
+import bench
+sys.argv = ["bench.py", "--workload", "7,16,5", "--steps", "2", "--warmup", "1", "--no-cpu-baseline", "--snapshot", "--snapshot-dir", sys.argv[3]]
+buf = io.StringIO()
+with contextlib.redirect_stdout(buf):
+    bench.main()
+print([l for l in buf.getvalue().splitlines() if l.startswith("{")][-1])
+'''
+
+
+def test_bench_b200_arm_on_the_emulated_library(emulated_library, tmp_path):
+    """bench.py's B200 arm from argument parsing to the JSON line (upload, CFL pre-pass, warm-up, the timed steps with
+    the per-kernel timers, the end-to-end leg, the snapshot timing, the report) against the emulated build; the
+    numbers mean nothing here, the code path and the keys of the driver contract do."""
+    import json
+    r = subprocess.run([sys.executable, "-c", BENCH_ON_EMULATION, ROOT, emulated_library, str(tmp_path)], cwd=ROOT,
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    assert d["metric"] == "rk3_timesteps_per_s" and d["n_gpus"] == 1 and d["steps"] == 2 and d["finite"] is True
+    assert d["gpu_launches"] > 0 and set(d["kernels"]) >= {"zfwd", "xpass", "zbwd", "rhs", "solve"}
+    assert {"roofline", "step_roofline", "e2e", "clocks", "config", "snapshot", "runtimedata_last"} <= set(d)
+    assert d["snapshot"]["bytes"] == 3 * 8 * 11 * 19 * 16 and abs(d["runtimedata_last"][5] - 2.0) < 1e-2
