@@ -134,3 +134,11 @@ def test_bench_b200_arm_on_the_emulated_library(emulated_library, tmp_path):
     assert d["gpu_launches"] > 0 and set(d["kernels"]) >= {"zfwd", "xpass", "zbwd", "rhs", "solve"}
     assert {"roofline", "step_roofline", "e2e", "clocks", "config", "snapshot", "runtimedata_last"} <= set(d)
     assert d["snapshot"]["bytes"] == 3 * 8 * 11 * 19 * 16 and abs(d["runtimedata_last"][5] - 2.0) < 1e-2
+
+
+def test_smoke_entry_point_on_the_emulated_library(emulated_library):
+    """__graft_entry__.smoke() (one RK3 step of config 1 against the oracle) on the emulated build."""
+    code = ("import sys; sys.path.insert(0, sys.argv[1]); import channel_b200._lib as L; L.LIB_PATH = sys.argv[2]; "
+            "import __graft_entry__ as g; g.smoke()")
+    r = subprocess.run([sys.executable, "-c", code, ROOT, emulated_library], cwd=ROOT, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "smoke ok" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
