@@ -48,6 +48,7 @@ SYMBOLS = {
     "chb_rk3_step": (C.c_int, [C.c_void_p, C.c_double]),
     "chb_get_step_scalars": (C.c_int, [C.c_void_p] + [c_double_p] * 10),
     "chb_download_rhs": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "chb_debug_capture_products": (C.c_int, [C.c_void_p, C.c_int]),
     "chb_download_products": (C.c_int, [C.c_void_p, C.c_void_p]),
     "chb_download_F_planes": (C.c_int, [C.c_void_p, C.c_void_p]),
     "chb_timing_enable": (C.c_int, [C.c_void_p, C.c_int]),

@@ -12,7 +12,7 @@
 static thread_local std::string g_err;
 void chb_set_error(const std::string& s) { g_err = s; }
 extern "C" const char* chb_last_error(void) { return g_err.c_str(); }
-extern "C" int chb_version(void) { return 1001; }   // 1001: restart files, body-force mask(iy,iz)
+extern "C" int chb_version(void) { return 2000; }   // 2000: RHS in place in V, products per chunk (chb_debug_capture_products), barrier timeouts
 
 #define CHB_REQUIRE(cond, msg)  \
     do {                        \
@@ -41,7 +41,8 @@ void chb_timer_flush(chb_handle_s* h) {
     if (h->timer.pending.empty()) return;
     cudaStreamSynchronize(h->stream);
     cudaStreamSynchronize(h->side_stream);
-    for (int L = 0; L < h->nlanes; ++L) cudaStreamSynchronize(h->lane[L].stream);
+    if (h->sA && h->sA != h->stream) cudaStreamSynchronize(h->sA);
+    if (h->sB && h->sB != h->stream) cudaStreamSynchronize(h->sB);
     for (auto& p : h->timer.pending) {
         float ms = 0;
         cudaEventElapsedTime(&ms, p.second.first, p.second.second);
@@ -132,11 +133,36 @@ extern "C" int chb_get_nccl_unique_id(char* id) { return chb_nccl_unique_id(id);
 void chb_select_lane(chb_handle_s* h, int L) {
     const Lane& ln = h->lane[L];
     h->cur_lane = L;
-    h->cstream = ln.stream;
-    h->A = ln.A; h->Ar = ln.Ar; h->B = ln.B; h->Br = ln.Br;
+    h->A = ln.A; h->Ar = ln.Ar; h->B = ln.B; h->Br = ln.Br; h->Pc = ln.Pc;
     h->Aw = ln.Aw; h->Bw = ln.Bw;
     h->flags = ln.flags;
     for (int q = 0; q < CHB_MAX_RANKS; ++q) h->peer_flags[q] = ln.peer_flags[q];
+}
+
+// Layout of the work arena: [0, 4096) barrier flags of every lane + the barrier error word; then, per lane, Ar, Br, Pc
+// (+ A, B in NCCL mode), each aligned to 256 bytes.  Identical on every rank (np is agreed on), so a peer's buffers are
+// its arena base + these offsets.
+#define CHB_ARENA_HEAD 4096
+struct ArenaLayout {
+    size_t ar, br, pc, a, b;   // offsets inside a lane
+    size_t lane_bytes, total;
+};
+static ArenaLayout arena_layout(const Geometry& g, size_t np, int nlanes, bool nccl_mode) {
+    auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t na = (size_t)3 * np * g.nzd * g.nxB * sizeof(cplx), nb = 2 * na, npc = (size_t)6 * np * g.M * sizeof(cplx);
+    ArenaLayout L;
+    size_t o = 0;
+    L.ar = o; o = up(o + na);
+    L.br = o; o = up(o + nb);
+    L.pc = o; o = up(o + npc);
+    L.a = L.b = 0;
+    if (nccl_mode) {
+        L.a = o; o = up(o + na);
+        L.b = o; o = up(o + nb);
+    }
+    L.lane_bytes = o;
+    L.total = CHB_ARENA_HEAD + (size_t)nlanes * o;
+    return L;
 }
 
 // ---- create / destroy ---------------------------------------------------------------------
@@ -151,6 +177,7 @@ extern "C" int chb_create(chb_handle* out, int nx, int ny, int nz, int nxd, int 
     CHB_REQUIRE(nxd >= nx + 1 && nxd % 2 == 0, "chb_create: nxd must be even and >= nx+1");
     CHB_REQUIRE(nzd >= 2 * nz + 1, "chb_create: nzd must be >= 2nz+1");
     CHB_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, "chb_create: bad rank/nranks");
+    CHB_REQUIRE(nranks <= CHB_MAX_RANKS, "chb_create: at most 8 ranks (one NVSwitch node)");
     CHB_REQUIRE((nx + 1) % nranks == 0 && nzd % nranks == 0,
                 "chb_create: nranks must divide nx+1 and nzd (README.md:154)");
     CHB_REQUIRE(nranks == 1 || nccl_id != nullptr, "chb_create: nccl_id required when nranks>1");
@@ -207,11 +234,13 @@ static int create_impl(chb_handle_s* h, int nx, int ny, int nz, int nxd, int nzd
         h->z_tpl = e ? atoi(e) : 0;
         e = getenv("CHB_SOLVE_PF");
         h->solve_pf = e ? atoi(e) : 0;
-        e = getenv("CHB_RHS_CHUNKED");
-        h->rhs_chunked = e ? atoi(e) : 0;
         h->rhs_state = nullptr;
+        // two threads per innermost butterfly position of the x-pass: measured 6 % faster at nxd = 1536 (one CTA per
+        // SM either way), 34 % slower at nxd = 768 (profiles/r2a_variants.md)
         e = getenv("CHB_XPASS_SPLIT");
-        h->xpass_split = e ? atoi(e) : 0;
+        h->xpass_split = e ? atoi(e) : (nxd == 1536 ? 1 : 0);
+        e = getenv("CHB_XPASS_PERSIST");
+        h->xpass_persist = e ? atoi(e) : 0;
         // x tiles of the work buffers (transpose_index.h): products 8 wide (128-byte store segments in
         // the x-pass), velocities as wide as the lines of one zfwd CTA
         g.tw = (g.nxB % 8 == 0) ? 3 : ((g.nxB % 4 == 0) ? 2 : 0);
@@ -247,39 +276,74 @@ static int create_impl(chb_handle_s* h, int nx, int ny, int nz, int nxd, int nzd
         h->Wz = (cplx*)pz; h->Wx = (cplx*)px; h->Wh = (cplx*)ph;
     }
     const size_t fld = (size_t)g.nyp * g.M;
-    if (dev_alloc(&h->V, 3 * fld) || dev_alloc(&h->rhs, 2 * fld) || dev_alloc(&h->oldrhs, 2 * fld) ||
-        dev_alloc(&h->P, 6 * fld) || dev_alloc(&h->ckpt, (size_t)((ny - 1) / CHB_SOLVE_K + 1) * 8 * g.M))
+    // resident state: V 3 + oldrhs 2 + UL checkpoints 0.5 complex per point (the RHS is written in place into V, the
+    // spectral products live per chunk in the arena): the reference's footprint, dnsdata.f90:144-146,667-671
+    if (dev_alloc(&h->V, 3 * fld) || dev_alloc(&h->oldrhs, 2 * fld) ||
+        dev_alloc(&h->ckpt, (size_t)((ny - 1) / CHB_SOLVE_K + 1) * 8 * g.M) || dev_alloc(&h->rhs_state, (size_t)32 * g.M))
         return 1;
-    // convolution work buffers: chunks of planes, ~3 GB of buffers in total over the lanes
+    if (dev_alloc(&h->t_y, (size_t)g.nyp) || dev_alloc(&h->t_dy, (size_t)g.nyp) ||
+        dev_alloc(&h->t_d0, (size_t)g.nyp * 5) || dev_alloc(&h->t_d1, (size_t)g.nyp * 5) ||
+        dev_alloc(&h->t_d2, (size_t)g.nyp * 5) || dev_alloc(&h->t_d4, (size_t)g.nyp * 5) ||
+        dev_alloc(&h->t_D0mat, (size_t)(ny + 1) * 5) || dev_alloc(&h->t_rows, (size_t)g.nyp * 25) || dev_alloc(&h->mean_scratch, (size_t)(ny + 1) * 5 + 3 * g.nyp + 8))
+        return 1;
+    if (dev_alloc(&h->sc, 1)) return 1;
+    CHB_CUDA_OK(cudaMallocHost((void**)&h->sc_host, sizeof(DevScalars)));
+    memset(h->sc_host, 0, sizeof(DevScalars));
+    if (nranks > 1 && chb_nccl_init(h, nccl_id)) return 1;
+    // ---- work arena: chunks of planes of the pencil transposes, one or two lanes ----
     {
         const char* e = getenv("CHB_P2P");
         h->p2p = (nranks > 1 && !(e && atoi(e) == 0)) ? 1 : 0;
+        // two lanes: the kernels that carry the transposes run on their own stream (and SM partition) one chunk ahead of
+        // the local kernels; default on several GPUs, where the former are NVLink-bound
         e = getenv("CHB_LANES");
-        h->nlanes = (e && atoi(e) == 2) ? 2 : 1;   // two lanes measured no faster on 1 or 2 GPUs (kernels of one lane fill the GPU)
+        h->nlanes = e ? (atoi(e) == 2 ? 2 : 1) : (nranks > 1 ? 2 : 1);
         const bool nccl_mode = nranks > 1 && !h->p2p;
-        const size_t per_plane = (size_t)9 * nzd * g.nxB * sizeof(cplx) * (nccl_mode ? 2 : 1);
-        // budget: CHB_WORK_GB (default 12 GB, at most a quarter of the free device memory); larger chunks
-        // mean fewer launches and fewer partially filled last waves per substep
+        // budget: CHB_WORK_GB (default 10 GB, at most a quarter of the free device memory); larger chunks mean fewer
+        // launches, fewer partially filled last waves and fewer carried-accumulator round trips of the RHS assembly
         size_t free_b = 0, total_b = 0;
         CHB_CUDA_OK(cudaMemGetInfo(&free_b, &total_b));
         e = getenv("CHB_WORK_GB");
-        size_t budget = (size_t)((e ? atof(e) : 12.0) * 1073741824.0);
+        size_t budget = (size_t)((e ? atof(e) : 10.0) * 1073741824.0);
         if (budget > free_b / 4) budget = free_b / 4;
-        size_t np = budget / h->nlanes;
-        np /= per_plane;
+        const size_t per_plane = arena_layout(g, 1, 1, nccl_mode).lane_bytes;
+        long long np = (long long)(budget / h->nlanes / per_plane);
         if (np < 1) np = 1;
-        if (np > (size_t)(g.nyp + h->nlanes - 1) / h->nlanes) np = (g.nyp + h->nlanes - 1) / h->nlanes;
+        // with two lanes at least four chunks per sweep, so that the pipeline has something to overlap
+        const long long cap = h->nlanes == 2 ? (g.nyp + 3) / 4 : g.nyp;
+        if (np > cap) np = cap;
+        // every rank must use the same chunk size (it is part of the peer-visible buffer layout and fixes the number of
+        // barriers per sweep) and the same mode switches: agree on the minimum, refuse differing switches
+        if (nranks > 1) {
+            long long v[5] = {np, h->nlanes, -(long long)h->nlanes, h->p2p, -(long long)h->p2p};
+            if (chb_allreduce_min_i64(h, v, 5)) return 1;
+            CHB_REQUIRE(v[1] == -v[2] && v[3] == -v[4], "chb_create: CHB_LANES / CHB_P2P differ between the ranks");
+            np = v[0];
+        }
         h->chunk_planes = (int)np;
-        const size_t na = (size_t)3 * np * nzd * g.nxB, nb = (size_t)6 * np * nzd * g.nxB;
+        const ArenaLayout AL = arena_layout(g, (size_t)np, h->nlanes, nccl_mode);
+        h->arena_bytes = AL.total;
+        h->stage_off = CHB_ARENA_HEAD;
+        CHB_CUDA_OK(cudaMalloc((void**)&h->arena, AL.total));
+        g_alloc_bytes += AL.total;
+        CHB_CUDA_OK(cudaMemset(h->arena, 0, AL.total));
+        h->p2p_error = reinterpret_cast<unsigned long long*>(h->arena + 2048);
         h->n_ipc_opened = 0;
+        const size_t na = (size_t)3 * np * nzd * g.nxB, nb = 2 * na;
         for (int L = 0; L < h->nlanes; ++L) {
             Lane& ln = h->lane[L];
             memset(&ln, 0, sizeof(ln));
-            CHB_CUDA_OK(cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking));
-            CHB_CUDA_OK(cudaEventCreateWithFlags(&ln.done, cudaEventDisableTiming));
-            if (dev_alloc(&ln.Ar, na) || dev_alloc(&ln.Br, nb)) return 1;
-            if (nccl_mode && (dev_alloc(&ln.A, na) || dev_alloc(&ln.B, nb))) return 1;
-            if (dev_alloc(&ln.flags, (size_t)CHB_MAX_RANKS)) return 1;
+            CHB_CUDA_OK(cudaEventCreateWithFlags(&ln.evA, cudaEventDisableTiming));
+            CHB_CUDA_OK(cudaEventCreateWithFlags(&ln.evB, cudaEventDisableTiming));
+            char* base = h->arena + CHB_ARENA_HEAD + (size_t)L * AL.lane_bytes;
+            ln.Ar = reinterpret_cast<cplx*>(base + AL.ar);
+            ln.Br = reinterpret_cast<cplx*>(base + AL.br);
+            ln.Pc = reinterpret_cast<cplx*>(base + AL.pc);
+            if (nccl_mode) {
+                ln.A = reinterpret_cast<cplx*>(base + AL.a);
+                ln.B = reinterpret_cast<cplx*>(base + AL.b);
+            }
+            ln.flags = reinterpret_cast<unsigned long long*>(h->arena) + (size_t)L * CHB_MAX_RANKS;
             // pack-side store targets (PeerPtrs): element for peer q at p[q] + index(block = rank, ...)
             const ptrdiff_t blkA = (ptrdiff_t)(na / nranks), blkB = (ptrdiff_t)(nb / nranks);
             for (int q = 0; q < nranks; ++q) {
@@ -288,19 +352,25 @@ static int create_impl(chb_handle_s* h, int nx, int ny, int nz, int nxd, int nzd
             }
         }
         chb_select_lane(h, 0);
+        // streams of the chunk pipeline
+        h->sA = h->sB = h->stream;
+        h->green[0] = h->green[1] = nullptr;
+        h->green_sms[0] = h->green_sms[1] = 0;
+        if (h->nlanes == 2) {
+            // CHB_GREEN=<SMs of the transpose partition> (default: 54 % of the SMs on several GPUs, off on one): the two
+            // streams get disjoint SM partitions through CUDA green contexts, so that the local kernels really run
+            // beside the NVLink-bound ones instead of behind them; plain streams if the driver refuses
+            e = getenv("CHB_GREEN");
+            int sms_a = e ? atoi(e) : (nranks > 1 ? -1 : 0);
+            if (sms_a != 0 && chb_green_create(h, sms_a) != 0) sms_a = 0;
+            if (sms_a == 0) {
+                CHB_CUDA_OK(cudaStreamCreateWithFlags(&h->sA, cudaStreamNonBlocking));
+                CHB_CUDA_OK(cudaStreamCreateWithFlags(&h->sB, cudaStreamNonBlocking));
+            }
+        }
+        h->cstream = h->sA;
     }
-    if (dev_alloc(&h->t_y, (size_t)g.nyp) || dev_alloc(&h->t_dy, (size_t)g.nyp) ||
-        dev_alloc(&h->t_d0, (size_t)g.nyp * 5) || dev_alloc(&h->t_d1, (size_t)g.nyp * 5) ||
-        dev_alloc(&h->t_d2, (size_t)g.nyp * 5) || dev_alloc(&h->t_d4, (size_t)g.nyp * 5) ||
-        dev_alloc(&h->t_D0mat, (size_t)(ny + 1) * 5) || dev_alloc(&h->t_rows, (size_t)g.nyp * 25) || dev_alloc(&h->mean_scratch, (size_t)(ny + 1) * 5 + 3 * g.nyp + 8))
-        return 1;
-    if (h->rhs_chunked && dev_alloc(&h->rhs_state, (size_t)32 * g.M)) return 1;
-    if (dev_alloc(&h->sc, 1)) return 1;
-    CHB_CUDA_OK(cudaMallocHost((void**)&h->sc_host, sizeof(DevScalars)));
-    memset(h->sc_host, 0, sizeof(DevScalars));
-    CHB_REQUIRE(nranks <= CHB_MAX_RANKS, "chb_create: at most 8 ranks (one NVSwitch node)");
-    if (nranks > 1 && chb_nccl_init(h, nccl_id)) return 1;
-    if (h->p2p && chb_p2p_setup(h, 0, 0)) return 1;
+    if (h->p2p && chb_p2p_setup(h)) return 1;
     CHB_CUDA_OK(cudaDeviceSynchronize());
     h->dev_bytes = g_alloc_bytes;
     return 0;
@@ -313,20 +383,22 @@ extern "C" int chb_destroy(chb_handle h) {
     chb_timer_flush(h);
     chb_restart_destroy(h);
     chb_nccl_destroy(h);
-    cudaFree(h->V); cudaFree(h->rhs); cudaFree(h->oldrhs); cudaFree(h->P); cudaFree(h->ckpt);
+    cudaFree(h->V); cudaFree(h->oldrhs); cudaFree(h->ckpt);
     if (h->F) cudaFree(h->F);
     if (h->rhs_state) cudaFree(h->rhs_state);
+    if (h->P_dbg) cudaFree(h->P_dbg);
     if (h->cv_Vold) cudaFree(h->cv_Vold);
     if (h->cv_uconv) cudaFree(h->cv_uconv);
     if (h->p2p) chb_p2p_teardown(h);
-    for (int L = 0; L < h->nlanes; ++L) {
+    for (int L = 0; L < CHB_MAX_LANES; ++L) {
         Lane& ln = h->lane[L];
-        if (ln.A) cudaFree(ln.A);
-        if (ln.B) cudaFree(ln.B);
-        cudaFree(ln.Ar); cudaFree(ln.Br); cudaFree(ln.flags);
-        if (ln.done) cudaEventDestroy(ln.done);
-        if (ln.stream) cudaStreamDestroy(ln.stream);
+        if (ln.evA) cudaEventDestroy(ln.evA);
+        if (ln.evB) cudaEventDestroy(ln.evB);
     }
+    if (h->sA && h->sA != h->stream) cudaStreamDestroy(h->sA);
+    if (h->sB && h->sB != h->stream) cudaStreamDestroy(h->sB);
+    chb_green_destroy(h);
+    if (h->arena) cudaFree(h->arena);
     cudaFree(h->Wz); cudaFree(h->Wx); cudaFree(h->Wh); cudaFree(h->rev_z);
     cudaFree(h->t_y); cudaFree(h->t_dy); cudaFree(h->t_d0); cudaFree(h->t_d1); cudaFree(h->t_d2); cudaFree(h->t_d4);
     cudaFree(h->t_D0mat); cudaFree(h->t_rows); cudaFree(h->mean_scratch); cudaFree(h->sc);
@@ -387,30 +459,44 @@ extern "C" int chb_set_tables(chb_handle h, const double* y, const double* d0, c
 }
 
 // ---- field transfer --------------------------------------------------------------------------
+// Host <-> device transfer of a 3-component field.  Fortran layout: the field crosses PCIe in x-slabs that are staged in
+// the work arena (dead between the sweeps of buildrhs) and transposed on the device; everything is enqueued on the
+// handle's stream in order and waited for once.
 static int transfer_V(chb_handle h, double* host, bool upload, bool fortran_layout, cplx* field) {
     CHB_REQUIRE(h, "null handle");
     CHB_CUDA_OK(cudaSetDevice(h->device));
     const Geometry& g = h->g;
     const size_t fld = (size_t)g.nyp * g.M;
-    CHB_CUDA_OK(cudaStreamSynchronize(h->stream));
-    for (int c = 0; c < 3; ++c) {
-        cplx* dev = field + c * fld;
-        cplx* hc = reinterpret_cast<cplx*>(host) + c * fld;
-        if (!fortran_layout) {
-            if (upload) CHB_CUDA_OK(cudaMemcpyAsync(dev, hc, fld * sizeof(cplx), cudaMemcpyHostToDevice, h->stream));
-            else CHB_CUDA_OK(cudaMemcpyAsync(hc, dev, fld * sizeof(cplx), cudaMemcpyDeviceToHost, h->stream));
-        } else {
-            cplx* stage = h->P;  // products buffer is dead outside buildrhs
-            if (upload) {
-                CHB_CUDA_OK(cudaMemcpyAsync(stage, hc, fld * sizeof(cplx), cudaMemcpyHostToDevice, h->stream));
-                launch_fortran_to_planes(h, stage, dev, c, 0, g.nxB);
-            } else {
-                launch_planes_to_fortran(h, dev, stage, c, 0, g.nxB);
-                CHB_CUDA_OK(cudaMemcpyAsync(hc, stage, fld * sizeof(cplx), cudaMemcpyDeviceToHost, h->stream));
+    if (!fortran_layout) {
+        const cudaMemcpyKind kind = upload ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
+        if (upload) CHB_CUDA_OK(cudaMemcpyAsync(field, host, 3 * fld * sizeof(cplx), kind, h->stream));
+        else CHB_CUDA_OK(cudaMemcpyAsync(host, field, 3 * fld * sizeof(cplx), kind, h->stream));
+    } else {
+        cplx* stage = reinterpret_cast<cplx*>(h->arena + h->stage_off);
+        const size_t cap = (h->arena_bytes - h->stage_off) / sizeof(cplx);
+        const size_t per_ix = (size_t)g.nzt * g.nyp;
+        CHB_REQUIRE(cap >= per_ix, "transfer: work arena smaller than one x-mode of the field (raise CHB_WORK_GB)");
+        const int halves = cap >= 2 * per_ix ? 2 : 1;
+        int nix_max = (int)((cap / halves) / per_ix);
+        if (nix_max > g.nxB) nix_max = g.nxB;
+        int k = 0;
+        for (int c = 0; c < 3; ++c) {
+            for (int ix0 = 0; ix0 < g.nxB; ix0 += nix_max, ++k) {
+                const int nix = (ix0 + nix_max <= g.nxB) ? nix_max : g.nxB - ix0;
+                cplx* st = stage + (size_t)(k % halves) * (cap / halves);
+                cplx* hc = reinterpret_cast<cplx*>(host) + ((size_t)c * g.nxB + ix0) * per_ix;
+                const size_t bytes = (size_t)nix * per_ix * sizeof(cplx);
+                if (upload) {
+                    CHB_CUDA_OK(cudaMemcpyAsync(st, hc, bytes, cudaMemcpyHostToDevice, h->stream));
+                    launch_fortran_to_planes(h, st, field + c * fld, ix0, nix, h->stream);
+                } else {
+                    launch_planes_to_fortran(h, field + c * fld, st, ix0, nix, h->stream);
+                    CHB_CUDA_OK(cudaMemcpyAsync(hc, st, bytes, cudaMemcpyDeviceToHost, h->stream));
+                }
             }
         }
-        CHB_CUDA_OK(cudaStreamSynchronize(h->stream));
     }
+    CHB_CUDA_OK(cudaStreamSynchronize(h->stream));
     CHB_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -455,8 +541,28 @@ static int download_n(chb_handle h, double* host, const cplx* dev, int ncomp) {
     CHB_CUDA_OK(cudaMemcpy(host, dev, n * sizeof(cplx), cudaMemcpyDeviceToHost));
     return 0;
 }
-extern "C" int chb_download_rhs(chb_handle h, double* p) { return download_n(h, p, h ? h->rhs : nullptr, 2); }
-extern "C" int chb_download_products(chb_handle h, double* p) { return download_n(h, p, h ? h->P : nullptr, 6); }
+// Between chb_buildrhs and chb_linsolve the RHS of the eta / D2v equations sits in V components 0 / 1 (rows 1..ny-1).
+extern "C" int chb_download_rhs(chb_handle h, double* p) { return download_n(h, p, h ? h->V : nullptr, 2); }
+// The spectral products exist one chunk of planes at a time; chb_debug_capture_products(h, 1) makes the following
+// sweeps keep a copy of every chunk (6 complex per point of extra device memory: tests and diagnostics only).
+extern "C" int chb_debug_capture_products(chb_handle h, int on) {
+    CHB_REQUIRE(h, "null handle");
+    CHB_CUDA_OK(cudaSetDevice(h->device));
+    if (on && !h->P_dbg) {
+        if (dev_alloc(&h->P_dbg, (size_t)6 * h->g.nyp * h->g.M)) return 1;
+        h->dev_bytes += (size_t)6 * h->g.nyp * h->g.M * sizeof(cplx);
+    } else if (!on && h->P_dbg) {
+        CHB_CUDA_OK(cudaStreamSynchronize(h->stream));
+        cudaFree(h->P_dbg);
+        h->P_dbg = nullptr;
+        h->dev_bytes -= (size_t)6 * h->g.nyp * h->g.M * sizeof(cplx);
+    }
+    return 0;
+}
+extern "C" int chb_download_products(chb_handle h, double* p) {
+    CHB_REQUIRE(h && h->P_dbg, "chb_download_products: call chb_debug_capture_products(h, 1) before chb_buildrhs");
+    return download_n(h, p, h->P_dbg, 6);
+}
 
 // ---- scalars ---------------------------------------------------------------------------------
 static int push_scalars(chb_handle h) {
@@ -498,7 +604,13 @@ static int set_body_force_common(chb_handle h, int enable, const double* A, int 
     if (!enable) return 0;
     memcpy(h->bf.A, A, sizeof(double) * 9);
     h->bf.exclude_mean = exclude_mean;
-    if (!h->F && dev_alloc(&h->F, (size_t)3 * h->g.nyp * h->g.M)) return 1;
+    if (!h->F) {
+        if (dev_alloc(&h->F, (size_t)3 * h->g.nyp * h->g.M)) return 1;
+    } else {
+        // a hook only assigns inside its mask: values a previous hook (or chb_upload_F) left outside the new mask must
+        // not survive the reconfiguration, the reference's F starts from 0 (dnsdata.f90:146)
+        CHB_CUDA_OK(cudaMemsetAsync(h->F, 0, (size_t)3 * h->g.nyp * h->g.M * sizeof(cplx), h->stream));
+    }
     return 0;
 }
 extern "C" int chb_set_body_force_linear(chb_handle h, int enable, const double* A, const double* mask_y,
@@ -538,44 +650,68 @@ extern "C" int chb_set_body_force(chb_handle h) {
 }
 
 // ---- the hot path ----------------------------------------------------------------------------
-// rhs_ode != null (chunked RHS assembly, experimental): after the backward z pass of every chunk the plane loop of
-// buildrhs runs for that chunk's planes on the main stream, concurrently with the next chunk's passes on the lane stream
+// One sweep of `convolutions` over all planes (dnsdata.f90:487-602), chunk by chunk, and - when rhs_ode is given - the
+// plane loop of buildrhs (:634-670) behind it.  Chunk c uses lane c % nlanes.  Two streams:
+//   sA: zfwd(c) -> barrier -> [convvel] -> xpass(c) -> barrier        the kernels whose stores ARE the pencil transposes
+//   sB: zbwd(c) -> rhs(c)                                              local kernels, one chunk behind
+// With two lanes sA and sB are different streams (on disjoint SM partitions when green contexts are available), so
+// the HBM-bound local kernels of chunk c run while the NVLink-bound kernels of chunk c+1 wait for their remote
+// stores: the role of the reference's nonblockingXZ variant (mpi_transpose.f90:149-168).  With one lane both are the
+// handle's stream and the sweep is strictly sequential.
+// Buffer reuse across ranks: a peer's zfwd(c) stores into this rank's Ar(lane) - free once every rank has passed the
+// barrier behind xpass(c - nlanes); a peer's xpass(c) stores into Br(lane) - it starts behind the barrier after
+// zfwd(c), at which this rank only arrives once its own zbwd(c - nlanes) has read Br(lane) (sA waits for evB).
 static int convolutions_all(chb_handle h, int compute_cfl, bool products, const double* rhs_ode = nullptr, double rhs_deltat = 0.0,
                             double deltat = 0.0) {
     // the first sweep of buildrhs after an outstats also feeds the convection-velocity diagnostic (dnsdata.f90:515-531)
     const bool convvel = products && h->cv_enabled && h->cv_compute;
     const Geometry& g = h->g;
     const int np = h->chunk_planes;
-    // fork: the lanes start after everything queued on the main stream (V complete)
-    CHB_CUDA_OK(cudaEventRecord(h->ev_fork, h->stream));
-    for (int L = 0; L < h->nlanes; ++L) CHB_CUDA_OK(cudaStreamWaitEvent(h->lane[L].stream, h->ev_fork, 0));
+    const bool two = h->sA != h->stream;
+    if (two) {   // fork: both streams start after everything queued on the main stream (V complete)
+        CHB_CUDA_OK(cudaEventRecord(h->ev_fork, h->stream));
+        CHB_CUDA_OK(cudaStreamWaitEvent(h->sA, h->ev_fork, 0));
+        CHB_CUDA_OK(cudaStreamWaitEvent(h->sB, h->ev_fork, 0));
+    }
     int c = 0;
     for (int p0 = 0; p0 < g.nyp; p0 += np, ++c) {
         const int n = (p0 + np <= g.nyp) ? np : g.nyp - p0;
-        chb_select_lane(h, c % h->nlanes);
+        const int L = c % h->nlanes;
+        Lane& ln = h->lane[L];
+        chb_select_lane(h, L);
+        h->cstream = h->sA;
+        if (two && c >= h->nlanes) CHB_CUDA_OK(cudaStreamWaitEvent(h->sA, ln.evB, 0));
         launch_zfwd(h, p0, n);                       // stores straight into the x-side owner's buffer
         if (chb_exchange(h, true)) return 1;         // zTOx, mpi_transpose.f90:50-83
         if (convvel) launch_convvel(h, p0, n, deltat);
         launch_xpass(h, p0, n, compute_cfl);
-        // xTOz, mpi_transpose.f90:88-117; in direct mode the barrier also frees Ar for the next chunk
+        // xTOz, mpi_transpose.f90:88-117; in direct mode the barrier also frees Ar for the chunk after next
         if ((products || h->p2p) && chb_exchange(h, false)) return 1;
-        if (products) launch_zbwd(h, p0, n);
-        if (products && rhs_ode) {
-            Lane& ln = h->lane[h->cur_lane];
-            CHB_CUDA_OK(cudaEventRecord(ln.done, ln.stream));
-            CHB_CUDA_OK(cudaStreamWaitEvent(h->stream, ln.done, 0));
-            launch_rhs_chunk(h, rhs_ode, rhs_deltat, p0, n, h->stream);
+        if (!products) continue;
+        if (two) {
+            CHB_CUDA_OK(cudaEventRecord(ln.evA, h->sA));
+            CHB_CUDA_OK(cudaStreamWaitEvent(h->sB, ln.evA, 0));
         }
+        h->cstream = h->sB;
+        launch_zbwd(h, p0, n);
+        if (h->P_dbg)   // debug capture: keep this chunk's products
+            for (int k = 0; k < 6; ++k)
+                CHB_CUDA_OK(cudaMemcpyAsync(h->P_dbg + ((size_t)k * g.nyp + p0) * g.M, ln.Pc + (size_t)k * np * g.M,
+                                            (size_t)n * g.M * sizeof(cplx), cudaMemcpyDeviceToDevice, h->sB));
+        if (rhs_ode) launch_rhs_chunk(h, rhs_ode, rhs_deltat, p0, n, h->sB);
+        if (two) CHB_CUDA_OK(cudaEventRecord(ln.evB, h->sB));
     }
     if (convvel) {   // IF (iy==nyN+2 .AND. compute_convvel): convvel_cnt=convvel_cnt+1; compute_convvel=.FALSE.   :546-549
         h->cv_cnt += 1;
         h->cv_compute = 0;
     }
-    // join
-    for (int L = 0; L < h->nlanes; ++L) {
-        CHB_CUDA_OK(cudaEventRecord(h->lane[L].done, h->lane[L].stream));
-        CHB_CUDA_OK(cudaStreamWaitEvent(h->stream, h->lane[L].done, 0));
+    if (two) {   // join
+        CHB_CUDA_OK(cudaEventRecord(h->ev_join, h->sA));
+        CHB_CUDA_OK(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+        CHB_CUDA_OK(cudaEventRecord(h->ev_join, h->sB));
+        CHB_CUDA_OK(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
     }
+    h->cstream = h->sA;
     CHB_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -594,12 +730,7 @@ extern "C" int chb_buildrhs(chb_handle h, const double* ode, double deltat, int 
     CHB_REQUIRE(deltat > 0.0, "chb_buildrhs: deltat must be > 0");
     CHB_CUDA_OK(cudaSetDevice(h->device));
     if (h->bf.enabled) launch_force_ghosts(h);
-    if (h->rhs_chunked) {
-        if (convolutions_all(h, compute_cfl, true, ode, deltat, deltat)) return 1;
-    } else {
-        if (convolutions_all(h, compute_cfl, true, nullptr, 0.0, deltat)) return 1;
-        launch_rhs(h, ode, deltat);
-    }
+    if (convolutions_all(h, compute_cfl, true, ode, deltat, deltat)) return 1;
     CHB_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -636,6 +767,7 @@ extern "C" int chb_get_step_scalars(chb_handle h, double* cfl, double* fr, doubl
         if (chb_bcast_scalars(h)) return 1;
     }
     if (pull_scalars(h)) return 1;
+    if (chb_p2p_check(h)) return 6;
     chb_timer_flush(h);
     if (h->cv_enabled) h->cv_compute = 1;   // compute_convvel=.TRUE.   dnsdata.f90:858-860
     DevScalars* s = h->sc_host;
@@ -664,6 +796,7 @@ extern "C" int chb_sync(chb_handle h) {
     CHB_CUDA_OK(cudaSetDevice(h->device));
     CHB_CUDA_OK(cudaStreamSynchronize(h->stream));
     CHB_CUDA_OK(cudaGetLastError());
+    if (chb_p2p_check(h)) return 6;
     return 0;
 }
 extern "C" int chb_stopwatch_begin(chb_handle h) {

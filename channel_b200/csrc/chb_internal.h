@@ -69,18 +69,20 @@ struct PeerPtrs {
     cplx* p[CHB_MAX_RANKS];
 };
 
-// One pipeline of the nonlinear term: its own stream and pencil-transpose work buffers.  Chunks of
-// y-planes alternate between the lanes, so that the NVLink-bound pack kernels (zfwd, xpass stores
-// into peer HBM) and the FP64-bound x-pass of one chunk overlap the HBM-bound z-passes of another.
+// One set of pencil-transpose work buffers for a chunk of y-planes.  Consecutive chunks alternate between the lanes
+// (chb_api.cu, convolutions_all): while the kernels that carry the transposes (zfwd, xpass: stores into peer HBM over
+// NVLink) work on chunk c+1 in one lane, the local kernels (zbwd, the plane loop of buildrhs) finish chunk c in the
+// other.  All lanes are carved out of one device allocation, the arena (one CUDA IPC handle per rank).
 #define CHB_MAX_LANES 2
 struct Lane {
-    cudaStream_t stream;
-    cplx *A, *Ar, *B, *Br;
+    cplx *A, *Ar, *B, *Br;   // A, B: NCCL mode only (send buffers)
+    cplx* Pc;                // spectral products of the chunk [6][np][M]: written by zbwd, read by the plane loop of buildrhs
     PeerPtrs Aw, Bw;
     unsigned long long* flags;
     unsigned long long* peer_flags[CHB_MAX_RANKS];
     unsigned long long epoch;
-    cudaEvent_t done;
+    cudaEvent_t evA;         // recorded on the transpose stream after xpass + its barrier: Br complete, Ar free
+    cudaEvent_t evB;         // recorded on the local stream after zbwd (+ rhs): Br and Pc free
 };
 
 struct KernelTimer {
@@ -97,36 +99,45 @@ struct chb_handle_s {
     cudaStream_t side_stream;      // mean-mode column, concurrent with S3/S4 of the solve
     cudaEvent_t ev_fork, ev_join;
     Lane lane[CHB_MAX_LANES];      // the fields A..epoch below are a copy of the lane in use (chb_select_lane)
-    int nlanes, cur_lane;          // CHB_LANES = 1 | 2
-    cudaStream_t cstream;          // stream of the lane in use
+    int nlanes, cur_lane;          // CHB_LANES = 1 | 2 (default 2 on several GPUs)
+    cudaStream_t sA, sB;           // transpose-carrying kernels (zfwd, xpass, barriers) / local kernels (zbwd, rhs); both = stream when nlanes == 1
+    cudaStream_t cstream;          // stream the conv launchers use (set by convolutions_all to sA or sB)
+    void* green[2];                // CUgreenCtx of sA / sB when the SMs are partitioned (CHB_GREEN, green_ctx.cu), else null
+    int green_sms[2];              // SMs of each partition (0 = not partitioned)
     // fields (device layout [c][iy+1][ixl][iz+nz], complex128)
-    cplx* V;        // [3][nyp][M]
-    cplx* rhs;      // [2][nyp][M]  0 = eta, 1 = D2v (also holds the Step1 result)
+    cplx* V;        // [3][nyp][M]; between chb_buildrhs and chb_linsolve components 0 / 1 hold the RHS of the eta / D2v
+                    // equations on rows 1..ny-1 (the reference's in-place write-back, dnsdata.f90:667-671)
     cplx* oldrhs;   // [2][nyp][M]
     cplx* F;        // [3][nyp][M] or null
-    cplx* P;        // [6][nyp][M]  spectral products
     double* ckpt;   // [nblk][8][M]  UL-recurrence state every CHB_SOLVE_K rows (solve_kernels.cu)
-    // convolution work buffers for a chunk of planes
+    // work arena: barrier flags + per lane Ar, Br, Pc (+ A, B in NCCL mode); also the staging area of the host <-> device
+    // field transfers and of the restart files
+    char* arena;
+    size_t arena_bytes;
+    size_t stage_off;     // first byte of the arena usable as staging (behind the flags)
     int chunk_planes;
     int zf_lines_per_cta, zb_lines_per_cta;  // lines per CTA of zfwd / zbwd (CHB_ZF_LPC, CHB_ZB_LPC: 2, 4 or 8)
     int use_fft3;         // register-resident three-stage FFT kernels for the large sizes (CHB_FFT3=0 disables)
-    int zf_direct;        // CHB_ZF_DIRECT=1: zfwd4 stage A reads global memory directly (no TMA staging); experimental
-    int z_tpl;            // CHB_Z_TPL=128|96: threads per line of the z passes at nzd = 1536 / 3072 (default 64); experimental
-    int solve_pf;         // CHB_SOLVE_PF=1: S1 / S3 / S4 with eight rows of loads in flight per thread; experimental
-    int rhs_chunked;      // CHB_RHS_CHUNKED=1: rhs_kernel per chunk of planes right after its zbwd; experimental
-    double* rhs_state;    // [32][M] accumulators carried between the chunks
-    int xpass_split;      // CHB_XPASS_SPLIT=1: xpass5 (two threads per innermost butterfly position) at nxd = 1536; experimental
+    int zf_direct;        // CHB_ZF_DIRECT=1: zfwd4 stage A reads global memory directly (no TMA staging); measured slower
+    int z_tpl;            // CHB_Z_TPL=128|96: threads per line of the z passes at nzd = 1536 / 3072 (default 64)
+    int solve_pf;         // CHB_SOLVE_PF=1: S1 / S3 / S4 with eight rows of loads in flight per thread; measured slower at config 3
+    double* rhs_state;    // [32][M] accumulators of the plane loop of buildrhs carried from chunk to chunk
+    int xpass_split;      // CHB_XPASS_SPLIT: two threads per innermost butterfly position (default on at nxd = 1536)
+    int xpass_persist;    // CHB_XPASS_PERSIST: persistent x-pass with the next line's inputs prefetched into shared memory
     cplx* A;        // NCCL mode only: send buffer of zTOx, [peer][3][np][nzB][nxB]
     cplx* Ar;       // z-padded velocity after zTOx, [src rank][3][np][nzB][nxB]
     cplx* B;        // NCCL mode only: send buffer of xTOz
     cplx* Br;       // products after xTOz, [src rank][6][np][nxB/2^tw][nzB][2^tw]
+    cplx* Pc;       // spectral products of the chunk in flight (lane)
     PeerPtrs Aw, Bw;   // where zfwd / xpass store (see PeerPtrs)
     int p2p;           // 1 = direct NVLink stores into peer buffers + flag barrier, 0 = NCCL all-to-all
     unsigned long long* flags;             // [CHB_MAX_RANKS] barrier flags of this rank (IPC-shared)
     unsigned long long* peer_flags[CHB_MAX_RANKS];
-    unsigned long long epoch;
-    void* ipc_opened[3 * CHB_MAX_RANKS * CHB_MAX_LANES];
+    unsigned long long* p2p_error;         // device word set by a barrier that timed out
+    void* ipc_opened[CHB_MAX_RANKS];
     int n_ipc_opened;
+    // debug capture of the spectral products of all planes (chb_debug_capture_products): [6][nyp][M] or null
+    cplx* P_dbg;
     // FFT plans and tables
     FftPlan plan_z, plan_x;
     cplx* Wz;       // exp(+2 pi i e/nzd)
@@ -166,19 +177,25 @@ void launch_zbwd(chb_handle_s* h, int plane0, int nplanes);
 bool launch_z3_fwd_or_bwd(chb_handle_s* h, int plane0, int nplanes, bool fwd);
 bool launch_x3_pass(chb_handle_s* h, int plane0, int nplanes, int compute_cfl);
 // ---- rhs_kernel.cu ----
-void launch_rhs(chb_handle_s* h, const double* ode, double deltat);
 void launch_rhs_chunk(chb_handle_s* h, const double* ode, double deltat, int plane0, int nplanes, cudaStream_t st);
 // ---- solve_kernels.cu ----
 void launch_linsolve(chb_handle_s* h, double lambda);
 void launch_meanflow_prepass(chb_handle_s* h);
 // ---- layout_kernels.cu ----
-void launch_fortran_to_planes(chb_handle_s* h, const cplx* src, cplx* dst, int c, int ix0, int nix);
-void launch_planes_to_fortran(chb_handle_s* h, const cplx* src, cplx* dst, int c, int ix0, int nix);
+// x-slab [ix0, ix0 + nix) of one component between the file / Fortran order (cols: [nix][2nz+1][ny+3], contiguous) and the
+// device layout (planes: the component's [ny+3][nxB][2nz+1] array), on stream st
+void launch_fortran_to_planes(chb_handle_s* h, const cplx* cols, cplx* planes, int ix0, int nix, cudaStream_t st);
+void launch_planes_to_fortran(chb_handle_s* h, const cplx* planes, cplx* cols, int ix0, int nix, cudaStream_t st);
 void launch_body_force(chb_handle_s* h);
 void launch_force_ghosts(chb_handle_s* h);
 // ---- transposes (transpose.cu) ----
 int chb_alltoall(chb_handle_s* h, const cplx* send, cplx* recv, size_t count_per_peer);
-int chb_p2p_setup(chb_handle_s* h, size_t na, size_t nb);   // maps peer Ar/Br/flags; 0 on success
+int chb_p2p_setup(chb_handle_s* h);                         // maps the peers' arenas (Ar/Br/flags of every lane); 0 on success
+int chb_p2p_check(chb_handle_s* h);                         // non-zero (and the error text) if a flag barrier timed out
+int chb_allreduce_min_i64(chb_handle_s* h, long long* v, int n);   // agreement of the ranks on sizes derived from local state
+// ---- green_ctx.cu: SM partitions for the two streams of the chunk pipeline (CUDA green contexts) ----
+int chb_green_create(chb_handle_s* h, int sms_a);           // 0 = sA / sB now run on disjoint SM partitions
+void chb_green_destroy(chb_handle_s* h);
 void chb_p2p_teardown(chb_handle_s* h);
 int chb_exchange(chb_handle_s* h, bool a_side);             // completes zTOx (a_side) / xTOz on the lane's stream
 void chb_select_lane(chb_handle_s* h, int lane);            // makes `lane` the one the conv launchers use

@@ -62,9 +62,9 @@ zbwd_kernel(const cplx* __restrict__ Br, cplx* __restrict__ P, Geometry g, FftPl
     const int ixl0 = blockIdx.x * tx;
     const int pli = blockIdx.y;
     const int c = blockIdx.z;  // product index 0..5
-    const int iyp = plane0 + pli;
     const int nl = min(tx, g.nxB - ixl0);
     const int nzd = g.nzd, nz = g.nz, nzt = g.nzt;
+    (void)plane0;
     for (int idx = threadIdx.x; idx < nl * nzd; idx += blockDim.x) {
         const int izd = idx / nl;
         const int t = idx - izd * nl;
@@ -73,7 +73,7 @@ zbwd_kernel(const cplx* __restrict__ Br, cplx* __restrict__ P, Geometry g, FftPl
         smem[(size_t)t * line_stride + CHB_PAD(izd)] = Br[chb_bufB_index(peer, 6, c, np, pli, g.nzB, izl, g.nxB, ixl0 + t, g.tw)];
     }
     fft_lines<-1, true>(smem, line_stride, nl, pl, W);
-    cplx* dst = P + (((size_t)c * g.nyp + iyp) * g.nxB + ixl0) * nzt;
+    cplx* dst = P + (((size_t)c * np + pli) * g.nxB + ixl0) * nzt;   // the chunk's spectral products [6][np][nxB][2nz+1]
     for (int idx = threadIdx.x; idx < nl * nzt; idx += blockDim.x) {
         const int t = idx / nzt;
         const int izp = idx - t * nzt;                                // iz + nz
@@ -245,7 +245,7 @@ void launch_zbwd(chb_handle_s* h, int plane0, int nplanes) {
     cudaFuncSetAttribute(zbwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dim3 grid((h->g.nxB + tx - 1) / tx, nplanes, 6);
     ScopedKernelTimer tm(h, "zbwd", h->cstream);
-    CHB_LAUNCH(grid, CONV_THREADS, smem, h->cstream, zbwd_kernel)(h->Br, h->P, h->g, h->plan_z, h->Wz, h->rev_z, plane0,
+    CHB_LAUNCH(grid, CONV_THREADS, smem, h->cstream, zbwd_kernel)(h->Br, h->Pc, h->g, h->plan_z, h->Wz, h->rev_z, plane0,
                                                          h->chunk_planes, tx, ls);
     h->launches++;
 }

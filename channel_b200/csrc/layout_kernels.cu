@@ -7,53 +7,55 @@
 
 #define TILE 32
 
-// src [ncols][nyp] -> dst [nyp][ncols]
-__global__ void transpose_cols_to_planes(const cplx* __restrict__ src, cplx* __restrict__ dst, long long ncols,
-                                         int nyp) {
+// An x-slab [ix0, ix0 + nix) of one component: `cols` is the slab in host / file order, a contiguous [ncols][nyp] matrix
+// (ncols = nix*(2nz+1)); `planes` points at column ix0*(2nz+1) of the component's device array, row length ld = M.
+// cols -> planes
+__global__ void transpose_cols_to_planes(const cplx* __restrict__ cols, cplx* __restrict__ planes, long long ncols,
+                                         int nyp, long long ld) {
     __shared__ cplx tile[TILE][TILE + 1];
     const long long c0 = (long long)blockIdx.x * TILE;
     const int y0 = blockIdx.y * TILE;
     for (int r = threadIdx.y; r < TILE; r += blockDim.y) {
         const long long c = c0 + r;
         const int y = y0 + threadIdx.x;
-        if (c < ncols && y < nyp) tile[r][threadIdx.x] = src[c * nyp + y];
+        if (c < ncols && y < nyp) tile[r][threadIdx.x] = cols[c * nyp + y];
     }
     __syncthreads();
     for (int r = threadIdx.y; r < TILE; r += blockDim.y) {
         const int y = y0 + r;
         const long long c = c0 + threadIdx.x;
-        if (c < ncols && y < nyp) dst[(size_t)y * ncols + c] = tile[threadIdx.x][r];
+        if (c < ncols && y < nyp) planes[(size_t)y * ld + c] = tile[threadIdx.x][r];
     }
 }
 
-// src [nyp][ncols] -> dst [ncols][nyp]
-__global__ void transpose_planes_to_cols(const cplx* __restrict__ src, cplx* __restrict__ dst, long long ncols,
-                                         int nyp) {
+// planes -> cols
+__global__ void transpose_planes_to_cols(const cplx* __restrict__ planes, cplx* __restrict__ cols, long long ncols,
+                                         int nyp, long long ld) {
     __shared__ cplx tile[TILE][TILE + 1];
     const long long c0 = (long long)blockIdx.x * TILE;
     const int y0 = blockIdx.y * TILE;
     for (int r = threadIdx.y; r < TILE; r += blockDim.y) {
         const int y = y0 + r;
         const long long c = c0 + threadIdx.x;
-        if (c < ncols && y < nyp) tile[r][threadIdx.x] = src[(size_t)y * ncols + c];
+        if (c < ncols && y < nyp) tile[r][threadIdx.x] = planes[(size_t)y * ld + c];
     }
     __syncthreads();
     for (int r = threadIdx.y; r < TILE; r += blockDim.y) {
         const long long c = c0 + r;
         const int y = y0 + threadIdx.x;
-        if (c < ncols && y < nyp) dst[c * nyp + y] = tile[threadIdx.x][r];
+        if (c < ncols && y < nyp) cols[c * nyp + y] = tile[threadIdx.x][r];
     }
 }
 
-void launch_fortran_to_planes(chb_handle_s* h, const cplx* src, cplx* dst, int, int, int) {
-    const long long ncols = h->g.M;
+void launch_fortran_to_planes(chb_handle_s* h, const cplx* cols, cplx* planes, int ix0, int nix, cudaStream_t st) {
+    const long long ncols = (long long)nix * h->g.nzt;
     dim3 grid((unsigned)((ncols + TILE - 1) / TILE), (h->g.nyp + TILE - 1) / TILE), block(TILE, 8);
-    CHB_LAUNCH(grid, block, 0, h->stream, transpose_cols_to_planes)(src, dst, ncols, h->g.nyp);
+    CHB_LAUNCH(grid, block, 0, st, transpose_cols_to_planes)(cols, planes + (size_t)ix0 * h->g.nzt, ncols, h->g.nyp, (long long)h->g.M);
     h->launches++;
 }
-void launch_planes_to_fortran(chb_handle_s* h, const cplx* src, cplx* dst, int, int, int) {
-    const long long ncols = h->g.M;
+void launch_planes_to_fortran(chb_handle_s* h, const cplx* planes, cplx* cols, int ix0, int nix, cudaStream_t st) {
+    const long long ncols = (long long)nix * h->g.nzt;
     dim3 grid((unsigned)((ncols + TILE - 1) / TILE), (h->g.nyp + TILE - 1) / TILE), block(TILE, 8);
-    CHB_LAUNCH(grid, block, 0, h->stream, transpose_planes_to_cols)(src, dst, ncols, h->g.nyp);
+    CHB_LAUNCH(grid, block, 0, st, transpose_planes_to_cols)(planes + (size_t)ix0 * h->g.nzt, cols, ncols, h->g.nyp, (long long)h->g.M);
     h->launches++;
 }

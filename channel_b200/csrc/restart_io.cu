@@ -10,9 +10,9 @@
 // is needed and several ranks (one process per GPU) write the same file concurrently.
 //
 // Save pipeline: (1) the device transposes its layout [c][iy][ix][iz] into file order (a tiled 2-D
-// transpose per component) -- blocking mode into the products buffer P, which is dead between
-// time steps; asynchronous mode into a dedicated snapshot buffer, after which the time loop may
-// continue at once; (2) CHB_IO_THREADS (default 4) host threads drain the snapshot, each with its own
+// transpose per x-slab of a component) -- blocking mode into the work arena of the pencil transposes,
+// which is dead between time steps, one slab of as many x-modes as fit after the other; asynchronous
+// mode into a dedicated snapshot buffer, after which the time loop may continue at once; (2) CHB_IO_THREADS (default 4) host threads drain the snapshot, each with its own
 // copy stream and two pinned buffers: thread w takes chunks w, w+NW, ... and pwrite()s chunk k while
 // its next chunk is in flight over PCIe (one thread's pwrite into the page cache runs at 2-3 GB/s,
 // far below PCIe, so the file side is what needs the parallelism); blocking mode joins them before
@@ -26,6 +26,7 @@
 #include <chrono>
 #include <cstdio>
 #include <cstring>
+#include <memory>
 #include <string>
 #include <thread>
 
@@ -160,30 +161,31 @@ void chb_restart_destroy(chb_handle_s* h) {
     h->rio = nullptr;
 }
 
-// The snapshot in chunks that never straddle a component: chunk k -> (offset in the device copy, offset in the file, bytes)
+// A slab = the x-modes [ix0, ix0 + nix) of component c, nix*(2nz+1)*(ny+3) complex that are contiguous both in the
+// file and in the device copy `dev` (file order).  Chunk k of a slab -> (offset in dev, offset in the file, bytes).
+struct Slab { int c, ix0, nix; const cplx* dev; };
 struct Chunk { size_t dev_off; off_t file_off; size_t n; };
-static bool chunk_at(const Geometry& g, size_t chunk_bytes, size_t k, Chunk* c) {
-    const size_t comp_bytes = (size_t)g.nyp * g.M * sizeof(cplx);
-    const size_t per_comp = (comp_bytes + chunk_bytes - 1) / chunk_bytes;
-    if (k >= 3 * per_comp) return false;
-    const size_t comp = k / per_comp, o = (k % per_comp) * chunk_bytes;
-    c->n = (o + chunk_bytes <= comp_bytes) ? chunk_bytes : comp_bytes - o;
-    c->dev_off = comp * comp_bytes + o;
-    c->file_off = (off_t)(chb_host_restart_offset(g.nx, g.ny, g.nz, g.nx0, (int)comp) + (long long)o);
+static bool chunk_at(const Geometry& g, const Slab& s, size_t chunk_bytes, size_t k, Chunk* c) {
+    const size_t slab_bytes = (size_t)s.nix * g.nzt * g.nyp * sizeof(cplx);
+    const size_t o = k * chunk_bytes;
+    if (o >= slab_bytes) return false;
+    c->n = (o + chunk_bytes <= slab_bytes) ? chunk_bytes : slab_bytes - o;
+    c->dev_off = o;
+    c->file_off = (off_t)(chb_host_restart_offset(g.nx, g.ny, g.nz, g.nx0 + s.ix0, s.c) + (long long)o);
     return true;
 }
 
-// host thread w of nw: drain chunks w, w+nw, ... of `src` (device, file order [c][ixl][iz][iy]) into the file;
-// chunk k is written while this thread's next chunk crosses PCIe
-static int drain_lane(chb_handle_s* h, RestartIO* r, int w, const cplx* src, int fd, std::string* err) {
+// host thread w of nw: drain chunks w, w+nw, ... of the slab into the file; chunk k is written while this thread's
+// next chunk crosses PCIe
+static int drain_lane(chb_handle_s* h, RestartIO* r, int w, const Slab& s, int fd, std::string* err) {
     cudaSetDevice(h->device);
     IoLane& ln = r->lane[w];
     const size_t nw = (size_t)r->nw;
     auto issue = [&](size_t i) -> int {   // i-th chunk of this lane
         Chunk c;
-        if (!chunk_at(h->g, r->chunk_bytes, w + i * nw, &c)) return 0;
+        if (!chunk_at(h->g, s, r->chunk_bytes, w + i * nw, &c)) return 0;
         const int b = (int)(i & 1);
-        if (cudaMemcpyAsync(ln.pinned[b], reinterpret_cast<const char*>(src) + c.dev_off, c.n, cudaMemcpyDeviceToHost,
+        if (cudaMemcpyAsync(ln.pinned[b], reinterpret_cast<const char*>(s.dev) + c.dev_off, c.n, cudaMemcpyDeviceToHost,
                             ln.stream) != cudaSuccess ||
             cudaEventRecord(ln.copied[b], ln.stream) != cudaSuccess) {
             *err = std::string("snapshot D2H: ") + cudaGetErrorString(cudaGetLastError());
@@ -194,7 +196,7 @@ static int drain_lane(chb_handle_s* h, RestartIO* r, int w, const cplx* src, int
     if (cudaStreamWaitEvent(ln.stream, r->snap_done, 0) != cudaSuccess) { *err = "snapshot: cudaStreamWaitEvent failed"; return 1; }
     if (issue(0)) return 1;
     Chunk c;
-    for (size_t i = 0; chunk_at(h->g, r->chunk_bytes, w + i * nw, &c); ++i) {
+    for (size_t i = 0; chunk_at(h->g, s, r->chunk_bytes, w + i * nw, &c); ++i) {
         if (cudaEventSynchronize(ln.copied[i & 1]) != cudaSuccess) {
             *err = std::string("snapshot D2H: ") + cudaGetErrorString(cudaGetLastError());
             return 1;
@@ -206,12 +208,12 @@ static int drain_lane(chb_handle_s* h, RestartIO* r, int w, const cplx* src, int
 }
 
 // all lanes: nw-1 extra threads + the calling one
-static int drain_to_file(chb_handle_s* h, RestartIO* r, const cplx* src, int fd, std::string* err) {
+static int drain_to_file(chb_handle_s* h, RestartIO* r, const Slab& s, int fd, std::string* err) {
     std::string errs[CHB_IO_MAX_THREADS];
     int rcs[CHB_IO_MAX_THREADS] = {0};
     std::thread th[CHB_IO_MAX_THREADS];
-    for (int w = 1; w < r->nw; ++w) th[w] = std::thread([&, w]() { rcs[w] = drain_lane(h, r, w, src, fd, &errs[w]); });
-    rcs[0] = drain_lane(h, r, 0, src, fd, &errs[0]);
+    for (int w = 1; w < r->nw; ++w) th[w] = std::thread([&, w]() { rcs[w] = drain_lane(h, r, w, s, fd, &errs[w]); });
+    rcs[0] = drain_lane(h, r, 0, s, fd, &errs[0]);
     int rc = 0;
     for (int w = 0; w < r->nw; ++w) {
         if (w) th[w].join();
@@ -219,6 +221,26 @@ static int drain_to_file(chb_handle_s* h, RestartIO* r, const cplx* src, int fd,
     }
     return rc;
 }
+
+// x-modes per slab when the work arena is the staging area
+static int arena_slab_width(const chb_handle_s* h) {
+    const Geometry& g = h->g;
+    const size_t per_ix = (size_t)g.nzt * g.nyp * sizeof(cplx);
+    size_t n = (h->arena_bytes - h->stage_off) / per_ix;
+    if (n > (size_t)g.nxB) n = g.nxB;
+    return (int)n;
+}
+
+// closes the file and destroys the events on every path out of chb_save_restart_file
+struct SaveGuard {
+    int fd = -1;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    ~SaveGuard() {
+        if (fd >= 0) close(fd);
+        if (e0) cudaEventDestroy(e0);
+        if (e1) cudaEventDestroy(e1);
+    }
+};
 
 extern "C" int chb_save_restart_file(chb_handle h, const char* filename, double time, int field, int async_mode) {
     if (!h || !filename) { chb_set_error("chb_save_restart_file: null argument"); return 2; }
@@ -231,69 +253,92 @@ extern "C" int chb_save_restart_file(chb_handle h, const char* filename, double 
     const Geometry& g = h->g;
     const size_t fld = (size_t)g.nyp * g.M;
     const auto t0 = std::chrono::steady_clock::now();
+    if (!async_mode && arena_slab_width(h) < 1) {
+        chb_set_error("chb_save_restart_file: work arena smaller than one x-mode of the field (raise CHB_WORK_GB)");
+        return 5;
+    }
 
     // open / size the file; rank 0 (has_terminal) writes the header
-    const int fd = open(filename, O_WRONLY | O_CREAT, 0644);
+    auto guard = std::make_shared<SaveGuard>();
+    guard->fd = open(filename, O_WRONLY | O_CREAT, 0644);
+    const int fd = guard->fd;
     if (fd < 0) { chb_set_error(std::string("chb_save_restart_file: open ") + filename + ": " + strerror(errno)); return 4; }
     std::string err;
     if (ftruncate(fd, (off_t)chb_host_restart_file_bytes(g.nx, g.ny, g.nz)) != 0) {
         chb_set_error(std::string("chb_save_restart_file: ftruncate: ") + strerror(errno));
-        close(fd);
         return 4;
     }
     if (g.rank == 0) {
         unsigned char hdr[CHB_RESTART_HEADER_BYTES];
         chb_host_restart_header(g.nx, g.ny, g.nz, g.alfa0, g.beta0, g.ni, h->grid_a, h->grid_ymin, h->grid_ymax, time, hdr);
-        if (write_all(fd, (const char*)hdr, sizeof(hdr), 0, &err)) { chb_set_error(err); close(fd); return 4; }
+        if (write_all(fd, (const char*)hdr, sizeof(hdr), 0, &err)) { chb_set_error(err); return 4; }
     }
+    const cplx* src = field == 0 ? h->V : h->F;
+    CHB_CUDA_OK(cudaEventCreate(&guard->e0));
+    CHB_CUDA_OK(cudaEventCreate(&guard->e1));
+    r->bytes = (double)(3 * fld * sizeof(cplx));
 
-    // (1) device-side snapshot in file order
-    cplx* dst = h->P;                   // blocking mode: the products buffer is dead between time steps
     if (async_mode) {
+        // (1) the whole field in file order into the private snapshot buffer, (2)+(3) drained by a worker thread
         if (!r->snap) {
             if (cudaMalloc((void**)&r->snap, 3 * fld * sizeof(cplx)) != cudaSuccess) {
                 cudaGetLastError();
                 chb_set_error("chb_save_restart_file: no device memory for the asynchronous snapshot buffer (use async=0)");
-                close(fd);
                 return 5;
             }
             h->dev_bytes += 3 * fld * sizeof(cplx);
         }
-        dst = r->snap;
-    }
-    const cplx* src = field == 0 ? h->V : h->F;
-    cudaEvent_t e0, e1;
-    CHB_CUDA_OK(cudaEventCreate(&e0));
-    CHB_CUDA_OK(cudaEventCreate(&e1));
-    CHB_CUDA_OK(cudaEventRecord(e0, h->stream));
-    for (int c = 0; c < 3; ++c) launch_planes_to_fortran(h, src + c * fld, dst + c * fld, c, 0, g.nxB);
-    CHB_CUDA_OK(cudaEventRecord(e1, h->stream));
-    CHB_CUDA_OK(cudaEventRecord(r->snap_done, h->stream));
-    r->bytes = (double)(3 * fld * sizeof(cplx));
-
-    // (2)+(3) drain
-    auto finish = [h, r, dst, fd, t0, e0, e1]() -> int {
-        std::string werr;
-        cudaSetDevice(h->device);
-        int rc = drain_to_file(h, r, dst, fd, &werr);
-        if (close(fd) != 0 && !rc) { werr = std::string("close: ") + strerror(errno); rc = 1; }
-        float ms = 0;
-        cudaEventSynchronize(e1);
-        cudaEventElapsedTime(&ms, e0, e1);
-        cudaEventDestroy(e0);
-        cudaEventDestroy(e1);
-        r->t_snapshot_ms = ms;
-        r->t_total_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-        r->worker_rc = rc ? 4 : 0;
-        r->worker_err = werr;
-        return r->worker_rc;
-    };
-    if (async_mode) {
+        CHB_CUDA_OK(cudaEventRecord(guard->e0, h->stream));
+        for (int c = 0; c < 3; ++c) launch_planes_to_fortran(h, src + c * fld, r->snap + c * fld, 0, g.nxB, h->stream);
+        CHB_CUDA_OK(cudaEventRecord(guard->e1, h->stream));
+        CHB_CUDA_OK(cudaEventRecord(r->snap_done, h->stream));
+        auto finish = [h, r, guard, t0]() -> int {
+            std::string werr;
+            cudaSetDevice(h->device);
+            int rc = 0;
+            for (int c = 0; c < 3 && !rc; ++c) {
+                const Slab s = {c, 0, h->g.nxB, r->snap + (size_t)c * h->g.nyp * h->g.M};
+                rc = drain_to_file(h, r, s, guard->fd, &werr);
+            }
+            if (close(guard->fd) != 0 && !rc) { werr = std::string("close: ") + strerror(errno); rc = 1; }
+            guard->fd = -1;
+            float ms = 0;
+            cudaEventSynchronize(guard->e1);
+            cudaEventElapsedTime(&ms, guard->e0, guard->e1);
+            r->t_snapshot_ms = ms;
+            r->t_total_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            r->worker_rc = rc ? 4 : 0;
+            r->worker_err = werr;
+            return r->worker_rc;
+        };
         r->worker_active = true;
         r->worker = std::thread(finish);
         return 0;
     }
-    if (finish()) { chb_set_error(r->worker_err); return 4; }
+
+    // blocking mode: slab by slab through the work arena (dead between time steps)
+    cplx* stage = reinterpret_cast<cplx*>(h->arena + h->stage_off);
+    const int wmax = arena_slab_width(h);
+    double t_ms = 0;
+    for (int c = 0; c < 3; ++c) {
+        for (int ix0 = 0; ix0 < g.nxB; ix0 += wmax) {
+            const int nix = (ix0 + wmax <= g.nxB) ? wmax : g.nxB - ix0;
+            CHB_CUDA_OK(cudaEventRecord(guard->e0, h->stream));
+            launch_planes_to_fortran(h, src + c * fld, stage, ix0, nix, h->stream);
+            CHB_CUDA_OK(cudaEventRecord(guard->e1, h->stream));
+            CHB_CUDA_OK(cudaEventRecord(r->snap_done, h->stream));
+            const Slab s = {c, ix0, nix, stage};
+            if (drain_to_file(h, r, s, fd, &err)) { chb_set_error(err); return 4; }
+            float ms = 0;
+            CHB_CUDA_OK(cudaEventElapsedTime(&ms, guard->e0, guard->e1));
+            t_ms += ms;
+        }
+    }
+    guard->fd = -1;
+    if (close(fd) != 0) { chb_set_error(std::string("close: ") + strerror(errno)); return 4; }
+    r->t_snapshot_ms = t_ms;
+    r->t_total_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    r->worker_rc = 0;
     return 0;
 }
 
@@ -312,6 +357,11 @@ extern "C" int chb_restart_stats(chb_handle h, double* bytes, double* snapshot_m
     return 0;
 }
 
+struct FdGuard {
+    int fd;
+    ~FdGuard() { if (fd >= 0) close(fd); }
+};
+
 extern "C" int chb_read_restart_file(chb_handle h, const char* filename, double* time) {
     if (!h || !filename) { chb_set_error("chb_read_restart_file: null argument"); return 2; }
     CHB_CUDA_OK(cudaSetDevice(h->device));
@@ -319,14 +369,15 @@ extern "C" int chb_read_restart_file(chb_handle h, const char* filename, double*
     if (!r) return 1;
     if (rio_join(r)) return 1;
     const Geometry& g = h->g;
-    const int fd = open(filename, O_RDONLY);
+    FdGuard fg = {open(filename, O_RDONLY)};
+    const int fd = fg.fd;
     if (fd < 0) {   // the reference generates an initial field instead (dnsdata.f90:705-719): the driver's job
         chb_set_error(std::string("chb_read_restart_file: cannot open ") + filename + ": " + strerror(errno));
         return 4;
     }
     std::string err;
     unsigned char hdr[CHB_RESTART_HEADER_BYTES];
-    if (read_all(fd, (char*)hdr, sizeof(hdr), 0, &err)) { chb_set_error(err); close(fd); return 4; }
+    if (read_all(fd, (char*)hdr, sizeof(hdr), 0, &err)) { chb_set_error(err); return 4; }
     int ints[3];
     double reals[7];
     memcpy(ints, hdr, 12);
@@ -334,44 +385,51 @@ extern "C" int chb_read_restart_file(chb_handle h, const char* filename, double*
     if (ints[0] != g.nx || ints[1] != g.ny || ints[2] != g.nz || reals[0] != g.alfa0 || reals[1] != g.beta0 ||
         reals[2] != g.ni || reals[3] != h->grid_a || reals[4] != h->grid_ymin || reals[5] != h->grid_ymax) {
         chb_set_error("ERROR: mismatch in metadata between restart file and dns.in. Stopping.");   // dnsdata.f90:696-703
-        close(fd);
         return 3;
     }
     if (time) *time = reals[6];
     struct stat st;
     if (fstat(fd, &st) != 0 || st.st_size < (off_t)chb_host_restart_file_bytes(g.nx, g.ny, g.nz)) {
         chb_set_error("chb_read_restart_file: file shorter than header + 3*(nx+1)*(2nz+1)*(ny+3) complex");
-        close(fd);
         return 4;
     }
-    // thread w: pread its chunk i into a pinned buffer while its chunk i-1 crosses PCIe; staged in P (file order)
+    // slab by slab through the work arena: thread w preads its chunk i into a pinned buffer while its chunk i-1 crosses
+    // PCIe; the slab, complete in file order, is then transposed into the device layout
     const size_t fld = (size_t)g.nyp * g.M;
+    const int wmax = arena_slab_width(h);
+    if (wmax < 1) { chb_set_error("chb_read_restart_file: work arena smaller than one x-mode of the field (raise CHB_WORK_GB)"); return 5; }
+    cplx* stage = reinterpret_cast<cplx*>(h->arena + h->stage_off);
     CHB_CUDA_OK(cudaStreamSynchronize(h->stream));
-    std::string errs[CHB_IO_MAX_THREADS];
-    int rcs[CHB_IO_MAX_THREADS] = {0};
-    std::thread th[CHB_IO_MAX_THREADS];
-    auto load_lane = [&](int w) {
-        cudaSetDevice(h->device);
-        IoLane& ln = r->lane[w];
-        Chunk c;
-        for (size_t i = 0; chunk_at(g, r->chunk_bytes, w + i * (size_t)r->nw, &c); ++i) {
-            const int b = (int)(i & 1);
-            if (i >= 2 && cudaEventSynchronize(ln.copied[b]) != cudaSuccess) { rcs[w] = 1; errs[w] = "restart H2D failed"; return; }
-            if (read_all(fd, ln.pinned[b], c.n, c.file_off, &errs[w])) { rcs[w] = 4; return; }
-            if (cudaMemcpyAsync(reinterpret_cast<char*>(h->P) + c.dev_off, ln.pinned[b], c.n, cudaMemcpyHostToDevice,
-                                ln.stream) != cudaSuccess ||
-                cudaEventRecord(ln.copied[b], ln.stream) != cudaSuccess) { rcs[w] = 1; errs[w] = "restart H2D failed"; return; }
+    for (int c = 0; c < 3; ++c) {
+        for (int ix0 = 0; ix0 < g.nxB; ix0 += wmax) {
+            const int nix = (ix0 + wmax <= g.nxB) ? wmax : g.nxB - ix0;
+            const Slab s = {c, ix0, nix, stage};
+            std::string errs[CHB_IO_MAX_THREADS];
+            int rcs[CHB_IO_MAX_THREADS] = {0};
+            std::thread th[CHB_IO_MAX_THREADS];
+            auto load_lane = [&](int w) {
+                cudaSetDevice(h->device);
+                IoLane& ln = r->lane[w];
+                Chunk ck;
+                for (size_t i = 0; chunk_at(g, s, r->chunk_bytes, w + i * (size_t)r->nw, &ck); ++i) {
+                    const int b = (int)(i & 1);
+                    if (i >= 2 && cudaEventSynchronize(ln.copied[b]) != cudaSuccess) { rcs[w] = 1; errs[w] = "restart H2D failed"; return; }
+                    if (read_all(fd, ln.pinned[b], ck.n, ck.file_off, &errs[w])) { rcs[w] = 4; return; }
+                    if (cudaMemcpyAsync(reinterpret_cast<char*>(stage) + ck.dev_off, ln.pinned[b], ck.n, cudaMemcpyHostToDevice,
+                                        ln.stream) != cudaSuccess ||
+                        cudaEventRecord(ln.copied[b], ln.stream) != cudaSuccess) { rcs[w] = 1; errs[w] = "restart H2D failed"; return; }
+                }
+                if (cudaStreamSynchronize(ln.stream) != cudaSuccess) { rcs[w] = 1; errs[w] = "restart H2D failed"; }
+            };
+            for (int w = 1; w < r->nw; ++w) th[w] = std::thread(load_lane, w);
+            load_lane(0);
+            for (int w = 1; w < r->nw; ++w) th[w].join();
+            for (int w = 0; w < r->nw; ++w)
+                if (rcs[w]) { chb_set_error("chb_read_restart_file: " + errs[w]); return rcs[w]; }
+            launch_fortran_to_planes(h, stage, h->V + c * fld, ix0, nix, h->stream);
+            CHB_CUDA_OK(cudaStreamSynchronize(h->stream));   // the arena is reused by the next slab
         }
-        if (cudaStreamSynchronize(ln.stream) != cudaSuccess) { rcs[w] = 1; errs[w] = "restart H2D failed"; }
-    };
-    for (int w = 1; w < r->nw; ++w) th[w] = std::thread(load_lane, w);
-    load_lane(0);
-    for (int w = 1; w < r->nw; ++w) th[w].join();
-    close(fd);
-    for (int w = 0; w < r->nw; ++w)
-        if (rcs[w]) { chb_set_error("chb_read_restart_file: " + errs[w]); return rcs[w]; }
-    for (int c = 0; c < 3; ++c) launch_fortran_to_planes(h, h->P + c * fld, h->V + c * fld, c, 0, g.nxB);
-    CHB_CUDA_OK(cudaStreamSynchronize(h->stream));
+    }
     CHB_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -26,17 +26,20 @@ struct RhsAcc {
     cplx ev, ee, lv, le;
 };
 
-// MINB = resident blocks per SM the register allocation is sized for: 3 = 152 registers, no spills;
-// 4 = 128 registers, 16 warps per SM, 56-96 bytes of spills (CHB_RHS_MINB)
-// CHUNKED (experimental, CHB_RHS_CHUNKED=1): the march covers the input planes ip0..ip1 only and carries the four
-// partially accumulated output planes to the next launch through `state` ([32][M] doubles), so that the plane loop
-// of buildrhs can follow the convolutions chunk by chunk (and run under the transposes of the next chunk) instead
-// of waiting for all planes.  Same operations in the same order: bit-identical to the single march.
-template <bool HAS_F, int MINB, bool CHUNKED = false>
+// MINB = resident blocks per SM the register allocation is sized for: 3 = 152 registers, no spills (4 = 128 registers
+// with 56-96 bytes of spills measured no faster).
+// The march covers the input planes ip0..ip1 of one chunk of the convolutions and carries the four partially
+// accumulated output planes to the next launch through `state` ([32][M] doubles): the plane loop of buildrhs follows
+// the convolutions chunk by chunk (and runs beside the transposes of the next chunk) instead of waiting for all
+// planes, so the spectral products P exist for one chunk only ([6][pnp][M], plane index relative to pplane0).  Same
+// operations in the same order as a single march.  The finished rows go where the reference puts them
+// (dnsdata.f90:667-671): into V itself, eta-RHS -> component 0, D2v-RHS -> component 1 of row iy-2, two planes behind
+// the march, where the old velocities are no longer needed (by this thread: same column; by the z-passes: earlier chunk).
+template <bool HAS_F, int MINB>
 __global__ void __launch_bounds__(RHS_THREADS, MINB)
-rhs_kernel(const cplx* __restrict__ V, const cplx* __restrict__ P, const cplx* __restrict__ F, cplx* __restrict__ rhs,
+rhs_kernel(cplx* V, const cplx* __restrict__ P, const cplx* __restrict__ F,
            cplx* __restrict__ oldrhs, Geometry g, DevTables tab, const DevScalars* __restrict__ sc, double ode1_dt,
-           double ode2, double ode3, int ip0, int ip1, double* __restrict__ state) {
+           double ode2, double ode3, int ip0, int ip1, double* __restrict__ state, int pnp, int pplane0) {
     const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= g.M) return;
     const int ixl = (int)(m / g.nzt);
@@ -51,6 +54,7 @@ rhs_kernel(const cplx* __restrict__ V, const cplx* __restrict__ P, const cplx* _
     const double ce0 = ode1_dt - ni * k2;                                           // coefficient of d0 in lin_eta
     const size_t plane = (size_t)g.M;
     const size_t comp = (size_t)g.nyp * plane;
+    const size_t pcomp = (size_t)pnp * plane;
     const int ny = g.ny;
 
     RhsAcc acc[5];
@@ -63,7 +67,7 @@ rhs_kernel(const cplx* __restrict__ V, const cplx* __restrict__ P, const cplx* _
         mpx = sc->meanpx;
         mpz = sc->meanpz;
     }
-    if constexpr (CHUNKED) {
+    {
         if (ip0 > -1) {   // resume: the four output planes ip0-2 .. ip0+1 are partially accumulated
             const double* st = state + m;
 #pragma unroll
@@ -75,12 +79,11 @@ rhs_kernel(const cplx* __restrict__ V, const cplx* __restrict__ P, const cplx* _
             }
         }
     }
-    const int ip_first = CHUNKED ? ip0 : -1, ip_last = CHUNKED ? ip1 : ny + 1;
-
-    for (int ip = ip_first; ip <= ip_last; ++ip) {
+    for (int ip = ip0; ip <= ip1; ++ip) {
         const size_t off = (size_t)(ip + 1) * plane + m;
-        const cplx p1 = P[0 * comp + off], p2 = P[1 * comp + off], p3 = P[2 * comp + off];
-        const cplx p4 = P[3 * comp + off], p5 = P[4 * comp + off], p6 = P[5 * comp + off];
+        const size_t poff = (size_t)(ip + 1 - pplane0) * plane + m;
+        const cplx p1 = P[0 * pcomp + poff], p2 = P[1 * pcomp + poff], p3 = P[2 * pcomp + poff];
+        const cplx p4 = P[3 * pcomp + poff], p5 = P[4 * pcomp + poff], p6 = P[5 * pcomp + poff];
         const cplx u = V[0 * comp + off], v = V[1 * comp + off], w = V[2 * comp + off];
         cplx f1 = make_double2(0, 0), f2 = f1, f3 = f1;
         if (HAS_F) {
@@ -163,8 +166,8 @@ rhs_kernel(const cplx* __restrict__ V, const cplx* __restrict__ P, const cplx* _
             re.y = acc[0].le.y + ode2 * ee.y - ode3 * oe.y;
             rv.x = acc[0].lv.x + ode2 * acc[0].ev.x - ode3 * ov.x;
             rv.y = acc[0].lv.y + ode2 * acc[0].ev.y - ode3 * ov.y;
-            rhs[0 * comp + oo] = re;
-            rhs[1 * comp + oo] = rv;
+            V[0 * comp + oo] = re;
+            V[1 * comp + oo] = rv;
             oldrhs[0 * comp + oo] = ee;
             oldrhs[1 * comp + oo] = acc[0].ev;
         }
@@ -172,7 +175,7 @@ rhs_kernel(const cplx* __restrict__ V, const cplx* __restrict__ P, const cplx* _
         for (int s = 0; s < 4; ++s) acc[s] = acc[s + 1];
         acc[4].ev = acc[4].ee = acc[4].lv = acc[4].le = make_double2(0.0, 0.0);
     }
-    if constexpr (CHUNKED) {
+    {
         if (ip1 < ny + 1) {
             double* st = state + m;
 #pragma unroll
@@ -188,27 +191,16 @@ rhs_kernel(const cplx* __restrict__ V, const cplx* __restrict__ P, const cplx* _
 
 
 #if !defined(CHB_HOST_EMUL) || defined(CHB_HOST_EMUL_FULL)   // the kernel-only emulation harnesses (tests/host_emul) stop here
-// one chunk of input planes [plane0, plane0 + nplanes) (plane index = iy + 1), on stream `st`; chunks must be
-// launched in ascending order on the same stream (the carried accumulators)
+// one chunk of input planes [plane0, plane0 + nplanes) (plane index = iy + 1) whose products are in the lane in use, on
+// stream `st`; chunks must be launched in ascending order on the same stream (the carried accumulators)
 void launch_rhs_chunk(chb_handle_s* h, const double* ode, double deltat, int plane0, int nplanes, cudaStream_t st) {
     const Geometry& g = h->g;
     const int blocks = (int)((g.M + RHS_THREADS - 1) / RHS_THREADS);
     ScopedKernelTimer tm(h, "rhs", st);
-    auto kern = h->bf.enabled ? rhs_kernel<true, 3, true> : rhs_kernel<false, 3, true>;
-    CHB_LAUNCH(blocks, RHS_THREADS, 0, st, kern)(h->V, h->P, h->bf.enabled ? h->F : nullptr, h->rhs, h->oldrhs, g, h->tab, h->sc,
-                                         ode[0] / deltat, ode[1], ode[2], plane0 - 1, plane0 + nplanes - 2, h->rhs_state);
-    h->launches++;
-}
-
-void launch_rhs(chb_handle_s* h, const double* ode, double deltat) {
-    const Geometry& g = h->g;
-    const int blocks = (int)((g.M + RHS_THREADS - 1) / RHS_THREADS);
-    static const int minb = []() { const char* e = getenv("CHB_RHS_MINB"); return (e && atoi(e) == 4) ? 4 : 3; }();
-    ScopedKernelTimer tm(h, "rhs");
-    auto kern = h->bf.enabled ? (minb == 4 ? rhs_kernel<true, 4> : rhs_kernel<true, 3>)
-                              : (minb == 4 ? rhs_kernel<false, 4> : rhs_kernel<false, 3>);
-    CHB_LAUNCH(blocks, RHS_THREADS, 0, h->stream, kern)(h->V, h->P, h->bf.enabled ? h->F : nullptr, h->rhs, h->oldrhs, g, h->tab,
-                                               h->sc, ode[0] / deltat, ode[1], ode[2], 0, 0, nullptr);
+    auto kern = h->bf.enabled ? rhs_kernel<true, 3> : rhs_kernel<false, 3>;
+    CHB_LAUNCH(blocks, RHS_THREADS, 0, st, kern)(h->V, h->Pc, h->bf.enabled ? h->F : nullptr, h->oldrhs, g, h->tab, h->sc,
+                                         ode[0] / deltat, ode[1], ode[2], plane0 - 1, plane0 + nplanes - 2, h->rhs_state,
+                                         h->chunk_planes, plane0);
     h->launches++;
 }
 #endif

@@ -3,7 +3,8 @@
 // rbparmat_blocking.f90:20-100 with npy=1; COMPLEXderiv, dnsdata.f90:339-373).
 //
 // One thread per column; the wavenumber index is the contiguous one, so every load/store of a
-// warp is a 512-byte coalesced segment.  Four sweeps:
+// warp is a 512-byte coalesced segment.  The right-hand sides arrive in V components 0 (eta) and 1 (v), rows
+// 1..ny-1, where buildrhs left them (dnsdata.f90:667-671), and every sweep works in place on V.  Four sweeps:
 //   S1 (iy = ny-1 -> 1): build the D2vmat / etamat rows (linsolve_blocking.inc:12-13), fold the
 //       wall BCs (applybc_0/n, dnsdata.f90:458-472), UL-factorise on the fly and apply
 //       LeftLU5divStep1 to both right-hand sides; the two L-multipliers per row and matrix go to
@@ -119,7 +120,7 @@ solve_s1_kernel(cplx* __restrict__ rhs, double* __restrict__ ckpt, Geometry g, D
 // ---------------------------------------------------------------------------------------------
 template <int COMP>
 __global__ void __launch_bounds__(SOLVE_THREADS, 4)
-solve_s2_kernel(const cplx* __restrict__ rhs, const double* __restrict__ ckpt, cplx* __restrict__ V, Geometry g,
+solve_s2_kernel(const double* __restrict__ ckpt, cplx* V, Geometry g,
                 DevTables tab, const DevScalars* __restrict__ sc, double lam) {
     const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= g.M) return;
@@ -140,8 +141,9 @@ solve_s2_kernel(const cplx* __restrict__ rhs, const double* __restrict__ ckpt, c
     const double* bcnp1 = COMP ? tab.vnp1bc : tab.etanp1bc;
     const double* bc0 = COMP ? tab.v0bc : tab.eta0bc;
     const double* bc0m1 = COMP ? tab.v0m1bc : tab.eta0m1bc;
-    const cplx* __restrict__ xin = rhs + COMP * comp + m;
-    cplx* __restrict__ out = V + COMP * comp + m;
+    // in place: the Step1 result of a block of rows is read (prefetched) before the block's rows are written
+    const cplx* xin = V + COMP * comp + m;
+    cplx* out = V + COMP * comp + m;
     cplx v1 = make_double2(0, 0), v2 = v1, v3 = v1;  // b(i-1), b(i-2), b(i-3)
     for (int i0 = 1; i0 <= ny - 1; i0 += SOLVE_K) {
         // ---- recompute the multipliers of rows i0..i0+K-1 (descending, as solve_s1 did) ----
@@ -530,17 +532,17 @@ void launch_linsolve(chb_handle_s* h, double lam) {
     {
         ScopedKernelTimer tm(h, "solve_s1");
         if (pf) {
-            CHB_LAUNCH(blocks, SOLVE_THREADS, 0, h->stream, solve_s1_kernel<0, 8>)(h->rhs, h->ckpt, g, h->tab, h->sc, lam);
-            CHB_LAUNCH(blocks, SOLVE_THREADS, 0, h->stream, solve_s1_kernel<1, 8>)(h->rhs, h->ckpt, g, h->tab, h->sc, lam);
+            CHB_LAUNCH(blocks, SOLVE_THREADS, 0, h->stream, solve_s1_kernel<0, 8>)(h->V, h->ckpt, g, h->tab, h->sc, lam);
+            CHB_LAUNCH(blocks, SOLVE_THREADS, 0, h->stream, solve_s1_kernel<1, 8>)(h->V, h->ckpt, g, h->tab, h->sc, lam);
         } else {
-            CHB_LAUNCH(blocks, SOLVE_THREADS, 0, h->stream, solve_s1_kernel<0>)(h->rhs, h->ckpt, g, h->tab, h->sc, lam);
-            CHB_LAUNCH(blocks, SOLVE_THREADS, 0, h->stream, solve_s1_kernel<1>)(h->rhs, h->ckpt, g, h->tab, h->sc, lam);
+            CHB_LAUNCH(blocks, SOLVE_THREADS, 0, h->stream, solve_s1_kernel<0>)(h->V, h->ckpt, g, h->tab, h->sc, lam);
+            CHB_LAUNCH(blocks, SOLVE_THREADS, 0, h->stream, solve_s1_kernel<1>)(h->V, h->ckpt, g, h->tab, h->sc, lam);
         }
     }
     {
         ScopedKernelTimer tm(h, "solve_s2");
-        CHB_LAUNCH(blocks, SOLVE_THREADS, 0, h->stream, solve_s2_kernel<0>)(h->rhs, h->ckpt, h->V, g, h->tab, h->sc, lam);
-        CHB_LAUNCH(blocks, SOLVE_THREADS, 0, h->stream, solve_s2_kernel<1>)(h->rhs, h->ckpt, h->V, g, h->tab, h->sc, lam);
+        CHB_LAUNCH(blocks, SOLVE_THREADS, 0, h->stream, solve_s2_kernel<0>)(h->ckpt, h->V, g, h->tab, h->sc, lam);
+        CHB_LAUNCH(blocks, SOLVE_THREADS, 0, h->stream, solve_s2_kernel<1>)(h->ckpt, h->V, g, h->tab, h->sc, lam);
     }
     h->launches += 6;
     // The mean column (0,0) only needs the result of S2 and is skipped by S3/S4: finish it on the

@@ -10,6 +10,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -131,51 +132,56 @@ int chb_bcast_scalars(chb_handle_s* h) {
     return 0;
 }
 
-// ---- direct NVLink mode ---------------------------------------------------------------------
-// Every rank maps every peer's receive buffers (Ar, Br) and barrier flags through CUDA IPC.  The
-// pack side of zTOx / xTOz then IS the transpose: zfwd / xpass store each element straight into
-// the owner's HBM over NVLink while they compute (PeerPtrs, chb_internal.h).  What is left of the
-// collective is a flag barrier between the producing and the consuming kernel.
-struct IpcBundle {
-    cudaIpcMemHandle_t ar, br, flags;
-};
+// agreement on values every rank derives from its own state (free memory, environment): element-wise minimum
+int chb_allreduce_min_i64(chb_handle_s* h, long long* v, int n) {
+    ncclComm_t comm = (ncclComm_t)h->nccl_comm;
+    long long* d = nullptr;
+    CHB_CUDA_OK(cudaMalloc((void**)&d, sizeof(long long) * n));
+    CHB_CUDA_OK(cudaMemcpy(d, v, sizeof(long long) * n, cudaMemcpyHostToDevice));
+    NCCL_OK(g_nccl.AllReduce(d, d, (size_t)n, ncclInt64, ncclMin, comm, h->stream));
+    CHB_CUDA_OK(cudaStreamSynchronize(h->stream));
+    CHB_CUDA_OK(cudaMemcpy(v, d, sizeof(long long) * n, cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    return 0;
+}
 
-int chb_p2p_setup(chb_handle_s* h, size_t na, size_t nb) {
-    (void)na; (void)nb;
+// ---- direct NVLink mode ---------------------------------------------------------------------
+// Every rank maps every peer's work arena (receive buffers Ar, Br and barrier flags of every lane, same offsets on
+// every rank) through CUDA IPC.  The pack side of zTOx / xTOz then IS the transpose: zfwd / xpass store each element
+// straight into the owner's HBM over NVLink while they compute (PeerPtrs, chb_internal.h).  What is left of the
+// collective is a flag barrier between the producing and the consuming kernel.
+int chb_p2p_setup(chb_handle_s* h) {
     const int P = h->g.nranks, r = h->g.rank;
     ncclComm_t comm = (ncclComm_t)h->nccl_comm;
     h->n_ipc_opened = 0;
+    cudaIpcMemHandle_t mine;
+    CHB_CUDA_OK(cudaIpcGetMemHandle(&mine, h->arena));
+    cudaIpcMemHandle_t* d_all = nullptr;
+    CHB_CUDA_OK(cudaMalloc((void**)&d_all, sizeof(mine) * P));
+    CHB_CUDA_OK(cudaMemcpy(d_all + r, &mine, sizeof(mine), cudaMemcpyHostToDevice));
+    NCCL_OK(g_nccl.AllGather(d_all + r, d_all, sizeof(mine), ncclChar, comm, h->stream));
+    CHB_CUDA_OK(cudaStreamSynchronize(h->stream));
+    cudaIpcMemHandle_t all[CHB_MAX_RANKS];
+    CHB_CUDA_OK(cudaMemcpy(all, d_all, sizeof(mine) * P, cudaMemcpyDeviceToHost));
+    cudaFree(d_all);
+    char* base[CHB_MAX_RANKS];
+    for (int q = 0; q < P; ++q) {
+        if (q == r) {
+            base[q] = h->arena;
+            continue;
+        }
+        void* pa = nullptr;
+        CHB_CUDA_OK(cudaIpcOpenMemHandle(&pa, all[q], cudaIpcMemLazyEnablePeerAccess));
+        h->ipc_opened[h->n_ipc_opened++] = pa;
+        base[q] = (char*)pa;
+    }
     for (int L = 0; L < h->nlanes; ++L) {
         Lane& ln = h->lane[L];
-        IpcBundle mine;
-        CHB_CUDA_OK(cudaIpcGetMemHandle(&mine.ar, ln.Ar));
-        CHB_CUDA_OK(cudaIpcGetMemHandle(&mine.br, ln.Br));
-        CHB_CUDA_OK(cudaIpcGetMemHandle(&mine.flags, ln.flags));
-        IpcBundle* d_all = nullptr;
-        CHB_CUDA_OK(cudaMalloc((void**)&d_all, sizeof(IpcBundle) * P));
-        CHB_CUDA_OK(cudaMemcpy(d_all + r, &mine, sizeof(IpcBundle), cudaMemcpyHostToDevice));
-        NCCL_OK(g_nccl.AllGather(d_all + r, d_all, sizeof(IpcBundle), ncclChar, comm, h->stream));
-        CHB_CUDA_OK(cudaStreamSynchronize(h->stream));
-        IpcBundle all[CHB_MAX_RANKS];
-        CHB_CUDA_OK(cudaMemcpy(all, d_all, sizeof(IpcBundle) * P, cudaMemcpyDeviceToHost));
-        cudaFree(d_all);
+        const ptrdiff_t oa = (char*)ln.Ar - h->arena, ob = (char*)ln.Br - h->arena, of = (char*)ln.flags - h->arena;
         for (int q = 0; q < P; ++q) {
-            if (q == r) {
-                ln.Aw.p[q] = ln.Ar;
-                ln.Bw.p[q] = ln.Br;
-                ln.peer_flags[q] = ln.flags;
-                continue;
-            }
-            void *pa = nullptr, *pb = nullptr, *pf = nullptr;
-            CHB_CUDA_OK(cudaIpcOpenMemHandle(&pa, all[q].ar, cudaIpcMemLazyEnablePeerAccess));
-            h->ipc_opened[h->n_ipc_opened++] = pa;
-            CHB_CUDA_OK(cudaIpcOpenMemHandle(&pb, all[q].br, cudaIpcMemLazyEnablePeerAccess));
-            h->ipc_opened[h->n_ipc_opened++] = pb;
-            CHB_CUDA_OK(cudaIpcOpenMemHandle(&pf, all[q].flags, cudaIpcMemLazyEnablePeerAccess));
-            h->ipc_opened[h->n_ipc_opened++] = pf;
-            ln.Aw.p[q] = (cplx*)pa;
-            ln.Bw.p[q] = (cplx*)pb;
-            ln.peer_flags[q] = (unsigned long long*)pf;
+            ln.Aw.p[q] = (cplx*)(base[q] + oa);
+            ln.Bw.p[q] = (cplx*)(base[q] + ob);
+            ln.peer_flags[q] = (unsigned long long*)(base[q] + of);
         }
     }
     chb_select_lane(h, 0);
@@ -194,24 +200,60 @@ struct FlagPtrs {
 // thread q: publish "rank `me` has finished epoch e" in peer q's flags, then wait until peer q has
 // published the same in mine.  The producing kernel precedes this one on the stream, so its
 // (remote) stores are complete; the fences order them with the flag for the other GPUs.
-__global__ void p2p_barrier_kernel(FlagPtrs peers, volatile unsigned long long* mine, int me, int P, unsigned long long e) {
+// A peer that never arrives (it failed between two collective calls) must not hang the others forever: after
+// `timeout_ns` the kernel gives up, records the fact in *err and the host turns it into an error return
+// (chb_p2p_check), the library's form of the reference's STOP.
+__global__ void p2p_barrier_kernel(FlagPtrs peers, volatile unsigned long long* mine, int me, int P, unsigned long long e,
+                                   unsigned long long* err, unsigned long long timeout_ns) {
     const int q = threadIdx.x;
     if (q >= P) return;
     __threadfence_system();
     *((volatile unsigned long long*)(peers.p[q] + me)) = e;
     __threadfence_system();
-    while (mine[q] < e) { __nanosleep(200); }
+#ifndef CHB_HOST_EMUL
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+#endif
+    while (mine[q] < e) {
+        __nanosleep(200);
+#ifndef CHB_HOST_EMUL
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        if (t - t0 > timeout_ns) {
+            atomicExch(err, ((unsigned long long)(q + 1) << 32) | (e & 0xffffffffull));
+            break;
+        }
+#endif
+    }
     __threadfence_system();
+}
+
+int chb_p2p_check(chb_handle_s* h) {
+    if (!h->p2p) return 0;
+    unsigned long long v = 0;
+    CHB_CUDA_OK(cudaMemcpyAsync(&v, h->p2p_error, sizeof(v), cudaMemcpyDeviceToHost, h->stream));
+    CHB_CUDA_OK(cudaStreamSynchronize(h->stream));
+    if (v) {
+        chb_set_error("pencil transpose: rank " + std::to_string((int)(v >> 32) - 1) + " did not reach barrier " +
+                      std::to_string((unsigned)(v & 0xffffffffull)) + " within the timeout (CHB_BARRIER_TIMEOUT_S); the field is invalid");
+        return 6;
+    }
+    return 0;
 }
 
 int chb_exchange(chb_handle_s* h, bool a_side) {
     const Geometry& g = h->g;
     if (g.nranks == 1) return 0;
     if (h->p2p) {
+        static const unsigned long long timeout_ns = []() {
+            const char* e = getenv("CHB_BARRIER_TIMEOUT_S");
+            return (unsigned long long)((e ? atof(e) : 60.0) * 1e9);
+        }();
         FlagPtrs fp;
         for (int q = 0; q < g.nranks; ++q) fp.p[q] = h->peer_flags[q];
         ScopedKernelTimer tm(h, "p2p_barrier", h->cstream);
-        CHB_LAUNCH(1, 32, 0, h->cstream, p2p_barrier_kernel)(fp, h->flags, g.rank, g.nranks, ++h->lane[h->cur_lane].epoch);
+        CHB_LAUNCH(1, 32, 0, h->cstream, p2p_barrier_kernel)(fp, h->flags, g.rank, g.nranks, ++h->lane[h->cur_lane].epoch,
+                                                             h->p2p_error, timeout_ns);
         h->launches++;
         return 0;
     }

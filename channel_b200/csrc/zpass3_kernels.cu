@@ -134,8 +134,8 @@ zbwd4_kernel(const cplx* __restrict__ Br, cplx* __restrict__ P, Geometry g, cons
     const int tl = threadIdx.x % TPL, wl = threadIdx.x / TPL;
     const int ixl0 = blockIdx.x * LPC;
     const int pli = blockIdx.y, comp = blockIdx.z;  // product index 0..5
-    const int iyp = plane0 + pli;
     const int nz = g.nz;
+    (void)plane0;
     {   // ---- staging, cross-line: per-thread 16-byte cp.async straight into the in-place layout
         const int l = threadIdx.x % LPC, q = threadIdx.x / LPC;
         cplx* sml = smem + l * LS;
@@ -176,7 +176,8 @@ zbwd4_kernel(const cplx* __restrict__ Br, cplx* __restrict__ P, Geometry g, cons
     }
     __syncthreads();
     {   // ---- stage C, line-major: smem -> registers -> global (z-contiguous, truncated to -nz..nz)
-        cplx* __restrict__ dst = P + (((size_t)comp * g.nyp + iyp) * g.nxB + ixl0 + wl) * g.nzt;
+        // P = the chunk's spectral products [6][np][nxB][2nz+1]
+        cplx* __restrict__ dst = P + (((size_t)comp * np + pli) * g.nxB + ixl0 + wl) * g.nzt;
 #pragma unroll 1
         for (int t = tl; t < G::AB; t += TPL) {
             const cplx* base = sm + (t % G::A) * BCP + (t / G::A) * G::C;
@@ -213,7 +214,7 @@ static bool launch_z4(chb_handle_s* h, int plane0, int nplanes, bool fwd) {
         cudaFuncSetAttribute(zbwd4_kernel<G, LPC, TPL, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(zbwd4_kernel<G, LPC, TPL, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         ScopedKernelTimer tm(h, "zbwd", h->cstream);
-        CHB_LAUNCH(grid, LPC * TPL, smem, h->cstream, zbwd4_kernel<G, LPC, TPL, MINB>)(h->Br, h->P, h->g, h->Wz, plane0, h->chunk_planes, LS);
+        CHB_LAUNCH(grid, LPC * TPL, smem, h->cstream, zbwd4_kernel<G, LPC, TPL, MINB>)(h->Br, h->Pc, h->g, h->Wz, plane0, h->chunk_planes, LS);
     }
     h->launches++;
     return true;
@@ -230,7 +231,10 @@ bool launch_z3_fwd_or_bwd(chb_handle_s* h, int plane0, int nplanes, bool fwd) {
     //   nzd = 3072: 128 threads/line, 2 CTAs/SM -> 16 warps (default 8), 128 registers, 0 / 8 bytes of spills
     //   nzd = 1536: 128 threads/line, 3 CTAs/SM -> 24 warps (default 16), 80 registers, no spills
     //               96 threads/line, 4 CTAs/SM -> 24 warps, 80 registers, no spills
-    if (h->z_tpl == 128 && lpc == 2 && h->g.nzd == 3072) return launch_z4<Fft3<3072, 12, 16, 16>, 2, 128, 2>(h, plane0, nplanes, fwd);
+    // measured (profiles/r2a_variants.md): 128 threads per line win for the backward pass at nzd = 3072 (7.2 against 7.5 ms),
+    // lose everywhere else; CHB_Z_TPL=64 forces the 64-thread kernels
+    if ((h->z_tpl == 128 || (h->z_tpl == 0 && !fwd)) && lpc == 2 && h->g.nzd == 3072)
+        return launch_z4<Fft3<3072, 12, 16, 16>, 2, 128, 2>(h, plane0, nplanes, fwd);
     if (h->z_tpl == 128 && lpc == 2 && h->g.nzd == 1536) return launch_z4<Fft3<1536, 12, 16, 8>, 2, 128, 3>(h, plane0, nplanes, fwd);
     if (h->z_tpl == 96 && lpc == 2 && h->g.nzd == 1536) return launch_z4<Fft3<1536, 12, 16, 8>, 2, 96, 4>(h, plane0, nplanes, fwd);
     switch (h->g.nzd * 16 + lpc) {

@@ -201,6 +201,11 @@ class Channel:
         _lib.check(self.lib.chb_download_rhs(self.h, r.ctypes.data), "chb_download_rhs")
         return r
 
+    def capture_products(self, on: bool = True):
+        """diagnostics: keep the spectral products of all planes of the following buildrhs sweeps (they normally
+        exist one chunk of planes at a time)"""
+        _lib.check(self.lib.chb_debug_capture_products(self.h, int(on)), "chb_debug_capture_products")
+
     def download_products(self):
         r = np.empty((6,) + self.field_shape()[1:], np.complex128)
         _lib.check(self.lib.chb_download_products(self.h, r.ctypes.data), "chb_download_products")

@@ -124,7 +124,8 @@ int chb_set_body_force(chb_handle h);
 
 /* Replaces buildrhs (dnsdata.f90:611-673) including every convolutions call
  * (dnsdata.f90:487-602).  ode = RK?_rai(1:3).  Leaves the RHS of the eta- and
- * D2v-equations on the device and accumulates cfl (max) when compute_cfl!=0. */
+ * D2v-equations in V(1:ny-1,:,:,1:2), as the reference does (dnsdata.f90:667-671; V holds
+ * velocities again after chb_linsolve), and accumulates cfl (max) when compute_cfl!=0. */
 int chb_buildrhs(chb_handle h, const double* ode, double deltat, int compute_cfl);
 
 /* Replaces linsolve (linsolve_blocking.inc:3-107, blocking semantics: includes the
@@ -187,10 +188,15 @@ int chb_get_convvel(chb_handle h, double* uconv_host, long long* count);
 int chb_save_convvel_file(chb_handle h, const char* filename);
 
 /* ---- test / diagnostics accessors (not part of the Fortran binding) ---------- */
-/* RHS left by chb_buildrhs: [2][ny+3][nxB][2nz+1] complex (0=eta, 1=D2v); rows 1..ny-1. */
+/* RHS left by chb_buildrhs: [2][ny+3][nxB][2nz+1] complex (0=eta, 1=D2v); rows 1..ny-1.  As in the reference
+ * (dnsdata.f90:667-671) the RHS lives in V itself between chb_buildrhs and chb_linsolve: components 0 and 1 of rows
+ * 1..ny-1 (the other rows of the returned array are the old velocities). */
 int chb_download_rhs(chb_handle h, double* rhs_host);
-/* Spectral products left by chb_buildrhs: [6][ny+3][nxB][2nz+1] complex
- * = VVdz(izd(iz)+1, ix+1-nx0, 1:6, slot) for every plane (dnsdata.f90:609). */
+/* The spectral products VVdz exist for one chunk of planes at a time (the reference keeps a 5-slot ring, ffts.f90:42).
+ * chb_debug_capture_products(h, 1) makes every following sweep of chb_buildrhs keep a copy of all planes (6 complex per
+ * point of extra device memory); chb_download_products then returns [6][ny+3][nxB][2nz+1] complex
+ * = VVdz(izd(iz)+1, ix+1-nx0, 1:6, slot) for every plane (dnsdata.f90:609) of the last sweep. */
+int chb_debug_capture_products(chb_handle h, int on);
 int chb_download_products(chb_handle h, double* prod_host);
 /* Body force field in the device layout [3][ny+3][nxB][2nz+1]. */
 int chb_download_F_planes(chb_handle h, double* F_host);

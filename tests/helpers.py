@@ -22,5 +22,6 @@ def make_pair(nx, ny, nz, deltat=2e-3, cflmax=0.0, re=2000.0, eps=1e-2, seed=202
     V0 = perturbed_laminar(nx, ny, nz, p.alfa0, p.beta0, p.a, p.ymin, p.ymax, eps=eps, seed=seed, couette=couette)
     o.V[:] = V0
     ch = Channel(p, tables=o)        # identical coefficient tables on both sides
+    ch.capture_products()            # the tests look at the spectral products of all planes (chb_download_products)
     ch.upload_V(V0)
     return p, o, ch, V0

@@ -7,7 +7,7 @@ SRC=$HERE/../../channel_b200/csrc
 OUT=$HERE/_build
 mkdir -p $OUT/full
 FLAGS="-O1 -std=c++17 -fPIC -w -pthread -ffp-contract=off -fvisibility=default -I/usr/local/cuda/include -I$HERE -include $HERE/emul_prelude.hpp"
-for f in chb_api conv_kernels layout_kernels bodyforce_kernels rhs_kernel solve_kernels xpass3_kernels zpass3_kernels transpose restart_io convvel; do
+for f in chb_api conv_kernels layout_kernels bodyforce_kernels rhs_kernel solve_kernels xpass3_kernels zpass3_kernels transpose restart_io convvel green_ctx; do
   g++ $FLAGS -x c++ -c $SRC/$f.cu -o $OUT/full/$f.o &
 done
 g++ -O2 -std=c++17 -fPIC -w -ffp-contract=off -c $SRC/host_tables.cpp -o $OUT/full/host_tables.o &

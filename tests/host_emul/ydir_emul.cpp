@@ -78,32 +78,38 @@ __attribute__((visibility("default"))) int chb_emul_ydir_substep(int nx, int ny,
     const cplx* Fc = reinterpret_cast<const cplx*>(F);
     cplx* oc = reinterpret_cast<cplx*>(oldrhs);
     cplx* rc = reinterpret_cast<cplx*>(rhs_out);
-    (void)fld;
     const int T = 128, blocks = (int)((g.M + T - 1) / T);
     const double lam = ode1 / deltat;
     {
-        if (mode == 2 || mode == -2) {   // chunked march with carried accumulators: uneven chunks of input planes
-            std::vector<double> state((size_t)32 * g.M, 0.0);
+        // the plane loop of buildrhs works in place: finished rows go to V components 0 / 1 (dnsdata.f90:667-671)
+        std::vector<double> state((size_t)32 * g.M, 0.0);
+        if (mode == 2 || mode == -2) {   // chunked march with carried accumulators: uneven chunks of input planes, each
+                                         // with its own products array [6][n][M] as the library's lanes hold them
             const int cuts[5] = {-1, 2, 3, ny / 2, ny + 2};    // chunks [-1,1], [2,2], [3,ny/2-1], [ny/2, ny+1]
             for (int c = 0; c < 4; ++c) {
-                if (F) emulate(rhs_kernel<true, 3, true>, blocks, T, Vc, Pc, Fc, rc, oc, g, tab, &sc, lam, ode2, ode3, cuts[c], cuts[c + 1] - 1, state.data());
-                else emulate(rhs_kernel<false, 3, true>, blocks, T, Vc, Pc, Fc, rc, oc, g, tab, &sc, lam, ode2, ode3, cuts[c], cuts[c + 1] - 1, state.data());
+                const int ip0 = cuts[c], ip1 = cuts[c + 1] - 1, n = ip1 - ip0 + 1, plane0 = ip0 + 1;
+                std::vector<cplx> Pk((size_t)6 * n * g.M);
+                for (int k = 0; k < 6; ++k)
+                    memcpy(&Pk[(size_t)k * n * g.M], Pc + ((size_t)k * nyp + plane0) * g.M, sizeof(cplx) * (size_t)n * g.M);
+                if (F) emulate(rhs_kernel<true, 3>, blocks, T, Vc, (const cplx*)Pk.data(), Fc, oc, g, tab, &sc, lam, ode2, ode3, ip0, ip1, state.data(), n, plane0);
+                else emulate(rhs_kernel<false, 3>, blocks, T, Vc, (const cplx*)Pk.data(), Fc, oc, g, tab, &sc, lam, ode2, ode3, ip0, ip1, state.data(), n, plane0);
             }
         } else {
-            if (F) emulate(rhs_kernel<true, 3>, blocks, T, Vc, Pc, Fc, rc, oc, g, tab, &sc, lam, ode2, ode3, 0, 0, (double*)nullptr);
-            else emulate(rhs_kernel<false, 3>, blocks, T, Vc, Pc, Fc, rc, oc, g, tab, &sc, lam, ode2, ode3, 0, 0, (double*)nullptr);
+            if (F) emulate(rhs_kernel<true, 3>, blocks, T, Vc, Pc, Fc, oc, g, tab, &sc, lam, ode2, ode3, -1, ny + 1, state.data(), nyp, 0);
+            else emulate(rhs_kernel<false, 3>, blocks, T, Vc, Pc, Fc, oc, g, tab, &sc, lam, ode2, ode3, -1, ny + 1, state.data(), nyp, 0);
         }
+        memcpy(rc, Vc, sizeof(cplx) * 2 * fld);   // what chb_download_rhs returns
         if (mode < 0) return 0;   // RHS only
         emulate(solve_rows_kernel, (nyp * 5 + 127) / 128, 128, tab, rows.data(), lam, ni, nyp);
         if (mode == 3) {   // S1 / S3 / S4 with eight rows of loads in flight per thread
-            emulate(solve_s1_kernel<0, 8>, blocks, T, rc, ckpt.data(), g, tab, &sc, lam);
-            emulate(solve_s1_kernel<1, 8>, blocks, T, rc, ckpt.data(), g, tab, &sc, lam);
+            emulate(solve_s1_kernel<0, 8>, blocks, T, Vc, ckpt.data(), g, tab, &sc, lam);
+            emulate(solve_s1_kernel<1, 8>, blocks, T, Vc, ckpt.data(), g, tab, &sc, lam);
         } else {
-            emulate(solve_s1_kernel<0, 1>, blocks, T, rc, ckpt.data(), g, tab, &sc, lam);
-            emulate(solve_s1_kernel<1, 1>, blocks, T, rc, ckpt.data(), g, tab, &sc, lam);
+            emulate(solve_s1_kernel<0, 1>, blocks, T, Vc, ckpt.data(), g, tab, &sc, lam);
+            emulate(solve_s1_kernel<1, 1>, blocks, T, Vc, ckpt.data(), g, tab, &sc, lam);
         }
-        emulate(solve_s2_kernel<0>, blocks, T, rc, ckpt.data(), Vc, g, tab, &sc, lam);
-        emulate(solve_s2_kernel<1>, blocks, T, rc, ckpt.data(), Vc, g, tab, &sc, lam);
+        emulate(solve_s2_kernel<0>, blocks, T, (const double*)ckpt.data(), Vc, g, tab, &sc, lam);
+        emulate(solve_s2_kernel<1>, blocks, T, (const double*)ckpt.data(), Vc, g, tab, &sc, lam);
         emulate(mean_mode_kernel, 1, MEAN_THREADS, Vc, g, tab, &sc, lam, scratch.data());
         if (mode == 3) {
             emulate(solve_s3_kernel<8>, blocks, T, Vc, g, tab);

@@ -27,6 +27,7 @@ def test_config2_full_size_properties(monkeypatch):
     V0 = perturbed_laminar(NX, NY, NZ, p.alfa0, p.beta0, p.a, p.ymin, p.ymax, eps=1e-3)
     ch = Channel(p)
     assert ch.nxd == 384 and ch.nzd == 768
+    ch.capture_products()
 
     # ---- products: exact quadratic scaling, Hermitian symmetry on ix = 0 ---------------------------
     ch.upload_V(V0)
@@ -47,6 +48,7 @@ def test_config2_full_size_properties(monkeypatch):
         err = np.abs(line - np.conj(line[:, ::-1])).max()
         assert err <= 1e-13 * np.abs(P1[k]).max(), ("hermitian", k, err)
     del P1
+    ch.capture_products(False)
 
     # ---- one RK3 step ----------------------------------------------------------------------------
     ch.upload_V(V0)

@@ -34,7 +34,7 @@ def test_gpu_reproduces_golden(path):
     ch.cfl_prepass()
     lines = [ch.outstats()]
     # first substep intermediates on a second handle
-    ch2 = Channel(p); ch2.upload_V(g["V0"])
+    ch2 = Channel(p); ch2.capture_products(); ch2.upload_V(g["V0"])
     if cor:
         ch2.config_coriolis(0.02, 9999999.0, 1.0)
     ch2.cfl_prepass(); ch2.outstats()

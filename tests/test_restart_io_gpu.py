@@ -38,6 +38,29 @@ def test_snapshot_file_is_byte_identical(nx, ny, nz, chunk_mb, async_mode, tmp_p
     ch.close()
 
 
+@pytest.mark.parametrize("async_mode", [False, True])
+def test_small_work_arena_stages_in_x_slabs(async_mode, tmp_path, monkeypatch):
+    """The work arena of the pencil transposes is the staging area of the blocking snapshot, of the restart read and of
+    the Fortran-layout transfers; when it is smaller than the field they go through it slab by slab of x-modes."""
+    monkeypatch.setenv("CHB_WORK_GB", "0.0005")           # one plane per chunk: room for 12 of the 32 x-modes
+    monkeypatch.setenv("CHB_IO_CHUNK_MB", "0.05")
+    p, ch, V0 = _channel(31, 48, 21)
+    Vf = np.ascontiguousarray(np.transpose(V0, (0, 2, 3, 1)))       # [c][ix][iz][iy]
+    assert np.array_equal(ch.download_V_fortran(), Vf)
+    ch.upload_V(np.zeros_like(V0)); ch.upload_V_fortran(Vf)
+    assert np.array_equal(ch.download_V(), V0)
+    ref = tmp_path / "ref.out"; got = tmp_path / "Dati.cart.out"
+    ch.time = 1.25
+    save_restart_file(ref, p, 1.25, Vf)
+    ch.save_restart_file(got, async_mode=async_mode)
+    ch.restart_wait()
+    assert got.read_bytes() == ref.read_bytes()
+    ch.upload_V(np.zeros_like(V0))
+    assert ch.read_restart_file(got) == 1.25
+    assert np.array_equal(ch.download_V(), V0)
+    ch.close()
+
+
 def test_async_snapshot_is_taken_at_call_time(tmp_path):
     """The time loop continues while the snapshot drains: the file holds the field of the call."""
     p, ch, V0 = _channel(31, 48, 21)

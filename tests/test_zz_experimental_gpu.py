@@ -120,25 +120,6 @@ def test_host_side_body_force_hook_matches_device_path():
     ch.close(); ch2.close()
 
 
-@pytest.mark.parametrize("lanes", ["1", "2"])
-def test_chunked_rhs_assembly(lanes, monkeypatch):
-    """CHB_RHS_CHUNKED=1: the plane loop of buildrhs follows the convolutions chunk by chunk, carrying its four
-    partially accumulated planes between the launches; same operations in the same order, so the fields must be
-    bit-identical to the default flow (one march after all chunks).  Small work buffers force several chunks."""
-    monkeypatch.setenv("CHB_WORK_GB", "0.002")
-    monkeypatch.setenv("CHB_LANES", lanes)
-    out = {}
-    for flag in ("0", "1"):
-        monkeypatch.setenv("CHB_RHS_CHUNKED", flag)
-        p, o, ch, V0 = make_pair(31, 48, 21, deltat=0.0, cflmax=1.0, re=3000.0)
-        ch.cfl_prepass(); ch.outstats()
-        lines = [ch.step() for _ in range(3)]
-        out[flag] = (ch.download_V(), np.array(lines))
-        ch.close()
-    assert np.array_equal(out["1"][0], out["0"][0])
-    assert np.array_equal(out["1"][1], out["0"][1])
-
-
 def test_prefetching_solve_sweeps(monkeypatch):
     """CHB_SOLVE_PF=1: S1 / S3 / S4 issue the loads of the next eight rows before processing them; the arithmetic and
     its order are unchanged, so the fields are bit-identical to the default kernels."""
