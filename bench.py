@@ -10,6 +10,12 @@ on a synthetic perturbed-laminar field.  The workload is a BASELI
 by default the largest one that fits a single B200 (config 3, nx,ny,nz = 511,512,511) at every N
 (strong scaling); --workload selects another (1..5 or nx,ny,nz).
 
+On several GPUs two more legs run outside the timed region of the main one:
+  parity_check     : two small grids stepped on all N ranks and compared with the CPU oracle (tests/mgpu_worker.py's
+                     check, made visible to the driver) - worst relative error over fields and ranks
+  headline_config4 : BASELINE.json's headline grid 1023x1024x1023 (configs[3]) where it fits the N GPUs (N >= 2):
+                     ms/step, steps/s, ns/DoF/step, fraction of the max(HBM, NVLink) roofline, kernels, NVLink GB/s
+
 Printed JSON (one line, rank 0): the driver contract plus
   roofline     : dominant kernel, algorithmic HBM bytes / CUDA-event time vs MEASURED_PEAKS.json
   step_roofline: whole step, B_step = 3*M*(ny+1)*(464+288r) bytes / t_step
@@ -49,6 +55,25 @@ def parse_workload(w: str):
         return d
     nx, ny, nz = (int(x) for x in w.split(","))
     return dict(nx=nx, ny=ny, nz=nz, name="custom")
+
+
+def padded(nx, nz):
+    """nxd, nzd: 3/2 rule rounded up to 2^k or 3*2^k (fftFIT, ffts.f90:78-86; dnsdata.f90:123)"""
+    def fit(n):
+        while True:
+            m = n
+            while m % 2 == 0:
+                m //= 2
+            if m in (1, 3):
+                return n
+            n += 1
+    return fit(3 * (nx + 1) // 2), fit(3 * nz)
+
+
+def workload_text(w, nx, ny, nz, nxd, nzd, couette):
+    """config.workload: the same string from both arms of the bench (B200 and reference)"""
+    return (f"{w['name']}: turbulent-channel grid nx,ny,nz={nx},{ny},{nz} (nxd,nzd={nxd},{nzd}), perturbed laminar "
+            f"{'Couette+coriolis' if couette else 'Poiseuille, CPI'} field, FP64, cflmax=1")
 
 
 def algorithmic_bytes(nx, ny, nz, nxd, nzd):
@@ -137,6 +162,10 @@ def measured_traffic(kernel, nx, ny, nz, world):
 
 
 FP64_PEAK_TFLOPS = 33.8   # measured FP64 FMA ceiling of one B200 (profiles/README.md, round 1 stage a)
+# what each kernel family is limited by according to its ncu capture (profiles/)
+LIMITERS = {"xpass": "fp64 pipe + shared-memory crossbar + barriers (not HBM: 0.34 of the HBM roofline at 55 % of the FP64 pipe)",
+            "zfwd": "hbm (latency-exposed, 24 % occupancy)", "zbwd": "hbm (latency-exposed, 24 % occupancy)",
+            "rhs": "hbm (streaming, 5.2 TB/s of DRAM traffic)", "solve": "hbm (streaming; 15 C moved where 5 C are compulsory)"}
 NVLINK_PEAK_GBS = 900.0   # NVLink 5 per direction and GPU (north_star; B200_PROFILING.md)
 
 
@@ -229,15 +258,15 @@ def build_report(args, w, nx, ny, nz, nxd, nzd, world, couette, ms_per_step, ker
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "ns_per_dof_step": ms_per_step * 1e6 / dof,
-        "config": {"workload": f"{w['name']}: turbulent-channel grid nx,ny,nz={nx},{ny},{nz} "
-                               f"(nxd,nzd={nxd},{nzd}), perturbed laminar "
-                               f"{'Couette+coriolis' if couette else 'Poiseuille, CPI'} field, FP64, cflmax=1",
+        "config": {"workload": workload_text(w, nx, ny, nz, nxd, nzd, couette),
                    "dof": dof, "decomposition": f"x-pencils over {world} GPU(s), npy=1",
                    "l2": "state (%.1f GB/GPU) far larger than the 126 MB L2; no flush needed" % (dev_bytes / 1e9),
                    "device_bytes_per_gpu": dev_bytes,
                    # library switches set in the environment; empty = every default
                    "switches": {k: v for k, v in sorted(os.environ.items()) if k.startswith("CHB_") and k != "CHB_WORKLOAD"}},
-        "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
+        # bound: the contract's roofline is the HBM one (algorithmic bytes / time against the measured copy bandwidth);
+        # limiter: what ncu shows the kernel actually waits for
+        "roofline": {"bound": "hbm", "limiter": LIMITERS.get(dom, "hbm"), "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
                      "frac": ach / peak, "traffic": traffic, "traffic_source": tsrc, "peak_source": peak_src,
                      "bytes_per_launch": bytes_per_launch, "launches": nl, "fp64": fp64},
         "step_roofline": {"bytes_per_step": step_bytes, "achieved": step_bytes / (ms_per_step * 1e-3) / 1e9,
@@ -272,46 +301,89 @@ def build_report(args, w, nx, ny, nz, nxd, nzd, world, couette, ms_per_step, ker
 
 
 # ---------------------------------------------------------------------------------------------
-def run_b200(args):
+def _nccl_id_factory(lib, _lib, rank, world):
+    """one NCCL unique id per communicator (= per chb_create), broadcast from rank 0 over torch.distributed"""
+    import ctypes as C
     import torch
     import torch.distributed as dist
-    from channel_b200 import Channel, DnsIn, _lib
-    from channel_b200.fields import perturbed_laminar_slab
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device (this implementation has no CPU fallback)")
-    torch.cuda.set_device(local_rank)
-    lib = _lib.load()
-    nccl_id = None
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        import ctypes as C
+    def new_id():
+        if world == 1:
+            return None
         buf = C.create_string_buffer(128)
         if rank == 0:
             _lib.check(lib.chb_get_nccl_unique_id(buf), "chb_get_nccl_unique_id")
         t = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).cuda()
         dist.broadcast(t, 0)
-        nccl_id = bytes(t.cpu().numpy().tobytes())
+        return bytes(t.cpu().numpy().tobytes())
+    return new_id
 
-    w = parse_workload(args.workload)
+
+def parity_check(rank, world, local_rank, new_id):
+    """Multi-rank parity made visible to the driver (the check of tests/mgpu_worker.py): two small grids are stepped on
+    all `world` ranks through the C ABI - pencil transposes, barriers and the chunk pipeline included - and every
+    rank compares its x-slab with the CPU oracle (test infrastructure, used here as the checker only, outside any timed
+    region).  Norm-wise relative error, the way utilities/compare_fields.py:17-54 compares fields."""
+    import torch
+    import torch.distributed as dist
+    from channel_b200 import Channel, DnsIn
+    from channel_b200.fields import perturbed_laminar
+    from oracle.channel_oracle import DnsIn as ODnsIn, Oracle
+    worst, cases = 0.0, []
+    t0 = time.perf_counter()
+    for nx, ny, nz, steps in ((31, 16, 16, 2), (255, 8, 255, 2)):
+        p = DnsIn(nx=nx, ny=ny, nz=nz, re=2000.0, deltat=0.0, cflmax=1.0)
+        o = Oracle(ODnsIn(**{k: getattr(p, k) for k in ODnsIn.__dataclass_fields__}))
+        V0 = perturbed_laminar(nx, ny, nz, p.alfa0, p.beta0, eps=2e-2)
+        o.V[:] = V0
+        ch = Channel(p, rank=rank, nranks=world, nccl_id=new_id(), device=local_rank, tables=o)
+        sl = slice(ch.nx0, ch.nxN + 1)
+        ch.upload_V(V0[:, :, sl, :])
+        ch.cfl_prepass(); o.cfl_prepass()
+        lg = ch.outstats(); lo = o.outstats()
+        err_lines = float(np.max(np.abs(lg - lo) / np.maximum(np.abs(lo), 1e-300) * (np.abs(lo) > 1e-12)))
+        for _ in range(steps):
+            lo = o.step(); lg = ch.step()
+            m = np.abs(lo[1:9]) > 1e-9
+            err_lines = max(err_lines, float(np.max(np.abs(lg[1:9] - lo[1:9])[m] / np.abs(lo[1:9])[m])) if m.any() else 0.0)
+        Vg = ch.download_V()
+        err = max(float(np.abs(Vg[c] - o.V[c][:, sl, :]).max() / np.abs(o.V[c]).max()) for c in range(3))
+        ch.close()
+        t = torch.tensor([err, err_lines], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        cases.append({"grid": [nx, ny, nz], "steps": steps, "field_rel_err": float(t[0].item()),
+                      "runtimedata_rel_err": float(t[1].item())})
+        worst = max(worst, float(t[0].item()))
+    return {"world": world, "worst_rel_err": worst, "tolerance": 1e-11, "ok": bool(worst < 1e-11), "cases": cases,
+            "oracle": "oracle/channel_oracle.py (numpy restatement of the reference; parity unpinned, DESIGN.md)",
+            "seconds": time.perf_counter() - t0}
+
+
+def timed_leg(args, w, rank, world, local_rank, new_id, steps, warmup, pinned, e2e, clock_sampler=True):
+    """One workload through the C ABI: upload the synthetic field, CFL pre-pass, `warmup` untimed steps, then `steps`
+    steps timed on the device (CUDA events on the launching stream, max over ranks); optionally the end-to-end leg
+    with host buffers.  Returns everything build_report needs."""
+    import torch
+    import torch.distributed as dist
+    from channel_b200 import Channel, DnsIn
+    from channel_b200.fields import perturbed_laminar_slab
+
     couette = bool(w.get("couette"))
     p = DnsIn(nx=w["nx"], ny=w["ny"], nz=w["nz"], deltat=0.0, cflmax=1.0,
               CPI=not couette, u0=-1.0 if couette else 0.0, uN=1.0 if couette else 0.0)
-    ch = Channel(p, rank=rank, nranks=world, nccl_id=nccl_id, device=local_rank)
+    ch = Channel(p, rank=rank, nranks=world, nccl_id=new_id(), device=local_rank)
     if couette:
         ch.config_coriolis(0.02, 9999999.0, 1.0)      # body_forces/coriolis/coriolis.in as shipped
     nx, ny, nz, nxd, nzd = ch.nx, ch.ny, ch.nz, ch.nxd, ch.nzd
-    dof = 3 * (2 * nx + 1) * (2 * nz + 1) * ny          # README.md:26 convention
 
     # synthetic perturbed-laminar field of this rank's x-slab, in the Fortran (Dati.cart.out)
-    # layout V(iy,iz,ix,c), pinned: this is what the driver's read_restart_file would hold
-    Vf = torch.empty((3, ch.nxB, 2 * nz + 1, ny + 3), dtype=torch.complex128).pin_memory()
-    Vn = Vf.numpy()
+    # layout V(iy,iz,ix,c): this is what the driver's read_restart_file would hold
+    shape = (3, ch.nxB, 2 * nz + 1, ny + 3)
+    if pinned:
+        Vf = torch.empty(shape, dtype=torch.complex128).pin_memory()
+        Vn = Vf.numpy()
+    else:
+        Vn = np.empty(shape, dtype=np.complex128)
     perturbed_laminar_slab(Vn, nx, ny, nz, p.alfa0, p.beta0, ch.nx0, ch.nxB, p.a, p.ymin, p.ymax,
                            eps=1e-3, couette=couette)
     vbytes = Vn.nbytes
@@ -324,22 +396,23 @@ def run_b200(args):
     ch.upload_V_fortran(Vn)
     ch.cfl_prepass()
     ch.outstats()                                      # deltat = cflmax / cfl  (channel.f90:116)
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         ch.step()
 
     # ---- timed region: K steps, device time on the launching stream, max over ranks ----------
     ch.timing_enable(True)
     l0 = ch.launch_count()
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank) if clock_sampler else None
     barrier()
-    sampler.start()
+    if sampler:
+        sampler.start()
     ch.stopwatch_begin()
     last_line = None
-    for _ in range(args.steps):
+    for _ in range(steps):
         last_line = ch.step()
     ms = ch.stopwatch_end()
     barrier()
-    clocks = sampler.stop()
+    clocks = sampler.stop() if sampler else None
     launches = ch.launch_count() - l0
     kern = ch.timing_report()
     ch.timing_enable(False)
@@ -347,21 +420,95 @@ def run_b200(args):
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    ms_per_step = ms / args.steps
+    out = dict(ch=ch, Vn=Vn, vbytes=vbytes, ms_per_step=ms / steps, kern=kern, launches=launches, clocks=clocks,
+               last_line=last_line, couette=couette, dims=(nx, ny, nz, nxd, nzd), barrier=barrier, e2e_s=None)
 
     # ---- end to end through the C ABI with host buffers ---------------------------------------
-    barrier()
-    t0 = time.perf_counter()
-    ch.upload_V_fortran(Vn)
-    for _ in range(args.steps):
-        ch.step()                                      # includes chb_get_step_scalars D2H per step
-    ch.download_V_fortran(out=Vn)
-    barrier()
-    e2e_s = time.perf_counter() - t0
+    if e2e:
+        barrier()
+        t0 = time.perf_counter()
+        ch.upload_V_fortran(Vn)
+        for _ in range(steps):
+            ch.step()                                  # includes chb_get_step_scalars D2H per step
+        ch.download_V_fortran(out=Vn)
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_s = float(t.item())
+        out["e2e_s"] = e2e_s
+    return out
+
+
+def headline_leg(args, rank, world, local_rank, new_id):
+    """BASELINE.json configs[3], the grid the metric is quoted on: 1023 x 1024 x 1023 on the N GPUs of this run, where
+    it fits (5.5 complex per point resident: 189 GB on one GPU - does not fit -, 95 GB per GPU on two)."""
+    import torch
+    w = parse_workload("4")
+    nx, ny, nz = w["nx"], w["ny"], w["nz"]
+    nxd, nzd = padded(nx, nz)
+    M = (nx + 1) * (2 * nz + 1)
+    need = 5.5 * C16 * (ny + 3) * M / world + 11e9          # resident fields + work arena + tables
+    free_b, total_b = torch.cuda.mem_get_info()
+    host_need = 3.0 * C16 * (ny + 3) * M / world * min(world, 8)     # the ranks of this node build their slabs at once
+    try:
+        with open("/proc/meminfo") as f:
+            host_avail = next(int(l.split()[1]) * 1024 for l in f if l.startswith("MemAvailable"))
+    except Exception:
+        host_avail = None
+    if need > free_b or (host_avail is not None and host_need > 0.8 * host_avail):
+        return {"ran": False, "why": f"needs {need / 1e9:.0f} GB per GPU ({free_b / 1e9:.0f} GB free) and "
+                                     f"{host_need / 1e9:.0f} GB of host memory for the synthetic field "
+                                     f"({(host_avail or 0) / 1e9:.0f} GB available)"}
+    r = timed_leg(args, w, rank, world, local_rank, new_id, args.headline_steps, args.headline_warmup, pinned=False,
+                  e2e=False, clock_sampler=True)
+    ch = r["ch"]
+    hargs = argparse.Namespace(steps=args.headline_steps, warmup=args.headline_warmup)
+    rep = build_report(hargs, w, nx, ny, nz, nxd, nzd, world, False, r["ms_per_step"], r["kern"], r["launches"], r["clocks"],
+                       1.0, r["vbytes"], ch.device_bytes(), bool(np.isfinite(r["last_line"]).all()), r["last_line"], None)
+    ch.close()
+    keep = {k: rep[k] for k in ("ms_per_step", "ns_per_dof_step", "step_roofline", "kernels", "nvlink", "gpu_launches",
+                                "clocks", "finite", "runtimedata_last", "roofline") if k in rep}
+    keep.update({"ran": True, "workload": rep["config"]["workload"], "steps_per_s": rep["value"], "steps": args.headline_steps,
+                 "warmup": args.headline_warmup, "n_gpus": world, "dof": rep["config"]["dof"],
+                 "device_bytes_per_gpu": rep["config"]["device_bytes_per_gpu"],
+                 "target": "north_star: >= 0.60 of the max(HBM, NVLink) roofline on 8 B200 (step_roofline.frac_of_max_hbm_nvlink)"})
+    return keep
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from channel_b200 import _lib
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (this implementation has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    lib = _lib.load()
     if world > 1:
-        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    new_id = _nccl_id_factory(lib, _lib, rank, world)
+
+    # ---- multi-rank parity against the oracle, before anything is timed ---------------------------
+    parity = None
+    if world > 1 and args.parity_check:
+        try:
+            parity = parity_check(rank, world, local_rank, new_id)
+        except Exception as e:      # a failed check must show up in the line, not kill the measurement
+            parity = {"world": world, "ok": False, "error": repr(e)[:300]}
+
+    w = parse_workload(args.workload)
+    r = timed_leg(args, w, rank, world, local_rank, new_id, args.steps, args.warmup, pinned=True, e2e=True)
+    ch, Vn, barrier = r["ch"], r["Vn"], r["barrier"]
+    nx, ny, nz, nxd, nzd = r["dims"]
+    ms_per_step, kern, launches, clocks, e2e_s, vbytes = (r[k] for k in ("ms_per_step", "kern", "launches", "clocks", "e2e_s", "vbytes"))
+    last_line, couette = r["last_line"], r["couette"]
     finite = bool(np.isfinite(last_line).all())
 
     # ---- optional: snapshot files from the device-resident field (SURVEY.md 8(f)1) ------------
@@ -389,13 +536,31 @@ def run_b200(args):
             if os.path.exists(path):
                 os.remove(path)
 
+    out = None
     if rank == 0:
         out = build_report(args, w, nx, ny, nz, nxd, nzd, world, couette, ms_per_step, kern, launches, clocks, e2e_s, vbytes,
                            ch.device_bytes(), finite, last_line, snap)
+        if parity is not None:
+            out["parity_check"] = parity
+    ch.close()
+    del Vn, r
+
+    # ---- the headline grid of BASELINE.json on the GPUs of this run (several GPUs only) -------------
+    if world > 1 and args.headline and args.workload != "4":
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+        try:
+            head = headline_leg(args, rank, world, local_rank, new_id)
+        except Exception as e:
+            head = {"ran": False, "why": repr(e)[:300]}
+        if rank == 0:
+            out["headline_config4"] = head
+
+    if rank == 0:
         if args.cpu_baseline and world == 1:
             out["cpu_baseline"] = cpu_baseline(w, sample_s=args.cpu_seconds)
         print(json.dumps(out), flush=True)
-    ch.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -403,29 +568,53 @@ def run_b200(args):
 # ---------------------------------------------------------------------------------------------
 def cpu_baseline(w, sample_s=20.0, threads=None):
     """The reference algorithm (oracle/channel_oracle_c.c, C + OpenMP, plane-by-plane like
-    dnsdata.f90) on this box's host cores, on a bounded sample of the same grid."""
+    dnsdata.f90) on this box's host cores (all of the affinity mask, whatever OMP_NUM_THREADS says), on a bounded
+    sample of the same grid."""
     from oracle import c_oracle
     return c_oracle.timed_sample(w["nx"], w["ny"], w["nz"], seconds=sample_s, threads=threads)
 
 
 def run_reference(args):
+    """The reference arm: the reference's algorithm on the host cores of this box (oracle/channel_oracle_c.c; the Fortran
+    / FFTW / MPI binary cannot be built in this image).  A "step" of this arm is one bounded sample of an RK3
+    step of the same workload (the task's definition), scaled to a full step: `value` and `ms_per_step` are the
+    extrapolated full-workload figures (`extrapolated: true`, the executed share in `sampled_fraction_of_step`, the
+    wall time actually spent per sample in `sample_wall_ms`).  `extrapolation_check` times one COMPLETE, unsampled RK3
+    step on config 2 next to the estimate the same sampling gives for it."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    from oracle import c_oracle
     w = parse_workload(args.workload)
-    vals = []
+    nxd, nzd = padded(w["nx"], w["nz"])
+    threads = c_oracle.host_cores()
+    vals, walls = [], []
     cb = None
     for i in range(args.warmup + args.steps):
-        cb = cpu_baseline(w, sample_s=args.cpu_seconds)
+        cb = cpu_baseline(w, sample_s=args.cpu_seconds, threads=threads)
         if i >= args.warmup:
             vals.append(cb["value"])
+            walls.append(cb["sample_wall_s"])
     v = float(np.mean(vals))
     cb["value"] = v
+    check = None
+    if args.extrapolation_check:
+        try:
+            c2 = parse_workload(args.extrapolation_grid)
+            check = c_oracle.timed_full_step(c2["nx"], c2["ny"], c2["nz"], threads=threads)
+            check["what"] = (f"one complete unsampled RK3 step of {c2['name']} (co_step, after one warm-up step) against the "
+                             "estimate the bounded sampling gives for the same grid")
+        except Exception as e:
+            check = {"error": repr(e)[:200]}
     out = {"impl": "reference", "metric": "rk3_timesteps_per_s", "value": v, "unit": "steps/s",
            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / v,
            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
            "data": "synthetic",
-           "config": {"workload": f"{w['name']}: nx,ny,nz={w['nx']},{w['ny']},{w['nz']} (bounded sample, see cpu_baseline.sample)"},
+           "config": {"workload": workload_text(w, w["nx"], w["ny"], w["nz"], nxd, nzd, bool(w.get("couette"))),
+                      "dof": 3 * (2 * w["nx"] + 1) * (2 * w["nz"] + 1) * w["ny"]},
+           "extrapolated": True, "sampled_fraction_of_step": cb["sampled_fraction_of_step"],
+           "sample_wall_ms": 1000.0 * float(np.mean(walls)),
+           "extrapolation_check": check,
            "cpu_baseline": cb,
            "e2e": {"value": v, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)
@@ -442,6 +631,12 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--snapshot", action="store_true", help="also time chb_save_restart_file (blocking and asynchronous)")
     ap.add_argument("--snapshot-dir", default=None)
+    ap.add_argument("--no-parity-check", dest="parity_check", action="store_false", help="several GPUs: skip the oracle comparison")
+    ap.add_argument("--no-headline", dest="headline", action="store_false", help="several GPUs: skip the config-4 leg")
+    ap.add_argument("--headline-steps", type=int, default=5)
+    ap.add_argument("--headline-warmup", type=int, default=3)
+    ap.add_argument("--no-extrapolation-check", dest="extrapolation_check", action="store_false")
+    ap.add_argument("--extrapolation-grid", default="2", help="reference arm: grid of the complete-step check (config number or nx,ny,nz)")
     args = ap.parse_args()
     if args.impl == "reference":
         # each "step" of the reference arm is one bounded sample; keep the whole run to minutes

@@ -295,10 +295,13 @@ static int create_impl(chb_handle_s* h, int nx, int ny, int nz, int nxd, int nzd
         const char* e = getenv("CHB_P2P");
         h->p2p = (nranks > 1 && !(e && atoi(e) == 0)) ? 1 : 0;
         // two lanes: the kernels that carry the transposes run on their own stream (and SM partition) one chunk ahead of
-        // the local kernels; default on several GPUs, where the former are NVLink-bound
-        e = getenv("CHB_LANES");
-        h->nlanes = e ? (atoi(e) == 2 ? 2 : 1) : (nranks > 1 ? 2 : 1);
+        // the local kernels; default from 4 GPUs on, where the former are NVLink-bound
+        // (measured, profiles/r2d_overlap.md: at 2 GPUs, where little of the step is NVLink-bound, the sequential
+        // sweep is faster: 137 against 147 ms/step at config 3).  The NCCL fallback always runs one lane.
         const bool nccl_mode = nranks > 1 && !h->p2p;
+        e = getenv("CHB_LANES");
+        h->nlanes = e ? (atoi(e) == 2 ? 2 : 1) : (nranks >= 4 ? 2 : 1);
+        if (nccl_mode) h->nlanes = 1;
         // budget: CHB_WORK_GB (default 10 GB, at most a quarter of the free device memory); larger chunks mean fewer
         // launches, fewer partially filled last waves and fewer carried-accumulator round trips of the RHS assembly
         size_t free_b = 0, total_b = 0;

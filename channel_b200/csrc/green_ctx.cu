@@ -8,14 +8,15 @@
 // side by side for the whole sweep.  This is the role of the reference's nonblockingXZ variant
 // (mpi_transpose.f90:149-168: MPI_IAlltoall progressing under the next plane's FFTs).
 //
-// The device is split into groups of 8 SMs (the granularity of compute capability 9.0+); the first groups form A,
-// the others B.  libcuda is reached through dlopen, like NCCL, so that the library links against the runtime only.
+// The device is split into the smallest groups the driver offers (2 SMs when SM co-scheduling is ignored - no kernel
+// here uses clusters -, else 8); the first groups form A, the others and the remainder of the split B.  libcuda is reached through dlopen, like NCCL, so that the library links against the runtime only.
 // Everything here is optional: any failure leaves the handle on plain streams (chb_green_create returns non-zero).
 #include <cuda.h>
 #include <dlfcn.h>
 
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <string>
 #include <vector>
 
@@ -68,19 +69,39 @@ int chb_green_create(chb_handle_s* h, int sms_a) {
     CUdevResource all;
     if (g_drv.DeviceGetDevResource(dev, &all, CU_DEV_RESOURCE_TYPE_SM) != CUDA_SUCCESS) return 1;
     const int total = (int)all.sm.smCount;
+    // groups of 8 SMs aligned to the GPC structure leave 28 of the 148 SMs of a B200 in the remainder; none of our
+    // kernels uses thread-block clusters, so the split may ignore SM co-scheduling and use the finest granularity
     unsigned int ng = 0;
-    if (g_drv.DevSmResourceSplitByCount(nullptr, &ng, &all, nullptr, 0, 8) != CUDA_SUCCESS || ng < 2) return 1;
-    std::vector<CUdevResource> grp(ng);
+    unsigned int flags = CU_DEV_SM_RESOURCE_SPLIT_IGNORE_SM_COSCHEDULING, gran = 2;
+    if (g_drv.DevSmResourceSplitByCount(nullptr, &ng, &all, nullptr, flags, gran) != CUDA_SUCCESS || ng < 2) {
+        flags = 0; gran = 8; ng = 0;
+        if (g_drv.DevSmResourceSplitByCount(nullptr, &ng, &all, nullptr, flags, gran) != CUDA_SUCCESS || ng < 2) return 1;
+    }
+    std::vector<CUdevResource> grp(ng + 1);
     CUdevResource rem;
-    if (g_drv.DevSmResourceSplitByCount(grp.data(), &ng, &all, &rem, 0, 8) != CUDA_SUCCESS || ng < 2) return 1;
+    memset(&rem, 0, sizeof(rem));
+    if (g_drv.DevSmResourceSplitByCount(grp.data(), &ng, &all, &rem, flags, gran) != CUDA_SUCCESS || ng < 2) return 1;
     const int per = (int)grp[0].sm.smCount;
     if (sms_a < 0) sms_a = (int)(0.54 * total + 0.5);
     int ka = (sms_a + per / 2) / per;
     if (ka < 1) ka = 1;
     if (ka > (int)ng - 1) ka = (int)ng - 1;
+    // partition B: the other groups and what the split left over
+    unsigned int nb = ng - (unsigned)ka;
+    int sms_b = (int)nb * per;
+    if (rem.type == CU_DEV_RESOURCE_TYPE_SM && rem.sm.smCount > 0) {
+        grp[ng] = rem;
+        nb += 1;
+        sms_b += (int)rem.sm.smCount;
+    }
     CUdevResourceDesc da, db;
     if (g_drv.DevResourceGenerateDesc(&da, grp.data(), (unsigned)ka) != CUDA_SUCCESS) return 1;
-    if (g_drv.DevResourceGenerateDesc(&db, grp.data() + ka, ng - (unsigned)ka) != CUDA_SUCCESS) return 1;
+    if (g_drv.DevResourceGenerateDesc(&db, grp.data() + ka, nb) != CUDA_SUCCESS) {
+        // without the remainder
+        nb = ng - (unsigned)ka;
+        sms_b = (int)nb * per;
+        if (g_drv.DevResourceGenerateDesc(&db, grp.data() + ka, nb) != CUDA_SUCCESS) return 1;
+    }
     CUgreenCtx ga = nullptr, gb = nullptr;
     if (g_drv.GreenCtxCreate(&ga, da, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) return 1;
     if (g_drv.GreenCtxCreate(&gb, db, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) {
@@ -98,7 +119,7 @@ int chb_green_create(chb_handle_s* h, int sms_a) {
     h->green[0] = ga;
     h->green[1] = gb;
     h->green_sms[0] = ka * per;
-    h->green_sms[1] = ((int)ng - ka) * per;
+    h->green_sms[1] = sms_b;
     h->sA = (cudaStream_t)sa;
     h->sB = (cudaStream_t)sb;
     if (getenv("CHB_VERBOSE"))

@@ -84,7 +84,8 @@ rhs_kernel(cplx* V, const cplx* __restrict__ P, const cplx* __restrict__ F,
         const size_t poff = (size_t)(ip + 1 - pplane0) * plane + m;
         const cplx p1 = P[0 * pcomp + poff], p2 = P[1 * pcomp + poff], p3 = P[2 * pcomp + poff];
         const cplx p4 = P[3 * pcomp + poff], p5 = P[4 * pcomp + poff], p6 = P[5 * pcomp + poff];
-        const cplx u = V[0 * comp + off], v = V[1 * comp + off], w = V[2 * comp + off];
+        // read-only path for V: a plane is read two iterations before this thread overwrites it, nobody else writes it
+        const cplx u = __ldg(V + 0 * comp + off), v = __ldg(V + 1 * comp + off), w = __ldg(V + 2 * comp + off);
         cplx f1 = make_double2(0, 0), f2 = f1, f3 = f1;
         if (HAS_F) {
             f1 = F[0 * comp + off];

@@ -157,7 +157,9 @@ solve_s2_kernel(const double* __restrict__ ckpt, cplx* V, Geometry g,
 #pragma unroll
         for (int k = 0; k < SOLVE_K; ++k) {
             const int iy = i0 + k;
-            xb[k] = (iy <= ny - 1) ? xin[(size_t)(iy + 1) * plane] : make_double2(0.0, 0.0);
+            // read-only path: a row is read before this thread (the only one that touches the column) overwrites it, and
+            // the compiler may hoist the next block's loads over this block's stores as it could with separate arrays
+            xb[k] = (iy <= ny - 1) ? __ldg(xin + (size_t)(iy + 1) * plane) : make_double2(0.0, 0.0);
         }
         double m2[SOLVE_K], m1[SOLVE_K];
 #pragma unroll

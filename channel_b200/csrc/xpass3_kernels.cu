@@ -46,11 +46,17 @@ __device__ __forceinline__ void apply_twiddle_seq(cplx* x, cplx w1) {
 // position run the radix-C butterflies of u, v, w (duplicated: 3 of the 9 innermost butterflies per position), then
 // one forms uu, vv, ww and the other uv, vw, uw.  Because two threads now read the u, v, w entries that the products
 // overwrite in place, a barrier separates the reads from the writes.
-template <class G, int LPC, int MINB, bool MULTI, int SPLIT = 1>
+// PERSIST (CHB_XPASS_PERSIST, default at nxd = 1536): a persistent CTA walks over the lines of the launch.  The
+// inputs of line n+1 (3 x (nx+1) modes) are copied into a shared-memory staging area with per-thread 16-byte
+// cp.async while line n runs its stages B ... merge, and the twiddle tables (Wh[0..nx], W[0..BC), W[A k]) are loaded
+// into shared memory once per CTA, so that no stage waits for a global load any more: at nxd = 1536, where the six
+// line buffers (148.6 KB) leave one CTA of 6-12 warps per SM, 23 % of the warp samples were long-scoreboard stalls of
+// stage A and of the merge pass (profiles/r2b_ncu_source_xpass.md).  216 KB of shared memory at nxd = 1536.
+template <class G, int LPC, int MINB, bool MULTI, int SPLIT = 1, bool PERSIST = false>
 __global__ void __launch_bounds__(SPLIT * LPC * (G::N / G::C), MINB)
 xpass4_kernel(const cplx* __restrict__ Ar, const __grid_constant__ PeerPtrs Bw, const __grid_constant__ Geometry g, const cplx* __restrict__ W,
               const cplx* __restrict__ Wh, const double* __restrict__ dy, DevScalars* sc, int plane0, int np,
-              int compute_cfl) {
+              int compute_cfl, int nplanes) {
     constexpr int M = G::N, A = G::A, B = G::B, C = G::C, BC = G::BC;
     constexpr int TP = M / C;          // butterfly positions of the innermost stage
     constexpr int T = SPLIT * TP;      // threads per line
@@ -59,14 +65,21 @@ xpass4_kernel(const cplx* __restrict__ Ar, const __grid_constant__ PeerPtrs Bw, 
     constexpr int NB = A * C;          // stage-B butterflies per transform
     static_assert(T % C == 0 && NB % C == 0, "stage-B twiddle must be a per-thread constant");
     static_assert(SPLIT == 1 || (SPLIT == 2 && LPC == 1 && TP % 32 == 0), "the two halves of a line must be whole warps");
+    static_assert(!PERSIST || LPC == 1, "the persistent variant handles one line per CTA at a time");
     CHB_DYN_SMEM(cplx, smem);
     const int tl = threadIdx.x % T, l = threadIdx.x / T;
-    const int izl = blockIdx.x * LPC + l;
-    const int pli = blockIdx.y;
-    const int iy = plane0 + pli - 1;
     const int nx = g.nx, nxB = g.nxB, nzB = g.nzB;
     constexpr bool multi = MULTI;
     cplx* S = smem + (size_t)l * 6 * LB;
+    // persistent variant: staging area of the next line's inputs [3][nx+1] and the twiddle tables, behind the six buffers
+    const int nxp = nx + 1;
+    cplx* const Xs = smem + 6 * LB;            // [3][nxp]
+    cplx* const WhS = Xs + 3 * nxp;            // Wh[0..nx]
+    cplx* const W1S = WhS + nxp;               // W[0..BC)
+    cplx* const WbS = W1S + BC;                // W[A k], k = 0..B-1
+    auto ldWh = [&](int i) -> cplx { if constexpr (PERSIST) return WhS[i]; else return __ldg(&Wh[i]); };
+    auto ldW1 = [&](int t1) -> cplx { if constexpr (PERSIST) return W1S[t1]; else return __ldg(&W[t1]); };
+    auto ldWb = [&](int k) -> cplx { if constexpr (PERSIST) return WbS[k]; else return __ldg(&W[A * k]); };
 
     // element (ka, t = b*C + c) of a transform buffer; for C = 4 the column index is swizzled so that
     // stage A (lanes = consecutive t), stage B (lanes = (ka, c)) and stage C (lanes = consecutive kb)
@@ -83,24 +96,53 @@ xpass4_kernel(const cplx* __restrict__ Ar, const __grid_constant__ PeerPtrs Bw, 
     // several: [src rank][comp][plane][x tile][z row][x in tile] (row-major if g.twa < 0)
     const unsigned planeA = (unsigned)((size_t)nzB * nxB), cstrA = (unsigned)np * planeA;
     const bool tiledA = multi && g.twa >= 0;
-    const unsigned rowA = (unsigned)pli * planeA + (tiledA ? ((unsigned)izl << g.twa) : (unsigned)izl * (unsigned)nxB);
     const unsigned tmaskA = tiledA ? (1u << g.twa) - 1u : 0u;
     const unsigned tstrA = tiledA ? ((unsigned)nzB << g.twa) : 0u;   // elements between x tiles
+    auto row_of = [&](int izl_, int pli_) -> unsigned {
+        return (unsigned)pli_ * planeA + (tiledA ? ((unsigned)izl_ << g.twa) : (unsigned)izl_ * (unsigned)nxB);
+    };
+    auto mode_off = [&](int n) -> unsigned {   // offset of mode n inside a (line, component)
+        unsigned o = (unsigned)n;
+        if (multi) {
+            const unsigned qr = (unsigned)n / (unsigned)nxB, nl = (unsigned)n - qr * (unsigned)nxB;
+            o = qr * 3u * cstrA + (tiledA ? ((nl >> g.twa) * tstrA + (nl & tmaskA)) : nl);
+        }
+        return o;
+    };
+    const int nlines = (nzB / LPC) * nplanes;
+    auto prefetch = [&](int line) {   // inputs of `line` -> Xs (asynchronous)
+        const unsigned rA = row_of(line % nzB, line / nzB);
+        for (int e = threadIdx.x; e < 3 * nxp; e += T) {
+            const int comp = e / nxp, n = e - comp * nxp;
+            cp_async16(Xs + e, Ar + rA + (unsigned)comp * cstrA + mode_off(n));
+        }
+    };
+    if constexpr (PERSIST) {
+        for (int i = threadIdx.x; i < nxp; i += T) WhS[i] = Wh[i];
+        for (int i = threadIdx.x; i < BC; i += T) W1S[i] = W[i];
+        for (int i = threadIdx.x; i < B; i += T) WbS[i] = W[A * i];
+        if ((int)blockIdx.x < nlines) prefetch(blockIdx.x);
+    }
+    auto do_line = [&](const int line) {
+    const int izl = PERSIST ? line % nzB : (int)blockIdx.x * LPC + l;
+    const int pli = PERSIST ? line / nzB : (int)blockIdx.y;
+    const int iy = plane0 + pli - 1;
+    const unsigned rowA = row_of(izl, pli);
+    if constexpr (PERSIST) {
+        cp_async_wait_all();
+        __syncthreads();   // this line's inputs (and, the first time, the tables) are in shared memory
+    }
     // ---- backward stage A: split pass -> radix-A -> smem; tasks = (component, mode group t1) --------
 #pragma unroll 1
     for (int task = tl; task < 3 * BC; task += T) {
         const int comp = task / BC, t1 = task - comp * BC;
-        const cplx wh1 = Wh[t1];   // exp(+i pi t1 / M)
-        const cplx w1 = W[t1];     // exp(+2 pi i t1 / M)
+        const cplx wh1 = ldWh(t1);   // exp(+i pi t1 / M)
+        const cplx w1 = ldW1(t1);    // exp(+2 pi i t1 / M)
         const cplx* __restrict__ Xc = Ar + rowA + (unsigned)comp * cstrA;
         auto X = [&](int n) -> cplx {   // mode n of this line, zero beyond nx (x zero-padding, dnsdata.f90:535)
             if (n > nx) return make_double2(0.0, 0.0);
-            unsigned o = (unsigned)n;
-            if (multi) {
-                const unsigned qr = (unsigned)n / (unsigned)nxB, nl = (unsigned)n - qr * (unsigned)nxB;
-                o = qr * 3u * cstrA + (tiledA ? ((nl >> g.twa) * tstrA + (nl & tmaskA)) : nl);
-            }
-            return __ldg(Xc + o);
+            if constexpr (PERSIST) return Xs[comp * nxp + n];
+            else return __ldg(Xc + mode_off(n));
         };
         cplx x[A];
         static_for<A>([&](auto a_) {
@@ -122,10 +164,13 @@ xpass4_kernel(const cplx* __restrict__ Ar, const __grid_constant__ PeerPtrs Bw, 
         static_for<A>([&](auto ka_) { constexpr int ka = decltype(ka_)::value; dst[ka * BCP] = x[ka]; });
     }
     __syncthreads();
+    if constexpr (PERSIST) {   // the staging area is free: fetch the next line's inputs under the remaining stages
+        if (line + (int)gridDim.x < nlines) prefetch(line + (int)gridDim.x);
+    }
     // ---- backward stage B, in place; tasks = (component, ka, c) ---------------------------------------
     {
         const int cc = tl % C;
-        const cplx w1 = W[A * cc];   // w_BC^cc
+        const cplx w1 = ldWb(cc);   // w_BC^cc
 #pragma unroll 1
         for (int task = tl; task < 3 * NB; task += T) {
             const int comp = task / NB, u = task - comp * NB;
@@ -172,7 +217,8 @@ xpass4_kernel(const cplx* __restrict__ Ar, const __grid_constant__ PeerPtrs Bw, 
                     atomicMax(&sc->cfl_bits, (unsigned long long)__double_as_longlong(cmax));
             }
             const double f = 0.5 * g.factor;       // the 1/2 of the merge pass is folded into the products
-            const cplx wk1 = ctw<-1>(W, A * kb);   // conj w_BC^kb
+            cplx wk1 = ldWb(kb);   // conj w_BC^kb
+            wk1.y = -wk1.y;
             auto forward_c = [&](cplx* x, int p) {
                 Dft<C, -1>::run(x);
                 if (kb != 0) apply_twiddle_seq<C>(x, wk1);
@@ -228,7 +274,8 @@ xpass4_kernel(const cplx* __restrict__ Ar, const __grid_constant__ PeerPtrs Bw, 
                     atomicMax(&sc->cfl_bits, (unsigned long long)__double_as_longlong(cmax));
             }
             const double f = 0.5 * g.factor;       // the 1/2 of the merge pass is folded into the products
-            const cplx wk1 = ctw<-1>(W, A * kb);   // conj w_BC^kb
+            cplx wk1 = ldWb(kb);   // conj w_BC^kb
+            wk1.y = -wk1.y;
             auto forward_c = [&](cplx* x, int p) {
                 Dft<C, -1>::run(x);
                 if (kb != 0) apply_twiddle_seq<C>(x, wk1);
@@ -270,7 +317,8 @@ xpass4_kernel(const cplx* __restrict__ Ar, const __grid_constant__ PeerPtrs Bw, 
 #pragma unroll 1
     for (int task = tl; task < 6 * BC; task += T) {
         const int p = task / BC, t1 = task - p * BC;
-        const cplx w1 = ctw<-1>(W, t1);
+        cplx w1 = ldW1(t1);
+        w1.y = -w1.y;
         cplx* col = S + p * LB + sig(t1);
         cplx x[A];
         static_for<A>([&](auto ka_) { constexpr int ka = decltype(ka_)::value; x[ka] = col[ka * BCP]; });
@@ -284,7 +332,7 @@ xpass4_kernel(const cplx* __restrict__ Ar, const __grid_constant__ PeerPtrs Bw, 
         const int pj = (j / BC) * BCP + sig(j % BC);
         const int jm = (j == 0) ? 0 : M - j;
         const int pm = (jm / BC) * BCP + sig(jm % BC);
-        cplx w = Wh[j];
+        cplx w = ldWh(j);
         w.y = -w.y;   // e^{-i pi j/M}
         const int q = multi ? j / nxB : 0;
         cplx* __restrict__ Bout = multi ? Bw.p[q] : Bw.p[0];   // the owner of x-mode j (this GPU's or a peer's HBM over NVLink)
@@ -300,50 +348,67 @@ xpass4_kernel(const cplx* __restrict__ Ar, const __grid_constant__ PeerPtrs Bw, 
             Bout[o0 + p * ostride] = cadd(e, cmul(w, o));
         }
     }
+    if constexpr (PERSIST) __syncthreads();   // the buffers are rewritten by the next line's stage A
+    };   // do_line
+    if constexpr (PERSIST) {
+#pragma unroll 1
+        for (int line = (int)blockIdx.x; line < nlines; line += (int)gridDim.x) do_line(line);
+    } else {
+        do_line(0);
+    }
 }
 
 #if !defined(CHB_HOST_EMUL) || defined(CHB_HOST_EMUL_FULL)   // the kernel-only emulation harnesses (tests/host_emul) stop here
-template <class G, int LPC, int MINB>
+// SMs the stream the conv launchers use can run on (its green-context partition, else the device)
+static int stream_sms(chb_handle_s* h) {
+    if (h->green_sms[0] && h->cstream == h->sA) return h->green_sms[0];
+    if (h->green_sms[1] && h->cstream == h->sB) return h->green_sms[1];
+    static int dev_sms = 0;
+    if (!dev_sms) cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, h->device);
+    return dev_sms > 0 ? dev_sms : 148;
+}
+
+// SPLIT = 1 | 2 threads per innermost butterfly position; PERSIST: persistent CTAs with prefetched inputs (LPC = 1)
+template <class G, int LPC, int MINB, int SPLIT, bool PERSIST>
 static bool launch_x4(chb_handle_s* h, int plane0, int nplanes, int compute_cfl) {
-    constexpr int T = G::N / G::C;
+    constexpr int T = SPLIT * (G::N / G::C);
     constexpr int LB = G::A * (G::BC + 1);
     if (h->g.nzB % LPC != 0) return false;
-    const size_t smem = (size_t)LPC * 6 * LB * sizeof(cplx);
-    auto kern = (h->g.nranks > 1) ? xpass4_kernel<G, LPC, MINB, true> : xpass4_kernel<G, LPC, MINB, false>;
+    size_t smem = (size_t)LPC * 6 * LB * sizeof(cplx);
+    if (PERSIST) smem += ((size_t)4 * (h->g.nx + 1) + G::BC + G::B) * sizeof(cplx);
+    if (smem > 227 * 1024) return false;
+    auto kern = (h->g.nranks > 1) ? xpass4_kernel<G, LPC, MINB, true, SPLIT, PERSIST> : xpass4_kernel<G, LPC, MINB, false, SPLIT, PERSIST>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     dim3 grid(h->g.nzB / LPC, nplanes);
+    if (PERSIST) {
+        const long long nlines = (long long)h->g.nzB * nplanes, ncta = (long long)stream_sms(h) * MINB;
+        grid = dim3((unsigned)(nlines < ncta ? nlines : ncta), 1);
+    }
     ScopedKernelTimer tm(h, "xpass", h->cstream);
     CHB_LAUNCH(grid, LPC * T, smem, h->cstream, kern)(h->Ar, h->Bw, h->g, h->Wx, h->Wh, h->t_dy, h->sc, plane0, h->chunk_planes,
-                                             compute_cfl);
-    h->launches++;
-    return true;
-}
-
-
-template <class G, int MINB>
-static bool launch_x5(chb_handle_s* h, int plane0, int nplanes, int compute_cfl) {
-    constexpr int T = 2 * (G::N / G::C);
-    constexpr int LB = G::A * (G::BC + 1);
-    const size_t smem = (size_t)6 * LB * sizeof(cplx);
-    auto kern = (h->g.nranks > 1) ? xpass4_kernel<G, 1, MINB, true, 2> : xpass4_kernel<G, 1, MINB, false, 2>;
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    dim3 grid(h->g.nzB, nplanes);
-    ScopedKernelTimer tm(h, "xpass", h->cstream);
-    CHB_LAUNCH(grid, T, smem, h->cstream, kern)(h->Ar, h->Bw, h->g, h->Wx, h->Wh, h->t_dy, h->sc, plane0, h->chunk_planes, compute_cfl);
+                                             compute_cfl, nplanes);
     h->launches++;
     return true;
 }
 
 // ---------------------------------------------------------------------------------------------
+// Variants measured on B200 (profiles/r2a_variants.md, r2e_xpass_persist.md): nxd = 768: one thread per position, three
+// CTAs per SM; nxd = 1536: two threads per position (CHB_XPASS_SPLIT), persistent with prefetch (CHB_XPASS_PERSIST).
 bool launch_x3_pass(chb_handle_s* h, int plane0, int nplanes, int compute_cfl) {
-    if (h->xpass_split && h->g.nxd == 1536) return launch_x5<Fft3<1536, 12, 16, 8>, 1>(h, plane0, nplanes, compute_cfl);
-    if (h->xpass_split && h->g.nxd == 768) return launch_x5<Fft3<768, 12, 16, 4>, 2>(h, plane0, nplanes, compute_cfl);
+    const int sp = h->xpass_split, pe = h->xpass_persist;
     switch (h->g.nxd) {
-        case 384: return launch_x4<Fft3<384, 12, 8, 4>, 1, 6>(h, plane0, nplanes, compute_cfl);
-        case 768: return launch_x4<Fft3<768, 12, 16, 4>, 1, 3>(h, plane0, nplanes, compute_cfl);
-        case 1536: return launch_x4<Fft3<1536, 12, 16, 8>, 1, 1>(h, plane0, nplanes, compute_cfl);
+        case 384: return launch_x4<Fft3<384, 12, 8, 4>, 1, 6, 1, false>(h, plane0, nplanes, compute_cfl);
+        case 768:
+            if (pe && sp) return launch_x4<Fft3<768, 12, 16, 4>, 1, 2, 2, true>(h, plane0, nplanes, compute_cfl);
+            if (pe) return launch_x4<Fft3<768, 12, 16, 4>, 1, 2, 1, true>(h, plane0, nplanes, compute_cfl);
+            if (sp) return launch_x4<Fft3<768, 12, 16, 4>, 1, 2, 2, false>(h, plane0, nplanes, compute_cfl);
+            return launch_x4<Fft3<768, 12, 16, 4>, 1, 3, 1, false>(h, plane0, nplanes, compute_cfl);
+        case 1536:
+            if (pe && sp) return launch_x4<Fft3<1536, 12, 16, 8>, 1, 1, 2, true>(h, plane0, nplanes, compute_cfl);
+            if (pe) return launch_x4<Fft3<1536, 12, 16, 8>, 1, 1, 1, true>(h, plane0, nplanes, compute_cfl);
+            if (sp) return launch_x4<Fft3<1536, 12, 16, 8>, 1, 1, 2, false>(h, plane0, nplanes, compute_cfl);
+            return launch_x4<Fft3<1536, 12, 16, 8>, 1, 1, 1, false>(h, plane0, nplanes, compute_cfl);
         default: return false;
     }
 }

@@ -16,6 +16,10 @@ MODULE channel_b200
       IMPORT :: C_PTR
       TYPE(C_PTR) :: msg
     END FUNCTION
+    FUNCTION chb_version() BIND(C, name="chb_version") RESULT(v)
+      IMPORT :: C_INT
+      INTEGER(C_INT) :: v
+    END FUNCTION
     FUNCTION chb_get_nccl_unique_id(id) BIND(C, name="chb_get_nccl_unique_id") RESULT(rc)
       IMPORT :: C_INT, C_CHAR
       CHARACTER(KIND=C_CHAR) :: id(128)
@@ -35,6 +39,12 @@ MODULE channel_b200
       TYPE(C_PTR), VALUE :: h
       INTEGER(C_INT) :: rc
     END FUNCTION
+    FUNCTION chb_get_decomposition(h, nx0, nxN, nz0, nzN) BIND(C, name="chb_get_decomposition") RESULT(rc)   ! mpi_transpose.f90:214-215
+      IMPORT :: C_PTR, C_INT
+      TYPE(C_PTR), VALUE :: h
+      INTEGER(C_INT) :: nx0, nxN, nz0, nzN
+      INTEGER(C_INT) :: rc
+    END FUNCTION
     FUNCTION chb_set_tables(h, y, d0, d1, d2, d4, d140, d14m1, d240, d24m1, d14n, d14np1, d24n, d24np1, &
                             v0bc, v0m1bc, vnbc, vnp1bc, eta0bc, eta0m1bc, etanbc, etanp1bc, D0mat) &
         BIND(C, name="chb_set_tables") RESULT(rc)
@@ -49,6 +59,11 @@ MODULE channel_b200
       IMPORT :: C_PTR, C_INT, C_SIZE_T
       TYPE(C_PTR), VALUE :: ptr
       INTEGER(C_SIZE_T), VALUE :: bytes
+      INTEGER(C_INT) :: rc
+    END FUNCTION
+    FUNCTION chb_host_unregister(ptr) BIND(C, name="chb_host_unregister") RESULT(rc)
+      IMPORT :: C_PTR, C_INT
+      TYPE(C_PTR), VALUE :: ptr
       INTEGER(C_INT) :: rc
     END FUNCTION
     FUNCTION chb_upload_V(h, V) BIND(C, name="chb_upload_V") RESULT(rc)
@@ -104,6 +119,12 @@ MODULE channel_b200
       COMPLEX(C_DOUBLE_COMPLEX) :: F(*)
       INTEGER(C_INT) :: rc
     END FUNCTION
+    FUNCTION chb_download_F(h, F) BIND(C, name="chb_download_F") RESULT(rc)   ! Force.cart.<n>.out through the driver's own writer
+      IMPORT :: C_PTR, C_INT, C_DOUBLE_COMPLEX
+      TYPE(C_PTR), VALUE :: h
+      COMPLEX(C_DOUBLE_COMPLEX) :: F(*)
+      INTEGER(C_INT) :: rc
+    END FUNCTION
     FUNCTION chb_set_body_force(h) BIND(C, name="chb_set_body_force") RESULT(rc)
       IMPORT :: C_PTR, C_INT
       TYPE(C_PTR), VALUE :: h
@@ -121,6 +142,25 @@ MODULE channel_b200
       IMPORT :: C_PTR, C_INT, C_DOUBLE
       TYPE(C_PTR), VALUE :: h
       REAL(C_DOUBLE), VALUE :: lambda
+      INTEGER(C_INT) :: rc
+    END FUNCTION
+    ! the nonblockingY variant of header.h calls vetaTOuvw and computeflowrate separately (channel.f90:137-139,
+    ! linsolve_nonblocking.inc:75-159); chb_linsolve has done both, these return at once
+    FUNCTION chb_vetaTOuvw(h) BIND(C, name="chb_vetaTOuvw") RESULT(rc)
+      IMPORT :: C_PTR, C_INT
+      TYPE(C_PTR), VALUE :: h
+      INTEGER(C_INT) :: rc
+    END FUNCTION
+    FUNCTION chb_computeflowrate(h, lambda) BIND(C, name="chb_computeflowrate") RESULT(rc)
+      IMPORT :: C_PTR, C_INT, C_DOUBLE
+      TYPE(C_PTR), VALUE :: h
+      REAL(C_DOUBLE), VALUE :: lambda
+      INTEGER(C_INT) :: rc
+    END FUNCTION
+    FUNCTION chb_rk3_step(h, deltat) BIND(C, name="chb_rk3_step") RESULT(rc)   ! the three substeps of channel.f90:125-166 in one call
+      IMPORT :: C_PTR, C_INT, C_DOUBLE
+      TYPE(C_PTR), VALUE :: h
+      REAL(C_DOUBLE), VALUE :: deltat
       INTEGER(C_INT) :: rc
     END FUNCTION
     FUNCTION chb_get_step_scalars(h, cfl, fr, corrpx, corrpz, meanpx, meanpz, U_lo, U_hi, W_lo, W_hi) &
@@ -145,6 +185,12 @@ MODULE channel_b200
       TYPE(C_PTR), VALUE :: h
       INTEGER(C_INT) :: rc
     END FUNCTION
+    FUNCTION chb_restart_stats(h, bytes, snapshot_ms, total_s) BIND(C, name="chb_restart_stats") RESULT(rc)
+      IMPORT :: C_PTR, C_INT, C_DOUBLE
+      TYPE(C_PTR), VALUE :: h
+      REAL(C_DOUBLE) :: bytes, snapshot_ms, total_s
+      INTEGER(C_INT) :: rc
+    END FUNCTION
     FUNCTION chb_read_restart_file(h, filename, time) BIND(C, name="chb_read_restart_file") RESULT(rc)
       IMPORT :: C_PTR, C_INT, C_DOUBLE, C_CHAR
       TYPE(C_PTR), VALUE :: h
@@ -157,6 +203,13 @@ MODULE channel_b200
       IMPORT :: C_PTR, C_INT
       TYPE(C_PTR), VALUE :: h
       INTEGER(C_INT), VALUE :: enable
+      INTEGER(C_INT) :: rc
+    END FUNCTION
+    FUNCTION chb_get_convvel(h, uconv, count) BIND(C, name="chb_get_convvel") RESULT(rc)
+      IMPORT :: C_PTR, C_INT, C_DOUBLE, C_LONG_LONG
+      TYPE(C_PTR), VALUE :: h
+      REAL(C_DOUBLE) :: uconv(*)
+      INTEGER(C_LONG_LONG) :: count
       INTEGER(C_INT) :: rc
     END FUNCTION
     FUNCTION chb_save_convvel_file(h, filename) BIND(C, name="chb_save_convvel_file") RESULT(rc)

@@ -29,6 +29,7 @@ def load():
     lib.co_create.argtypes = [C.c_int] * 3 + [C.c_double] * 6
     lib.co_destroy.argtypes = [C.c_void_p]
     lib.co_set_params.argtypes = [C.c_void_p] + [C.c_double] * 4 + [C.c_int, C.c_int] + [C.c_double] * 6
+    lib.co_global_threads.argtypes = [C.c_int]
     lib.co_set_threads.argtypes = [C.c_void_p, C.c_int]
     lib.co_threads.argtypes = [C.c_void_p]
     lib.co_threads.restype = C.c_int
@@ -151,22 +152,31 @@ def fft_lines(x, sign):
 _sample_state = {}
 
 
+def host_cores():
+    """cores this process may run on (the affinity mask, not OMP_NUM_THREADS: torchrun exports OMP_NUM_THREADS=1)"""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def timed_sample(nx, ny, nz, seconds=15.0, threads=None, alfa0=0.5, beta0=1.0, re=12431.0):
     """Time a bounded sample of one RK3 step of the reference algorithm on the host cores and
     scale it to a full step.  Sample = `iters` iterations of buildrhs's y-plane loop (each a
     full-plane `convolutions` plus the RHS assembly of one plane) and the columns of `nix`
     x-wavenumbers of linsolve, of RK substep 2; a full step is 3 substeps of ny+3 convolution
-    planes, ny-1 RHS planes and nx+1 x-wavenumbers."""
+    planes, ny-1 RHS planes and nx+1 x-wavenumbers.  threads=None: every core of the affinity mask."""
     from .channel_oracle import DnsIn
     lib = load()
-    key = (nx, ny, nz)
+    threads = int(threads) if threads else host_cores()
+    key = (nx, ny, nz, threads)
     if key not in _sample_state:
         _sample_state.clear()
+        lib.co_global_threads(threads)
         p = DnsIn(nx=nx, ny=ny, nz=nz, alfa0=alfa0, beta0=beta0, re=re, deltat=1e-3, cflmax=0.0)
         _sample_state[key] = COracle(p)
     o = _sample_state[key]
-    if threads:
-        lib.co_set_threads(o.h, int(threads))
+    lib.co_set_threads(o.h, threads)
     cores = lib.co_threads(o.h)
     out = np.zeros(6)
 
@@ -183,14 +193,42 @@ def timed_sample(nx, ny, nz, seconds=15.0, threads=None, alfa0=0.5, beta0=1.0, r
     budget = max(1.0, seconds - (time.perf_counter() - t0))
     iters = int(min(ny + 5, max(8, 0.8 * budget / max(per_plane, 1e-9))))
     nix = int(min(nx + 1, max(1, 0.2 * budget / max(per_ix, 1e-9))))
+    t1 = time.perf_counter()
     r = run(iters, nix)
+    wall = time.perf_counter() - t1
     t_sub = r[0] / r[1] * (ny + 3) + r[2] / max(r[3], 1) * (ny - 1) + r[4] / r[5] * (nx + 1)
     t_step = 3.0 * t_sub
+    frac = (r[0] + r[2] + r[4]) / t_step            # share of a full step's CPU work that was actually executed
     return {"value": 1.0 / t_step, "unit": "steps/s", "cores": int(cores), "kind": "port",
             "sample": f"{int(r[1])} of {ny + 3} convolution planes + {int(r[3])} of {ny - 1} RHS planes + "
                       f"{int(r[5])} of {nx + 1} x-wavenumbers of linsolve (RK substep 2), scaled to 3 substeps; "
                       f"C99+OpenMP restatement of the reference algorithm with its own Stockham FFT (no FFTW/MPI/"
-                      f"gfortran in this image), {time.perf_counter() - t0:.1f} s of CPU work",
+                      f"gfortran in this image), {time.perf_counter() - t0:.1f} s of CPU work on {int(cores)} threads",
+            "extrapolated": True, "sampled_fraction_of_step": frac, "sample_wall_s": wall,
             "seconds_per_step_est": t_step,
             "split_s_per_substep": {"convolutions": r[0] / r[1] * (ny + 3), "rhs": r[2] / max(r[3], 1) * (ny - 1),
                                     "linsolve": r[4] / r[5] * (nx + 1)}}
+
+
+def timed_full_step(nx, ny, nz, threads=None, alfa0=0.5, beta0=1.0, re=12431.0):
+    """One COMPLETE, unsampled RK3 step of the reference algorithm (co_step: 3 x buildrhs + linsolve, outstats) on the
+    host cores, next to what timed_sample extrapolates for the same grid: the check of the extrapolation."""
+    from .channel_oracle import DnsIn
+    lib = load()
+    threads = int(threads) if threads else host_cores()
+    lib.co_global_threads(threads)
+    p = DnsIn(nx=nx, ny=ny, nz=nz, alfa0=alfa0, beta0=beta0, re=re, deltat=1e-3, cflmax=0.0)
+    o = COracle(p)
+    lib.co_fill_synthetic(o.h)
+    lib.co_set_params(o.h, 0.0, 0.0, 0.0, 0.0, 1, 1, 0.161436, 0.0, 0.0, 1e-3, 0.0, 0.0)
+    line = np.zeros(11)
+    lib.co_step(o.h, line.ctypes.data_as(_dp))      # warm-up: first touch of the work arrays
+    t0 = time.perf_counter()
+    lib.co_step(o.h, line.ctypes.data_as(_dp))
+    t_full = time.perf_counter() - t0
+    cores = lib.co_threads(o.h)
+    o.close()
+    est = timed_sample(nx, ny, nz, seconds=min(8.0, max(2.0, t_full)), threads=threads, alfa0=alfa0, beta0=beta0, re=re)
+    return {"grid": [nx, ny, nz], "cores": int(cores), "full_step_s": t_full, "finite": bool(np.isfinite(line).all()),
+            "sampled_estimate_s": est["seconds_per_step_est"], "sampled_fraction_of_step": est["sampled_fraction_of_step"],
+            "estimate_over_full": est["seconds_per_step_est"] / t_full}

@@ -393,6 +393,15 @@ void co_set_params(co_state* st, double meanpx, double meanpz, double meanflowx,
     st->CPI = CPI; st->CPI_type = CPI_type; st->gamma = gamma; st->u0 = u0; st->uN = uN;
     st->deltat = deltat; st->cflmax = cflmax; st->time = time;
 }
+/* Number of OpenMP threads for handles created afterwards (and their per-thread work arrays).  Launchers such as
+ * torchrun export OMP_NUM_THREADS=1; the CPU baseline of bench.py must not inherit that. */
+void co_global_threads(int n) {
+#ifdef _OPENMP
+    if (n >= 1) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
 void co_set_threads(co_state* st, int n) {
 #ifdef _OPENMP
     if (n >= 1 && n <= st->nthreads) omp_set_num_threads(n);

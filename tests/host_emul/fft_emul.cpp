@@ -28,7 +28,20 @@ static void run_x4(const cplx* Ar, cplx* Br, const Geometry& g, const cplx* W, c
     Bw.p[0] = Br;
     constexpr int T = G::N / G::C;
     cta_emul::launch(xpass4_kernel<G, LPC, MINB, false>, dim3(g.nzB / LPC, np, 1), LPC * T, Ar, Bw, g, W, Wh, dy, sc, 0, np,
-                     compute_cfl);
+                     compute_cfl, np);
+}
+
+// persistent variant (inputs of the next line prefetched into shared memory): two CTAs walk over the nzB * np lines
+template <class G, int MINB, int SPLIT>
+static void run_xp(const cplx* Ar, cplx* Br, const Geometry& g, const cplx* W, const cplx* Wh, const double* dy, DevScalars* sc,
+                   int np, int compute_cfl) {
+    PeerPtrs Bw;
+    memset(&Bw, 0, sizeof(Bw));
+    Bw.p[0] = Br;
+    constexpr int T = SPLIT * (G::N / G::C);
+    constexpr int LB = G::A * (G::BC + 1);
+    if (((size_t)6 * LB + 4 * (g.nx + 1) + G::BC + G::B) * sizeof(cplx) > sizeof(cta_emul::g_dyn_smem)) abort();
+    cta_emul::launch(xpass4_kernel<G, 1, MINB, false, SPLIT, true>, dim3(2, 1, 1), T, Ar, Bw, g, W, Wh, dy, sc, 0, np, compute_cfl, np);
 }
 
 template <class G, int MINB>
@@ -38,7 +51,7 @@ static void run_x5(const cplx* Ar, cplx* Br, const Geometry& g, const cplx* W, c
     memset(&Bw, 0, sizeof(Bw));
     Bw.p[0] = Br;
     constexpr int T = 2 * (G::N / G::C);
-    cta_emul::launch(xpass4_kernel<G, 1, MINB, false, 2>, dim3(g.nzB, np, 1), T, Ar, Bw, g, W, Wh, dy, sc, 0, np, compute_cfl);
+    cta_emul::launch(xpass4_kernel<G, 1, MINB, false, 2>, dim3(g.nzB, np, 1), T, Ar, Bw, g, W, Wh, dy, sc, 0, np, compute_cfl, np);
 }
 
 template <class G, int LPC, int TPL, int MINB>
@@ -67,7 +80,7 @@ extern "C" {
 // Br = products for the backward z pass in the tiled layout of transpose_index.h (tile width 2^tw),
 // [6][np][(nx+1) >> tw][nzB][1 << tw]; dy[ny+3]; cfl_out = max of the CFL expression (dnsdata.f90:552-556).
 // Planes are iy = -1 .. np-2 (plane0 = 0).  variant 0: xpass4 (one thread per innermost butterfly position),
-// 1: the split x-pass (two threads per position; nxd = 768, 1536).  Returns 2 if no such kernel exists for nxd.
+// 1: the split x-pass (two threads per position; nxd = 768, 1536), 2 / 3: the persistent x-pass (prefetched inputs) with one / two threads per position.  Returns 2 if no such kernel exists for nxd.
 __attribute__((visibility("default"))) int chb_emul_xpass(int nx, int ny, int nzB, int np, int nxd, int nzd, double alfa0,
                                                           double beta0, int tw, const double* Ar, double* Br,
                                                           const double* dy, int compute_cfl, double* cfl_out, int variant) {
@@ -91,6 +104,12 @@ __attribute__((visibility("default"))) int chb_emul_xpass(int nx, int ny, int nz
     if (variant == 1) {
         if (nxd == 1536) run_x5<Fft3<1536, 12, 16, 8>, 1>(A, B, g, Wc, Whc, dy, &sc, np, compute_cfl);
         else if (nxd == 768) run_x5<Fft3<768, 12, 16, 4>, 2>(A, B, g, Wc, Whc, dy, &sc, np, compute_cfl);
+        else return 2;
+    } else if (variant == 2 || variant == 3) {   // persistent, one / two threads per position
+        if (nxd == 1536 && variant == 2) run_xp<Fft3<1536, 12, 16, 8>, 1, 1>(A, B, g, Wc, Whc, dy, &sc, np, compute_cfl);
+        else if (nxd == 1536) run_xp<Fft3<1536, 12, 16, 8>, 1, 2>(A, B, g, Wc, Whc, dy, &sc, np, compute_cfl);
+        else if (nxd == 768 && variant == 2) run_xp<Fft3<768, 12, 16, 4>, 2, 1>(A, B, g, Wc, Whc, dy, &sc, np, compute_cfl);
+        else if (nxd == 768) run_xp<Fft3<768, 12, 16, 4>, 2, 2>(A, B, g, Wc, Whc, dy, &sc, np, compute_cfl);
         else return 2;
     } else
     switch (nxd) {
@@ -184,13 +203,16 @@ __attribute__((visibility("default"))) int chb_emul_convolutions_multi(int P, co
     for (int r = 0; r < P; ++r)   // z-pad + backward z FFT + zTOx into the owners' buffers
         cta_emul::launch(zfwd4_kernel<GZ, LPC, TPL, 4, false>, dim3(nxB / LPC, np, 3), LPC * TPL,
                          reinterpret_cast<const cplx*>(V) + (size_t)r * 3 * nv, Aw, geom(r), reinterpret_cast<const cplx*>(Wz.data()), 0, np, LS);
+    const bool persist = getenv("CHB_EMUL_XPERSIST") != nullptr;   // the persistent x-pass (prefetched inputs), two CTAs per rank
     for (int r = 0; r < P; ++r) { // x pass on the z-lines of rank r, xTOz into the owners' buffers
-        if (P > 1)
-            cta_emul::launch(xpass4_kernel<GX, 1, 6, true>, dim3(nzB, np, 1), GX::N / GX::C, (const cplx*)Ar[r].data(), Bw, geom(r),
-                             reinterpret_cast<const cplx*>(Wx.data()), reinterpret_cast<const cplx*>(Wh.data()), (const double*)dy.data(), &sc, 0, np, 0);
-        else
-            cta_emul::launch(xpass4_kernel<GX, 1, 6, false>, dim3(nzB, np, 1), GX::N / GX::C, (const cplx*)Ar[r].data(), Bw, geom(r),
-                             reinterpret_cast<const cplx*>(Wx.data()), reinterpret_cast<const cplx*>(Wh.data()), (const double*)dy.data(), &sc, 0, np, 0);
+        const cplx* a = (const cplx*)Ar[r].data();
+        const cplx* wx = reinterpret_cast<const cplx*>(Wx.data());
+        const cplx* wh = reinterpret_cast<const cplx*>(Wh.data());
+        const double* dyp = (const double*)dy.data();
+        if (P > 1 && persist) cta_emul::launch(xpass4_kernel<GX, 1, 6, true, 1, true>, dim3(2, 1, 1), GX::N / GX::C, a, Bw, geom(r), wx, wh, dyp, &sc, 0, np, 0, np);
+        else if (persist) cta_emul::launch(xpass4_kernel<GX, 1, 6, false, 1, true>, dim3(2, 1, 1), GX::N / GX::C, a, Bw, geom(r), wx, wh, dyp, &sc, 0, np, 0, np);
+        else if (P > 1) cta_emul::launch(xpass4_kernel<GX, 1, 6, true>, dim3(nzB, np, 1), GX::N / GX::C, a, Bw, geom(r), wx, wh, dyp, &sc, 0, np, 0, np);
+        else cta_emul::launch(xpass4_kernel<GX, 1, 6, false>, dim3(nzB, np, 1), GX::N / GX::C, a, Bw, geom(r), wx, wh, dyp, &sc, 0, np, 0, np);
     }
     for (int r = 0; r < P; ++r)   // forward z FFT + truncation
         cta_emul::launch(zbwd4_kernel<GZ, LPC, TPL, 4>, dim3(nxB / LPC, np, 6), LPC * TPL, (const cplx*)Br[r].data(),

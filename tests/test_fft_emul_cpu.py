@@ -69,7 +69,8 @@ def xpass_reference(A, nx, nxd, nzd, alfa0, beta0, dy, ny, compute_cfl):
 
 @pytest.mark.parametrize("nx,nxd,tw,variant", [(255, 384, 3, 0), (255, 384, 0, 0), (511, 768, 3, 0), (1023, 1536, 3, 0),
                                                (300, 768, 0, 0), (1023, 1536, 3, 1), (703, 1536, 2, 1),
-                                               (511, 768, 3, 1), (300, 768, 0, 1)])
+                                               (511, 768, 3, 1), (300, 768, 0, 1),
+                                               (1023, 1536, 3, 2), (703, 1536, 2, 3), (511, 768, 3, 2), (300, 768, 0, 3)])
 def test_xpass_kernel_on_cpu_threads(emul, nx, nxd, tw, variant):
     ny, nzd, nzB, npl = 6, 6, 2, 3            # planes iy = -1, 0, 1: the CFL expression sees iy = 1 only
     rng = np.random.default_rng(nx + tw)
@@ -130,10 +131,15 @@ def test_zpass_kernels_on_cpu_threads(emul, nz, nzd, lpc):
 
 
 @pytest.mark.parametrize("P", [1, 2, 8])
-def test_nonlinear_term_on_emulated_ranks(emul, P):
+@pytest.mark.parametrize("persist", [False, True])
+def test_nonlinear_term_on_emulated_ranks(emul, P, persist, monkeypatch):
     """zfwd -> (direct-store zTOx) -> xpass -> (direct-store xTOz) -> zbwd for one plane on P emulated ranks, each
     storing straight into the owners' buffers the way the GPUs do over NVLink (mpi_transpose.f90:50-117,214-215):
     the per-rank products must equal the single-domain numpy result, for every P (transpose invariance)."""
+    if persist:        # the persistent x-pass: inputs of the next line prefetched into shared memory
+        monkeypatch.setenv("CHB_EMUL_XPERSIST", "1")
+    else:
+        monkeypatch.delenv("CHB_EMUL_XPERSIST", raising=False)
     nx, nz, nxd, nzd = 255, 255, 384, 768
     nzt = 2 * nz + 1
     rng = np.random.default_rng(17)

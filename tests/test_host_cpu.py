@@ -290,17 +290,79 @@ def test_bench_reference_arm_runs_on_the_cpu():
     metric / unit, "impl": "reference", its own cpu_baseline description and a zero-copy e2e."""
     import json, subprocess, sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    # launched the way torchrun launches it: OMP_NUM_THREADS=1 in the environment must not reach the CPU arm
+    env1 = dict(os.environ, OMP_NUM_THREADS="1")
     r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--workload", "1", "--steps", "1",
-                        "--warmup", "0", "--cpu-seconds", "1"], capture_output=True, text=True, timeout=300)
+                        "--warmup", "0", "--cpu-seconds", "1", "--extrapolation-grid", "31,32,31"], env=env1,
+                       capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "rk3_timesteps_per_s" and d["unit"] == "steps/s" and d["value"] > 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"]
+    assert d["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
+    assert d["extrapolated"] is True and 0 < d["sampled_fraction_of_step"] <= 1 and d["sample_wall_ms"] > 0
+    chk = d["extrapolation_check"]
+    assert chk["grid"] == [31, 32, 31] and chk["full_step_s"] > 0 and chk["finite"] and 0.2 < chk["estimate_over_full"] < 5
+    import bench
+    assert d["config"]["workload"] == bench.workload_text(bench.parse_workload("1"), 16, 64, 16, 32, 48, False)
     assert d["e2e"] == {"value": d["value"], "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     # other ranks of a torchrun launch exit without work and without output
     env = dict(os.environ, RANK="1", WORLD_SIZE="2")
     r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2"], env=env,
                        capture_output=True, text=True, timeout=60)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def _c_prototypes(header_text):
+    """{name: [(is_pointer, is_handle)]} of every `int|long long|const char* chb_*(...)` prototype of the header"""
+    import re
+    text = re.sub(r"/\*.*?\*/", " ", header_text, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\b(?:int|long long|const char\*)\s+(chb_\w+)\s*\(([^)]*)\)\s*;", text):
+        name, args = m.group(1), m.group(2).strip()
+        lst = []
+        if args and args != "void":
+            for a in args.split(","):
+                a = a.strip()
+                lst.append(("*" in a, a.startswith("chb_handle ") or a.startswith("void* ")))
+        protos[name] = lst
+    return protos
+
+
+def test_fortran_shim_matches_the_c_header():
+    """fortran/channel_b200_mod.f90 (the iso_c_binding interfaces a maintainer adds to the reference) against
+    include/channel_b200.h: every entry point of the Fortran-facing part of the ABI has an interface, every
+    BIND(C, name=...) names an exported symbol, the argument counts agree, and an argument is passed by VALUE exactly
+    when the C parameter is a scalar or the handle (channel.f90:137-139 needs chb_vetaTOuvw / chb_computeflowrate)."""
+    import re
+    from channel_b200 import _lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    header = open(os.path.join(root, "include", "channel_b200.h")).read()
+    protos = _c_prototypes(header)
+    fortran_part = _c_prototypes(header.split("test / diagnostics accessors")[0])
+    src = open(os.path.join(root, "fortran", "channel_b200_mod.f90")).read()
+    src = re.sub(r"&\s*\n\s*", " ", src)                 # join continuation lines
+    src = re.sub(r"!.*", "", src)                        # strip comments
+    bound = {}
+    for m in re.finditer(r"FUNCTION\s+(\w+)\s*\(([^)]*)\)\s*BIND\(C,\s*name=\"(\w+)\"\)(.*?)END FUNCTION", src, flags=re.S):
+        fname, args, cname, body = m.group(1), m.group(2), m.group(3), m.group(4)
+        assert fname == cname, (fname, cname)
+        args = [a.strip().lower() for a in args.split(",") if a.strip()]
+        by_value = set()
+        for decl in re.finditer(r"^[^\n]*,\s*VALUE\s*::\s*([^\n]*)$", body, flags=re.M):
+            by_value |= {re.sub(r"\(.*?\)", "", v).strip().lower() for v in decl.group(1).split(",")}
+        bound[cname] = [(a in by_value) for a in args]
+    assert len(bound) >= 30
+    exported = set(_lib.SYMBOLS)
+    for name, vals in bound.items():
+        assert name in protos, f"{name}: bound in the Fortran shim but not declared in channel_b200.h"
+        assert name in exported, f"{name}: not exported by libchannel_b200.so"
+        cargs = protos[name]
+        assert len(vals) == len(cargs), (name, len(vals), len(cargs))
+        for i, ((is_ptr, is_handle), v) in enumerate(zip(cargs, vals)):
+            want_value = (not is_ptr) or is_handle
+            assert v == want_value, f"{name} argument {i + 1}: VALUE={v}, C parameter {'scalar/handle' if want_value else 'pointer'}"
+    missing = sorted(set(fortran_part) - set(bound) - {"chb_upload_V_planes", "chb_download_V_planes"})   # device-layout transfers: tests only
+    assert not missing, f"no Fortran interface for {missing}"

@@ -31,6 +31,30 @@ def test_xpass_split_variant(nx, ny, nz, monkeypatch):
     assert abs(out["1"][1] - out["0"][1]) <= 1e-13 * out["0"][1]
 
 
+@pytest.mark.parametrize("split", ["0", "1"])
+@pytest.mark.parametrize("nx,ny,nz", [(1023, 8, 3), (511, 8, 4), (703, 12, 7)])
+def test_xpass_persistent_variant(nx, ny, nz, split, monkeypatch):
+    """CHB_XPASS_PERSIST=1: persistent x-pass CTAs that walk over the lines of a launch with the next line's inputs
+    prefetched into shared memory (cp.async) and the twiddle tables resident there; with one or two threads per innermost
+    butterfly position.  Same arithmetic as the one-CTA-per-line kernel: products equal to rounding, and to the oracle."""
+    out = {}
+    monkeypatch.setenv("CHB_XPASS_SPLIT", split)
+    for flag in ("0", "1"):
+        monkeypatch.setenv("CHB_XPASS_PERSIST", flag)
+        p, o, ch, V0 = make_pair(nx, ny, nz, eps=5e-2)
+        ch.cfl_prepass(); ch.get_step_scalars()
+        ch.buildrhs(RK1_rai, True)
+        out[flag] = (ch.download_products(), ch.get_step_scalars()["cfl"])
+        if flag == "1":
+            Pref = o.convolutions(o.V, False)[..., o.izd]
+            for k in range(6):
+                assert relerr(out[flag][0][k], Pref[k]) < 1e-12, ("product vs oracle", k)
+        ch.close()
+    for k in range(6):
+        assert relerr(out["1"][0][k], out["0"][0][k]) < 1e-13
+    assert abs(out["1"][1] - out["0"][1]) <= 1e-13 * out["0"][1]
+
+
 @pytest.mark.parametrize("nx,ny,nz", [(7, 8, 255), (15, 8, 511), (7, 8, 1023)])
 def test_zfwd_direct_variant(nx, ny, nz, monkeypatch):
     """CHB_ZF_DIRECT=1: zfwd4 with stage A reading global memory directly instead of through the TMA staging copy
