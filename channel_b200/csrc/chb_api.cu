@@ -239,8 +239,10 @@ static int create_impl(chb_handle_s* h, int nx, int ny, int nz, int nxd, int nzd
         // SM either way), 34 % slower at nxd = 768 (profiles/r2a_variants.md)
         e = getenv("CHB_XPASS_SPLIT");
         h->xpass_split = e ? atoi(e) : (nxd == 1536 ? 1 : 0);
+        // persistent x-pass with prefetched inputs: measured 16 % faster at nxd = 1536 on top of the split (14.0 against
+        // 16.6 ms), 14 % slower at nxd = 768 where it costs the third CTA per SM (profiles/r2e_xpass_persist.md)
         e = getenv("CHB_XPASS_PERSIST");
-        h->xpass_persist = e ? atoi(e) : 0;
+        h->xpass_persist = e ? atoi(e) : (nxd == 1536 ? 1 : 0);
         // x tiles of the work buffers (transpose_index.h): products 8 wide (128-byte store segments in
         // the x-pass), velocities as wide as the lines of one zfwd CTA
         g.tw = (g.nxB % 8 == 0) ? 3 : ((g.nxB % 4 == 0) ? 2 : 0);
@@ -337,7 +339,7 @@ static int create_impl(chb_handle_s* h, int nx, int ny, int nz, int nxd, int nzd
             Lane& ln = h->lane[L];
             memset(&ln, 0, sizeof(ln));
             CHB_CUDA_OK(cudaEventCreateWithFlags(&ln.evA, cudaEventDisableTiming));
-            CHB_CUDA_OK(cudaEventCreateWithFlags(&ln.evB, cudaEventDisableTiming));
+            CHB_CUDA_OK(cudaEventCreateWithFlags(&ln.evZ, cudaEventDisableTiming));
             char* base = h->arena + CHB_ARENA_HEAD + (size_t)L * AL.lane_bytes;
             ln.Ar = reinterpret_cast<cplx*>(base + AL.ar);
             ln.Br = reinterpret_cast<cplx*>(base + AL.br);
@@ -360,9 +362,10 @@ static int create_impl(chb_handle_s* h, int nx, int ny, int nz, int nxd, int nzd
         h->green[0] = h->green[1] = nullptr;
         h->green_sms[0] = h->green_sms[1] = 0;
         if (h->nlanes == 2) {
-            // CHB_GREEN=<SMs of the transpose partition> (default: 54 % of the SMs on several GPUs, off on one): the two
-            // streams get disjoint SM partitions through CUDA green contexts, so that the local kernels really run
-            // beside the NVLink-bound ones instead of behind them; plain streams if the driver refuses
+            // CHB_GREEN=<SMs of the x-pass partition> (default: 44 % of the SMs on several GPUs - the x-pass's share of
+            // the SM time of a sweep -, off on one): the two streams get disjoint SM partitions through CUDA green
+            // contexts, so that the z-passes really run beside the x-pass instead of behind it; plain streams if the
+            // driver refuses
             e = getenv("CHB_GREEN");
             int sms_a = e ? atoi(e) : (nranks > 1 ? -1 : 0);
             if (sms_a != 0 && chb_green_create(h, sms_a) != 0) sms_a = 0;
@@ -396,7 +399,7 @@ extern "C" int chb_destroy(chb_handle h) {
     for (int L = 0; L < CHB_MAX_LANES; ++L) {
         Lane& ln = h->lane[L];
         if (ln.evA) cudaEventDestroy(ln.evA);
-        if (ln.evB) cudaEventDestroy(ln.evB);
+        if (ln.evZ) cudaEventDestroy(ln.evZ);
     }
     if (h->sA && h->sA != h->stream) cudaStreamDestroy(h->sA);
     if (h->sB && h->sB != h->stream) cudaStreamDestroy(h->sB);
@@ -654,65 +657,99 @@ extern "C" int chb_set_body_force(chb_handle h) {
 
 // ---- the hot path ----------------------------------------------------------------------------
 // One sweep of `convolutions` over all planes (dnsdata.f90:487-602), chunk by chunk, and - when rhs_ode is given - the
-// plane loop of buildrhs (:634-670) behind it.  Chunk c uses lane c % nlanes.  Two streams:
-//   sA: zfwd(c) -> barrier -> [convvel] -> xpass(c) -> barrier        the kernels whose stores ARE the pencil transposes
-//   sB: zbwd(c) -> rhs(c)                                              local kernels, one chunk behind
-// With two lanes sA and sB are different streams (on disjoint SM partitions when green contexts are available), so
-// the HBM-bound local kernels of chunk c run while the NVLink-bound kernels of chunk c+1 wait for their remote
-// stores: the role of the reference's nonblockingXZ variant (mpi_transpose.f90:149-168).  With one lane both are the
-// handle's stream and the sweep is strictly sequential.
+// plane loop of buildrhs (:634-670) behind it.  Chunk c uses lane c % nlanes.
+//
+// One lane (one GPU, two GPUs, NCCL fallback): everything on the handle's stream,
+//     zfwd(c) -> barrier -> [convvel] -> xpass(c) -> barrier -> zbwd(c) -> rhs(c)          for c = 0, 1, ...
+//
+// Two lanes (default from 4 GPUs on): a software pipeline over two streams that sit on disjoint SM partitions when
+// green contexts are available (green_ctx.cu):
+//     sA:  [convvel(c)] xpass(c) -> barrier                      the FP64-heavy x-pass, whose stores are the xTOz transpose
+//     sB:  zfwd(c+1) -> barrier -> zbwd(c) -> rhs(c)             the HBM-bound z-passes (zfwd's stores are zTOx) and the RHS
+// so that the x-pass of chunk c runs beside the z-passes of its neighbours: NVLink carries zTOx(c+1) and xTOz(c) at
+// the same time, HBM serves zbwd / rhs while the x-pass computes, and the SMs that one kernel leaves idle while its
+// remote stores drain work for the other stream.  This is the role of the reference's nonblockingXZ variant
+// (mpi_transpose.f90:149-168: MPI_IAlltoall progressing under the next plane's FFTs).  Measured at 4 GPUs
+// (profiles/r2g_overlap_n4.md): the first version, transposes (zfwd + xpass) on one partition and local kernels on the
+// other, lost to the sequential sweep because zfwd leaves its SMs idle and the x-pass is compute-bound on a partition.
+//
 // Buffer reuse across ranks: a peer's zfwd(c) stores into this rank's Ar(lane) - free once every rank has passed the
-// barrier behind xpass(c - nlanes); a peer's xpass(c) stores into Br(lane) - it starts behind the barrier after
-// zfwd(c), at which this rank only arrives once its own zbwd(c - nlanes) has read Br(lane) (sA waits for evB).
+// barrier behind xpass(c - nlanes) (sB waits for evA of the lane); a peer's xpass(c) stores into Br(lane) - it starts
+// behind the barrier after zfwd(c), at which this rank only arrives once its own zbwd(c - nlanes) has read Br(lane)
+// (earlier on sB).
 static int convolutions_all(chb_handle h, int compute_cfl, bool products, const double* rhs_ode = nullptr, double rhs_deltat = 0.0,
                             double deltat = 0.0) {
     // the first sweep of buildrhs after an outstats also feeds the convection-velocity diagnostic (dnsdata.f90:515-531)
     const bool convvel = products && h->cv_enabled && h->cv_compute;
     const Geometry& g = h->g;
     const int np = h->chunk_planes;
-    const bool two = h->sA != h->stream;
-    if (two) {   // fork: both streams start after everything queued on the main stream (V complete)
+    const int nch = (g.nyp + np - 1) / np;
+    auto first = [&](int c) { return c * np; };
+    auto count = [&](int c) { return (c + 1) * np <= g.nyp ? np : g.nyp - c * np; };
+    auto local_part = [&](int c, cudaStream_t st) -> int {   // zbwd(c) -> rhs(c) on st, lane of chunk c selected
+        Lane& ln = h->lane[c % h->nlanes];
+        h->cstream = st;
+        launch_zbwd(h, first(c), count(c));
+        if (h->P_dbg)   // debug capture: keep this chunk's products
+            for (int k = 0; k < 6; ++k)
+                CHB_CUDA_OK(cudaMemcpyAsync(h->P_dbg + ((size_t)k * g.nyp + first(c)) * g.M, ln.Pc + (size_t)k * np * g.M,
+                                            (size_t)count(c) * g.M * sizeof(cplx), cudaMemcpyDeviceToDevice, st));
+        if (rhs_ode) launch_rhs_chunk(h, rhs_ode, rhs_deltat, first(c), count(c), st);
+        return 0;
+    };
+    if (h->sA == h->stream) {   // one lane, one stream
+        h->cstream = h->stream;
+        for (int c = 0; c < nch; ++c) {
+            chb_select_lane(h, c % h->nlanes);
+            launch_zfwd(h, first(c), count(c));          // stores straight into the x-side owner's buffer
+            if (chb_exchange(h, true)) return 1;         // zTOx, mpi_transpose.f90:50-83
+            if (convvel) launch_convvel(h, first(c), count(c), deltat);
+            launch_xpass(h, first(c), count(c), compute_cfl);
+            // xTOz, mpi_transpose.f90:88-117; in direct mode the barrier also frees Ar for the next chunk
+            if ((products || h->p2p) && chb_exchange(h, false)) return 1;
+            if (products && local_part(c, h->stream)) return 1;
+        }
+    } else {
+        // fork: both streams start after everything queued on the main stream (V complete)
         CHB_CUDA_OK(cudaEventRecord(h->ev_fork, h->stream));
         CHB_CUDA_OK(cudaStreamWaitEvent(h->sA, h->ev_fork, 0));
         CHB_CUDA_OK(cudaStreamWaitEvent(h->sB, h->ev_fork, 0));
-    }
-    int c = 0;
-    for (int p0 = 0; p0 < g.nyp; p0 += np, ++c) {
-        const int n = (p0 + np <= g.nyp) ? np : g.nyp - p0;
-        const int L = c % h->nlanes;
-        Lane& ln = h->lane[L];
-        chb_select_lane(h, L);
-        h->cstream = h->sA;
-        if (two && c >= h->nlanes) CHB_CUDA_OK(cudaStreamWaitEvent(h->sA, ln.evB, 0));
-        launch_zfwd(h, p0, n);                       // stores straight into the x-side owner's buffer
-        if (chb_exchange(h, true)) return 1;         // zTOx, mpi_transpose.f90:50-83
-        if (convvel) launch_convvel(h, p0, n, deltat);
-        launch_xpass(h, p0, n, compute_cfl);
-        // xTOz, mpi_transpose.f90:88-117; in direct mode the barrier also frees Ar for the chunk after next
-        if ((products || h->p2p) && chb_exchange(h, false)) return 1;
-        if (!products) continue;
-        if (two) {
+        auto zfwd_part = [&](int c) -> int {   // sB: zfwd(c) -> barrier; evZ of the lane
+            Lane& ln = h->lane[c % h->nlanes];
+            chb_select_lane(h, c % h->nlanes);
+            h->cstream = h->sB;
+            if (c >= h->nlanes) CHB_CUDA_OK(cudaStreamWaitEvent(h->sB, ln.evA, 0));   // Ar(lane) read by every rank's xpass(c - nlanes)
+            launch_zfwd(h, first(c), count(c));
+            if (chb_exchange(h, true)) return 1;
+            CHB_CUDA_OK(cudaEventRecord(ln.evZ, h->sB));
+            return 0;
+        };
+        if (zfwd_part(0)) return 1;
+        for (int c = 0; c < nch; ++c) {
+            Lane& ln = h->lane[c % h->nlanes];
+            chb_select_lane(h, c % h->nlanes);
+            h->cstream = h->sA;
+            CHB_CUDA_OK(cudaStreamWaitEvent(h->sA, ln.evZ, 0));
+            if (convvel) launch_convvel(h, first(c), count(c), deltat);
+            launch_xpass(h, first(c), count(c), compute_cfl);
+            if (chb_exchange(h, false)) return 1;
             CHB_CUDA_OK(cudaEventRecord(ln.evA, h->sA));
-            CHB_CUDA_OK(cudaStreamWaitEvent(h->sB, ln.evA, 0));
+            if (c + 1 < nch && zfwd_part(c + 1)) return 1;
+            if (products) {
+                chb_select_lane(h, c % h->nlanes);
+                CHB_CUDA_OK(cudaStreamWaitEvent(h->sB, ln.evA, 0));
+                if (local_part(c, h->sB)) return 1;
+            }
         }
-        h->cstream = h->sB;
-        launch_zbwd(h, p0, n);
-        if (h->P_dbg)   // debug capture: keep this chunk's products
-            for (int k = 0; k < 6; ++k)
-                CHB_CUDA_OK(cudaMemcpyAsync(h->P_dbg + ((size_t)k * g.nyp + p0) * g.M, ln.Pc + (size_t)k * np * g.M,
-                                            (size_t)n * g.M * sizeof(cplx), cudaMemcpyDeviceToDevice, h->sB));
-        if (rhs_ode) launch_rhs_chunk(h, rhs_ode, rhs_deltat, p0, n, h->sB);
-        if (two) CHB_CUDA_OK(cudaEventRecord(ln.evB, h->sB));
-    }
-    if (convvel) {   // IF (iy==nyN+2 .AND. compute_convvel): convvel_cnt=convvel_cnt+1; compute_convvel=.FALSE.   :546-549
-        h->cv_cnt += 1;
-        h->cv_compute = 0;
-    }
-    if (two) {   // join
+        // join
         CHB_CUDA_OK(cudaEventRecord(h->ev_join, h->sA));
         CHB_CUDA_OK(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
         CHB_CUDA_OK(cudaEventRecord(h->ev_join, h->sB));
         CHB_CUDA_OK(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+    }
+    if (convvel) {   // IF (iy==nyN+2 .AND. compute_convvel): convvel_cnt=convvel_cnt+1; compute_convvel=.FALSE.   :546-549
+        h->cv_cnt += 1;
+        h->cv_compute = 0;
     }
     h->cstream = h->sA;
     CHB_CUDA_OK(cudaGetLastError());

@@ -70,9 +70,8 @@ struct PeerPtrs {
 };
 
 // One set of pencil-transpose work buffers for a chunk of y-planes.  Consecutive chunks alternate between the lanes
-// (chb_api.cu, convolutions_all): while the kernels that carry the transposes (zfwd, xpass: stores into peer HBM over
-// NVLink) work on chunk c+1 in one lane, the local kernels (zbwd, the plane loop of buildrhs) finish chunk c in the
-// other.  All lanes are carved out of one device allocation, the arena (one CUDA IPC handle per rank).
+// (chb_api.cu, convolutions_all): while the x-pass works on chunk c in one lane, the z-passes and the plane loop of
+// buildrhs work on chunks c+1 / c-1 in the other.  All lanes are carved out of one device allocation, the arena (one CUDA IPC handle per rank).
 #define CHB_MAX_LANES 2
 struct Lane {
     cplx *A, *Ar, *B, *Br;   // A, B: NCCL mode only (send buffers)
@@ -81,8 +80,8 @@ struct Lane {
     unsigned long long* flags;
     unsigned long long* peer_flags[CHB_MAX_RANKS];
     unsigned long long epoch;
-    cudaEvent_t evA;         // recorded on the transpose stream after xpass + its barrier: Br complete, Ar free
-    cudaEvent_t evB;         // recorded on the local stream after zbwd (+ rhs): Br and Pc free
+    cudaEvent_t evZ;         // recorded on sB after zfwd + its barrier: Ar complete on every rank
+    cudaEvent_t evA;         // recorded on sA after xpass + its barrier: Br complete, Ar free on every rank
 };
 
 struct KernelTimer {
@@ -100,7 +99,7 @@ struct chb_handle_s {
     cudaEvent_t ev_fork, ev_join;
     Lane lane[CHB_MAX_LANES];      // the fields A..epoch below are a copy of the lane in use (chb_select_lane)
     int nlanes, cur_lane;          // CHB_LANES = 1 | 2 (default 2 on several GPUs)
-    cudaStream_t sA, sB;           // transpose-carrying kernels (zfwd, xpass, barriers) / local kernels (zbwd, rhs); both = stream when nlanes == 1
+    cudaStream_t sA, sB;           // x-pass / z-passes + RHS assembly of the chunk pipeline; both = stream when nlanes == 1
     cudaStream_t cstream;          // stream the conv launchers use (set by convolutions_all to sA or sB)
     void* green[2];                // CUgreenCtx of sA / sB when the SMs are partitioned (CHB_GREEN, green_ctx.cu), else null
     int green_sms[2];              // SMs of each partition (0 = not partitioned)

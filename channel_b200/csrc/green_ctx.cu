@@ -1,11 +1,10 @@
 // green_ctx.cu - SM partitions for the two streams of the chunk pipeline (chb_api.cu, convolutions_all).
 //
-// On several GPUs the kernels that carry the pencil transposes (zfwd, xpass: every store goes to a peer's HBM) are
-// bound by NVLink, the local kernels (zbwd, the plane loop of buildrhs) by HBM.  Two plain streams do not make them
-// overlap: each kernel's grid fills every SM (and its whole shared memory), so the block scheduler runs them one
-// after the other.  CUDA green contexts (driver API, CUDA >= 12.4) give each stream a fixed, disjoint set of SMs:
-// partition A (the transposes) gets enough SMs to keep NVLink busy, partition B (local work) the rest, and both run
-// side by side for the whole sweep.  This is the role of the reference's nonblockingXZ variant
+// On several GPUs the kernels whose stores are the pencil transposes (zfwd, xpass) wait for NVLink, the others for
+// HBM or the FP64 pipe.  Two plain streams do not make them overlap: each kernel's grid fills every SM (and its whole
+// shared memory), so the block scheduler runs them one after the other.  CUDA green contexts (driver API, CUDA >= 12.4)
+// give each stream a fixed, disjoint set of SMs: partition A runs the x-pass, partition B the z-passes and the RHS
+// assembly of the neighbouring chunks, side by side for the whole sweep (chb_api.cu, convolutions_all).  This is the role of the reference's nonblockingXZ variant
 // (mpi_transpose.f90:149-168: MPI_IAlltoall progressing under the next plane's FFTs).
 //
 // The device is split into the smallest groups the driver offers (2 SMs when SM co-scheduling is ignored - no kernel
@@ -60,7 +59,7 @@ bool load_driver() {
 }
 }  // namespace
 
-// sms_a > 0: SMs of partition A (rounded to groups of 8); sms_a < 0: the default share, 54 % of the device.
+// sms_a > 0: SMs of partition A (rounded to whole groups); sms_a < 0: the default share, 44 % of the device.
 int chb_green_create(chb_handle_s* h, int sms_a) {
     if (!load_driver()) return 1;
     cudaFree(0);   // the primary context exists and is current
@@ -82,7 +81,7 @@ int chb_green_create(chb_handle_s* h, int sms_a) {
     memset(&rem, 0, sizeof(rem));
     if (g_drv.DevSmResourceSplitByCount(grp.data(), &ng, &all, &rem, flags, gran) != CUDA_SUCCESS || ng < 2) return 1;
     const int per = (int)grp[0].sm.smCount;
-    if (sms_a < 0) sms_a = (int)(0.54 * total + 0.5);
+    if (sms_a < 0) sms_a = (int)(0.44 * total + 0.5);
     int ka = (sms_a + per / 2) / per;
     if (ka < 1) ka = 1;
     if (ka > (int)ng - 1) ka = (int)ng - 1;

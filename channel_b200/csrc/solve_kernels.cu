@@ -416,22 +416,37 @@ __device__ void store_wall_columns(cplx* V, DevScalars* sc, const Geometry& g, s
     }
 }
 
-// mean column (0,0) after S2: linsolve_blocking.inc:62-97.  One block: the strided accesses to the column (one
-// 16-byte element per plane of M columns) are spread over the threads, the recurrences (factorisation of
-// etamat(0,0), the ucor solve, the three y-integrals, in the reference's order of operations) run on thread 0 over
-// contiguous copies.  scratch: eta00mat [ny+1][5], ucor [ny+3], U [ny+3], W [ny+3].
+// mean column (0,0) after S2: linsolve_blocking.inc:62-97.  One block, everything in shared memory.  Parallel over the
+// threads: the strided accesses to the column (one 16-byte element per plane of M columns), the rows of etamat(0,0)
+// with their wall-BC folding, the weights of yintegr.  Sequential, in the reference's order of operations, but as three
+// independent chains on three warps: (a) UL factorisation of etamat(0,0) -> ucor solve -> its integral, (b) the integral
+// of U, (c) the integral of W.  (As one thread reading tables and scratch from global memory this kernel took 2 ms per
+// substep at ny = 512 - nothing on one GPU, where it hides under S3 / S4, but 7 % of the step on eight.)
+// Dynamic shared memory (doubles): A [ny+1][5] | ucor [ny+3] | U [ny+3] | W [ny+3] | wts [3][ny/2+1].
 #define MEAN_THREADS 128
+__host__ __device__ inline size_t mean_mode_smem_doubles(int ny) { return (size_t)(ny + 1) * 5 + 3 * (size_t)(ny + 3) + 3 * (size_t)(ny / 2 + 1); }
+
+// yintegr (dnsdata.f90:312-324) with the weights a1, a2, a3 of every odd node precomputed (same expressions)
+__device__ __forceinline__ double yintegr_weighted(const double* __restrict__ wts, const double* f, int ny) {
+    double II = 0.0;
+    for (int iy = 1, k = 0; iy <= ny - 1; iy += 2, ++k)
+        II = II + wts[3 * k + 0] * f[iy] + wts[3 * k + 1] * f[iy + 1] + wts[3 * k + 2] * f[iy + 2];
+    return II;
+}
+
 __global__ void __launch_bounds__(MEAN_THREADS)
-mean_mode_kernel(cplx* __restrict__ V, Geometry g, DevTables tab, DevScalars* sc, double lam, double* __restrict__ scratch) {
+mean_mode_kernel(cplx* __restrict__ V, Geometry g, DevTables tab, DevScalars* sc, double lam) {
     if (blockIdx.x != 0) return;
+    CHB_DYN_SMEM(double, sm);
     const int ny = g.ny, nz = g.nz, nyp = g.nyp;
     const int tid = threadIdx.x, nth = blockDim.x;
     const size_t plane = (size_t)g.M, comp = (size_t)g.nyp * plane;
     const size_t m00 = (size_t)nz;  // ixl=0, izp=nz
-    double* A = scratch;                             // [ny+1][5]
-    double* ucor = scratch + (size_t)(ny + 1) * 5;   // [ny+3], index iy+1
+    double* A = sm;                                  // [ny+1][5]: folded rows of etamat(0,0), then its UL factors
+    double* ucor = A + (size_t)(ny + 1) * 5;         // [ny+3], index iy+1
     double* U = ucor + nyp;                          // Re eta -> u(0,0)
     double* W = U + nyp;                             // Im eta -> w(0,0)
+    double* wts = W + nyp;                           // [ny/2+1][3]
     // V(:,0,0,3) = Im eta ; V(:,0,0,1) = Re eta            :63-64
     for (int i = tid; i < nyp; i += nth) {
         const cplx e = V[0 * comp + (size_t)i * plane + m00];
@@ -439,29 +454,44 @@ mean_mode_kernel(cplx* __restrict__ V, Geometry g, DevTables tab, DevScalars* sc
         V[0 * comp + (size_t)i * plane + m00] = make_double2(e.x, 0.0);
         U[i] = e.x;
         W[i] = e.y;
+        ucor[i] = (i >= 2 && i <= ny) ? 1.0 : 0.0;   // rhs 1 on rows 1..ny-1                                :65-68
+    }
+    // rows of etamat(0,0) (k2 = 0) with the wall BCs folded in
+    for (int iy = 1 + tid; iy <= ny - 1; iy += nth) {
+        Row5 rv, re;
+        build_rows(tab, iy, 0.0, lam, g.ni, rv, re);
+        if (iy == ny - 1) { fold_top1(re, tab.etanbc, tab.etanp1bc); re.a[3] = re.a[4] = 0.0; }
+        else if (iy == ny - 2) { fold_top2(re, tab.etanbc); re.a[4] = 0.0; }
+        if (iy == 1) fold_bot1(re, tab.eta0bc, tab.eta0m1bc);
+        else if (iy == 2) fold_bot2(re, tab.eta0bc);
+        double* r = A + (size_t)(iy - 1) * 5;
+        for (int j = 0; j < 5; ++j) r[j] = re.a[j];
+    }
+    for (int j = tid; j < 10; j += nth) A[(size_t)(ny - 1) * 5 + j] = 0.0;   // rows ny, ny+1 are zero
+    // weights of yintegr at the odd nodes
+    for (int k = tid; 1 + 2 * k <= ny - 1; k += nth) {
+        const int iy = 1 + 2 * k;
+        const double yp1 = tab.y[iy + 2] - tab.y[iy + 1], ym1 = tab.y[iy] - tab.y[iy + 1];
+        const double a1 = -1.0 / 3.0 * ym1 + 1.0 / 6.0 * yp1 + 1.0 / 6.0 * yp1 * yp1 / ym1;
+        const double a3 = +1.0 / 3.0 * yp1 - 1.0 / 6.0 * ym1 - 1.0 / 6.0 * ym1 * ym1 / yp1;
+        wts[3 * k + 0] = a1;
+        wts[3 * k + 1] = yp1 - ym1 - a1 - a3;
+        wts[3 * k + 2] = a3;
     }
     __syncthreads();
     if (tid == 0) {
-        // etamat(0,0), factorised again (k2 = 0)
+        // etamat(0,0), factorised again
         LUState st = {0, 0, 0, 0};
-        for (int i = 0; i < 5; ++i) { A[(size_t)(ny - 1) * 5 + i] = 0.0; A[(size_t)ny * 5 + i] = 0.0; }
         for (int iy = ny - 1; iy >= 1; --iy) {
-            Row5 rv, re;
-            build_rows(tab, iy, 0.0, lam, g.ni, rv, re);
-            if (iy == ny - 1) { fold_top1(re, tab.etanbc, tab.etanp1bc); re.a[3] = re.a[4] = 0.0; }
-            else if (iy == ny - 2) { fold_top2(re, tab.etanbc); re.a[4] = 0.0; }
-            if (iy == 1) fold_bot1(re, tab.eta0bc, tab.eta0m1bc);
-            else if (iy == 2) fold_bot2(re, tab.eta0bc);
+            double* r = A + (size_t)(iy - 1) * 5;
+            Row5 re;
+            for (int j = 0; j < 5; ++j) re.a[j] = r[j];
             double inv, u1, u2;
             lu_row(re, st, inv, u1, u2);
-            double* r = A + (size_t)(iy - 1) * 5;
             r[0] = st.l1m2; r[1] = st.l1m1; r[2] = inv; r[3] = u1; r[4] = u2;
         }
         A[0] = A[1] = 0.0;  // rbparmat_blocking.f90:45
         A[5] = 0.0;
-        // ucor: rhs 1 on rows 1..ny-1                                :65-68
-        for (int i = 0; i < ny + 3; ++i) ucor[i] = 0.0;
-        for (int iy = 1; iy <= ny - 1; ++iy) ucor[iy + 1] = 1.0;
         for (int iy = ny - 1; iy >= 1; --iy) {
             const double* r = A + (size_t)(iy - 1) * 5;
             ucor[iy + 1] = (ucor[iy + 1] - (r[3] * ucor[iy + 2] + r[4] * ucor[iy + 3])) * r[2];
@@ -478,12 +508,19 @@ mean_mode_kernel(cplx* __restrict__ V, Geometry g, DevTables tab, DevScalars* sc
             ucor[ny + 1] = -(ucor[ny - 2] * enbc[0] + ucor[ny - 1] * enbc[1] + ucor[ny] * enbc[2]) / enbc[3];      // :74
             ucor[ny + 2] = -(ucor[ny - 2] * enp1[0] + ucor[ny - 1] * enp1[1] + ucor[ny] * enp1[2] + ucor[ny + 1] * enp1[3]) / enp1[4];  // :75
         }
-        sc->fr[0] = yintegr_dev(tab.y, U, 1, ny, 0);  // :77
-        sc->fr[1] = yintegr_dev(tab.y, W, 1, ny, 0);
-        sc->fr[2] = yintegr_dev(tab.y, ucor, 1, ny, 0);
+        sc->fr[2] = yintegr_weighted(wts, ucor, ny);
+    } else if (tid == 32) {
+        sc->fr[0] = yintegr_weighted(wts, U, ny);  // :77
+    } else if (tid == 64) {
+        sc->fr[1] = yintegr_weighted(wts, W, ny);
+    }
+    __threadfence_block();
+    __syncthreads();
+    if (tid == 0) {
         if (fabs(sc->meanflowx) > 1.0e-7 && !sc->CPI) sc->corrpx = (sc->meanflowx - sc->fr[0]) / sc->fr[2];   // :79-82
         if (fabs(sc->meanflowz) > 1.0e-7 && !sc->CPI) sc->corrpz = (sc->meanflowz - sc->fr[1]) / sc->fr[2];   // :83-86
     }
+    __threadfence_block();
     __syncthreads();
     if (fabs(sc->meanflowx) > 1.0e-7 && !sc->CPI) {
         const double c = sc->corrpx;
@@ -554,7 +591,9 @@ void launch_linsolve(chb_handle_s* h, double lam) {
         cudaEventRecord(h->ev_fork, h->stream);
         cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0);
         ScopedKernelTimer tm(h, "mean_mode", h->side_stream);
-        CHB_LAUNCH(1, MEAN_THREADS, 0, h->side_stream, mean_mode_kernel)(h->V, g, h->tab, h->sc, lam, h->mean_scratch);
+        const size_t msm = mean_mode_smem_doubles(g.ny) * sizeof(double);
+        cudaFuncSetAttribute(mean_mode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msm);
+        CHB_LAUNCH(1, MEAN_THREADS, msm, h->side_stream, mean_mode_kernel)(h->V, g, h->tab, h->sc, lam);
         h->launches++;
     }
     {

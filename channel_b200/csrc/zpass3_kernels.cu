@@ -47,6 +47,10 @@ zfwd4_kernel(const cplx* __restrict__ V, PeerPtrs Aw, Geometry g, const cplx* __
     const int iyp = plane0 + pli;
     const int nz = g.nz;
     __shared__ unsigned long long mbar[LPC];
+    // the twiddles this thread needs first, loaded while the line is on its way from HBM (they are L1 / L2 hits, but
+    // their latency sat right behind the barriers: 17-36 % of the stall samples of stages A and B)
+    cplx wa_next = ctw<+1>(W, tl);
+    const cplx wb1 = ctw<+1>(W, G::A * (tl % G::C));
     {   // ---- stage A, line-major; the V line is staged by TMA bulk copies into the in-place layout
         const cplx* __restrict__ src = V + (((size_t)comp * g.nyp + iyp) * g.nxB + ixl0 + wl) * g.nzt;
         cplx* sm = smem + wl * LS;
@@ -69,6 +73,8 @@ zfwd4_kernel(const cplx* __restrict__ V, PeerPtrs Aw, Geometry g, const cplx* __
         }
 #pragma unroll 1
         for (int t1 = tl; t1 < G::BC; t1 += TPL) {
+            const cplx wa = wa_next;
+            if (t1 + TPL < G::BC) wa_next = ctw<+1>(W, t1 + TPL);   // next iteration's twiddle under this one's butterfly
             cplx x[G::A];
             static_for<G::A>([&](auto a_) {
                 constexpr int a = decltype(a_)::value;
@@ -79,7 +85,7 @@ zfwd4_kernel(const cplx* __restrict__ V, PeerPtrs Aw, Geometry g, const cplx* __
                     x[a] = (n <= nz || n >= G::N - nz) ? sm[a * BCP + t1] : make_double2(0.0, 0.0);
             });
             Dft<G::A, +1>::run(x);
-            if (t1 != 0) z_twiddle_seq<G::A>(x, ctw<+1>(W, t1));
+            if (t1 != 0) z_twiddle_seq<G::A>(x, wa);
             static_for<G::A>([&](auto ka_) {
                 constexpr int ka = decltype(ka_)::value;
                 sm[ka * BCP + t1] = x[ka];
@@ -90,7 +96,7 @@ zfwd4_kernel(const cplx* __restrict__ V, PeerPtrs Aw, Geometry g, const cplx* __
     {   // ---- stage B, line-major, in place
         cplx* sm = smem + wl * LS;
         const int cc = tl % G::C;
-        const cplx w1 = ctw<+1>(W, G::A * cc);
+        const cplx w1 = wb1;
 #pragma unroll 1
         for (int u = tl; u < G::A * G::C; u += TPL) {
             cplx* base = sm + (u / G::C) * BCP + cc;
@@ -136,6 +142,8 @@ zbwd4_kernel(const cplx* __restrict__ Br, cplx* __restrict__ P, Geometry g, cons
     const int pli = blockIdx.y, comp = blockIdx.z;  // product index 0..5
     const int nz = g.nz;
     (void)plane0;
+    cplx wa_next = ctw<-1>(W, tl);                              // see zfwd4
+    const cplx wb1 = ctw<-1>(W, G::A * (tl % G::C));
     {   // ---- staging, cross-line: per-thread 16-byte cp.async straight into the in-place layout
         const int l = threadIdx.x % LPC, q = threadIdx.x / LPC;
         cplx* sml = smem + l * LS;
@@ -154,16 +162,18 @@ zbwd4_kernel(const cplx* __restrict__ Br, cplx* __restrict__ P, Geometry g, cons
     // ---- stage A, line-major, in place
 #pragma unroll 1
     for (int t1 = tl; t1 < G::BC; t1 += TPL) {
+        const cplx wa = wa_next;
+        if (t1 + TPL < G::BC) wa_next = ctw<-1>(W, t1 + TPL);
         cplx x[G::A];
         static_for<G::A>([&](auto a_) { constexpr int a = decltype(a_)::value; x[a] = sm[a * BCP + t1]; });
         Dft<G::A, -1>::run(x);
-        if (t1 != 0) z_twiddle_seq<G::A>(x, ctw<-1>(W, t1));
+        if (t1 != 0) z_twiddle_seq<G::A>(x, wa);
         static_for<G::A>([&](auto ka_) { constexpr int ka = decltype(ka_)::value; sm[ka * BCP + t1] = x[ka]; });
     }
     __syncthreads();
     {   // ---- stage B, line-major, in place
         const int cc = tl % G::C;
-        const cplx w1 = ctw<-1>(W, G::A * cc);
+        const cplx w1 = wb1;
 #pragma unroll 1
         for (int u = tl; u < G::A * G::C; u += TPL) {
             cplx* base = sm + (u / G::C) * BCP + cc;

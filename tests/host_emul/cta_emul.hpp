@@ -65,6 +65,7 @@ template <class T>
 static inline cudaError_t cudaFuncSetAttribute(T* /*kernel*/, cudaFuncAttribute, int) { return cudaSuccess; }
 static inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 static inline void __threadfence_system() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+static inline void __threadfence_block() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 static inline void __nanosleep(unsigned) { std::this_thread::yield(); }
 
 namespace cta_emul {

@@ -110,7 +110,8 @@ __attribute__((visibility("default"))) int chb_emul_ydir_substep(int nx, int ny,
         }
         emulate(solve_s2_kernel<0>, blocks, T, (const double*)ckpt.data(), Vc, g, tab, &sc, lam);
         emulate(solve_s2_kernel<1>, blocks, T, (const double*)ckpt.data(), Vc, g, tab, &sc, lam);
-        emulate(mean_mode_kernel, 1, MEAN_THREADS, Vc, g, tab, &sc, lam, scratch.data());
+        if (mean_mode_smem_doubles(ny) * sizeof(double) > sizeof(cta_emul::g_dyn_smem)) return 3;
+        emulate(mean_mode_kernel, 1, MEAN_THREADS, Vc, g, tab, &sc, lam);
         if (mode == 3) {
             emulate(solve_s3_kernel<8>, blocks, T, Vc, g, tab);
             emulate(solve_s4_kernel<8>, blocks, T, Vc, g, tab);
