@@ -139,20 +139,26 @@ void chb_select_lane(chb_handle_s* h, int L) {
     for (int q = 0; q < CHB_MAX_RANKS; ++q) h->peer_flags[q] = ln.peer_flags[q];
 }
 
-// Layout of the work arena: [0, 4096) barrier flags of every lane + the barrier error word; then, per lane, Ar, Br, Pc
-// (+ A, B in NCCL mode), each aligned to 256 bytes.  Identical on every rank (np is agreed on), so a peer's buffers are
-// its arena base + these offsets.
+// Layout of the work arena: [0, 4096) barrier flags of every lane + the barrier error word; then the velocity receive
+// buffers Ar of all lanes; then, per lane, Br, Pc (+ A, B in NCCL mode); everything aligned to 256 bytes.  Identical on
+// every rank (np is agreed on), so a peer's buffers are its arena base + these offsets.
+// The part behind the Ar buffers doubles as the staging area of the host <-> device field transfers and of the restart
+// files.  Ar is excluded on purpose: between two sweeps a peer that is ahead may already run zfwd of its next sweep,
+// whose stores land in this rank's Ar; Br is only written behind a barrier this rank takes part in (after its own
+// staging work, in stream order), Pc / A / B are private.
 #define CHB_ARENA_HEAD 4096
 struct ArenaLayout {
-    size_t ar, br, pc, a, b;   // offsets inside a lane
-    size_t lane_bytes, total;
+    size_t ar_bytes;           // one lane's Ar
+    size_t br, pc, a, b;       // offsets inside a lane's private part
+    size_t lane_bytes;         // private part of one lane
+    size_t stage_off, total;
 };
 static ArenaLayout arena_layout(const Geometry& g, size_t np, int nlanes, bool nccl_mode) {
     auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
     const size_t na = (size_t)3 * np * g.nzd * g.nxB * sizeof(cplx), nb = 2 * na, npc = (size_t)6 * np * g.M * sizeof(cplx);
     ArenaLayout L;
+    L.ar_bytes = up(na);
     size_t o = 0;
-    L.ar = o; o = up(o + na);
     L.br = o; o = up(o + nb);
     L.pc = o; o = up(o + npc);
     L.a = L.b = 0;
@@ -161,7 +167,8 @@ static ArenaLayout arena_layout(const Geometry& g, size_t np, int nlanes, bool n
         L.b = o; o = up(o + nb);
     }
     L.lane_bytes = o;
-    L.total = CHB_ARENA_HEAD + (size_t)nlanes * o;
+    L.stage_off = CHB_ARENA_HEAD + (size_t)nlanes * L.ar_bytes;
+    L.total = L.stage_off + (size_t)nlanes * o;
     return L;
 }
 
@@ -240,7 +247,7 @@ static int create_impl(chb_handle_s* h, int nx, int ny, int nz, int nxd, int nzd
         e = getenv("CHB_XPASS_SPLIT");
         h->xpass_split = e ? atoi(e) : (nxd == 1536 ? 1 : 0);
         // persistent x-pass with prefetched inputs: measured 16 % faster at nxd = 1536 on top of the split (14.0 against
-        // 16.6 ms), 14 % slower at nxd = 768 where it costs the third CTA per SM (profiles/r2e_xpass_persist.md)
+        // 16.6 ms), 14 % slower at nxd = 768 where it costs the third CTA per SM (profiles/r2c_r2e_single_gpu.md)
         e = getenv("CHB_XPASS_PERSIST");
         h->xpass_persist = e ? atoi(e) : (nxd == 1536 ? 1 : 0);
         // x tiles of the work buffers (transpose_index.h): products 8 wide (128-byte store segments in
@@ -298,7 +305,7 @@ static int create_impl(chb_handle_s* h, int nx, int ny, int nz, int nxd, int nzd
         h->p2p = (nranks > 1 && !(e && atoi(e) == 0)) ? 1 : 0;
         // two lanes: the kernels that carry the transposes run on their own stream (and SM partition) one chunk ahead of
         // the local kernels; default from 4 GPUs on, where the former are NVLink-bound
-        // (measured, profiles/r2d_overlap.md: at 2 GPUs, where little of the step is NVLink-bound, the sequential
+        // (measured, profiles/r2_multi_gpu.md: at 2 GPUs, where little of the step is NVLink-bound, the sequential
         // sweep is faster: 137 against 147 ms/step at config 3).  The NCCL fallback always runs one lane.
         const bool nccl_mode = nranks > 1 && !h->p2p;
         e = getenv("CHB_LANES");
@@ -311,7 +318,8 @@ static int create_impl(chb_handle_s* h, int nx, int ny, int nz, int nxd, int nzd
         e = getenv("CHB_WORK_GB");
         size_t budget = (size_t)((e ? atof(e) : 10.0) * 1073741824.0);
         if (budget > free_b / 4) budget = free_b / 4;
-        const size_t per_plane = arena_layout(g, 1, 1, nccl_mode).lane_bytes;
+        const ArenaLayout AL1 = arena_layout(g, 1, 1, nccl_mode);
+        const size_t per_plane = AL1.ar_bytes + AL1.lane_bytes;
         long long np = (long long)(budget / h->nlanes / per_plane);
         if (np < 1) np = 1;
         // with two lanes at least four chunks per sweep, so that the pipeline has something to overlap
@@ -328,7 +336,7 @@ static int create_impl(chb_handle_s* h, int nx, int ny, int nz, int nxd, int nzd
         h->chunk_planes = (int)np;
         const ArenaLayout AL = arena_layout(g, (size_t)np, h->nlanes, nccl_mode);
         h->arena_bytes = AL.total;
-        h->stage_off = CHB_ARENA_HEAD;
+        h->stage_off = AL.stage_off;
         CHB_CUDA_OK(cudaMalloc((void**)&h->arena, AL.total));
         g_alloc_bytes += AL.total;
         CHB_CUDA_OK(cudaMemset(h->arena, 0, AL.total));
@@ -340,8 +348,8 @@ static int create_impl(chb_handle_s* h, int nx, int ny, int nz, int nxd, int nzd
             memset(&ln, 0, sizeof(ln));
             CHB_CUDA_OK(cudaEventCreateWithFlags(&ln.evA, cudaEventDisableTiming));
             CHB_CUDA_OK(cudaEventCreateWithFlags(&ln.evZ, cudaEventDisableTiming));
-            char* base = h->arena + CHB_ARENA_HEAD + (size_t)L * AL.lane_bytes;
-            ln.Ar = reinterpret_cast<cplx*>(base + AL.ar);
+            char* base = h->arena + AL.stage_off + (size_t)L * AL.lane_bytes;
+            ln.Ar = reinterpret_cast<cplx*>(h->arena + CHB_ARENA_HEAD + (size_t)L * AL.ar_bytes);
             ln.Br = reinterpret_cast<cplx*>(base + AL.br);
             ln.Pc = reinterpret_cast<cplx*>(base + AL.pc);
             if (nccl_mode) {
@@ -670,7 +678,7 @@ extern "C" int chb_set_body_force(chb_handle h) {
 // the same time, HBM serves zbwd / rhs while the x-pass computes, and the SMs that one kernel leaves idle while its
 // remote stores drain work for the other stream.  This is the role of the reference's nonblockingXZ variant
 // (mpi_transpose.f90:149-168: MPI_IAlltoall progressing under the next plane's FFTs).  Measured at 4 GPUs
-// (profiles/r2g_overlap_n4.md): the first version, transposes (zfwd + xpass) on one partition and local kernels on the
+// (profiles/r2_multi_gpu.md): the first version, transposes (zfwd + xpass) on one partition and local kernels on the
 // other, lost to the sequential sweep because zfwd leaves its SMs idle and the x-pass is compute-bound on a partition.
 //
 // Buffer reuse across ranks: a peer's zfwd(c) stores into this rank's Ar(lane) - free once every rank has passed the

@@ -113,7 +113,7 @@ struct chb_handle_s {
     // field transfers and of the restart files
     char* arena;
     size_t arena_bytes;
-    size_t stage_off;     // first byte of the arena usable as staging (behind the flags)
+    size_t stage_off;     // first byte of the arena usable as staging (behind the flags and the Ar buffers, which peers may write)
     int chunk_planes;
     int zf_lines_per_cta, zb_lines_per_cta;  // lines per CTA of zfwd / zbwd (CHB_ZF_LPC, CHB_ZB_LPC: 2, 4 or 8)
     int use_fft3;         // register-resident three-stage FFT kernels for the large sizes (CHB_FFT3=0 disables)

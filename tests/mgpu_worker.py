@@ -47,7 +47,14 @@ def main():
         o.V[:] = V0
         ch = Channel(p, rank=rank, nranks=world, nccl_id=new_nccl_id(), device=local, tables=o)
         sl = slice(ch.nx0, ch.nxN + 1)
-        ch.upload_V(V0[:, :, sl, :])
+        if not opts:
+            # Fortran-layout upload (staged through the work arena) with the ranks out of step: the early ranks are
+            # already storing their zfwd output into the late ranks' receive buffers while those still upload
+            import time
+            time.sleep(0.25 * rank)
+            ch.upload_V_fortran(np.ascontiguousarray(np.transpose(V0[:, :, sl, :], (0, 2, 3, 1))))
+        else:
+            ch.upload_V(V0[:, :, sl, :])
         if couette:
             o.set_body_force(coriolis_force(0.02, 9999999.0, 1.0)); ch.config_coriolis(0.02, 9999999.0, 1.0)
         ch.cfl_prepass(); o.cfl_prepass()
