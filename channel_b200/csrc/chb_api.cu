@@ -239,6 +239,8 @@ static int create_impl(chb_handle_s* h, int nx, int ny, int nz, int nxd, int nzd
         h->zf_direct = e ? atoi(e) : 0;
         e = getenv("CHB_Z_TPL");
         h->z_tpl = e ? atoi(e) : 0;
+        e = getenv("CHB_Z_L2PF");
+        h->z_l2pf = e ? atoi(e) : 0;
         e = getenv("CHB_SOLVE_PF");
         h->solve_pf = e ? atoi(e) : 0;
         h->rhs_state = nullptr;
@@ -304,12 +306,14 @@ static int create_impl(chb_handle_s* h, int nx, int ny, int nz, int nxd, int nzd
         const char* e = getenv("CHB_P2P");
         h->p2p = (nranks > 1 && !(e && atoi(e) == 0)) ? 1 : 0;
         // two lanes: the kernels that carry the transposes run on their own stream (and SM partition) one chunk ahead of
-        // the local kernels; default from 4 GPUs on, where the former are NVLink-bound
-        // (measured, profiles/r2_multi_gpu.md: at 2 GPUs, where little of the step is NVLink-bound, the sequential
-        // sweep is faster: 137 against 147 ms/step at config 3).  The NCCL fallback always runs one lane.
+        // the z-passes; default from 4 GPUs on for the large transforms
+        // Measured (profiles/r2_multi_gpu.md): the pipeline wins 11 % on the headline grid at 4 GPUs (nxd = 1536: the
+        // persistent x-pass is one CTA per SM and scales with its SM count) and loses to the sequential sweep at
+        // nxd = 768 (three x-pass CTAs per SM hide each other's phases; on fewer SMs it loses more than its share) and
+        // at 2 GPUs (little of the step is NVLink-bound).  The NCCL fallback always runs one lane.
         const bool nccl_mode = nranks > 1 && !h->p2p;
         e = getenv("CHB_LANES");
-        h->nlanes = e ? (atoi(e) == 2 ? 2 : 1) : (nranks >= 4 ? 2 : 1);
+        h->nlanes = e ? (atoi(e) == 2 ? 2 : 1) : ((nranks >= 4 && nxd >= 1536) ? 2 : 1);
         if (nccl_mode) h->nlanes = 1;
         // budget: CHB_WORK_GB (default 10 GB, at most a quarter of the free device memory); larger chunks mean fewer
         // launches, fewer partially filled last waves and fewer carried-accumulator round trips of the RHS assembly
@@ -370,10 +374,10 @@ static int create_impl(chb_handle_s* h, int nx, int ny, int nz, int nxd, int nzd
         h->green[0] = h->green[1] = nullptr;
         h->green_sms[0] = h->green_sms[1] = 0;
         if (h->nlanes == 2) {
-            // CHB_GREEN=<SMs of the x-pass partition> (default: 44 % of the SMs on several GPUs - the x-pass's share of
-            // the SM time of a sweep -, off on one): the two streams get disjoint SM partitions through CUDA green
-            // contexts, so that the z-passes really run beside the x-pass instead of behind it; plain streams if the
-            // driver refuses
+            // CHB_GREEN=<SMs of the x-pass partition> (default: 54 % of the SMs on several GPUs - 80 + 68 measured
+            // best of 52 / 66 / 80 at 4 GPUs -, off on one): the two streams get disjoint SM partitions through CUDA
+            // green contexts, so that the z-passes really run beside the x-pass instead of behind it; plain streams
+            // if the driver refuses
             e = getenv("CHB_GREEN");
             int sms_a = e ? atoi(e) : (nranks > 1 ? -1 : 0);
             if (sms_a != 0 && chb_green_create(h, sms_a) != 0) sms_a = 0;

@@ -59,7 +59,7 @@ bool load_driver() {
 }
 }  // namespace
 
-// sms_a > 0: SMs of partition A (rounded to whole groups); sms_a < 0: the default share, 44 % of the device.
+// sms_a > 0: SMs of partition A (rounded to whole groups); sms_a < 0: the default share, 54 % of the device.
 int chb_green_create(chb_handle_s* h, int sms_a) {
     if (!load_driver()) return 1;
     cudaFree(0);   // the primary context exists and is current
@@ -81,7 +81,7 @@ int chb_green_create(chb_handle_s* h, int sms_a) {
     memset(&rem, 0, sizeof(rem));
     if (g_drv.DevSmResourceSplitByCount(grp.data(), &ng, &all, &rem, flags, gran) != CUDA_SUCCESS || ng < 2) return 1;
     const int per = (int)grp[0].sm.smCount;
-    if (sms_a < 0) sms_a = (int)(0.44 * total + 0.5);
+    if (sms_a < 0) sms_a = (int)(0.54 * total + 0.5);
     int ka = (sms_a + per / 2) / per;
     if (ka < 1) ka = 1;
     if (ka > (int)ng - 1) ka = (int)ng - 1;

@@ -31,10 +31,13 @@ def main():
         return bytes(t.cpu().numpy().tobytes())
     # (grid, couette, library options): direct NVLink stores (default), NCCL all-to-all, row-major velocity
     # buffer + two-lane chunk pipeline
-    # (default = two lanes on green-context SM partitions), one lane, two lanes on plain streams with small chunks
+    # default (one lane at these transform sizes), two lanes on green-context SM partitions (the default of the headline
+    # grid from 4 GPUs on), two lanes on plain streams with small chunks
     grids = [(31, 16, 16, False, {}), (255, 8, 255, False, {}), (255, 8, 255, False, {"CHB_P2P": "0"}),
              (255, 8, 255, False, {"CHB_TWA": "-1", "CHB_LANES": "1"}), (31, 16, 16, True, {}),
-             (255, 8, 255, False, {"CHB_GREEN": "0", "CHB_WORK_GB": "0.02"}), (31, 16, 16, True, {"CHB_P2P": "0", "CHB_LANES": "1"})]
+             (255, 8, 255, False, {"CHB_LANES": "2"}), (31, 16, 16, True, {"CHB_LANES": "2", "CHB_WORK_GB": "0.0005"}),
+             (255, 8, 255, False, {"CHB_LANES": "2", "CHB_GREEN": "0", "CHB_WORK_GB": "0.02"}),
+             (31, 16, 16, True, {"CHB_P2P": "0", "CHB_LANES": "1"})]
     worst = 0.0
     for nx, ny, nz, couette, opts in grids:
         for k in ("CHB_P2P", "CHB_TWA", "CHB_LANES", "CHB_GREEN", "CHB_WORK_GB"):
