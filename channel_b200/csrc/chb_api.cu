@@ -239,8 +239,6 @@ static int create_impl(chb_handle_s* h, int nx, int ny, int nz, int nxd, int nzd
         h->zf_direct = e ? atoi(e) : 0;
         e = getenv("CHB_Z_TPL");
         h->z_tpl = e ? atoi(e) : 0;
-        e = getenv("CHB_Z_L2PF");
-        h->z_l2pf = e ? atoi(e) : 0;
         e = getenv("CHB_SOLVE_PF");
         h->solve_pf = e ? atoi(e) : 0;
         h->rhs_state = nullptr;

@@ -119,7 +119,6 @@ struct chb_handle_s {
     int use_fft3;         // register-resident three-stage FFT kernels for the large sizes (CHB_FFT3=0 disables)
     int zf_direct;        // CHB_ZF_DIRECT=1: zfwd4 stage A reads global memory directly (no TMA staging); measured slower
     int z_tpl;            // CHB_Z_TPL=128|96: threads per line of the z passes at nzd = 1536 / 3072 (default 64)
-    int z_l2pf;           // CHB_Z_L2PF=<CTAs ahead>: L2 prefetch of the z-pass inputs of the CTA that runs that many CTAs later (0 = off)
     int solve_pf;         // CHB_SOLVE_PF=1: S1 / S3 / S4 with eight rows of loads in flight per thread; measured slower at config 3
     double* rhs_state;    // [32][M] accumulators of the plane loop of buildrhs carried from chunk to chunk
     int xpass_split;      // CHB_XPASS_SPLIT: two threads per innermost butterfly position (default on at nxd = 1536)

@@ -37,7 +37,7 @@ __device__ __forceinline__ void z_twiddle_seq(cplx* x, cplx w1) {
 template <class G, int LPC, int TPL, int MINB, bool DIRECT = false>
 __global__ void __launch_bounds__(LPC * TPL, MINB)
 zfwd4_kernel(const cplx* __restrict__ V, PeerPtrs Aw, Geometry g, const cplx* __restrict__ W, int plane0, int np,
-             int LS, int pf) {
+             int LS) {
     CHB_DYN_SMEM(cplx, smem);
     constexpr int BCP = G::BC + 1;
     static_assert(TPL % G::C == 0, "stage-B twiddle must be a per-thread constant");
@@ -48,20 +48,11 @@ zfwd4_kernel(const cplx* __restrict__ V, PeerPtrs Aw, Geometry g, const cplx* __
     const int nz = g.nz;
     __shared__ unsigned long long mbar[LPC];
     // the twiddles this thread needs first, loaded while the line is on its way from HBM (they are L1 / L2 hits, but
-    // their latency sat right behind the barriers: 17-36 % of the stall samples of stages A and B)
+    // their latency sat right behind the barriers: 17-36 % of the stall samples of stages A and B).  An L2 prefetch
+    // (cp.async.bulk.prefetch.L2) of the lines of the CTA that runs 300-2400 CTAs later was measured too and rejected:
+    // zbwd 45.6 -> 47.8-50.6 ms/step at config 3 (profiles/r2c_r2e_single_gpu.md)
     cplx wa_next = ctw<+1>(W, tl);
     const cplx wb1 = ctw<+1>(W, G::A * (tl % G::C));
-    if (pf > 0 && threadIdx.x == 0) {
-        // L2 prefetch (cp.async.bulk.prefetch.L2) of the lines of the CTA that runs `pf` CTAs later in launch order (x
-        // fastest, then plane, then component): the LPC lines of a CTA are one contiguous block of V
-        long long vb = (long long)blockIdx.x + (long long)gridDim.x * (blockIdx.y + (long long)gridDim.y * blockIdx.z) + pf;
-        if (vb < (long long)gridDim.x * gridDim.y * gridDim.z) {
-            const int bx = (int)(vb % gridDim.x), by = (int)((vb / gridDim.x) % gridDim.y), bz = (int)(vb / ((long long)gridDim.x * gridDim.y));
-            const cplx* nxt = V + (((size_t)bz * g.nyp + plane0 + by) * g.nxB + (size_t)bx * LPC) * g.nzt;
-            const unsigned bytes = (unsigned)((size_t)LPC * g.nzt * sizeof(cplx));
-            bulk_prefetch_l2(nxt, bytes);
-        }
-    }
     {   // ---- stage A, line-major; the V line is staged by TMA bulk copies into the in-place layout
         const cplx* __restrict__ src = V + (((size_t)comp * g.nyp + iyp) * g.nxB + ixl0 + wl) * g.nzt;
         cplx* sm = smem + wl * LS;
@@ -144,7 +135,7 @@ zfwd4_kernel(const cplx* __restrict__ V, PeerPtrs Aw, Geometry g, const cplx* __
 template <class G, int LPC, int TPL, int MINB>
 __global__ void __launch_bounds__(LPC * TPL, MINB)
 zbwd4_kernel(const cplx* __restrict__ Br, cplx* __restrict__ P, Geometry g, const cplx* __restrict__ W, int plane0, int np,
-             int LS, int pf) {
+             int LS) {
     CHB_DYN_SMEM(cplx, smem);
     constexpr int BCP = G::BC + 1;
     static_assert(TPL % G::C == 0, "stage-B twiddle must be a per-thread constant");
@@ -155,23 +146,6 @@ zbwd4_kernel(const cplx* __restrict__ Br, cplx* __restrict__ P, Geometry g, cons
     (void)plane0;
     cplx wa_next = ctw<-1>(W, tl);                              // see zfwd4
     const cplx wb1 = ctw<-1>(W, G::A * (tl % G::C));
-    if (pf > 0 && g.nranks == 1) {
-        // L2 prefetch of the x tile (2^tw lines x nzB rows, contiguous in the products buffer) that the CTAs `pf` tiles
-        // later in launch order will read; issued by the first CTA of each tile, one 16 KB piece per thread
-        const int tile = 1 << g.tw, cpt = tile / LPC;               // CTAs per tile
-        if (cpt >= 1 && (blockIdx.x % cpt) == 0) {
-            const long long tiles_x = gridDim.x / cpt;
-            long long vt = (long long)(blockIdx.x / cpt) + tiles_x * (blockIdx.y + (long long)gridDim.y * blockIdx.z) + pf;
-            if (vt < tiles_x * gridDim.y * gridDim.z) {
-                const int tx = (int)(vt % tiles_x), by = (int)((vt / tiles_x) % gridDim.y), bz = (int)(vt / (tiles_x * gridDim.y));
-                const cplx* nxt = Br + chb_bufB_index(0, 6, bz, np, by, g.nzB, 0, g.nxB, tx * tile, g.tw);
-                const size_t bytes = (size_t)g.nzB * tile * sizeof(cplx);
-                const size_t piece = 16384;
-                for (size_t o = (size_t)threadIdx.x * piece; o < bytes; o += (size_t)blockDim.x * piece)
-                    bulk_prefetch_l2(reinterpret_cast<const char*>(nxt) + o, (unsigned)(bytes - o < piece ? bytes - o : piece));
-            }
-        }
-    }
     {   // ---- staging, cross-line: per-thread 16-byte cp.async straight into the in-place layout
         const int l = threadIdx.x % LPC, q = threadIdx.x / LPC;
         cplx* sml = smem + l * LS;
@@ -247,12 +221,12 @@ static bool launch_z4(chb_handle_s* h, int plane0, int nplanes, bool fwd) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         ScopedKernelTimer tm(h, "zfwd", h->cstream);
-        CHB_LAUNCH(grid, LPC * TPL, smem, h->cstream, kern)(h->V, h->Aw, h->g, h->Wz, plane0, h->chunk_planes, LS, h->z_l2pf);
+        CHB_LAUNCH(grid, LPC * TPL, smem, h->cstream, kern)(h->V, h->Aw, h->g, h->Wz, plane0, h->chunk_planes, LS);
     } else {
         cudaFuncSetAttribute(zbwd4_kernel<G, LPC, TPL, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(zbwd4_kernel<G, LPC, TPL, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         ScopedKernelTimer tm(h, "zbwd", h->cstream);
-        CHB_LAUNCH(grid, LPC * TPL, smem, h->cstream, zbwd4_kernel<G, LPC, TPL, MINB>)(h->Br, h->Pc, h->g, h->Wz, plane0, h->chunk_planes, LS, h->z_l2pf > 0 ? (h->z_l2pf * LPC + (1 << h->g.tw) - 1) / (1 << h->g.tw) : 0);
+        CHB_LAUNCH(grid, LPC * TPL, smem, h->cstream, zbwd4_kernel<G, LPC, TPL, MINB>)(h->Br, h->Pc, h->g, h->Wz, plane0, h->chunk_planes, LS);
     }
     h->launches++;
     return true;

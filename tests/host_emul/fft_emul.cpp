@@ -66,11 +66,11 @@ static void run_z4(int fwd, const cplx* in, cplx* out, const Geometry& g, const 
         memset(&Aw, 0, sizeof(Aw));
         Aw.p[0] = out;
         if (fwd == 2)   // DIRECT: stage A reads global memory
-            cta_emul::launch(zfwd4_kernel<G, LPC, TPL, MINB, true>, dim3(g.nxB / LPC, np, 3), LPC * TPL, in, Aw, g, W, 0, np, LS, 0);
+            cta_emul::launch(zfwd4_kernel<G, LPC, TPL, MINB, true>, dim3(g.nxB / LPC, np, 3), LPC * TPL, in, Aw, g, W, 0, np, LS);
         else
-            cta_emul::launch(zfwd4_kernel<G, LPC, TPL, MINB, false>, dim3(g.nxB / LPC, np, 3), LPC * TPL, in, Aw, g, W, 0, np, LS, 0);
+            cta_emul::launch(zfwd4_kernel<G, LPC, TPL, MINB, false>, dim3(g.nxB / LPC, np, 3), LPC * TPL, in, Aw, g, W, 0, np, LS);
     } else {
-        cta_emul::launch(zbwd4_kernel<G, LPC, TPL, MINB>, dim3(g.nxB / LPC, np, 6), LPC * TPL, in, out, g, W, 0, np, LS, 0);
+        cta_emul::launch(zbwd4_kernel<G, LPC, TPL, MINB>, dim3(g.nxB / LPC, np, 6), LPC * TPL, in, out, g, W, 0, np, LS);
     }
 }
 
@@ -202,7 +202,7 @@ __attribute__((visibility("default"))) int chb_emul_convolutions_multi(int P, co
     memset(&sc, 0, sizeof(sc));
     for (int r = 0; r < P; ++r)   // z-pad + backward z FFT + zTOx into the owners' buffers
         cta_emul::launch(zfwd4_kernel<GZ, LPC, TPL, 4, false>, dim3(nxB / LPC, np, 3), LPC * TPL,
-                         reinterpret_cast<const cplx*>(V) + (size_t)r * 3 * nv, Aw, geom(r), reinterpret_cast<const cplx*>(Wz.data()), 0, np, LS, 0);
+                         reinterpret_cast<const cplx*>(V) + (size_t)r * 3 * nv, Aw, geom(r), reinterpret_cast<const cplx*>(Wz.data()), 0, np, LS);
     const bool persist = getenv("CHB_EMUL_XPERSIST") != nullptr;   // the persistent x-pass (prefetched inputs), two CTAs per rank
     for (int r = 0; r < P; ++r) { // x pass on the z-lines of rank r, xTOz into the owners' buffers
         const cplx* a = (const cplx*)Ar[r].data();
@@ -216,7 +216,7 @@ __attribute__((visibility("default"))) int chb_emul_convolutions_multi(int P, co
     }
     for (int r = 0; r < P; ++r)   // forward z FFT + truncation
         cta_emul::launch(zbwd4_kernel<GZ, LPC, TPL, 4>, dim3(nxB / LPC, np, 6), LPC * TPL, (const cplx*)Br[r].data(),
-                         reinterpret_cast<cplx*>(Pout) + (size_t)r * 6 * nv, geom(r), reinterpret_cast<const cplx*>(Wz.data()), 0, np, LS, 0);
+                         reinterpret_cast<cplx*>(Pout) + (size_t)r * 6 * nv, geom(r), reinterpret_cast<const cplx*>(Wz.data()), 0, np, LS);
     return 0;
 }
 
