@@ -305,13 +305,14 @@ static int create_impl(chb_handle_s* h, int nx, int ny, int nz, int nxd, int nzd
         h->p2p = (nranks > 1 && !(e && atoi(e) == 0)) ? 1 : 0;
         // two lanes: the kernels that carry the transposes run on their own stream (and SM partition) one chunk ahead of
         // the z-passes; default from 4 GPUs on for the large transforms
-        // Measured (profiles/r2_multi_gpu.md): the pipeline wins 11 % on the headline grid at 4 GPUs (nxd = 1536: the
-        // persistent x-pass is one CTA per SM and scales with its SM count) and loses to the sequential sweep at
-        // nxd = 768 (three x-pass CTAs per SM hide each other's phases; on fewer SMs it loses more than its share) and
-        // at 2 GPUs (little of the step is NVLink-bound).  The NCCL fallback always runs one lane.
+        // Measured (profiles/r2_multi_gpu.md): the pipeline wins 11-12 % on the headline grid at 4 and 8 GPUs (nxd = 1536:
+        // the persistent x-pass is one CTA per SM and scales with its SM count) and 4 % on config 3 at 8 GPUs; at
+        // nxd = 768 on 4 GPUs it loses to the sequential sweep (three x-pass CTAs per SM hide each other's phases;
+        // on fewer SMs the kernel loses more than its share), as it does at 2 GPUs (little of the step is
+        // NVLink-bound).  The NCCL fallback always runs one lane.
         const bool nccl_mode = nranks > 1 && !h->p2p;
         e = getenv("CHB_LANES");
-        h->nlanes = e ? (atoi(e) == 2 ? 2 : 1) : ((nranks >= 4 && nxd >= 1536) ? 2 : 1);
+        h->nlanes = e ? (atoi(e) == 2 ? 2 : 1) : ((nranks >= 8 || (nranks >= 4 && nxd >= 1536)) ? 2 : 1);
         if (nccl_mode) h->nlanes = 1;
         // budget: CHB_WORK_GB (default 10 GB, at most a quarter of the free device memory); larger chunks mean fewer
         // launches, fewer partially filled last waves and fewer carried-accumulator round trips of the RHS assembly
@@ -373,7 +374,7 @@ static int create_impl(chb_handle_s* h, int nx, int ny, int nz, int nxd, int nzd
         h->green_sms[0] = h->green_sms[1] = 0;
         if (h->nlanes == 2) {
             // CHB_GREEN=<SMs of the x-pass partition> (default: 54 % of the SMs on several GPUs - 80 + 68 measured
-            // best of 52 / 66 / 80 at 4 GPUs -, off on one): the two streams get disjoint SM partitions through CUDA
+            // best of 52 / 66 / 80 at 4 GPUs and of 64 / 72 / 80 at 8 -, off on one): the two streams get disjoint SM partitions through CUDA
             // green contexts, so that the z-passes really run beside the x-pass instead of behind it; plain streams
             // if the driver refuses
             e = getenv("CHB_GREEN");
