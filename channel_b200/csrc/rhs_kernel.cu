@@ -35,7 +35,7 @@ struct RhsAcc {
 // operations in the same order as a single march.  The finished rows go where the reference puts them
 // (dnsdata.f90:667-671): into V itself, eta-RHS -> component 0, D2v-RHS -> component 1 of row iy-2, two planes behind
 // the march, where the old velocities are no longer needed (by this thread: same column; by the z-passes: earlier chunk).
-template <bool HAS_F, int MINB>
+template <bool HAS_F, int MINB, bool CG = false>
 __global__ void __launch_bounds__(RHS_THREADS, MINB)
 rhs_kernel(cplx* V, const cplx* __restrict__ P, const cplx* __restrict__ F,
            cplx* __restrict__ oldrhs, Geometry g, DevTables tab, const DevScalars* __restrict__ sc, double ode1_dt,
@@ -85,7 +85,14 @@ rhs_kernel(cplx* V, const cplx* __restrict__ P, const cplx* __restrict__ F,
         const cplx p1 = P[0 * pcomp + poff], p2 = P[1 * pcomp + poff], p3 = P[2 * pcomp + poff];
         const cplx p4 = P[3 * pcomp + poff], p5 = P[4 * pcomp + poff], p6 = P[5 * pcomp + poff];
         // read-only path for V: a plane is read two iterations before this thread overwrites it, nobody else writes it
-        const cplx u = __ldg(V + 0 * comp + off), v = __ldg(V + 1 * comp + off), w = __ldg(V + 2 * comp + off);
+        cplx u, v, w;
+        if constexpr (CG) {   // L2 only: the rows are overwritten two planes later
+            u = __ldcg(reinterpret_cast<const double2*>(V + 0 * comp + off));
+            v = __ldcg(reinterpret_cast<const double2*>(V + 1 * comp + off));
+            w = __ldcg(reinterpret_cast<const double2*>(V + 2 * comp + off));
+        } else {
+            u = __ldg(V + 0 * comp + off); v = __ldg(V + 1 * comp + off); w = __ldg(V + 2 * comp + off);
+        }
         cplx f1 = make_double2(0, 0), f2 = f1, f3 = f1;
         if (HAS_F) {
             f1 = F[0 * comp + off];
@@ -167,8 +174,13 @@ rhs_kernel(cplx* V, const cplx* __restrict__ P, const cplx* __restrict__ F,
             re.y = acc[0].le.y + ode2 * ee.y - ode3 * oe.y;
             rv.x = acc[0].lv.x + ode2 * acc[0].ev.x - ode3 * ov.x;
             rv.y = acc[0].lv.y + ode2 * acc[0].ev.y - ode3 * ov.y;
-            V[0 * comp + oo] = re;
-            V[1 * comp + oo] = rv;
+            if constexpr (CG) {
+                __stcg(reinterpret_cast<double2*>(V + 0 * comp + oo), re);
+                __stcg(reinterpret_cast<double2*>(V + 1 * comp + oo), rv);
+            } else {
+                V[0 * comp + oo] = re;
+                V[1 * comp + oo] = rv;
+            }
             oldrhs[0 * comp + oo] = ee;
             oldrhs[1 * comp + oo] = acc[0].ev;
         }
@@ -198,7 +210,9 @@ void launch_rhs_chunk(chb_handle_s* h, const double* ode, double deltat, int pla
     const Geometry& g = h->g;
     const int blocks = (int)((g.M + RHS_THREADS - 1) / RHS_THREADS);
     ScopedKernelTimer tm(h, "rhs", st);
-    auto kern = h->bf.enabled ? rhs_kernel<true, 3> : rhs_kernel<false, 3>;
+    static const bool cg = []() { const char* e = getenv("CHB_RHS_CG"); return e ? atoi(e) != 0 : true; }();   // V rows through L2 only (see solve_kernels.cu)
+    auto kern = cg ? (h->bf.enabled ? rhs_kernel<true, 3, true> : rhs_kernel<false, 3, true>)
+                   : (h->bf.enabled ? rhs_kernel<true, 3> : rhs_kernel<false, 3>);
     CHB_LAUNCH(blocks, RHS_THREADS, 0, st, kern)(h->V, h->Pc, h->bf.enabled ? h->F : nullptr, h->oldrhs, g, h->tab, h->sc,
                                          ode[0] / deltat, ode[1], ode[2], plane0 - 1, plane0 + nplanes - 2, h->rhs_state,
                                          h->chunk_planes, plane0);

@@ -15,6 +15,7 @@
 //   S4 (iy = -1 -> ny+1): LeftLU5divStep2 with D0mat, then u=(ia*vy-ib*eta)/k2, w=(ib*vy+ia*eta)/k2
 //       (linsolve_blocking.inc:99-103).
 // The mean column (0,0) is finished by a single-thread kernel (linsolve_blocking.inc:62-97).
+#include <cstdlib>
 #include "chb_internal.h"
 #include "solve_device.cuh"
 
@@ -40,7 +41,8 @@ __global__ void solve_rows_kernel(DevTables tab, double* __restrict__ rows, doub
 // PF (experimental, CHB_SOLVE_PF=1): the loads of the next PF rows are issued before the rows are processed (as S2
 // does with its blocks), so that a thread keeps PF instead of one or two 16-byte loads in flight: for the
 // strong-scaled runs, where a GPU has too few columns to hide the latency with threads alone.
-template <int COMP, int PF = 1>
+// CG: the in-place row traffic with ld.global.cg / st.global.cg (L2 only), as in S2
+template <int COMP, int PF = 1, bool CG = false>
 __global__ void __launch_bounds__(SOLVE_THREADS)
 solve_s1_kernel(cplx* __restrict__ rhs, double* __restrict__ ckpt, Geometry g, DevTables tab,
                 const DevScalars* __restrict__ sc, double lam) {
@@ -95,7 +97,7 @@ solve_s1_kernel(cplx* __restrict__ rhs, double* __restrict__ ckpt, Geometry g, D
         x.y = (b.y - (u1 * x1.y + u2 * x2.y)) * inv;
         x2 = x1;
         x1 = x;
-        col[off] = x;
+        if constexpr (CG) __stcg(reinterpret_cast<double2*>(col + off), x); else col[off] = x;
         // The L-multipliers Step2 needs are not stored: the state of the UL recurrence is
         // checkpointed every SOLVE_K rows and solve_s2_kernel recomputes them block by block.
         if (iy > 1 && (iy - 1) % SOLVE_K == 0) {
@@ -113,12 +115,30 @@ solve_s1_kernel(cplx* __restrict__ rhs, double* __restrict__ ckpt, Geometry g, D
                 if (i0 - k >= 1) row(i0 - k, bb[k]);
         }
     } else {
-        for (int iy = ny - 1; iy >= 1; --iy) row(iy, col[(size_t)(iy + 1) * plane]);
+        for (int iy = ny - 1; iy >= 1; --iy) {
+            cplx b;
+            if constexpr (CG) b = __ldcg(reinterpret_cast<const double2*>(col + (size_t)(iy + 1) * plane)); else b = col[(size_t)(iy + 1) * plane];
+            row(iy, b);
+        }
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-template <int COMP>
+// MEMV: cache operators of the in-place row traffic (0: ld.global.nc / st; 1: ld.cg / st; 2: ld.cg / st.cg; 3: ld.cs / st.cs)
+template <int MEMV>
+__device__ __forceinline__ cplx s2_load(const cplx* p) {
+    if constexpr (MEMV == 0) return __ldg(p);
+    else if constexpr (MEMV == 3) { const double2 v = __ldcs(reinterpret_cast<const double2*>(p)); return v; }
+    else { const double2 v = __ldcg(reinterpret_cast<const double2*>(p)); return v; }
+}
+template <int MEMV>
+__device__ __forceinline__ void s2_store(cplx* p, cplx v) {
+    if constexpr (MEMV == 2) __stcg(reinterpret_cast<double2*>(p), v);
+    else if constexpr (MEMV == 3) __stcs(reinterpret_cast<double2*>(p), v);
+    else *p = v;
+}
+
+template <int COMP, int MEMV = 0>
 __global__ void __launch_bounds__(SOLVE_THREADS, 4)
 solve_s2_kernel(const double* __restrict__ ckpt, cplx* V, Geometry g,
                 DevTables tab, const DevScalars* __restrict__ sc, double lam) {
@@ -159,7 +179,7 @@ solve_s2_kernel(const double* __restrict__ ckpt, cplx* V, Geometry g,
             const int iy = i0 + k;
             // read-only path: a row is read before this thread (the only one that touches the column) overwrites it, and
             // the compiler may hoist the next block's loads over this block's stores as it could with separate arrays
-            xb[k] = (iy <= ny - 1) ? __ldg(xin + (size_t)(iy + 1) * plane) : make_double2(0.0, 0.0);
+            xb[k] = (iy <= ny - 1) ? s2_load<MEMV>(xin + (size_t)(iy + 1) * plane) : make_double2(0.0, 0.0);
         }
         double m2[SOLVE_K], m1[SOLVE_K];
 #pragma unroll
@@ -193,7 +213,7 @@ solve_s2_kernel(const double* __restrict__ ckpt, cplx* V, Geometry g,
                 cplx v = xb[k];
                 v.x -= m2[k] * v2.x + m1[k] * v1.x;
                 v.y -= m2[k] * v2.y + m1[k] * v1.y;
-                out[(size_t)(iy + 1) * plane] = v;
+                s2_store<MEMV>(out + (size_t)(iy + 1) * plane, v);
                 v3 = v2; v2 = v1; v1 = v;
                 if (iy == 3) {  // bottom closure needs nodes 1..3 (linsolve_blocking.inc:51-54)
                     const cplx a1 = v3, a2 = v2, a3 = v1;
@@ -327,7 +347,7 @@ solve_s3_kernel(cplx* __restrict__ V, Geometry g, DevTables tab) {
 }
 
 // S4: Step2 with D0mat, then u,w
-template <int PF = 1>
+template <int PF = 1, bool CG = false>
 __global__ void __launch_bounds__(SOLVE_THREADS)
 solve_s4_kernel(cplx* __restrict__ V, Geometry g, DevTables tab) {
     const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -357,8 +377,13 @@ solve_s4_kernel(cplx* __restrict__ V, Geometry g, DevTables tab) {
         u.y = (al * vy.x - be * eta.x) * rk2;
         w.x = (-be * vy.y - al * eta.y) * rk2;
         w.y = (be * vy.x + al * eta.x) * rk2;
-        V[0 * comp + off] = u;
-        V[2 * comp + off] = w;
+        if constexpr (CG) {
+            __stcg(reinterpret_cast<double2*>(V + 0 * comp + off), u);
+            __stcg(reinterpret_cast<double2*>(V + 2 * comp + off), w);
+        } else {
+            V[0 * comp + off] = u;
+            V[2 * comp + off] = w;
+        }
     };
     if constexpr (PF > 1) {
         for (int i0 = -1; i0 <= ny + 1; i0 += PF) {
@@ -377,7 +402,8 @@ solve_s4_kernel(cplx* __restrict__ V, Geometry g, DevTables tab) {
     } else {
         for (int iy = -1; iy <= ny + 1; ++iy) {
             const size_t off = (size_t)(iy + 1) * plane + m;
-            row(iy, V[2 * comp + off], V[0 * comp + off]);
+            if constexpr (CG) row(iy, __ldcg(reinterpret_cast<const double2*>(V + 2 * comp + off)), __ldcg(reinterpret_cast<const double2*>(V + 0 * comp + off)));
+            else row(iy, V[2 * comp + off], V[0 * comp + off]);
         }
     }
 }
@@ -567,6 +593,9 @@ void launch_linsolve(chb_handle_s* h, double lam) {
     const int blocks = (int)((g.M + SOLVE_THREADS - 1) / SOLVE_THREADS);
     CHB_LAUNCH((g.nyp * 5 + 127) / 128, 128, 0, h->stream, solve_rows_kernel)(h->tab, h->t_rows, lam, g.ni, g.nyp);
     h->launches++;
+    // the sweeps that work in place move their rows through L2 only (ld.global.cg / st.global.cg): reading rows through L1
+    // that the same kernel overwrites cost S2 2 ms/step (19.4 -> 17.2), S1 / S4 0.4 ms (profiles/r2c_r2e_single_gpu.md)
+    static const bool ycg = []() { const char* e = getenv("CHB_Y_CG"); return e ? atoi(e) != 0 : true; }();
     const bool pf = h->solve_pf != 0;   // experimental: eight rows of loads in flight per thread in S1 / S3 / S4
     {
         ScopedKernelTimer tm(h, "solve_s1");
@@ -574,14 +603,23 @@ void launch_linsolve(chb_handle_s* h, double lam) {
             CHB_LAUNCH(blocks, SOLVE_THREADS, 0, h->stream, solve_s1_kernel<0, 8>)(h->V, h->ckpt, g, h->tab, h->sc, lam);
             CHB_LAUNCH(blocks, SOLVE_THREADS, 0, h->stream, solve_s1_kernel<1, 8>)(h->V, h->ckpt, g, h->tab, h->sc, lam);
         } else {
-            CHB_LAUNCH(blocks, SOLVE_THREADS, 0, h->stream, solve_s1_kernel<0>)(h->V, h->ckpt, g, h->tab, h->sc, lam);
-            CHB_LAUNCH(blocks, SOLVE_THREADS, 0, h->stream, solve_s1_kernel<1>)(h->V, h->ckpt, g, h->tab, h->sc, lam);
+            if (ycg) {
+                CHB_LAUNCH(blocks, SOLVE_THREADS, 0, h->stream, solve_s1_kernel<0, 1, true>)(h->V, h->ckpt, g, h->tab, h->sc, lam);
+                CHB_LAUNCH(blocks, SOLVE_THREADS, 0, h->stream, solve_s1_kernel<1, 1, true>)(h->V, h->ckpt, g, h->tab, h->sc, lam);
+            } else {
+                CHB_LAUNCH(blocks, SOLVE_THREADS, 0, h->stream, solve_s1_kernel<0>)(h->V, h->ckpt, g, h->tab, h->sc, lam);
+                CHB_LAUNCH(blocks, SOLVE_THREADS, 0, h->stream, solve_s1_kernel<1>)(h->V, h->ckpt, g, h->tab, h->sc, lam);
+            }
         }
     }
     {
         ScopedKernelTimer tm(h, "solve_s2");
-        CHB_LAUNCH(blocks, SOLVE_THREADS, 0, h->stream, solve_s2_kernel<0>)(h->ckpt, h->V, g, h->tab, h->sc, lam);
-        CHB_LAUNCH(blocks, SOLVE_THREADS, 0, h->stream, solve_s2_kernel<1>)(h->ckpt, h->V, g, h->tab, h->sc, lam);
+        static const int memv = []() { const char* e = getenv("CHB_S2_MEMV"); return e ? atoi(e) : 2; }();   // measured: 19.4 / 17.5 / 17.2 / 17.2 ms for 0..3
+#define CHB_S2(MV)                                                                                                            \
+        CHB_LAUNCH(blocks, SOLVE_THREADS, 0, h->stream, solve_s2_kernel<0, MV>)(h->ckpt, h->V, g, h->tab, h->sc, lam); \
+        CHB_LAUNCH(blocks, SOLVE_THREADS, 0, h->stream, solve_s2_kernel<1, MV>)(h->ckpt, h->V, g, h->tab, h->sc, lam)
+        if (memv == 1) { CHB_S2(1); } else if (memv == 2) { CHB_S2(2); } else if (memv == 3) { CHB_S2(3); } else { CHB_S2(0); }
+#undef CHB_S2
     }
     h->launches += 6;
     // The mean column (0,0) only needs the result of S2 and is skipped by S3/S4: finish it on the
@@ -604,6 +642,7 @@ void launch_linsolve(chb_handle_s* h, double lam) {
     {
         ScopedKernelTimer tm(h, "solve_s4");
         if (pf) CHB_LAUNCH(blocks, SOLVE_THREADS, 0, h->stream, solve_s4_kernel<8>)(h->V, g, h->tab);
+        else if (ycg) CHB_LAUNCH(blocks, SOLVE_THREADS, 0, h->stream, solve_s4_kernel<1, true>)(h->V, g, h->tab);
         else CHB_LAUNCH(blocks, SOLVE_THREADS, 0, h->stream, solve_s4_kernel<1>)(h->V, g, h->tab);
     }
     if (mean_here) {

@@ -43,6 +43,14 @@ alignas(16) inline unsigned char g_dyn_smem[232448];   // 227 KB of dynamic shar
 
 template <class T>
 static inline T __ldg(const T* p) { return *p; }
+template <class T>
+static inline T __ldcg(const T* p) { return *p; }
+template <class T>
+static inline T __ldcs(const T* p) { return *p; }
+template <class T>
+static inline void __stcg(T* p, T v) { *p = v; }
+template <class T>
+static inline void __stcs(T* p, T v) { *p = v; }
 static inline void __syncthreads() { pthread_barrier_wait(&cta_emul::g_block_barrier); }
 static inline double __shfl_xor_sync(unsigned, double v, int o) {
     const int tid = cta_emul::t_linear_tid, w = tid >> 5, l = tid & 31;
