@@ -190,3 +190,23 @@ def test_convection_velocity_diagnostic(tmp_path):
     for c in range(3):
         assert relerr(Vg[c], o.V[c]) < 1e-10
     ch.close()
+
+
+def test_body_force_reconfiguration_clears_the_old_mask():
+    """A hook only assigns F inside its mask and the reference's F starts from zero (dnsdata.f90:146): when the force is
+    reconfigured with another mask (or after a host-side F from chb_upload_F), nothing of the previous configuration may
+    survive outside the new mask."""
+    p, o, ch, V0 = make_pair(15, 24, 10, CPI=False, u0=-1.0, uN=1.0, couette=True)
+    ch.config_coriolis(0.02, 9999999.0, 1.0)                   # mask: every z mode, y <= 1 or y >= 1 (all rows)
+    F1 = ch.download_F()
+    assert np.abs(F1).max() > 0
+    ch.config_coriolis(0.02, 2.5, 0.3)                         # narrower: |iz| <= 2, y <= 0.3 or y >= 1.7
+    F2 = ch.download_F()
+    y = ch.y
+    iz = np.arange(-p.nz, p.nz + 1)
+    inside = ((y <= 0.3) | (y >= 1.7))[:, None, None] & (np.abs(iz) <= 2)[None, None, :]
+    inside = np.broadcast_to(inside, F2.shape[1:])
+    assert np.abs(F2[:, ~inside]).max() == 0.0                 # no leftovers of the wide mask
+    assert np.abs(F2[:, inside]).max() > 0
+    assert np.array_equal(F2[:, inside], F1[:, inside])        # same force where both masks are on
+    ch.close()
