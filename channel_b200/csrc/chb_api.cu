@@ -293,7 +293,7 @@ static int create_impl(chb_handle_s* h, int nx, int ny, int nz, int nxd, int nzd
     if (dev_alloc(&h->t_y, (size_t)g.nyp) || dev_alloc(&h->t_dy, (size_t)g.nyp) ||
         dev_alloc(&h->t_d0, (size_t)g.nyp * 5) || dev_alloc(&h->t_d1, (size_t)g.nyp * 5) ||
         dev_alloc(&h->t_d2, (size_t)g.nyp * 5) || dev_alloc(&h->t_d4, (size_t)g.nyp * 5) ||
-        dev_alloc(&h->t_D0mat, (size_t)(ny + 1) * 5) || dev_alloc(&h->t_rows, (size_t)g.nyp * 25) || dev_alloc(&h->mean_scratch, (size_t)(ny + 1) * 5 + 3 * g.nyp + 8))
+        dev_alloc(&h->t_D0mat, (size_t)(ny + 1) * 5) || dev_alloc(&h->t_rows, (size_t)g.nyp * 25))
         return 1;
     if (dev_alloc(&h->sc, 1)) return 1;
     CHB_CUDA_OK(cudaMallocHost((void**)&h->sc_host, sizeof(DevScalars)));
@@ -418,7 +418,7 @@ extern "C" int chb_destroy(chb_handle h) {
     if (h->arena) cudaFree(h->arena);
     cudaFree(h->Wz); cudaFree(h->Wx); cudaFree(h->Wh); cudaFree(h->rev_z);
     cudaFree(h->t_y); cudaFree(h->t_dy); cudaFree(h->t_d0); cudaFree(h->t_d1); cudaFree(h->t_d2); cudaFree(h->t_d4);
-    cudaFree(h->t_D0mat); cudaFree(h->t_rows); cudaFree(h->mean_scratch); cudaFree(h->sc);
+    cudaFree(h->t_D0mat); cudaFree(h->t_rows); cudaFree(h->sc);
     if (h->bf.mask_y) cudaFree(h->bf.mask_y);
     if (h->bf.mask_z) cudaFree(h->bf.mask_z);
     if (h->bf.mask_yz) cudaFree(h->bf.mask_yz);

@@ -149,7 +149,6 @@ struct chb_handle_s {
     bool tables_set;
     DevScalars* sc;       // device
     DevScalars* sc_host;  // pinned
-    double* mean_scratch; // [ny+1][5] + 3*(ny+3): eta00mat, ucor, U, W of the mean column
     BodyForce bf;
     // multi-GPU
     void* nccl_comm;

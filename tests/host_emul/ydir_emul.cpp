@@ -72,7 +72,6 @@ __attribute__((visibility("default"))) int chb_emul_ydir_substep(int nx, int ny,
 
     const size_t fld = (size_t)nyp * g.M;
     std::vector<double> ckpt((size_t)((ny - 1) / CHB_SOLVE_K + 1) * 8 * g.M, 0.0);
-    std::vector<double> scratch((size_t)(ny + 1) * 5 + 3 * nyp + 8, 0.0);
     cplx* Vc = reinterpret_cast<cplx*>(V);
     const cplx* Pc = reinterpret_cast<const cplx*>(P);
     const cplx* Fc = reinterpret_cast<const cplx*>(F);
