@@ -188,6 +188,8 @@ extern "C" int chb_create(chb_handle* out, int nx, int ny, int nz, int nxd, int 
     CHB_REQUIRE((nx + 1) % nranks == 0 && nzd % nranks == 0,
                 "chb_create: nranks must divide nx+1 and nzd (README.md:154)");
     CHB_REQUIRE(nranks == 1 || nccl_id != nullptr, "chb_create: nccl_id required when nranks>1");
+    CHB_REQUIRE(mean_mode_smem_doubles(ny) * sizeof(double) <= 227 * 1024,
+                "chb_create: ny too large for the mean-mode kernel (its column lives in shared memory: ny <= 3056)");
     int ndev = 0;
     CHB_CUDA_OK(cudaGetDeviceCount(&ndev));
     CHB_REQUIRE(ndev > 0, "chb_create: no CUDA device (this library has no CPU fallback)");

@@ -167,6 +167,9 @@ struct chb_handle_s {
     KernelTimer timer;
 };
 
+// doubles of dynamic shared memory of mean_mode_kernel (solve_kernels.cu): A [ny+1][5] | ucor, U, W [ny+3] | wts [ny/2+1][3]
+inline size_t mean_mode_smem_doubles(int ny) { return (size_t)(ny + 1) * 5 + 3 * (size_t)(ny + 3) + 3 * (size_t)(ny / 2 + 1); }
+
 // ---- launchers (conv_kernels.cu) ----
 void launch_zfwd(chb_handle_s* h, int plane0, int nplanes);
 void launch_xpass(chb_handle_s* h, int plane0, int nplanes, int compute_cfl);

@@ -450,7 +450,6 @@ __device__ void store_wall_columns(cplx* V, DevScalars* sc, const Geometry& g, s
 // substep at ny = 512 - nothing on one GPU, where it hides under S3 / S4, but 7 % of the step on eight.)
 // Dynamic shared memory (doubles): A [ny+1][5] | ucor [ny+3] | U [ny+3] | W [ny+3] | wts [3][ny/2+1].
 #define MEAN_THREADS 128
-__host__ __device__ inline size_t mean_mode_smem_doubles(int ny) { return (size_t)(ny + 1) * 5 + 3 * (size_t)(ny + 3) + 3 * (size_t)(ny / 2 + 1); }
 
 // yintegr (dnsdata.f90:312-324) with the weights a1, a2, a3 of every odd node precomputed (same expressions)
 __device__ __forceinline__ double yintegr_weighted(const double* __restrict__ wts, const double* f, int ny) {

@@ -54,6 +54,10 @@ def test_argument_validation_precedes_device_use():
     assert lib.chb_create(C.byref(h), 16, 64, 16, 33, 48, 0.5, 1.0, 1e-3, 1.5, 0.0, 2.0, 0, 1, None, 0) == 2   # odd nxd
     assert lib.chb_create(C.byref(h), 16, 64, 16, 32, 48, 0.5, 1.0, 1e-3, 1.5, 0.0, 2.0, 0, 2, None, 0) == 2   # 2 !| 17
     assert b"README.md:154" in lib.chb_last_error()
+    assert lib.chb_create(C.byref(h), 16, 64, 16, 32, 48, 0.5, 1.0, 1e-3, 1.5, 0.0, 2.0, 0, 9, None, 0) == 2   # more than 8 ranks
+    assert lib.chb_create(C.byref(h), 16, 4000, 16, 32, 48, 0.5, 1.0, 1e-3, 1.5, 0.0, 2.0, 0, 1, None, 0) == 2  # mean-mode column > shared memory
+    assert b"ny too large" in lib.chb_last_error()
+    assert lib.chb_download_products(None, None) != 0 and lib.chb_debug_capture_products(None, 1) != 0
     assert lib.chb_buildrhs(None, None, 1.0, 0) != 0
     assert lib.chb_linsolve(None, 1.0) != 0
 
