@@ -577,8 +577,8 @@ def cpu_baseline(w, sample_s=20.0, threads=None):
 def run_reference(args):
     """The reference arm: the reference's algorithm on the host cores of this box (oracle/channel_oracle_c.c; the Fortran
     / FFTW / MPI binary cannot be built in this image).  A "step" of this arm is one bounded sample of an RK3
-    step of the same workload (the task's definition), scaled to a full step: `value` and `ms_per_step` are the
-    extrapolated full-workload figures (`extrapolated: true`, the executed share in `sampled_fraction_of_step`, the
+    step of the same workload (the task's definition; with the driver's 25 steps one complete RK substep, a third of a
+    step), scaled to a full step: `value` and `ms_per_step` are the extrapolated full-workload figures (`extrapolated: true`, the executed share in `sampled_fraction_of_step`, the
     wall time actually spent per sample in `sample_wall_ms`).  `extrapolation_check` times one COMPLETE, unsampled RK3
     step on config 2 next to the estimate the same sampling gives for it."""
     rank = int(os.environ.get("RANK", "0"))
@@ -639,8 +639,9 @@ def main():
     ap.add_argument("--extrapolation-grid", default="2", help="reference arm: grid of the complete-step check (config number or nx,ny,nz)")
     args = ap.parse_args()
     if args.impl == "reference":
-        # each "step" of the reference arm is one bounded sample; keep the whole run to minutes
-        args.cpu_seconds = min(args.cpu_seconds, max(3.0, 120.0 / max(1, args.steps + args.warmup)))
+        # each "step" of the reference arm is one bounded sample, at best one complete RK substep of the workload (a third of
+        # a step: 11 s for config 3 on 16 cores); the whole run stays within about eight minutes
+        args.cpu_seconds = min(max(args.cpu_seconds, 20.0), max(3.0, 480.0 / max(1, args.steps + args.warmup)))
         run_reference(args)
     else:
         run_b200(args)
