@@ -457,7 +457,13 @@ def headline_leg(args, rank, world, local_rank, new_id):
             host_avail = next(int(l.split()[1]) * 1024 for l in f if l.startswith("MemAvailable"))
     except Exception:
         host_avail = None
-    if need > free_b or (host_avail is not None and host_need > 0.8 * host_avail):
+    fits = not (need > free_b or (host_avail is not None and host_need > 0.8 * host_avail))
+    if world > 1:      # every rank takes the same decision (a rank that skipped alone would leave the others in a collective)
+        import torch.distributed as dist
+        t = torch.tensor([1 if fits else 0], dtype=torch.int32, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        fits = bool(t.item())
+    if not fits:
         return {"ran": False, "why": f"needs {need / 1e9:.0f} GB per GPU ({free_b / 1e9:.0f} GB free) and "
                                      f"{host_need / 1e9:.0f} GB of host memory for the synthetic field "
                                      f"({(host_avail or 0) / 1e9:.0f} GB available)"}
