@@ -38,7 +38,7 @@ __global__ void solve_rows_kernel(DevTables tab, double* __restrict__ rows, doub
 // COMP = 0: eta equation (etamat), COMP = 1: v equation (D2vmat); blockIdx.y selects nothing, the
 // two components are separate launches of the same grid so that each thread carries one recurrence
 // (half the registers, twice the resident warps).
-// PF (experimental, CHB_SOLVE_PF=1): the loads of the next PF rows are issued before the rows are processed (as S2
+// PF (CHB_SOLVE_PF=1; measured slower at 524 k and at 262 k columns per GPU, kept as a comparator): the loads of the next PF rows are issued before the rows are processed (as S2
 // does with its blocks), so that a thread keeps PF instead of one or two 16-byte loads in flight: for the
 // strong-scaled runs, where a GPU has too few columns to hide the latency with threads alone.
 // CG: the in-place row traffic with ld.global.cg / st.global.cg (L2 only), as in S2
@@ -595,7 +595,7 @@ void launch_linsolve(chb_handle_s* h, double lam) {
     // the sweeps that work in place move their rows through L2 only (ld.global.cg / st.global.cg): reading rows through L1
     // that the same kernel overwrites cost S2 2 ms/step (19.4 -> 17.2), S1 / S4 0.4 ms (profiles/r2c_r2e_single_gpu.md)
     static const bool ycg = []() { const char* e = getenv("CHB_Y_CG"); return e ? atoi(e) != 0 : true; }();
-    const bool pf = h->solve_pf != 0;   // experimental: eight rows of loads in flight per thread in S1 / S3 / S4
+    const bool pf = h->solve_pf != 0;   // eight rows of loads in flight per thread in S1 / S3 / S4 (measured slower, off)
     {
         ScopedKernelTimer tm(h, "solve_s1");
         if (pf) {

@@ -38,7 +38,7 @@ __device__ __forceinline__ void apply_twiddle_seq(cplx* x, cplx w1) {
 // radix C (T = M/C threads per line, e.g. C = 4 -> 192 threads for M = 768) keeps all threads busy in
 // every stage and MINB CTAs (lines) per SM give 4-5 warps per scheduler.
 //
-// SPLIT = 2 (experimental, CHB_XPASS_SPLIT=1; proven on the CPU emulator, not yet measured on a GPU): TWO threads per
+// SPLIT = 2 (CHB_XPASS_SPLIT; default at nxd = 1536, where it measured 6 % faster; 34 % slower at nxd = 768): TWO threads per
 // innermost butterfly position (T = 2 M/C threads per line).  For M = 1536, whose six line buffers (148.6 KB) leave
 // room for one CTA per SM only, that is twice the resident warps at the same shared memory (12 instead of 6, 140
 // registers); for M = 768, two CTAs of 12 warps at 80 registers instead of three of 6 warps at 96.  The flattened

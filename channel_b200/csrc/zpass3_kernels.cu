@@ -31,7 +31,7 @@ __device__ __forceinline__ void z_twiddle_seq(cplx* x, cplx w1) {
 // zfwd4 / zbwd4: the same three stages with TPL (a multiple of 32) threads per line and
 // block-wide barriers between stages, sized so that MINB CTAs are resident per SM: while one CTA
 // waits for its lines to arrive from HBM another one computes.
-// DIRECT (experimental, CHB_ZF_DIRECT=1, proven on the CPU emulator, not yet measured): stage A reads its inputs
+// DIRECT (CHB_ZF_DIRECT=1; measured slower, 25.7 against 21.3 ms/step at config 3, kept as a comparator): stage A reads its inputs
 // straight from global memory (a warp reads 512 contiguous bytes per radix digit) instead of through the TMA
 // staging copy: two of the six shared-memory passes per point disappear, the load latency moves into the threads.
 template <class G, int LPC, int TPL, int MINB, bool DIRECT = false>
@@ -238,7 +238,7 @@ static bool launch_z4(chb_handle_s* h, int plane0, int nplanes, bool fwd) {
 bool launch_z3_fwd_or_bwd(chb_handle_s* h, int plane0, int nplanes, bool fwd) {
     if (h->g.nz < 2) return false;
     const int lpc = fwd ? h->zf_lines_per_cta : h->zb_lines_per_cta;
-    // experimental (CHB_Z_TPL=128 | 96, proven on the CPU emulator, not yet measured): more threads per line, i.e. more
+    // CHB_Z_TPL=128 | 96 (measured, profiles/r2a_variants.md): more threads per line, i.e. more
     // resident warps per SM at the same shared memory, with two lines per CTA:
     //   nzd = 3072: 128 threads/line, 2 CTAs/SM -> 16 warps (default 8), 128 registers, 0 / 8 bytes of spills
     //   nzd = 1536: 128 threads/line, 3 CTAs/SM -> 24 warps (default 16), 80 registers, no spills

@@ -1,5 +1,5 @@
-"""Kernel variants that are proven on the CPU emulator (tests/test_fft_emul_cpu.py) but not yet measured on a
-GPU; they are off by default.  The file name sorts last on purpose: with `pytest -x` a problem here cannot hide
+"""Optional kernel variants (environment switches; DESIGN.md 5b lists what each measured on B200 and which are defaults
+for which sizes), each against the kernels it replaces.  The file name sorts last on purpose: with `pytest -x` a problem here cannot hide
 the results of the validated suite."""
 import numpy as np
 import pytest
